@@ -1,0 +1,91 @@
+"""The CPU oracle (oracle/) against fixtures produced by the REAL reference modules
+(tools/make_golden.py, run in the build container).  CPU-only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cost as ocost
+from oracle.lgunet import lgunet_forward, to_torch, shift_mask
+from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+from vaevar_b200.synth import make_case, make_state_dict
+
+DS, FS = small(DECODER_FULL), small(FLOW_FULL)
+
+
+def _net_check(g, cfg):
+    sd = to_torch(make_state_dict(cfg, seed=int(g["seed"]), gain=float(g["gain"]), rich=bool(g["rich"])))
+    rng = np.random.Generator(np.random.PCG64(int(g["seed"]) + 77))
+    x = torch.from_numpy(rng.standard_normal((1, cfg.in_chans, *cfg.img_size), dtype=np.float32)).requires_grad_(True)
+    dy = torch.from_numpy(rng.standard_normal((1, cfg.out_chans, *cfg.img_size), dtype=np.float32))
+    y = lgunet_forward(x, sd, cfg)
+    (y * dy).sum().backward()
+    yv, dx = y.detach().numpy().ravel(), x.grad.numpy().ravel()
+    np.testing.assert_allclose(yv[g["y_idx"]], g["y_val"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(dx[g["dx_idx"]], g["dx_val"], rtol=2e-4, atol=2e-5)
+    assert abs(np.abs(yv.astype(np.float64)).sum() / float(g["y_abs"]) - 1) < 1e-5
+    assert abs(np.linalg.norm(dx.astype(np.float64)) / float(g["dx_norm"]) - 1) < 1e-5
+
+
+def test_net_small_decoder_matches_reference(gold):
+    _net_check(gold("net_small_dec.npz"), DS)
+
+
+def test_net_small_flow_rich_matches_reference(gold):
+    _net_check(gold("net_small_flow_rich.npz"), FS)
+
+
+@pytest.mark.parametrize("tag", ["small_T1", "small_T3_rich"])
+def test_cost_and_grad_matches_reference(gold, tag):
+    g = gold(f"cost_{tag}.npz")
+    seed, gain, rich, T = int(g["seed"]), float(g["gain"]), bool(g["rich"]), int(g["T"])
+    nets = ocost.OracleNets(to_torch(make_state_dict(DS, seed=seed, gain=gain, rich=rich)), DS,
+                            to_torch(make_state_dict(FS, seed=seed + 1, gain=gain, rich=rich)), FS)
+    case = make_case(T, *DS.img_size, obs_frac=float(g["obs_frac"]), seed=seed)
+    assert int(case["H"].sum()) == int(g["n_obs"])
+    J, Jr, Jo, grad = ocost.cost_and_grad(case["z"], ocost.Case(case), nets)
+    assert abs(J / float(g["J"]) - 1) < 2e-5
+    assert abs(Jr / float(g["J_reg"]) - 1) < 1e-6
+    assert abs(Jo / float(g["J_obs"]) - 1) < 2e-5
+    ref = g["g_full"]
+    cos = float((grad.ravel() @ ref.ravel()) / np.linalg.norm(grad) / np.linalg.norm(ref))
+    assert cos > 1 - 1e-6
+    assert abs(np.linalg.norm(grad) / float(g["g_norm"]) - 1) < 1e-4
+
+
+def test_lbfgs_analysis_matches_reference(gold):
+    g = gold("cost_small_T1.npz")
+    nets = ocost.OracleNets(to_torch(make_state_dict(DS, seed=0)), DS)
+    case = make_case(1, *DS.img_size, obs_frac=0.10, seed=0)
+    r = ocost.one_step_da(ocost.Case(case), nets, nit=1, max_iter=10)
+    np.testing.assert_allclose(r["bg_wrmse"], g["bg_wrmse"], rtol=1e-5)
+    np.testing.assert_allclose(r["ana_wrmse"], g["ana_wrmse"], rtol=1e-2)   # north_star gate: 1 %
+    assert r["n_evals"] == int(g["n_evals"])
+
+
+def test_metrics_match_reference(gold):
+    g = gold("metrics.npz")
+    from vaevar_b200.config import era5_stats
+    std = torch.from_numpy(era5_stats()[1])
+    pred, gt = torch.from_numpy(g["pred"]), torch.from_numpy(g["gt"])
+    np.testing.assert_allclose(ocost.wrmse(pred, gt, std).numpy(), g["wrmse"], rtol=1e-6)
+    np.testing.assert_allclose(ocost.bias(pred, gt, std).numpy(), g["bias"], rtol=1e-5, atol=1e-12)
+
+
+def test_shift_mask_is_latitude_only():
+    m = shift_mask(8, 16, 4, 2)           # (8 windows, 16, 16)
+    assert m.shape == (8, 16, 16)
+    assert float(m[:4].abs().sum()) == 0.0          # first window row: no masking
+    last = m[4]
+    rows = torch.arange(16) // 4                    # token row inside the window
+    expect = torch.where((rows[:, None] < 2) != (rows[None, :] < 2), -100.0, 0.0)
+    assert torch.equal(last, expect)
+    assert all(torch.equal(m[i], last) for i in range(4, 8))   # same for every longitude
+
+
+def test_state_dict_keys_match_reference_decoder():
+    import pathlib
+    want = (pathlib.Path(__file__).parent / "golden" / "decoder_state_dict_keys.txt").read_text().split("\n")
+    want = {w for w in want if w and "relative_position_index" not in w and "attn_mask" not in w}
+    sd = make_state_dict(DECODER_FULL, seed=0)
+    got = {f"{k}:{tuple(v.shape)}" for k, v in sd.items()}
+    assert got == want

@@ -1,0 +1,190 @@
+"""Generate tests/golden/*.npz by running the REAL reference modules on CPU.
+
+Runs only in the build container (needs /root/reference).  Imports the reference's
+own `networks_old.transformer.LGUnet_all`, `nf_model.vae.VAE_lr` and
+`utils.metrics.Metrics` unmodified through the 3-module import shim of SURVEY.md
+appendix C (timm / fairscale / turtle stubs), loads the repo's seeded synthetic
+weights into them by name (strict), and records outputs the CPU oracle
+(`oracle/`) and the CUDA engine are then checked against.  Nothing here is used
+at run time; the fixtures it writes are committed.
+
+    python tools/make_golden.py [--full]     # --full adds the 128x256 fixtures (minutes)
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import os
+import pathlib
+import sys
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+REF = "/root/reference"
+GOLD = ROOT / "tests" / "golden"
+
+
+def install_shim():
+    """Stub the three absent third-party modules before importing the reference."""
+    class DropPath(torch.nn.Module):
+        def __init__(self, p=0.0):
+            super().__init__()
+
+        def forward(self, x):
+            return x
+
+    def to_2tuple(x):
+        return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+    def mk(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    mk("timm"); mk("timm.models")
+    mk("timm.models.layers", DropPath=DropPath, to_2tuple=to_2tuple, trunc_normal_=torch.nn.init.trunc_normal_)
+    mk("fairscale"); mk("fairscale.nn"); mk("fairscale.nn.checkpoint")
+    mk("fairscale.nn.checkpoint.checkpoint_activations", checkpoint_wrapper=lambda m, **kw: m)
+    mk("turtle", forward=None)
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    os.chdir(REF)
+
+
+def ref_net(cfg, sd_np):
+    from networks_old.transformer import LGUnet_all
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = LGUnet_all(**cfg.to_reference_kwargs()).eval()
+    want = {k for k, _ in net.named_parameters()}
+    assert want == set(sd_np), (sorted(want ^ set(sd_np))[:10])
+    missing, unexpected = net.load_state_dict({k: torch.from_numpy(v) for k, v in sd_np.items()}, strict=False)
+    assert not unexpected and all(("relative_position_index" in m or "attn_mask" in m) for m in missing), (missing[:5], unexpected[:5])
+    return net
+
+
+class RefNets:
+    def __init__(self, dec, flow):
+        self._dec, self._flow = dec, flow
+
+    def decode(self, z):
+        return self._dec(z)
+
+    def flow(self, x):
+        return self._flow(x)
+
+
+def sample_idx(n, k=4096, seed=7):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return np.sort(rng.choice(n, min(k, n), replace=False))
+
+
+def golden_net(tag, cfg, seed, gain, rich):
+    from vaevar_b200.synth import make_state_dict
+    sd = make_state_dict(cfg, seed=seed, gain=gain, rich=rich)
+    net = ref_net(cfg, sd)
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    x = rng.standard_normal((1, cfg.in_chans, *cfg.img_size), dtype=np.float32)
+    dy = rng.standard_normal((1, cfg.out_chans, *cfg.img_size), dtype=np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    y = net(xt)
+    (y * torch.from_numpy(dy)).sum().backward()
+    y = y.detach().numpy(); dx = xt.grad.numpy()
+    iy, ix = sample_idx(y.size), sample_idx(dx.size, seed=8)
+    np.savez_compressed(GOLD / f"net_{tag}.npz", seed=seed, gain=gain, rich=rich,
+                        y_idx=iy, y_val=y.ravel()[iy], y_sum=np.float64(y.astype(np.float64).sum()),
+                        y_abs=np.float64(np.abs(y.astype(np.float64)).sum()),
+                        dx_idx=ix, dx_val=dx.ravel()[ix], dx_norm=np.float64(np.linalg.norm(dx.astype(np.float64))))
+    print(f"net_{tag}: |y|_1={np.abs(y).sum():.6g} |dx|_2={np.linalg.norm(dx):.6g}")
+    return sd, net
+
+
+def golden_cost(tag, cfg_dec, cfg_flow, T, obs_frac, seed, gain, rich, lbfgs_iters=0):
+    from oracle.cost import Case, cost_and_grad, one_step_da
+    from vaevar_b200.synth import make_case, make_state_dict
+    sd_d = make_state_dict(cfg_dec, seed=seed, gain=gain, rich=rich)
+    dec = ref_net(cfg_dec, sd_d)
+    flow = None
+    if T > 1:
+        sd_f = make_state_dict(cfg_flow, seed=seed + 1, gain=gain, rich=rich)
+        flow = ref_net(cfg_flow, sd_f)
+    nets = RefNets(dec, flow)
+    case = make_case(T, *cfg_dec.img_size, obs_frac=obs_frac, seed=seed)
+    c = Case(case)
+    t0 = time.time()
+    J, Jr, Jo, g = cost_and_grad(case["z"], c, nets)
+    dt = time.time() - t0
+    ig = sample_idx(g.size, 8192, seed=9)
+    out = dict(seed=seed, gain=gain, rich=rich, T=T, obs_frac=obs_frac, J=J, J_reg=Jr, J_obs=Jo,
+               g_idx=ig, g_val=g.ravel()[ig], g_norm=np.float64(np.linalg.norm(g.astype(np.float64))),
+               n_obs=np.int64(case["H"].sum()), seconds=dt, threads=torch.get_num_threads())
+    if g.size <= 1 << 17:
+        out["g_full"] = g
+    if lbfgs_iters:
+        r = one_step_da(c, nets, nit=1, max_iter=lbfgs_iters)
+        out.update(bg_wrmse=r["bg_wrmse"], ana_wrmse=r["ana_wrmse"], bg_bias=r["bg_bias"], ana_bias=r["ana_bias"],
+                   J_history=r["J_history"], n_evals=r["n_evals"])
+    np.savez_compressed(GOLD / f"cost_{tag}.npz", **out)
+    print(f"cost_{tag}: J={J:.8g} J_reg={Jr:.6g} J_obs={Jo:.8g} |g|={out['g_norm']:.6g} ({dt:.1f}s)", flush=True)
+
+
+def golden_metrics():
+    from utils.metrics import Metrics
+    rng = np.random.Generator(np.random.PCG64(5))
+    from vaevar_b200.config import era5_stats
+    std = torch.from_numpy(era5_stats()[1])
+    pred = torch.from_numpy(rng.standard_normal((1, 69, 32, 64), dtype=np.float32))
+    gt = torch.from_numpy(rng.standard_normal((1, 69, 32, 64), dtype=np.float32))
+    m = Metrics()
+    np.savez_compressed(GOLD / "metrics.npz", pred=pred.numpy(), gt=gt.numpy(),
+                        wrmse=m.WRMSE(pred, gt, None, None, std).numpy(),
+                        bias=m.Bias(pred, gt, None, None, std).numpy())
+    print("metrics ok")
+
+
+def golden_vae_surface():
+    """VAE_lr('parameters0_old') key names / shapes and the decoder channel shuffle (vae.py:54-90)."""
+    from nf_model.vae import VAE_lr
+    with contextlib.redirect_stdout(io.StringIO()):
+        vae = VAE_lr("parameters0_old")
+    names = sorted(f"{k}:{tuple(v.shape)}" for k, v in vae.dec.state_dict().items())
+    (GOLD / "decoder_state_dict_keys.txt").write_text("\n".join(names) + "\n")
+    print("VAE_lr decoder tensors:", len(names))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    install_shim()
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    jobs = {
+        "metrics": golden_metrics,
+        "vae": golden_vae_surface,
+        "net_small_dec": lambda: golden_net("small_dec", ds, 0, 1.0, False),
+        "net_small_flow_rich": lambda: golden_net("small_flow_rich", fs, 1, 3.0, True),
+        "cost_small_T1": lambda: golden_cost("small_T1", ds, fs, 1, 0.10, 0, 1.0, False, lbfgs_iters=10),
+        "cost_small_T3_rich": lambda: golden_cost("small_T3_rich", ds, fs, 3, 0.10, 2, 3.0, True, lbfgs_iters=10),
+    }
+    if a.full:
+        jobs.update({
+            "net_full_dec": lambda: golden_net("full_dec", DECODER_FULL, 0, 1.0, False),
+            "net_full_flow_rich": lambda: golden_net("full_flow_rich", FLOW_FULL, 1, 3.0, True),
+            "cost_full_T1": lambda: golden_cost("full_T1", DECODER_FULL, FLOW_FULL, 1, 0.10, 0, 1.0, False, lbfgs_iters=10),
+            "cost_full_T6": lambda: golden_cost("full_T6", DECODER_FULL, FLOW_FULL, 6, 0.10, 0, 1.0, False),
+            "cost_full_T2_rich": lambda: golden_cost("full_T2_rich", DECODER_FULL, FLOW_FULL, 2, 0.10, 3, 3.0, True),
+        })
+    for name, fn in jobs.items():
+        if a.only and a.only not in name:
+            continue
+        fn()
