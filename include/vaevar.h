@@ -1,0 +1,124 @@
+/* vaevar_b200 -- C ABI of the B200-native 4D-Var cost-and-gradient engine.
+ *
+ * The reference (xiaoyi018/VAE-Var) has no FFI of its own: its boundary for this path is the Python call
+ * surface of da_4dvar.py / nf_model/vae.py / networks_old/transformer.py.  Every entry point below names the
+ * reference line range it stands in for; vaevar_b200/*.py binds them with ctypes behind that same Python surface
+ * (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions: plain pointers and sizes only.  `*_dev` pointers are CUDA device pointers owned by the caller;
+ * `stream` is a cudaStream_t passed as void*; every call only ENQUEUES work on that stream unless stated.
+ * Return value 0 = ok, negative = error (text from vv_last_error()).  Nothing throws across the boundary.
+ * One engine per process / GPU; an engine is not thread-safe.  There is no CPU fallback anywhere.
+ */
+#ifndef VAEVAR_H_
+#define VAEVAR_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VV_API __attribute__((visibility("default")))
+#else
+#define VV_API
+#endif
+
+#define VV_MAX_GROUPS 8
+#define VV_MAX_LG 8
+
+/* Hyper-parameters of one LGUnet_all (networks_old/transformer.py:717-718; nf_model/parameters0_old.yaml). */
+typedef struct {
+  int img_h, img_w;
+  int n_groups;
+  int in_chans[VV_MAX_GROUPS];   /* inchans_list  */
+  int out_chans[VV_MAX_GROUPS];  /* outchans_list */
+  int enc_dim, embed_dim, window;
+  int enc_depth[2], enc_heads[2];
+  int n_lg;
+  int lg_depth[VV_MAX_LG], lg_heads[VV_MAX_LG];
+  int keep_out; /* leading output channels that are produced / differentiated (69 for `model(x)[:, :69]`,
+                   da_4dvar.py:674); 0 = all of them */
+} vv_net_config;
+
+typedef struct {
+  vv_net_config dec;  /* VAE decoder D: VAE_lr.dec, nf_model/vae.py:69-70,83-85 */
+  vv_net_config flow; /* forecast operator M: self.flow_model, da_4dvar.py:571-588 (ignored when T == 1 and has_flow == 0) */
+  int has_flow;
+  int T;         /* da_win: states in the assimilation window (>= 1) */
+  int recompute; /* 0 = stash every application's activations; 1 = keep each application's input only and
+                    recompute its forward inside the backward sweep */
+  int use_graph; /* 1 = capture cost+grad into a CUDA graph on first use */
+} vv_config;
+
+typedef struct vv_engine vv_engine;
+
+VV_API const char* vv_last_error(void);
+/* Select the CUDA device of the calling thread for this library (one process per GPU: pass LOCAL_RANK). */
+VV_API int vv_set_device(int ordinal);
+
+/* cyclic_4dvar.__init__ -> init_vae_model / init_model_flow (da_4dvar.py:571-603): build both networks. */
+VV_API int vv_engine_create(const vv_config* cfg, vv_engine** out);
+VV_API void vv_engine_destroy(vv_engine* e);
+
+/* load_state_dict (da_4dvar.py:575-585, 592-601): one fp32 tensor by its reference state_dict name.
+ * net: 0 = decoder, 1 = flow.  Copies synchronously. Unknown names are an error; buffers
+ * (relative_position_index, attn_mask) are recomputed by the engine and may be skipped by the caller. */
+VV_API int vv_set_weight(vv_engine* e, int net, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+/* Pack to bf16 (+ transposes for the input-gradient GEMMs), gather the relative-position bias tables. */
+VV_API int vv_finalize_weights(vv_engine* e);
+
+/* get_model_mean_std + stdTr (da_4dvar.py:640-647, 1181): host pointers, n_state floats each. */
+VV_API int vv_set_constants(vv_engine* e, const float* mean, const float* std, const float* stdTr);
+
+/* Observation operator as an ordered compaction of the dense 0/1 mask H (da_4dvar.py:290-297, 1207):
+ * idx_out = flat indices of the non-zeros in ascending order (== torch.nonzero(H.flatten())), y_out = yo[idx],
+ * rinv_out = 1 / R[idx].  Outputs must hold n elements; *n_out_host receives the count (synchronises). */
+VV_API int vv_compact_mask(const float* H_dev, const float* yo_dev, const float* R_dev, int64_t n, int32_t* idx_out_dev,
+                    float* y_out_dev, float* rinv_out_dev, int64_t* n_out_host, void* stream);
+
+/* The tensors the closure captures (da_4dvar.py:1248-1251): xb (C,H,W); yo, H, R (T,C,H,W); obs_coeff. Synchronises. */
+VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev,
+                float obs_coeff, void* stream);
+VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs);
+
+/* closure() (da_4dvar.py:1242-1246): J_out_dev[3] = {J, J_reg, J_obs} (fp64), grad_dev = dJ/dz (same shape as z). */
+VV_API int vv_cost_grad(vv_engine* e, const float* z_dev, double* J_out_dev, float* grad_dev, void* stream);
+/* cal_loss() (da_4dvar.py:1210-1236): forward sweep only. */
+VV_API int vv_cost(vv_engine* e, const float* z_dev, double* J_out_dev, void* stream);
+/* xb + D(z) * stdTr * sigma, physical units (da_4dvar.py:1256-1259, 1301-1306). */
+VV_API int vv_decode(vv_engine* e, const float* z_dev, float* x_phys_out_dev, void* stream);
+/* cyclic_4dvar.integrate(xa, flow_model, steps) (da_4dvar.py:666-681) on the engine grid. */
+VV_API int vv_integrate(vv_engine* e, const float* x_phys_in_dev, float* x_phys_out_dev, int steps, void* stream);
+
+/* LGUnet_all.forward (transformer.py:747-752) and its input-VJP, for parity tests.
+ * in: (sum in_chans, H, W); out / dout: (kept out channels, H, W); din like in. */
+VV_API int vv_net_forward(vv_engine* e, int net, const float* in_dev, float* out_dev, void* stream);
+VV_API int vv_net_vjp(vv_engine* e, int net, const float* in_dev, const float* dout_dev, float* din_dev, void* stream);
+
+/* torch.optim.LBFGS([z], history_size, max_iter, line_search_fn="strong_wolfe") + .step(closure)
+ * (da_4dvar.py:1240, 1298-1299; torch/optim/lbfgs.py:333-537).  State persists across steps; the vectors never
+ * leave the device, the controller reads back O(10) scalars per closure evaluation. */
+typedef struct vv_lbfgs vv_lbfgs;
+VV_API int vv_lbfgs_create(vv_engine* e, int history_size, int max_iter, vv_lbfgs** out);
+VV_API void vv_lbfgs_destroy(vv_lbfgs* o);
+/* One optimizer.step(closure) on z_dev (updated in place). info_host[8] = {loss at entry, final loss, n closure evals
+ * this step, n_iter total, last step length, |g|_inf, 0, 0}. Synchronises. */
+VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z_dev, double* info_host, void* stream);
+
+/* Kernel-level hooks used by tests/ and bench.py (roofline of the dominant kernel). */
+VV_API int vv_test_gemm(const void* A_bf16_dev, const void* B_bf16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
+                 void* out_bf16_dev, void* aux_bf16_dev, int M, int N, int K, int batch, int epi, void* stream);
+VV_API int vv_test_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, float* y_dev, const float* dy_dev,
+                      float* dx_dev, int rows, int C, float eps, void* stream);
+VV_API int vv_test_winattn(const void* qkv_bf16_dev, const float* relbias_dev, void* out_bf16_dev, const void* dout_bf16_dev,
+                    void* dqkv_bf16_dev, int gh, int gw, int heads, int hd, int shift, void* stream);
+/* J_obs and residuals for a given normalised trajectory xn (T,C,H,W) with the case already set. */
+VV_API int vv_test_obs(vv_engine* e, const float* xn_dev, double* J_obs_dev, float* grad_xn_dev, void* stream);
+/* Number of kernel launches the last vv_cost_grad enqueued (for bench.py's gpu_launches). */
+VV_API int vv_last_launch_count(vv_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEVAR_H_ */

@@ -1,0 +1,373 @@
+"""Stage-by-stage bring-up checks on a real B200 (each stage in its own process so a faulting kernel cannot
+poison the rest).   python tools/gpu_check.py all   |   python tools/gpu_check.py <stage>
+Prints one line per check: `[stage] name: metric ... OK/FAIL`.  Test infrastructure: may import oracle/."""
+from __future__ import annotations
+
+import os
+import pathlib
+import subprocess
+import sys
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+STAGES = ["gemm", "ln", "attn", "obs", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
+
+
+def rel(a, b):
+    import torch
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def report(stage, name, val, tol):
+    ok = val <= tol
+    print(f"[{stage}] {name}: {val:.3e} (tol {tol:.1e}) {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def stage_gemm():
+    import ctypes as C
+    import torch
+    from vaevar_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda:0"
+    ok = True
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    for (M, N, K, B) in [(128, 128, 64, 1), (256, 128, 128, 1), (2048, 1152, 1152, 1), (2048, 3456, 1152, 1), (2048, 1152, 4608, 1),
+                         (8192, 288, 96, 6), (8192, 96, 384, 6), (2048, 192, 768, 6), (512, 192, 64, 6), (128, 1536, 384, 1),
+                         (2048, 4608, 1152, 1)]:
+        g = torch.Generator(device=dev).manual_seed(M + N + K)
+        A = (torch.randn(B, M, K, device=dev, generator=g)).bfloat16()
+        W = (torch.randn(B, N, K, device=dev, generator=g) * 0.05).bfloat16()
+        bias = torch.randn(B, N, device=dev, generator=g)
+        res = torch.randn(B, M, N, device=dev, generator=g)
+        ref = torch.einsum("bmk,bnk->bmn", A.float(), W.float()) + bias[:, None, :]
+        of = torch.empty(B, M, N, device=dev)
+        ob = torch.empty(B, M, N, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), P(res), P(of), P(ob), None, M, N, K, B, 0, st))
+        torch.cuda.synchronize()
+        ok &= report("gemm", f"linear+bias+res {M}x{N}x{K}x{B} f32", rel(of, ref + res), 2e-5)
+        ok &= report("gemm", f"linear+bias+res {M}x{N}x{K}x{B} bf16", rel(ob.float(), ref + res), 4e-3)
+        # GELU epilogue: saves u, returns gelu(u)
+        aux = torch.empty(B, M, N, device=dev, dtype=torch.bfloat16)
+        _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), None, P(of), None, P(aux), M, N, K, B, 1, st))
+        torch.cuda.synchronize()
+        ok &= report("gemm", f"gelu {M}x{N}x{K}x{B}", rel(of, torch.nn.functional.gelu(ref)), 2e-5)
+        ok &= report("gemm", f"gelu-aux {M}x{N}x{K}x{B}", rel(aux.float(), ref), 4e-3)
+        # DGELU epilogue: acc * gelu'(u)
+        u = aux.float().requires_grad_(True)
+        torch.nn.functional.gelu(u).sum().backward()
+        _lib.check(lib.vv_test_gemm(P(A), P(W), None, None, P(of), None, P(aux), M, N, K, B, 2, st))
+        torch.cuda.synchronize()
+        ok &= report("gemm", f"dgelu {M}x{N}x{K}x{B}", rel(of, (ref - bias[:, None, :]) * u.grad), 5e-5)
+    # timing of the dominant shapes
+    for (M, N, K) in [(2048, 1152, 1152), (2048, 3456, 1152), (2048, 4608, 1152), (2048, 1152, 4608)]:
+        A = torch.randn(1, M, K, device=dev).bfloat16(); W = torch.randn(1, N, K, device=dev).bfloat16()
+        ob = torch.empty(1, M, N, device=dev, dtype=torch.bfloat16)
+        for _ in range(5):
+            lib.vv_test_gemm(P(A), P(W), None, None, None, P(ob), None, M, N, K, 1, 0, st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            lib.vv_test_gemm(P(A), P(W), None, None, None, P(ob), None, M, N, K, 1, 0, st)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 50
+        e0.record()
+        for _ in range(50):
+            torch.matmul(A[0], W[0].t())
+        e1.record(); torch.cuda.synchronize()
+        ms_t = e0.elapsed_time(e1) / 50
+        print(f"[gemm] time {M}x{N}x{K}: {ms*1e3:.1f} us = {2*M*N*K/ms/1e9:.0f} TFLOP/s (incl. launch) | cuBLAS {ms_t*1e3:.1f} us", flush=True)
+    return ok
+
+
+def stage_ln():
+    import ctypes as C
+    import torch
+    from vaevar_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda:0"
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    ok = True
+    for C_ in (64, 96, 128, 192, 384, 1152):
+        rows = 2048
+        x = torch.randn(rows, C_, device=dev) * 2 + 0.5
+        g = torch.randn(C_, device=dev); b = torch.randn(C_, device=dev); dy = torch.randn(rows, C_, device=dev)
+        y = torch.empty_like(x); dx = torch.empty_like(x)
+        _lib.check(lib.vv_test_layernorm(P(x), P(g), P(b), P(y), P(dy), P(dx), rows, C_, 1e-5, st))
+        xr = x.clone().requires_grad_(True)
+        yr = torch.nn.functional.layer_norm(xr, (C_,), g, b, 1e-5)
+        (yr * dy).sum().backward()
+        torch.cuda.synchronize()
+        ok &= report("ln", f"fwd C={C_}", rel(y, yr.detach()), 2e-6)
+        ok &= report("ln", f"bwd C={C_}", rel(dx, xr.grad), 2e-5)
+    return ok
+
+
+def attn_ref(qkv, relbias, gh, gw, heads, hd, shift):
+    """Window attention on (tokens, 3*heads*hd) in original token order -> (tokens, heads*hd). fp32 torch."""
+    import torch
+    from oracle.lgunet import shift_mask
+    d = heads * hd
+    x = qkv.view(1, gh, gw, 3 * d)
+    if shift:
+        x = torch.roll(x, (-shift, -shift), (1, 2))
+    x = x.view(1, gh // 4, 4, gw // 4, 4, 3 * d).permute(0, 1, 3, 2, 4, 5).reshape(-1, 16, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = x[0] * hd ** -0.5, x[1], x[2]
+    a = q @ k.transpose(-2, -1) + relbias.view(1, heads, 16, 16)
+    if shift:
+        a = a + shift_mask(gh, gw, 4, shift).to(a)[:, None]
+    a = torch.softmax(a, -1)
+    o = (a @ v).transpose(1, 2).reshape(-1, 16, d)
+    o = o.view(1, gh // 4, gw // 4, 4, 4, d).permute(0, 1, 3, 2, 4, 5).reshape(1, gh, gw, d)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o.reshape(gh * gw, d)
+
+
+def stage_attn():
+    import ctypes as C
+    import torch
+    from vaevar_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda:0"
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    ok = True
+    for (gh, gw, heads, hd) in [(8, 16, 2, 32), (64, 128, 3, 32), (32, 64, 6, 32), (32, 64, 6, 192), (8, 16, 2, 192)]:
+        for shift in (0, 2):
+            d = heads * hd
+            qkv = (torch.randn(gh * gw, 3 * d, device=dev) * 1.5).bfloat16()
+            rb = torch.randn(heads, 16, 16, device=dev)
+            dout = torch.randn(gh * gw, d, device=dev).bfloat16()
+            out = torch.empty(gh * gw, d, device=dev, dtype=torch.bfloat16)
+            dqkv = torch.empty_like(qkv)
+            _lib.check(lib.vv_test_winattn(P(qkv), P(rb), P(out), P(dout), P(dqkv), gh, gw, heads, hd, shift, st))
+            q32 = qkv.float().requires_grad_(True)
+            o = attn_ref(q32, rb, gh, gw, heads, hd, shift)
+            (o * dout.float()).sum().backward()
+            torch.cuda.synchronize()
+            ok &= report("attn", f"fwd {gh}x{gw} h{heads} hd{hd} s{shift}", rel(out.float(), o.detach()), 4e-3)
+            ok &= report("attn", f"bwd {gh}x{gw} h{heads} hd{hd} s{shift}", rel(dqkv.float(), q32.grad), 5e-3)
+    return ok
+
+
+def _engine_small(T, seed=0, gain=1.0, rich=False, recompute=False, graph=True):
+    import torch
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import Engine
+    from vaevar_b200.synth import make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    sd_d = make_state_dict(ds, seed=seed, gain=gain, rich=rich)
+    sd_f = make_state_dict(fs, seed=seed + 1, gain=gain, rich=rich)
+    e = Engine(ds, fs, T=T, recompute=recompute, use_graph=graph)
+    e.load_state_dict(0, sd_d); e.load_state_dict(1, sd_f); e.finalize()
+    return e, ds, fs, sd_d, sd_f
+
+
+def stage_obs():
+    import numpy as np
+    import torch
+    from oracle import cost as oc
+    from vaevar_b200.engine import compact_mask
+    from vaevar_b200.synth import make_case
+    ok = True
+    dev = "cuda:0"
+    case = make_case(3, 32, 64, obs_frac=0.1, seed=4)
+    H, yo, R = (torch.from_numpy(case[k]).to(dev) for k in ("H", "yo", "R"))
+    idx, y, ri = compact_mask(H, yo, R)
+    ref_idx = torch.nonzero(H.flatten()).flatten()
+    ok &= report("obs", "index list == torch.nonzero (count)", abs(idx.numel() - ref_idx.numel()), 0)
+    ok &= report("obs", "index list == torch.nonzero (values)", float((idx.long() != ref_idx).sum()), 0)
+    ok &= report("obs", "gathered y bit-exact", float((y != yo.flatten()[ref_idx]).sum()), 0)
+    ok &= report("obs", "gathered 1/R bit-exact", float((ri != (1.0 / R.flatten()[ref_idx])).sum()), 0)
+    # ragged mask: random density, different per t and channel; empty mask
+    g = torch.Generator(device=dev).manual_seed(1)
+    Hr = (torch.rand(3, 69, 32, 64, device=dev, generator=g) < 0.03).float()
+    idx, y, ri = compact_mask(Hr, yo, R)
+    ok &= report("obs", "ragged mask indices", float((idx.long() != torch.nonzero(Hr.flatten()).flatten()).sum()), 0)
+    idx, _, _ = compact_mask(torch.zeros_like(Hr), yo, R)
+    ok &= report("obs", "empty mask", idx.numel(), 0)
+    # misfit + adjoint against the oracle formula on a given trajectory
+    e, ds, fs, _, _ = _engine_small(3)
+    e.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+    c = oc.Case(case)
+    xn = torch.randn(3, 69, 32, 64, generator=torch.Generator().manual_seed(3))
+    xp = (xn * c.std + c.mean).requires_grad_(True)
+    Jref = torch.sum(c.H * (xp - c.yo) ** 2 / c.R) / 2
+    Jref.backward()
+    gref = xp.grad * c.std          # d/d(xn)
+    J, g = e.obs_term(xn.to(dev))
+    torch.cuda.synchronize()
+    ok &= report("obs", "J_obs vs oracle", abs(float(J[0]) / float(Jref) - 1), 1e-6)
+    ok &= report("obs", "dJ_obs/dxn vs oracle", rel(g.cpu(), gref), 1e-5)
+    ok &= report("obs", "n_obs", abs(e.n_obs - int(case["H"].sum())), 0)
+    return ok
+
+
+def _net_stage(stage, cfg_fn, full):
+    import numpy as np
+    import torch
+    from oracle.lgunet import lgunet_forward, to_torch
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import Engine
+    from vaevar_b200.synth import make_state_dict
+    ok = True
+    dev = "cuda:0"
+    for (name, seed, gain, rich) in [("plain", 0, 1.0, False), ("rich", 1, 3.0, True)]:
+        dcfg = DECODER_FULL if full else small(DECODER_FULL)
+        fcfg = FLOW_FULL if full else small(FLOW_FULL)
+        sd_d = make_state_dict(dcfg, seed=seed, gain=gain, rich=rich)
+        sd_f = make_state_dict(fcfg, seed=seed + 1, gain=gain, rich=rich)
+        e = Engine(dcfg, fcfg, T=2, use_graph=False)
+        e.load_state_dict(0, sd_d); e.load_state_dict(1, sd_f); e.finalize()
+        for net, cfg, sd in ((0, dcfg, sd_d), (1, fcfg, sd_f)):
+            rng = np.random.Generator(np.random.PCG64(seed + 77))
+            x = torch.from_numpy(rng.standard_normal((1, cfg.in_chans, *cfg.img_size), dtype=np.float32))
+            dy = torch.from_numpy(rng.standard_normal((1, 69, *cfg.img_size), dtype=np.float32))
+            xr = x.clone().requires_grad_(True)
+            t0 = time.time()
+            yr = lgunet_forward(xr, to_torch(sd), cfg)[:, :69]
+            (yr * dy).sum().backward()
+            t_cpu = time.time() - t0
+            y = e.net_forward(net, x[0].to(dev))
+            dx = e.net_vjp(net, x[0].to(dev), dy[0].to(dev))
+            torch.cuda.synchronize()
+            ok &= report(stage, f"{name} net{net} forward", rel(y.cpu(), yr.detach()[0]), 1e-2)
+            ok &= report(stage, f"{name} net{net} vjp", rel(dx.cpu(), xr.grad[0]), 2e-2)
+            print(f"[{stage}] oracle fwd+bwd {t_cpu:.2f}s on {torch.get_num_threads()} threads", flush=True)
+        e.close()
+    return ok
+
+
+def stage_net_small():
+    return _net_stage("net_small", None, False)
+
+
+def stage_net_full():
+    return _net_stage("net_full", None, True)
+
+
+def _cost_stage(stage, full, T, tag=None):
+    import numpy as np
+    import torch
+    from oracle import cost as oc
+    from oracle.lgunet import to_torch
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import Engine
+    from vaevar_b200.synth import make_case, make_state_dict
+    ok = True
+    dev = "cuda:0"
+    dcfg = DECODER_FULL if full else small(DECODER_FULL)
+    fcfg = FLOW_FULL if full else small(FLOW_FULL)
+    for (name, seed, gain, rich) in [("plain", 0, 1.0, False), ("rich", 2, 3.0, True)]:
+        if full and name == "rich":
+            continue
+        sd_d = make_state_dict(dcfg, seed=seed, gain=gain, rich=rich)
+        sd_f = make_state_dict(fcfg, seed=seed + 1, gain=gain, rich=rich)
+        case = make_case(T, *dcfg.img_size, obs_frac=0.10, seed=seed)
+        for recompute, graph in ((False, False), (True, True)):
+            e = Engine(dcfg, fcfg, T=T, recompute=recompute, use_graph=graph)
+            e.load_state_dict(0, sd_d); e.load_state_dict(1, sd_f); e.finalize()
+            e.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+            z = torch.from_numpy(case["z"]).to(dev)
+            for rep in range(3 if graph else 1):
+                J, g = e.cost_grad(z)
+            torch.cuda.synchronize()
+            if recompute is False:
+                t0 = time.time()
+                nets = oc.OracleNets(to_torch(sd_d), dcfg, to_torch(sd_f), fcfg)
+                Jr, Jreg, Jobs, gr = oc.cost_and_grad(case["z"], oc.Case(case), nets)
+                print(f"[{stage}] oracle cost+grad T={T}: {time.time()-t0:.1f}s; J={Jr:.8g} launches={e.last_launch_count}", flush=True)
+            gr_t = torch.from_numpy(gr)
+            tagn = f"{name} T={T} recompute={int(recompute)} graph={int(graph)}"
+            ok &= report(stage, f"{tagn} J", abs(float(J[0]) / Jr - 1), 1e-3)
+            ok &= report(stage, f"{tagn} J_reg", abs(float(J[1]) / Jreg - 1), 1e-6)
+            ok &= report(stage, f"{tagn} |grad|", abs(float(g.double().norm()) / float(gr_t.double().norm()) - 1), 1e-2)
+            cos = float((g.cpu().double().flatten() @ gr_t.double().flatten()) / g.double().norm().cpu() / gr_t.double().norm())
+            ok &= report(stage, f"{tagn} 1-cos(grad)", 1 - cos, 1e-3)
+            # timing
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            Jb = torch.empty(3, dtype=torch.float64, device=dev); gb = torch.empty_like(z)
+            for _ in range(3):
+                e.cost_grad(z, Jb, gb)
+            e0.record()
+            for _ in range(10):
+                e.cost_grad(z, Jb, gb)
+            e1.record(); torch.cuda.synchronize()
+            print(f"[{stage}] {tagn}: {e0.elapsed_time(e1)/10:.3f} ms per cost+grad", flush=True)
+            e.close()
+    return ok
+
+
+def stage_cost_small():
+    return _cost_stage("cost_small", False, 3)
+
+
+def stage_cost_full():
+    return _cost_stage("cost_full", True, 2)
+
+
+def stage_lbfgs_small():
+    import numpy as np
+    import torch
+    from oracle import cost as oc
+    from oracle.lgunet import to_torch
+    from vaevar_b200.engine import LBFGS
+    from vaevar_b200.synth import make_case
+    ok = True
+    dev = "cuda:0"
+    for T in (1, 3):
+        e, ds, fs, sd_d, sd_f = _engine_small(T)
+        case = make_case(T, *ds.img_size, obs_frac=0.10, seed=0)
+        e.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+        z = torch.zeros(1, 32, *ds.img_size, device=dev)
+        opt = LBFGS(e, 10, 10)
+        info = opt.step(z)
+        torch.cuda.synchronize()
+        nets = oc.OracleNets(to_torch(sd_d), ds, to_torch(sd_f), fs)
+        c = oc.Case(case)
+        r = oc.one_step_da(c, nets, nit=1, max_iter=10)
+        print(f"[lbfgs_small] T={T} engine: {info}; oracle: evals={r['n_evals']} J0={r['J_history'][0]:.6g} Jend={r['J_history'][-1]:.6g}", flush=True)
+        xa = e.decode(z)
+        xa_n = ((xa.cpu() - c.mean) / c.std).unsqueeze(0)
+        gn = ((c.gt[0] - c.mean) / c.std).unsqueeze(0)
+        w = oc.wrmse(xa_n, gn, c.std64).numpy()
+        ok &= report("lbfgs_small", f"T={T} loss at entry", abs(info["loss0"] / r["J_history"][0] - 1), 1e-3)
+        ok &= report("lbfgs_small", f"T={T} analysis WRMSE max rel diff", float(np.max(np.abs(w / r["ana_wrmse"] - 1))), 1e-2)
+        ok &= report("lbfgs_small", f"T={T} analysis field", rel(xa.cpu(), torch.from_numpy(r["xa"])), 1e-2)
+        e.close()
+    return ok
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "all":
+        out = ROOT / "gpurun_out"
+        out.mkdir(exist_ok=True)
+        failed = []
+        for s in STAGES:
+            t0 = time.time()
+            try:
+                r = subprocess.run([sys.executable, __file__, s], capture_output=True, text=True, timeout=600)
+                txt = r.stdout + r.stderr[-3000:]
+                rc = r.returncode
+            except subprocess.TimeoutExpired as ex:
+                txt = (ex.stdout or b"").decode() + "\nTIMEOUT"
+                rc = -9
+            (out / f"check_{s}.log").write_text(txt)
+            lines = [l for l in txt.splitlines() if l.startswith("[")]
+            nfail = sum("FAIL" in l for l in lines)
+            print(f"== {s}: rc={rc} checks={len(lines)} fail={nfail} ({time.time()-t0:.0f}s)", flush=True)
+            for l in lines:
+                if "FAIL" in l or "time" in l or "ms per" in l or "oracle" in l:
+                    print("   ", l)
+            if rc != 0:
+                print(txt[-1500:])
+                failed.append(s)
+        sys.exit(1 if failed else 0)
+    ok = globals()["stage_" + which]()
+    sys.exit(0 if ok else 1)

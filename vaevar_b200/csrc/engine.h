@@ -1,0 +1,106 @@
+// Engine internals shared between engine.cu (plans, cost/grad) and lbfgs.cu (optimiser).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vaevar.h"
+#include "ops.h"
+
+namespace vv {
+
+void set_error(const char* fmt, ...);
+
+struct Op {
+  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P } kind;
+  GemmDesc gemm;
+  LnArgs lnf;
+  LnBwdArgs lnb;
+  AttnArgs att;
+  PatchArgs patch;
+};
+struct Plan {
+  std::vector<Op> ops;
+  int run(cudaStream_t s) const;   // returns number of launches
+};
+
+// One stack of G identically shaped Swin blocks (G towers batched, or G = 1 for the trunk).
+struct BlockW {
+  int d = 0, heads = 0, G = 0;
+  bf16 *Wqkv = nullptr, *WqkvT = nullptr, *Wproj = nullptr, *WprojT = nullptr, *W1 = nullptr, *W1T = nullptr, *W2 = nullptr, *W2T = nullptr;
+  float *bqkv = nullptr, *bproj = nullptr, *b1 = nullptr, *b2 = nullptr, *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
+  float* relbias = nullptr;
+};
+struct BlkStash {
+  bf16* qkv; float* x1; bf16* u;
+};
+struct StageStash {
+  std::vector<float*> x;        // x[0] = stage input ... x[depth] = stage output (fp32 residual stream)
+  std::vector<BlkStash> b;
+};
+struct Stash {
+  StageStash e0, e1, lg, u0, u1;
+  float* EX = nullptr;          // PatchExpand GEMM output, input of its LayerNorm
+};
+
+struct PatchPack {
+  int* kcnt = nullptr; int* cbase = nullptr; int* chan = nullptr;   // device
+  float* Wp = nullptr; float* bias = nullptr;
+  int nslots = 0;
+};
+
+struct Net {
+  vv_net_config c{};
+  int G = 0, D = 0, E = 0, H = 0, W = 0, h0 = 0, w0 = 0, h1 = 0, w1 = 0, L0 = 0, L1 = 0;
+  int cin = 0, cout = 0, ckeep = 0;
+  std::map<std::string, std::pair<float*, std::vector<int64_t>>> staged;   // fp32 device copies by reference name
+  bool finalized = false;
+  // packed weights
+  PatchPack embed, fin;
+  float* ape = nullptr;           // [G][L0][D]
+  std::vector<BlockW> e0, e1, lg, u0, u1;
+  float *mg_g = nullptr, *mg_b = nullptr; bf16 *Wred = nullptr, *WredT = nullptr;
+  float *en_g = nullptr, *en_b = nullptr;
+  bf16 *Wep = nullptr, *WepT = nullptr; float* bep = nullptr; float* pos = nullptr;
+  bf16 *Wdp = nullptr, *WdpT = nullptr; float* bdp = nullptr;
+  bf16 *Wc0 = nullptr, *Wc0T = nullptr; float* bc0 = nullptr;
+  bf16 *Wex = nullptr, *WexT = nullptr; float *ex_g = nullptr, *ex_b = nullptr;
+  bf16 *Wc1 = nullptr, *Wc1T = nullptr; float* bc1 = nullptr;
+  float *nu_g = nullptr, *nu_b = nullptr;
+};
+
+}  // namespace vv
+
+struct vv_engine {
+  vv_config cfg{};
+  vv::Net net[2];
+  int C = 0;                 // state channels (flow in/out kept = decoder out)
+  int Zc = 0;                // latent channels
+  long long HW = 0;
+  std::vector<void*> allocs;
+  // constants
+  float *mean = nullptr, *sigma = nullptr, *stdTr = nullptr, *inv_sigma = nullptr, *neg_mu_sig = nullptr;
+  bool have_consts = false;
+  // buffers
+  float *Z = nullptr, *DOUT = nullptr, *XN = nullptr, *Gb[2] = {nullptr, nullptr}, *GD = nullptr, *GZ = nullptr, *XB = nullptr;
+  // observation data
+  int* idx = nullptr; float *yobs = nullptr, *rinv = nullptr, *resid = nullptr;
+  int* chunk_counts = nullptr;
+  long long n_obs = 0, obs_cap = 0;
+  std::vector<long long> obs_off;   // [T+1]
+  float obs_coeff = 1.f;
+  bool have_case = false;
+  double *partials = nullptr, *dots = nullptr, *dot_scratch = nullptr, *Jbuf = nullptr;
+  // plans: index 0 = decoder application, 1..T-1 = flow applications
+  std::vector<vv::Stash> stash;
+  std::vector<vv::Plan> fwd, bwd;
+  bool plans_built = false;
+  // graphs
+  cudaGraphExec_t graph_cg = nullptr;
+  int eager_runs = 0;
+  int last_launches = 0;
+};
+
+namespace vv {
+int engine_cost_grad(vv_engine* e, const float* z, double* Jout, float* grad, cudaStream_t s);
+}

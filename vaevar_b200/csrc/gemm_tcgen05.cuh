@@ -1,0 +1,205 @@
+// Batched TN GEMM on the 5th-gen tensor cores:  C[b] = epilogue( A[b] (M x K, K-major bf16) * B[b]^T (N x K, K-major bf16) )
+//
+// Every Linear of the Swin blocks (swinblock.py:18,20,105,115) and of the U-Net seams
+// (transformer.py:73,103,435,552,596) -- forward y = x W^T + b and input-gradient dx = dy W (with W^T packed once) --
+// goes through this one kernel.  fp32 accumulation in TMEM, operands staged by TMA into 128B-swizzled shared memory,
+// tcgen05.mma issued by a single elected thread, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+// (+ TMEM owner), warps 2..5 = epilogue (TMEM -> registers -> fused bias / GELU / GELU' / residual -> global).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace vv {
+
+enum GemmEpi : int {
+  EPI_LINEAR = 0,  // v = acc + bias
+  EPI_GELU = 1,    // u = acc + bias ; aux_out = bf16(u) ; v = gelu(u)
+  EPI_DGELU = 2,   // v = acc * gelu'(aux_in)
+};
+
+struct GemmArgs {
+  int M, N, K, batch;
+  int epi;
+  const float* bias;          // [batch][N] or null
+  long long bias_bs;
+  const float* res;           // fp32 residual added to v, [batch][M][ld_res] or null
+  long long ld_res, res_bs;
+  const __nv_bfloat16* aux_in;  // EPI_DGELU: saved pre-activation u
+  __nv_bfloat16* aux_out;       // EPI_GELU: where to save u
+  long long ld_aux, aux_bs;
+  float* out_f32;             // optional fp32 output
+  long long ld_f32, f32_bs;
+  __nv_bfloat16* out_bf16;    // optional bf16 output
+  long long ld_bf16, bf16_bs;
+  int split_n;                // >0: bf16 output column n goes to block n / split_n (stride split_stride), column n % split_n
+  long long split_stride;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // +1024: manual alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+  using L = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * GEMM_BM;
+  const int b = blockIdx.z;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        tma_load_3d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0, b);
+        tma_load_3d(sa + L::A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, n0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t da = make_smem_desc_sw128(sa);
+        const uint64_t db = make_smem_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);            // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [(w%4)*32, +32) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
+    const float* res = p.res ? p.res + (long long)b * p.res_bs + (long long)m * p.ld_res : nullptr;
+    const __nv_bfloat16* aux_in = p.aux_in ? p.aux_in + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
+    __nv_bfloat16* aux_out = p.aux_out ? p.aux_out + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
+    float* of = p.out_f32 ? p.out_f32 + (long long)b * p.f32_bs + (long long)m * p.ld_f32 : nullptr;
+    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)b * p.bf16_bs + (long long)m * p.ld_bf16 : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {            // 4 groups of 8 columns
+        const int n = n0 + c0 + g * 8;
+        if (!row_ok || n + 8 > p.N) continue;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+        if (bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (p.epi == EPI_GELU) {
+          if (aux_out) {
+            uint4 w;
+            w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+            w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(aux_out + n) = w;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        } else if (p.epi == EPI_DGELU) {
+          const uint4 w = *reinterpret_cast<const uint4*>(aux_in + n);
+          const float2 u0 = unpack_bf16(w.x), u1 = unpack_bf16(w.y), u2 = unpack_bf16(w.z), u3 = unpack_bf16(w.w);
+          v[0] *= gelu_erf_grad(u0.x); v[1] *= gelu_erf_grad(u0.y);
+          v[2] *= gelu_erf_grad(u1.x); v[3] *= gelu_erf_grad(u1.y);
+          v[4] *= gelu_erf_grad(u2.x); v[5] *= gelu_erf_grad(u2.y);
+          v[6] *= gelu_erf_grad(u3.x); v[7] *= gelu_erf_grad(u3.y);
+        }
+        if (res) {
+          const float4 r0 = *reinterpret_cast<const float4*>(res + n);
+          const float4 r1 = *reinterpret_cast<const float4*>(res + n + 4);
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        if (of) {
+          *reinterpret_cast<float4*>(of + n) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(of + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (ob) {
+          uint4 w;
+          w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+          w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
+          long long off = n;
+          if (p.split_n > 0) off = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
+          *reinterpret_cast<uint4*>(ob + off) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace vv

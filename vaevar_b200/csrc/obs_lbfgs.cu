@@ -1,0 +1,272 @@
+// HBM-bound kernels of the cost function outside the networks:
+//  * observation operator H as an ordered compaction of the 0/1 mask (indices == torch.nonzero order),
+//    fused gather + (de)normalisation + R^-1-weighted misfit with warp-shuffle reductions, and its adjoint scatter
+//    (da_4dvar.py:1195,1207; 667,681);
+//  * the vector algebra of the L-BFGS two-loop recursion with device-resident scalars (torch/optim/lbfgs.py:428-443).
+#include "ops.h"
+
+namespace vv {
+
+constexpr int RED_BLOCKS = 296;   // 2 x 148 SMs
+constexpr int RED_THREADS = 256;
+int reduce_blocks() { return RED_BLOCKS; }
+
+VV_DEVINL double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide fp64 sum; result valid in thread 0.
+VV_DEVINL double block_sum_d(double v) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    v = warp_sum_d(v);
+  }
+  return v;
+}
+
+// ---- ordered compaction ---------------------------------------------------------------------
+constexpr int CHUNK = 1024;   // elements per block: 256 threads x 4 consecutive elements
+
+__global__ void __launch_bounds__(256) compact_count_kernel(const float* H, long long n, int* counts) {
+  const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 4;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (base + k < n && H[base + k] != 0.f) ++c;
+  __shared__ int sh[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+// In-place exclusive scan of counts[0..n) by one block; counts[n] receives the total.
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* counts, long long n) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += 1024) {
+    const long long i = base + threadIdx.x;
+    const int v = i < n ? counts[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {       // Hillis-Steele inclusive scan
+      const int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int incl = sh[threadIdx.x];
+    const int c0 = carry;
+    if (i < n) counts[i] = c0 + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c0 + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[n] = carry;
+}
+
+__global__ void __launch_bounds__(256) compact_write_kernel(const float* H, const float* yo, const float* R, long long n,
+                                                            const int* offsets, int* idx, float* y, float* rinv) {
+  const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 4;
+  bool nz[4];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    nz[k] = base + k < n && H[base + k] != 0.f;
+    c += nz[k];
+  }
+  // exclusive scan of c over the block (thread order == index order)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __shared__ int wsum[8];
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int k = 0; k < w; ++k) woff += wsum[k];
+  int pos = offsets[blockIdx.x] + woff + incl - c;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (nz[k]) {
+      idx[pos] = (int)(base + k);
+      y[pos] = yo[base + k];
+      rinv[pos] = 1.0f / R[base + k];
+      ++pos;
+    }
+  }
+}
+
+void launch_compact_count(const float* H, long long n, int* counts, cudaStream_t s) {
+  compact_count_kernel<<<(unsigned)((n + CHUNK - 1) / CHUNK), 256, 0, s>>>(H, n, counts);
+}
+void launch_compact_scan(int* counts, long long nchunks, cudaStream_t s) { compact_scan_kernel<<<1, 1024, 0, s>>>(counts, nchunks); }
+void launch_compact_write(const float* H, const float* yo, const float* R, long long n, const int* offsets, int* idx, float* y,
+                          float* rinv, cudaStream_t s) {
+  compact_write_kernel<<<(unsigned)((n + CHUNK - 1) / CHUNK), 256, 0, s>>>(H, yo, R, n, offsets, idx, y, rinv);
+}
+
+// ---- misfit + adjoint -----------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) obs_misfit_kernel(const float* __restrict__ xn, const int* __restrict__ idx,
+                                                                 const float* __restrict__ y, const float* __restrict__ rinv,
+                                                                 const float* __restrict__ sigma, const float* __restrict__ mu,
+                                                                 long long n_obs, long long HW, int C, float coeff,
+                                                                 float* __restrict__ resid, double* __restrict__ partials) {
+  double acc = 0.0;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_obs; k += (long long)gridDim.x * blockDim.x) {
+    const int id = idx[k];
+    const int c = (int)((id / HW) % C);
+    const float sg = sigma[c];
+    const float x = fmaf(xn[id], sg, mu[c]);        // de-normalise (da_4dvar.py:681)
+    const float r = x - y[k];
+    const float ri = rinv[k];
+    resid[k] = coeff * sg * ri * r;                 // d(coeff*J_obs)/d(xn)
+    acc += 0.5 * (double)(ri * r * r);
+  }
+  acc = block_sum_d(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+void launch_obs_misfit(const float* xn_all, const int* idx, const float* y, const float* rinv, const float* sigma, const float* mu,
+                       long long n_obs, long long HW, int C, float coeff, float* resid, double* block_partials, int nblocks,
+                       cudaStream_t s) {
+  obs_misfit_kernel<<<nblocks, RED_THREADS, 0, s>>>(xn_all, idx, y, rinv, sigma, mu, n_obs, HW, C, coeff, resid, block_partials);
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* partials, int n, double* out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+  acc = block_sum_d(acc);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t s) {
+  reduce_partials_kernel<<<1, 256, 0, s>>>(partials, n, out);
+}
+
+__global__ void __launch_bounds__(256) obs_adjoint_kernel(float* G, const int* idx, const float* resid, long long k0, long long k1,
+                                                          long long base) {
+  for (long long k = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += (long long)gridDim.x * blockDim.x)
+    G[idx[k] - base] += resid[k];
+}
+void launch_obs_adjoint(float* G, const int* idx, const float* resid, long long k0, long long k1, long long base, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const long long n = k1 - k0;
+  const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  obs_adjoint_kernel<<<blocks, 256, 0, s>>>(G, idx, resid, k0, k1, base);
+}
+
+// ---- vector algebra -------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS) multi_dot_kernel(const DotPairs p, long long n, double* scratch) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < p.n_pairs) acc[j] += (double)(p.a[j][i] * p.b[j][i]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < p.n_pairs) {
+      const double v = block_sum_d(acc[j]);
+      if (threadIdx.x == 0) scratch[j * RED_BLOCKS + blockIdx.x] = v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) multi_dot_final_kernel(const double* scratch, int n_pairs, double* out) {
+  for (int j = 0; j < n_pairs; ++j) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < RED_BLOCKS; i += blockDim.x) acc += scratch[j * RED_BLOCKS + i];
+    acc = block_sum_d(acc);
+    if (threadIdx.x == 0) out[j] = acc;
+  }
+}
+void launch_multi_dot(const DotPairs& p, long long n, double* out, double* scratch, cudaStream_t s) {
+  multi_dot_kernel<<<RED_BLOCKS, RED_THREADS, 0, s>>>(p, n, scratch);
+  multi_dot_final_kernel<<<1, 256, 0, s>>>(scratch, p.n_pairs, out);
+}
+
+__global__ void __launch_bounds__(256) axpby_kernel(float* y, const float* x, const double* alpha_dev, double alpha_host,
+                                                    const double* beta_dev, double beta_host, long long n) {
+  const float al = (float)((alpha_dev ? *alpha_dev : 1.0) * alpha_host);
+  const float be = (float)((beta_dev ? *beta_dev : 1.0) * beta_host);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float yv = be == 0.f ? 0.f : be * y[i];
+    y[i] = fmaf(al, x[i], yv);
+  }
+}
+void launch_axpby(float* y, const float* x, const double* alpha_dev, double alpha_host, const double* beta_dev, double beta_host,
+                  long long n, cudaStream_t s) {
+  axpby_kernel<<<1184, 256, 0, s>>>(y, x, alpha_dev, alpha_host, beta_dev, beta_host, n);
+}
+
+__global__ void __launch_bounds__(256) axpy_diff_kernel(float* y, const float* x, const double* a1, const double* a2, double scale,
+                                                        long long n) {
+  const float al = (float)(scale * (*a1 - (a2 ? *a2 : 0.0)));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaf(al, x[i], y[i]);
+}
+void launch_axpy_diff(float* y, const float* x, const double* a1_dev, const double* a2_dev, double scale, long long n, cudaStream_t s) {
+  axpy_diff_kernel<<<1184, 256, 0, s>>>(y, x, a1_dev, a2_dev, scale, n);
+}
+
+__global__ void __launch_bounds__(RED_THREADS) absmax_l1_kernel(const float* x, long long n, double* scratch) {
+  double mx = 0.0, l1 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = fabs((double)x[i]);
+    mx = v > mx ? v : mx;
+    l1 += v;
+  }
+  l1 = block_sum_d(l1);
+  // block max via shared memory
+  __shared__ double shm[RED_THREADS];
+  shm[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = RED_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) shm[threadIdx.x] = fmax(shm[threadIdx.x], shm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    scratch[blockIdx.x] = shm[0];
+    scratch[RED_BLOCKS + blockIdx.x] = l1;
+  }
+}
+__global__ void __launch_bounds__(256) absmax_l1_final_kernel(const double* scratch, double* out) {
+  __shared__ double shm[256];
+  double mx = 0.0, l1 = 0.0;
+  for (int i = threadIdx.x; i < RED_BLOCKS; i += blockDim.x) {
+    mx = fmax(mx, scratch[i]);
+    l1 += scratch[RED_BLOCKS + i];
+  }
+  l1 = block_sum_d(l1);
+  shm[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) shm[threadIdx.x] = fmax(shm[threadIdx.x], shm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = shm[0];
+    out[1] = l1;
+  }
+}
+void launch_absmax_l1(const float* x, long long n, double* out, double* scratch, cudaStream_t s) {
+  absmax_l1_kernel<<<RED_BLOCKS, RED_THREADS, 0, s>>>(x, n, scratch);
+  absmax_l1_final_kernel<<<1, 256, 0, s>>>(scratch, out);
+}
+
+}  // namespace vv

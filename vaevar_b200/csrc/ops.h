@@ -1,0 +1,122 @@
+// Host-side launch descriptors for every kernel of the cost-and-gradient path.
+// An application plan is a flat vector<Op>; running it is a loop of launches on one stream
+// (captured into a CUDA graph by the engine).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tcgen05.cuh"
+
+namespace vv {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- GEMM -----------------------------------------------------------------------------------
+struct GemmDesc {
+  CUtensorMap tmA, tmB;
+  GemmArgs a;
+  int bn;
+};
+// A: [batch][M][K] bf16 with row stride lda / batch stride a_bs (elements); B: [batch][N][K] likewise.
+const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,
+                           long long b_bs, const GemmArgs& args);
+void launch_gemm(const GemmDesc& d, cudaStream_t s);
+
+// ---- LayerNorm (one warp per row, fp32 statistics) -------------------------------------------
+enum RowMap : int {
+  MAP_PLAIN = 0,   // row r <-> token r
+  MAP_MERGE = 1,   // PatchMerging gather (transformer.py:86-90): row (i,j) of width 4D = tokens (2i+a, 2j+b), chunk order (0,0),(1,0),(0,1),(1,1)
+  MAP_EXPAND = 2,  // PatchExpand pixel shuffle (transformer.py:114): row (I,J) of width D = chunk (I%2, J%2) of token (I/2, J/2), width 4D
+};
+struct LnArgs {
+  int rows, C, batch, map, gh, gw;   // gh,gw: the FINE token grid (MERGE: source grid, EXPAND: destination grid)
+  float eps;
+  const float* x; long long ld_x, x_bs;            // fp32 input (addressed through `map`)
+  const float *gamma, *beta; long long gb_bs;
+  bf16* out_bf16; long long ld_ob, ob_bs;          // outputs are plain rows
+  float* out_f32; long long ld_of, of_bs;
+};
+struct LnBwdArgs {
+  int rows, C, batch, map, gh, gw;
+  float eps;
+  const float* x; long long ld_x, x_bs;            // the forward input (same addressing as forward)
+  const float* gamma; long long gb_bs;
+  const float* dy; long long ld_dy, dy_bs;         // gradient w.r.t. the LN output, plain rows, fp32
+  const float* dres; long long ld_dres, dres_bs;   // optional extra gradient added to dx (addressed like x)
+  float* dx; long long ld_dx, dx_bs;               // gradient w.r.t. the LN input (addressed like x)
+  bf16* dx_bf16; long long ld_dxb, dxb_bs;         // optional bf16 copy of dx (addressed like x)
+};
+void launch_ln_fwd(const LnArgs& a, cudaStream_t s);
+void launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s);
+
+// ---- 4x4-window attention (swinblock.py:133-172, 265-302) ------------------------------------
+struct AttnArgs {
+  int gh, gw, heads, hd, shift, batch;
+  const bf16* qkv; long long ld_qkv, qkv_bs;       // [batch][gh*gw][3*heads*hd], token order = original grid
+  const float* relbias; long long relbias_bs;      // [batch][heads][16][16] (table gathered at pack time)
+  bf16* out; long long ld_o, o_bs;                 // forward: attention output [batch][tokens][heads*hd]
+  const bf16* dout;                                // backward: gradient of `out` (same strides as out)
+  bf16* dqkv;                                      // backward: gradient of qkv (same strides as qkv)
+};
+void launch_attn_fwd(const AttnArgs& a, cudaStream_t s);
+void launch_attn_bwd(const AttnArgs& a, cudaStream_t s);
+
+// ---- 2x2 / stride-2 patch operators as tiny GEMMs on CUDA cores --------------------------------
+// P2T (pixels -> tokens): PatchEmbed forward (transformer.py:35,46 + APE :394) and ConvTranspose2d backward.
+// T2P (tokens -> pixels): ConvTranspose2d forward (transformer.py:593-594,606) and PatchEmbed backward.
+struct PatchArgs {
+  int H, W, G, D;              // image size, groups, token width
+  const int* kcnt;             // [G]   channels per group (device)
+  const int* cbase;            // [G]   first slot of the group in `chan`
+  const int* chan;             // [sum] NCHW channel index of every packed channel (device)
+  const float* Wp;             // [sum*4][D] packed weights, row = (slot*4 + p1*2 + p2)
+  const float* bias;           // P2T: [G][D] or null; T2P: [sum] or null
+  const float* ape;            // P2T only: [G][L0][D] or null
+  const float* img_in;         // P2T: NCHW image
+  float* tok_out;              // P2T: [G][L0][D]
+  const float* tok_in;         // T2P: [G][L0][D]
+  float* img_out;              // T2P: NCHW image
+};
+void launch_p2t(const PatchArgs& a, cudaStream_t s);
+void launch_t2p(const PatchArgs& a, cudaStream_t s);
+
+// ---- per-channel affine seams (da_4dvar.py:667,681,1187) ---------------------------------------
+// out[c,p] = a[c,p]*sa[c] + (b ? b[c,p]*sb[c] : 0) + t[c]       (any of sa/sb/t may be null -> 1/1/0)
+void launch_chan_affine(float* out, const float* a, const float* sa, const float* b, const float* sb, const float* t,
+                        int C, long long HW, cudaStream_t s);
+
+// ---- observation operator (da_4dvar.py:1195,1207) ----------------------------------------------
+// Phase 1 of the ordered compaction: count nonzeros per 1024-element chunk.
+void launch_compact_count(const float* H, long long n, int* chunk_counts, cudaStream_t s);
+// Phase 2: exclusive scan of the chunk counts (single block), total in counts[nchunks].
+void launch_compact_scan(int* chunk_counts, long long nchunks, cudaStream_t s);
+// Phase 3: ordered write of the flat indices (ascending == torch.nonzero order) + gather of y and 1/R.
+void launch_compact_write(const float* H, const float* yo, const float* R, long long n, const int* chunk_offsets,
+                          int* idx, float* y, float* rinv, cudaStream_t s);
+// J_obs partials + residuals: for obs k: x = xn[idx]*sigma_c + mu_c ; r = x - y ; J += 0.5*rinv*r^2 ; resid = coeff*sigma_c*rinv*r
+void launch_obs_misfit(const float* xn_all, const int* idx, const float* y, const float* rinv, const float* sigma,
+                       const float* mu, long long n_obs, long long HW, int C, float coeff, float* resid,
+                       double* block_partials, int nblocks, cudaStream_t s);
+// out[0] = sum(partials[0..n))  (fp64, one block)
+void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t s);
+// G[idx - base] += resid for obs in [k0,k1)   (indices unique -> no atomics)
+void launch_obs_adjoint(float* G, const int* idx, const float* resid, long long k0, long long k1, long long base,
+                        cudaStream_t s);
+
+// ---- vector algebra for L-BFGS and J_reg (torch/optim/lbfgs.py:428-443) ---------------------------
+// out[j] = sum_i a_j[i]*b_j[i] for up to 4 (a,b) pairs sharing one pass; fp64 block partials, finalised in-kernel
+struct DotPairs { const float* a[4]; const float* b[4]; int n_pairs; };
+void launch_multi_dot(const DotPairs& p, long long n, double* out /*[4] device*/, double* scratch, cudaStream_t s);
+// y = alpha*x + beta*y with alpha/beta read from device doubles (null -> given host constant)
+void launch_axpby(float* y, const float* x, const double* alpha_dev, double alpha_host, const double* beta_dev,
+                  double beta_host, long long n, cudaStream_t s);
+// y += scale * (*a1 - (a2 ? *a2 : 0)) * x   (second loop of the two-loop recursion: (al_i - be_i) s_i)
+void launch_axpy_diff(float* y, const float* x, const double* a1_dev, const double* a2_dev, double scale, long long n, cudaStream_t s);
+// max-abs and L1 norm of a vector: out[0]=max|x|, out[1]=sum|x|
+void launch_absmax_l1(const float* x, long long n, double* out, double* scratch, cudaStream_t s);
+
+int reduce_blocks();  // number of blocks the reduction kernels use (size of scratch in doubles * 4)
+
+}  // namespace vv

@@ -1,0 +1,200 @@
+"""Python handle on the CUDA engine (one per process / GPU).  Plumbing only: torch supplies device memory and
+streams, every computation happens in libvaevar.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import NetConfig, era5_stats
+
+
+def _net_c(cfg: NetConfig, keep_out: int = 0) -> _lib.NetConfigC:
+    c = _lib.NetConfigC()
+    c.img_h, c.img_w = cfg.img_size
+    c.n_groups = cfg.groups
+    for i, v in enumerate(cfg.inchans_list):
+        c.in_chans[i] = v
+    for i, v in enumerate(cfg.outchans_list):
+        c.out_chans[i] = v
+    c.enc_dim, c.embed_dim, c.window = cfg.enc_dim, cfg.embed_dim, cfg.window_size
+    c.enc_depth[0], c.enc_depth[1] = cfg.enc_depths
+    c.enc_heads[0], c.enc_heads[1] = cfg.enc_heads
+    c.n_lg = len(cfg.lg_depths)
+    for i, (d, h) in enumerate(zip(cfg.lg_depths, cfg.lg_heads)):
+        c.lg_depth[i], c.lg_heads[i] = d, h
+    c.keep_out = keep_out
+    return c
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev32(x, device) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(x)
+    return x.to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """cost J(z) and grad_z J of da_4dvar.py:1183-1208 / 1242-1246 on one B200."""
+
+    def __init__(self, dec: NetConfig, flow: Optional[NetConfig] = None, T: int = 1, recompute: bool = False,
+                 use_graph: bool = True, device: str = "cuda:0", flow_keep: int = 69, dec_keep: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vaevar_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.current_stream()          # make sure the primary context exists before the library touches it
+        _lib.check(self.lib.vv_set_device(self.device.index or 0))
+        self.dec_cfg, self.flow_cfg, self.T = dec, flow, T
+        cfg = _lib.ConfigC()
+        cfg.dec = _net_c(dec, dec_keep)
+        if flow is not None:
+            cfg.flow = _net_c(flow, flow_keep)
+        cfg.has_flow = int(flow is not None)
+        cfg.T, cfg.recompute, cfg.use_graph = T, int(recompute), int(use_graph)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.vv_engine_create(C.byref(cfg), C.byref(self._h)))
+        self.n_state = dec_keep or dec.out_chans
+        self.n_latent = dec.in_chans
+        self.grid = dec.img_size
+        self._keep = []
+        mean, std, stdtr = era5_stats()
+        if self.n_state == len(mean):
+            self.set_constants(mean, std, stdtr)
+
+    # -- weights --------------------------------------------------------------------------------
+    def load_state_dict(self, net: int, sd: Dict[str, "np.ndarray | torch.Tensor"]):
+        """net 0 = decoder (VAE_lr.dec), 1 = flow model; keys are the reference state_dict names."""
+        for k, v in sd.items():
+            if "relative_position_index" in k or "attn_mask" in k:
+                continue
+            t = _dev32(v, self.device)
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.lib.vv_set_weight(self._h, net, k.encode(), _ptr(t), shape, t.dim()))
+        torch.cuda.synchronize()
+
+    def finalize(self):
+        _lib.check(self.lib.vv_finalize_weights(self._h))
+
+    def set_constants(self, mean, std, stdtr):
+        a = [np.ascontiguousarray(np.asarray(x, np.float32)) for x in (mean, std, stdtr)]
+        _lib.check(self.lib.vv_set_constants(self._h, *[x.ctypes.data_as(C.c_void_p) for x in a]))
+
+    # -- case -----------------------------------------------------------------------------------
+    def set_case(self, xb, yo, H, R, obs_coeff: float = 1.0):
+        xb, yo, H, R = (_dev32(x, self.device) for x in (xb, yo, H, R))
+        _lib.check(self.lib.vv_set_case(self._h, _ptr(xb), _ptr(yo), _ptr(H), _ptr(R), float(obs_coeff), _stream()))
+
+    @property
+    def n_obs(self) -> int:
+        n = C.c_int64()
+        _lib.check(self.lib.vv_num_obs(self._h, C.byref(n)))
+        return n.value
+
+    # -- evaluation -----------------------------------------------------------------------------
+    def cost_grad(self, z: torch.Tensor, J_out: Optional[torch.Tensor] = None, grad_out: Optional[torch.Tensor] = None):
+        """One closure(): returns (J[3] float64 device tensor = {J, J_reg, J_obs}, grad like z). Asynchronous."""
+        z = z.contiguous()
+        J = torch.empty(3, dtype=torch.float64, device=self.device) if J_out is None else J_out
+        g = torch.empty_like(z) if grad_out is None else grad_out
+        _lib.check(self.lib.vv_cost_grad(self._h, _ptr(z), _ptr(J), _ptr(g), _stream()))
+        return J, g
+
+    def cost(self, z: torch.Tensor):
+        J = torch.empty(3, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.vv_cost(self._h, _ptr(z.contiguous()), _ptr(J), _stream()))
+        return J
+
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.n_state, *self.grid, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.vv_decode(self._h, _ptr(z.contiguous()), _ptr(out), _stream()))
+        return out
+
+    def integrate(self, x: torch.Tensor, steps: int = 1) -> torch.Tensor:
+        out = torch.empty_like(x)
+        _lib.check(self.lib.vv_integrate(self._h, _ptr(x.contiguous()), _ptr(out), steps, _stream()))
+        return out
+
+    def net_forward(self, net: int, x: torch.Tensor) -> torch.Tensor:
+        cfg = self.dec_cfg if net == 0 else self.flow_cfg
+        keep = self.n_state
+        out = torch.empty(keep, *cfg.img_size, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.vv_net_forward(self._h, net, _ptr(x.contiguous()), _ptr(out), _stream()))
+        return out
+
+    def net_vjp(self, net: int, x: torch.Tensor, dout: torch.Tensor) -> torch.Tensor:
+        din = torch.empty_like(x)
+        _lib.check(self.lib.vv_net_vjp(self._h, net, _ptr(x.contiguous()), _ptr(dout.contiguous()), _ptr(din), _stream()))
+        return din
+
+    def obs_term(self, xn: torch.Tensor, want_grad: bool = True):
+        J = torch.empty(1, dtype=torch.float64, device=self.device)
+        g = torch.empty_like(xn) if want_grad else None
+        _lib.check(self.lib.vv_test_obs(self._h, _ptr(xn.contiguous()), _ptr(J), _ptr(g), _stream()))
+        return J, g
+
+    @property
+    def last_launch_count(self) -> int:
+        return self.lib.vv_last_launch_count(self._h)
+
+    def close(self):
+        if self._h:
+            self.lib.vv_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LBFGS:
+    """torch.optim.LBFGS(history_size, max_iter, line_search_fn='strong_wolfe') bound to an Engine (da_4dvar.py:1240)."""
+
+    def __init__(self, engine: Engine, history_size: int = 10, max_iter: int = 10):
+        self.engine = engine
+        self._h = C.c_void_p()
+        _lib.check(engine.lib.vv_lbfgs_create(engine._h, history_size, max_iter, C.byref(self._h)))
+
+    def step(self, z: torch.Tensor):
+        info = (C.c_double * 8)()
+        _lib.check(self.engine.lib.vv_lbfgs_step(self._h, _ptr(z), info, _stream()))
+        return dict(loss0=info[0], loss=info[1], n_evals=int(info[2]), n_iter=int(info[3]), t=info[4], gmax=info[5],
+                    func_evals=int(info[6]))
+
+    def close(self):
+        if self._h:
+            self.engine.lib.vv_lbfgs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def compact_mask(H: torch.Tensor, yo: torch.Tensor, R: torch.Tensor):
+    """(idx int32, y, 1/R) of the non-zeros of the dense mask, ascending flat order (== torch.nonzero)."""
+    lib = _lib.load()
+    n = H.numel()
+    idx = torch.empty(n, dtype=torch.int32, device=H.device)
+    y = torch.empty(n, dtype=torch.float32, device=H.device)
+    ri = torch.empty(n, dtype=torch.float32, device=H.device)
+    cnt = C.c_int64()
+    _lib.check(lib.vv_compact_mask(_ptr(H.contiguous()), _ptr(yo.contiguous()), _ptr(R.contiguous()), n, _ptr(idx), _ptr(y),
+                                   _ptr(ri), C.byref(cnt), _stream()))
+    k = cnt.value
+    return idx[:k], y[:k], ri[:k]
