@@ -1,0 +1,276 @@
+"""Headline benchmark: one 4D-Var cost+gradient evaluation J(z), grad_z J (da_4dvar.py:1183-1208, 1242-1246).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--T 6] [--obs-frac 0.1]
+
+Workload (BASELINE.json configs[1]): 6-step window, 69x128x256 state, VAE decoder + 5 applications of the flow
+model (both 216 M-parameter U-shaped Swin networks, random init), 10 % column observations, one case per GPU.
+A "step" is one closure() = cost + gradient.  N > 1: one process per GPU (torchrun), independent cases, no
+data-path collective (replicas), only the timing reduction goes through NCCL.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# Algorithmic work per cost+grad: forward + input-gradient, no weight gradients, no recompute.
+GMAC_DEC, GMAC_FLOW = 446.05, 446.17   # flow: discarded log-var half of the final projection not counted
+
+
+def algorithmic_tflop(T: int) -> float:
+    return 2 * 2 * (GMAC_DEC + (T - 1) * GMAC_FLOW) * 1e9 / 1e12
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), d["hbm_gbs"], "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(T, obs_frac, seed):
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL
+    from vaevar_b200.synth import make_case, make_state_dict
+    sd_d = make_state_dict(DECODER_FULL, seed=0)
+    sd_f = make_state_dict(FLOW_FULL, seed=1) if T > 1 else None
+    case = make_case(T, 128, 256, obs_frac=obs_frac, seed=seed)
+    return DECODER_FULL, FLOW_FULL, sd_d, sd_f, case
+
+
+def cpu_oracle_eval(T, obs_frac, seed, repeats=1, budget_s=180.0):
+    """Times the CPU oracle (oracle/: reference algorithm, fp32, torch CPU, all host threads) on closure() calls."""
+    import torch
+    from oracle import cost as oc
+    from oracle.lgunet import to_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    dcfg, fcfg, sd_d, sd_f, case = build_inputs(T, obs_frac, seed)
+    nets = oc.OracleNets(to_torch(sd_d), dcfg, to_torch(sd_f) if sd_f else None, fcfg)
+    c = oc.Case(case)
+    times, t_start = [], time.time()
+    J = None
+    for _ in range(repeats):
+        t0 = time.time()
+        J, _, _, _ = oc.cost_and_grad(case["z"], c, nets)
+        times.append(time.time() - t0)
+        if time.time() - t_start > budget_s:
+            break
+    return times, J, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU path (oracle port; the reference is pure PyTorch and its
+    driver cannot be imported: da_4dvar.py:18,23-25) on this box's host cores, same workload and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Ts = args.T
+    times, J, threads = cpu_oracle_eval(Ts, args.obs_frac, 0, repeats=args.warmup + args.steps, budget_s=240.0)
+    timed = times[min(args.warmup, max(len(times) - 1, 0)):] or times
+    ms = 1e3 * sum(timed) / len(timed)
+    sample = f"{len(timed)} full closure() calls (T={Ts}, 69x128x256, {int(args.obs_frac*100)}% obs) after {len(times)-len(timed)} warm-up; fp32 torch CPU"
+    line = {"impl": "reference", "metric": "ms per 4D-Var cost+grad eval (69x128x256)", "value": ms, "unit": "ms",
+            "n_gpus": args.gpus, "steps": len(timed), "warmup": len(times) - len(timed), "ms_per_step": ms,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"4D-Var {Ts}-step window cost+grad, 1 case, 69x128x256, {int(args.obs_frac*100)}% obs", "T": Ts},
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "J": J}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--T", type=int, default=6)
+    ap.add_argument("--obs-frac", type=float, default=0.10)
+    ap.add_argument("--recompute", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from vaevar_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    T = args.T
+    dcfg, fcfg, sd_d, sd_f, case = build_inputs(T, args.obs_frac, seed=rank)     # one independent case per GPU
+    eng = Engine(dcfg, fcfg if T > 1 else None, T=T, recompute=bool(args.recompute), use_graph=not args.no_graph, device=f"cuda:{local}")
+    eng.load_state_dict(0, sd_d)
+    if T > 1:
+        eng.load_state_dict(1, sd_f)
+    eng.finalize()
+    eng.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+    z = torch.from_numpy(case["z"]).to(dev)
+    Jb = torch.empty(3, dtype=torch.float64, device=dev)
+    gb = torch.empty_like(z)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ("value") --------------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.cost_grad(z, Jb, gb)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.cost_grad(z, Jb, gb)
+    e1.record()
+    barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.last_launch_count
+
+    # ---- end-to-end through the public API with HOST buffers ("e2e") -----------------------------------
+    z_host = torch.from_numpy(case["z"]).pin_memory()
+    g_host = torch.empty_like(z_host).pin_memory()
+    J_host = torch.empty(3, dtype=torch.float64).pin_memory()
+    for _ in range(2):
+        z.copy_(z_host, non_blocking=True); eng.cost_grad(z, Jb, gb); g_host.copy_(gb, non_blocking=True); J_host.copy_(Jb, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        z.copy_(z_host, non_blocking=True)
+        eng.cost_grad(z, Jb, gb)
+        g_host.copy_(gb, non_blocking=True)
+        J_host.copy_(Jb, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads J and grad on the host every step
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the tcgen05 GEMM on the trunk's largest shape, timed alone ----
+    import ctypes as C
+    M, N, K = 2048, 4608, 1152
+    A = torch.randn(1, M, K, device=dev).bfloat16(); W = torch.randn(1, N, K, device=dev).bfloat16()
+    ob = torch.empty(1, M, N, device=dev, dtype=torch.bfloat16)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    tk = []
+    for i in range(25):
+        flush.zero_()                                       # evict L2 (256 MiB > 126 MB) between timed launches
+        e0.record()
+        eng.lib.vv_test_gemm(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), None, None, None, C.c_void_p(ob.data_ptr()), None,
+                             M, N, K, 1, 0, st)
+        e1.record(); torch.cuda.synchronize()
+        if i >= 5:
+            tk.append(e0.elapsed_time(e1))
+    k_ms = statistics.median(tk)
+    burst, sustained, hbm, src = peaks()
+    tflop = algorithmic_tflop(T)
+    ms_eval = total_ms / args.steps
+    step_tfs = tflop / (ms_eval * 1e-3)
+    k_tfs = 2.0 * M * N * K / (k_ms * 1e-3) / 1e12
+
+    line = {
+        "metric": "ms per 4D-Var cost+grad eval (69x128x256)", "value": total_ms / (args.steps * world), "unit": "ms",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eval, "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"4D-Var {T}-step window cost+grad (VAE decoder + {T-1} flow-model applications, fwd + hand-derived adjoint), "
+                               f"1 case per GPU, 69x128x256 state, {int(args.obs_frac*100)}% column obs",
+                   "T": T, "obs_frac": args.obs_frac, "n_obs": eng.n_obs, "recompute": int(args.recompute), "cuda_graph": not args.no_graph,
+                   "parallelism": f"replicas x{world} (independent cases)",
+                   "l2": "per-eval working set (2 x 0.86 GB bf16 weights + ~1 GB stash per application) >> 126 MB L2; no flush needed"},
+        "evals_per_s": 1e3 * args.steps * world / total_ms,
+        "da_cycles_per_hour": 3600e3 * args.steps * world / total_ms / (12 * 4 + 5 + 1),
+        "da_cycle_definition": "Nit=4 L-BFGS steps x <=12 closure evals + 5 diagnostic sweeps + 1 forecast (da_4dvar_script.sh:14), in cost+grad-eval units",
+        "clocks": clocks,
+        "e2e": {"value": e2e_ms / (args.steps * world), "unit": "ms", "h2d_bytes_per_step": z_host.numel() * 4,
+                "d2h_bytes_per_step": g_host.numel() * 4 + 24},
+        "gpu_launches": launches * args.steps,
+        "gpu_launches_per_step": launches,
+        "roofline": {"bound": "tensor", "achieved": k_tfs, "peak": burst, "unit": "TFLOP/s", "frac": k_tfs / burst, "traffic": None,
+                     "kernel": "gemm_tn_tcgen05_kernel<128,3> 2048x4608x1152 (fc1 of the d=1152 trunk blocks), timed alone, L2 flushed",
+                     "peak_source": f"{src} burst"},
+        "roofline_step": {"bound": "tensor", "achieved": step_tfs, "peak": sustained, "unit": "TFLOP/s", "frac": step_tfs / sustained,
+                          "algorithmic_tflop": tflop, "peak_source": f"{src} sustained"},
+        "J": [float(v) for v in Jb.cpu()],
+    }
+    if not args.no_cpu_baseline:
+        times, Jcpu, threads = cpu_oracle_eval(T, args.obs_frac, 0, repeats=1)
+        line["cpu_baseline"] = {"value": 1e3 * times[0], "unit": "ms", "cores": threads, "kind": "port",
+                                "sample": f"1 full closure() (T={T}) of the CPU oracle (reference algorithm, fp32 torch, weight grads off), J={Jcpu:.8g}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -662,6 +662,16 @@ static int enqueue_backward(vv_engine* e, cudaStream_t s) {
 }
 
 namespace vv {
+int fence_in(vv_engine* e, cudaStream_t user) {
+  VV_CUDA(cudaEventRecord(e->ev_in, user));
+  VV_CUDA(cudaStreamWaitEvent(e->stream, e->ev_in, 0));
+  return 0;
+}
+int fence_out(vv_engine* e, cudaStream_t user) {
+  VV_CUDA(cudaEventRecord(e->ev_out, e->stream));
+  VV_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return 0;
+}
 int engine_cost_grad(vv_engine* e, const float* z, double* Jout, float* grad, cudaStream_t s) {
   VV_CHECK(e->have_consts, "vv_set_constants has not been called");
   VV_CHECK(e->have_case, "vv_set_case has not been called");
@@ -723,6 +733,12 @@ VV_API int vv_engine_create(const vv_config* cfg, vv_engine** out) {
   e->C = e->net[0].ckeep;
   e->Zc = e->net[0].cin;
   e->HW = (long long)cfg->dec.img_h * cfg->dec.img_w;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("could not create the engine stream / events");
+    delete e; return -1;
+  }
   if (cfg->has_flow) {
     Net& f = e->net[1];
     if (f.cin != e->C || f.ckeep != e->C || f.H != e->net[0].H || f.W != e->net[0].W) {
@@ -738,6 +754,9 @@ VV_API void vv_engine_destroy(vv_engine* e) {
   if (!e) return;
   cudaDeviceSynchronize();
   if (e->graph_cg) cudaGraphExecDestroy(e->graph_cg);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
   for (int k = 0; k < 2; ++k)
     for (auto& kv : e->net[k].staged) cudaFree(kv.second.first);
   for (void* p : e->allocs) cudaFree(p);
@@ -844,7 +863,11 @@ VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs) {
 
 VV_API int vv_cost_grad(vv_engine* e, const float* z_dev, double* J_out_dev, float* grad_dev, void* stream) {
   VV_CHECK(e && z_dev, "null argument");
-  return engine_cost_grad(e, z_dev, J_out_dev, grad_dev, (cudaStream_t)stream);
+  cudaStream_t user = (cudaStream_t)stream;
+  int rc = fence_in(e, user);
+  if (!rc) rc = engine_cost_grad(e, z_dev, J_out_dev, grad_dev, e->stream);
+  if (!rc) rc = fence_out(e, user);
+  return rc;
 }
 
 VV_API int vv_cost(vv_engine* e, const float* z_dev, double* J_out_dev, void* stream) {

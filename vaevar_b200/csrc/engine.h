@@ -95,6 +95,9 @@ struct vv_engine {
   std::vector<vv::Stash> stash;
   std::vector<vv::Plan> fwd, bwd;
   bool plans_built = false;
+  // private capturable stream (the caller's stream may be the legacy default stream, which cannot be captured)
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // graphs
   cudaGraphExec_t graph_cg = nullptr;
   int eager_runs = 0;
@@ -102,5 +105,9 @@ struct vv_engine {
 };
 
 namespace vv {
+// Runs on stream s, which must be capturable (not the legacy default stream): use e->stream.
 int engine_cost_grad(vv_engine* e, const float* z, double* Jout, float* grad, cudaStream_t s);
+// Order the engine's private stream after `user` (fence_in) / `user` after the private stream (fence_out).
+int fence_in(vv_engine* e, cudaStream_t user);
+int fence_out(vv_engine* e, cudaStream_t user);
 }

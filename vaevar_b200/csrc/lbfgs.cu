@@ -235,7 +235,9 @@ VV_API void vv_lbfgs_destroy(vv_lbfgs* o) {
 
 VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   if (!o || !z) { set_error("vv_lbfgs_step: null argument"); return -2; }
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t s = o->e->stream;               // everything runs on the engine's capturable stream
+  if (fence_in(o->e, user)) return -1;
   const long long n = o->n;
   double loss, gmax, gl1;
   int rc = eval(o, z, o->g, nullptr, &loss, nullptr, s);             // lbfgs.py:361-366

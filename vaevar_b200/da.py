@@ -1,0 +1,106 @@
+"""The VAE-Var inner loop behind the reference driver's call surface.
+
+    cyclic_4dvar.integrate      da_4dvar.py:666-681
+    cyclic_4dvar.one_step_DA    da_4dvar.py:933, vae4dvar branch :1179-1306
+    cal_loss / closure / LBFGS  da_4dvar.py:1210-1246, 1298-1299
+    Metrics.WRMSE / Bias        utils/metrics.py:282-296, 65-82 (kept bit-for-bit incl. pi ~ 3.1416)
+
+The latent z, its gradient, the L-BFGS history and the trajectory never leave the GPU; per closure evaluation the
+controller reads back four doubles.  Resampling to 721x1440 (vae.py:90, da_4dvar.py:671,679) is the identity on the
+engine grid and is not performed.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .config import NetConfig, era5_stats
+from .engine import LBFGS, Engine
+
+
+def lat_weight(num_lat: int, device, dtype=torch.float32) -> torch.Tensor:
+    """utils/metrics.py:5-10 -- note the literal 3.1416."""
+    j = torch.arange(0, num_lat, device=device)
+    lat = 90.0 - j * 180.0 / float(num_lat - 1)
+    cosl = torch.cos(3.1416 / 180.0 * lat)
+    return (num_lat * cosl / torch.sum(cosl)).to(dtype).reshape(1, 1, -1, 1)
+
+
+def wrmse(pred, gt, data_std):
+    w = lat_weight(pred.shape[2], pred.device)
+    return torch.mean(torch.sqrt(torch.mean(w * (pred - gt) ** 2.0, dim=(-1, -2))), dim=0) * data_std
+
+
+def bias(pred, gt, data_std):
+    w = lat_weight(pred.shape[2], pred.device)
+    return torch.mean(torch.mean(w * (pred - gt), dim=(-1, -2)), dim=0) * data_std
+
+
+class VaeVar4D:
+    """Engine-backed stand-in for `cyclic_4dvar` restricted to da_mode == "vae4dvar"."""
+
+    def __init__(self, dec_cfg: NetConfig, flow_cfg: Optional[NetConfig], dec_sd: Dict, flow_sd: Optional[Dict],
+                 da_win: int = 1, Nit: int = 4, obs_coeff: float = 1.0, device: str = "cuda:0",
+                 recompute: bool = False, use_graph: bool = True, verbose: bool = True):
+        self.da_win, self.Nit, self.obs_coeff, self.verbose = da_win, Nit, obs_coeff, verbose
+        self.device = torch.device(device)
+        self.engine = Engine(dec_cfg, flow_cfg, T=da_win, recompute=recompute, use_graph=use_graph, device=device)
+        self.engine.load_state_dict(0, dec_sd)
+        if flow_cfg is not None:
+            self.engine.load_state_dict(1, flow_sd)
+        self.engine.finalize()
+        mean, std, _ = era5_stats()
+        self.model_mean, self.model_std = mean, std                        # float64, da_4dvar.py:645-646
+        self.model_mean_gpu = torch.from_numpy(mean).float().to(self.device)
+        self.model_std_gpu = torch.from_numpy(std).float().to(self.device)
+        self.nchannel = 69
+        self.nlat, self.nlon = dec_cfg.img_size
+        self.latent = dec_cfg.in_chans
+        self.metrics_list = {k: [] for k in ("bg_wrmse", "bg_bias", "ana_wrmse", "ana_bias")}
+        self.history = []
+
+    def integrate(self, xa: torch.Tensor, model=None, step: int = 1, interpolation: bool = False, detach: bool = True):
+        """(69,nlat,nlon) physical -> physical after `step` applications of the flow model (da_4dvar.py:666-681)."""
+        return self.engine.integrate(xa.to(self.device, torch.float32), step)
+
+    def _diagnostics(self, z, gt_norm):
+        xhat = self.engine.decode(z)
+        xn = ((xhat - self.model_mean_gpu.reshape(-1, 1, 1)) / self.model_std_gpu.reshape(-1, 1, 1)).unsqueeze(0)
+        std = torch.from_numpy(self.model_std).to(self.device)
+        return wrmse(xn, gt_norm, std), bias(xn, gt_norm, std)
+
+    def one_step_DA(self, gt, xb, yo, H, R, mode: str = "vae4dvar"):
+        if mode != "vae4dvar":
+            raise NotImplementedError("not implemented da mode")            # da_4dvar.py:1308-1309
+        dev = self.device
+        gt0 = torch.as_tensor(gt[0]).to(dev, torch.float32)
+        gt_norm = ((gt0 - self.model_mean_gpu.reshape(-1, 1, 1)) / self.model_std_gpu.reshape(-1, 1, 1)).unsqueeze(0)
+        self.engine.set_case(xb, yo, H, R, self.obs_coeff)
+        z = torch.zeros(1, self.latent, self.nlat, self.nlon, device=dev)   # da_4dvar.py:1238
+        opt = LBFGS(self.engine, history_size=10, max_iter=10)              # da_4dvar.py:1240
+        t0 = time.time()
+        for kk in range(self.Nit + 1):
+            w, b = self._diagnostics(z, gt_norm)
+            J = self.engine.cost(z).cpu()                                   # cal_loss, da_4dvar.py:1265
+            if self.verbose:
+                print("iter: %d, RMSE (z500): %.4g Bias (z500): %.4g q500: %.4g, t2m: %.4g t850: %.4g u500: %.4g, v500: %.4g, "
+                      "loss reg: %.4g loss obs: %.4g loss: %.4g" % (kk, w[11], b[11], w[24], w[2], w[66], w[37], w[50],
+                                                                   J[1], J[2], J[0]), flush=True)
+            if kk == 0:
+                self.metrics_list["bg_wrmse"].append(w.cpu())
+                self.metrics_list["bg_bias"].append(b.cpu())
+            elif kk == self.Nit:
+                self.metrics_list["ana_wrmse"].append(w.cpu())
+                self.metrics_list["ana_bias"].append(b.cpu())
+            if kk < self.Nit:
+                self.history.append(opt.step(z))                            # lbfgs.step(closure), da_4dvar.py:1298-1299
+        xa = self.engine.decode(z)
+        torch.cuda.synchronize()
+        if self.verbose:
+            print("DA finished. Time consumed: %.3f (s)" % (time.time() - t0), flush=True)
+        opt.close()
+        self.z = z
+        return xa
