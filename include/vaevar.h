@@ -105,6 +105,11 @@ VV_API void vv_lbfgs_destroy(vv_lbfgs* o);
 /* One optimizer.step(closure) on z_dev (updated in place). info_host[8] = {loss at entry, final loss, n closure evals
  * this step, n_iter total, last step length, |g|_inf, 0, 0}. Synchronises. */
 VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z_dev, double* info_host, void* stream);
+/* Losses of every closure evaluation so far (returns the total count; copies at most cap). */
+VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out_host, int cap);
+/* Same controller on an analytic device function (pairwise Rosenbrock over n floats) -- lets tests compare the
+ * optimiser's decisions with torch.optim.LBFGS on an identical objective. */
+VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, vv_lbfgs** out);
 
 /* Kernel-level hooks used by tests/ and bench.py (roofline of the dominant kernel). */
 VV_API int vv_test_gemm(const void* A_bf16_dev, const void* B_bf16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
@@ -115,6 +120,10 @@ VV_API int vv_test_winattn(const void* qkv_bf16_dev, const float* relbias_dev, v
                     void* dqkv_bf16_dev, int gh, int gw, int heads, int hd, int shift, void* stream);
 /* J_obs and residuals for a given normalised trajectory xn (T,C,H,W) with the case already set. */
 VV_API int vv_test_obs(vv_engine* e, const float* xn_dev, double* J_obs_dev, float* grad_xn_dev, void* stream);
+/* Steady-state time of every launch of one application plan (app 0 = decoder, >= 1 = flow; bwd = 0/1): each op is run
+ * `reps` times between CUDA events. ms_out / kind_out / flop_out hold `cap` entries; returns the number of ops.
+ * kind: 0 GEMM, 1 LN fwd, 2 LN bwd, 3 attention fwd, 4 attention bwd, 5 P2T, 6 T2P. */
+VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap);
 /* Number of kernel launches the last vv_cost_grad enqueued (for bench.py's gpu_launches). */
 VV_API int vv_last_launch_count(vv_engine* e);
 

@@ -12,7 +12,7 @@ import time
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
-STAGES = ["gemm", "ln", "attn", "obs", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
+STAGES = ["gemm", "gemm_1cta", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
 
 
 def rel(a, b):
@@ -81,6 +81,11 @@ def stage_gemm():
         ms_t = e0.elapsed_time(e1) / 50
         print(f"[gemm] time {M}x{N}x{K}: {ms*1e3:.1f} us = {2*M*N*K/ms/1e9:.0f} TFLOP/s (incl. launch) | cuBLAS {ms_t*1e3:.1f} us", flush=True)
     return ok
+
+
+def stage_gemm_1cta():
+    os.environ["VV_GEMM_1CTA"] = "1"
+    return stage_gemm()
 
 
 def stage_ln():
@@ -311,6 +316,46 @@ def stage_cost_full():
     return _cost_stage("cost_full", True, 2)
 
 
+def stage_lbfgs_testfn():
+    """The device controller against torch.optim.LBFGS on the same analytic objective (pairwise Rosenbrock)."""
+    import torch
+    from vaevar_b200.engine import LBFGS
+    ok = True
+    n = 4096
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(n, generator=g) * 0.5
+
+    def f(x):
+        a, b = x[0::2], x[1::2]
+        return (100 * (b - a * a) ** 2 + (1 - a) ** 2).sum()
+
+    for steps in (1, 3):
+        xt = x0.clone().requires_grad_(True)
+        opt = torch.optim.LBFGS([xt], history_size=10, max_iter=10, line_search_fn="strong_wolfe")
+        hist = []
+
+        def closure():
+            opt.zero_grad()
+            l = f(xt)
+            l.backward()
+            hist.append(float(l))
+            return l
+        for _ in range(steps):
+            opt.step(closure)
+        z = x0.clone().cuda()
+        o = LBFGS(None, 10, 10, testfn_n=n)
+        for _ in range(steps):
+            info = o.step(z)
+        h = o.history()
+        ok &= report("lbfgs_testfn", f"steps={steps} closure evaluations", abs(len(h) - len(hist)), 0)
+        k = min(len(h), len(hist))
+        worst = max(abs(h[i] / hist[i] - 1) for i in range(k))
+        ok &= report("lbfgs_testfn", f"steps={steps} loss history max rel diff", worst, 1e-3)
+        ok &= report("lbfgs_testfn", f"steps={steps} final iterate", rel(z.cpu(), xt.detach()), 1e-3)
+        print(f"[lbfgs_testfn] torch: {hist[:4]} ... {hist[-1]:.6g}; engine: {h[:4]} ... {h[-1]:.6g}", flush=True)
+    return ok
+
+
 def stage_lbfgs_small():
     import numpy as np
     import torch
@@ -332,6 +377,8 @@ def stage_lbfgs_small():
         c = oc.Case(case)
         r = oc.one_step_da(c, nets, nit=1, max_iter=10)
         print(f"[lbfgs_small] T={T} engine: {info}; oracle: evals={r['n_evals']} J0={r['J_history'][0]:.6g} Jend={r['J_history'][-1]:.6g}", flush=True)
+        print(f"[lbfgs_small] T={T} engine J history {['%.6g' % v for v in opt.history()]}", flush=True)
+        print(f"[lbfgs_small] T={T} oracle J history {['%.6g' % v for v in r['J_history']]}", flush=True)
         xa = e.decode(z)
         xa_n = ((xa.cpu() - c.mean) / c.std).unsqueeze(0)
         gn = ((c.gt[0] - c.mean) / c.std).unsqueeze(0)

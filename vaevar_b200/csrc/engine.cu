@@ -971,6 +971,44 @@ VV_API int vv_test_obs(vv_engine* e, const float* xn_dev, double* J_obs_dev, flo
 
 VV_API int vv_last_launch_count(vv_engine* e) { return e ? e->last_launches : 0; }
 
+VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap) {
+  VV_CHECK(e && ms_out && kind_out && reps >= 1, "bad argument");
+  int rc = build_plans(e);
+  if (rc) return rc;
+  VV_CHECK(app >= 0 && app < (int)e->fwd.size(), "no such application");
+  const Plan& P = bwd ? e->bwd[app] : e->fwd[app];
+  cudaEvent_t e0, e1;
+  VV_CUDA(cudaEventCreate(&e0)); VV_CUDA(cudaEventCreate(&e1));
+  cudaStream_t s = e->stream;
+  e->fwd[app].run(s);                       // make sure the stash holds finite values
+  int k = 0;
+  for (const Op& o : P.ops) {
+    Plan one; one.ops.push_back(o);
+    one.run(s);
+    cudaEventRecord(e0, s);
+    for (int r = 0; r < reps; ++r) one.run(s);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (k < cap) {
+      ms_out[k] = ms / reps;
+      kind_out[k] = (int)o.kind;
+      if (flop_out) flop_out[k] = o.kind == Op::GEMM ? 2.0 * o.gemm.a.M * o.gemm.a.N * o.gemm.a.K * o.gemm.a.batch : 0.0;
+      if (mnk_out) {
+        mnk_out[4 * k] = o.kind == Op::GEMM ? o.gemm.a.M : (o.kind == Op::LN_F ? o.lnf.rows : o.kind == Op::LN_B ? o.lnb.rows : 0);
+        mnk_out[4 * k + 1] = o.kind == Op::GEMM ? o.gemm.a.N : (o.kind == Op::LN_F ? o.lnf.C : o.kind == Op::LN_B ? o.lnb.C : (o.kind == Op::ATT_F || o.kind == Op::ATT_B) ? o.att.hd : 0);
+        mnk_out[4 * k + 2] = o.kind == Op::GEMM ? o.gemm.a.K : 0;
+        mnk_out[4 * k + 3] = o.kind == Op::GEMM ? o.gemm.a.batch : (o.kind == Op::LN_F ? o.lnf.batch : o.kind == Op::LN_B ? o.lnb.batch : (o.kind == Op::ATT_F || o.kind == Op::ATT_B) ? o.att.batch : 0);
+      }
+    }
+    ++k;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  VV_CUDA(cudaGetLastError());
+  return k;
+}
+
 // ---- kernel-level hooks -----------------------------------------------------------------------
 VV_API int vv_test_gemm(const void* A, const void* B, const float* bias, const float* res, float* out_f32, void* out_bf16, void* aux, int M,
                  int N, int K, int batch, int epi, void* stream) {

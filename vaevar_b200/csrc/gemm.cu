@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: TMA descriptor encoding and tile-shape dispatch.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ops.h"
@@ -43,13 +44,34 @@ static const char* encode_map(CUtensorMap* tm, const bf16* base, long long K, lo
   return nullptr;
 }
 
-static int pick_bn(int M, int N, int batch) {
-  (void)M; (void)batch;
+static bool use_1cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VV_GEMM_1CTA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// Single-CTA kernel (fallback / A-B comparison): 128 x BN tiles.
+static int pick_bn_1cta(int N) {
   if (N <= 64) return 64;
   if (N % 128 == 0) return 128;
   if (N % 96 == 0) return 96;
   if (N % 64 == 0 && N < 256) return 64;
   return 128;
+}
+// CTA-pair kernel: 256 x BN tiles.  Largest BN dividing N that still yields about one CTA per SM; otherwise the
+// dividing BN with the most CTAs.
+static int pick_bn_2cta(int M, int N, int batch) {
+  static const int cand[5] = {256, 192, 128, 96, 64};
+  const long long pair_rows = (M + 255) / 256;
+  int best = 0; long long best_ctas = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (N % bn) continue;
+    const long long ctas = 2 * pair_rows * (N / bn) * batch;
+    if (ctas >= 140) return bn;
+    if (ctas > best_ctas) { best_ctas = ctas; best = bn; }
+  }
+  return best ? best : 128;
 }
 
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs,
@@ -58,10 +80,11 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   if (args.K % 8) return "GEMM K must be a multiple of 8";
   if (args.split_n > 0 && args.split_n % 8) return "GEMM split_n must be a multiple of 8";
   d->a = args;
-  d->bn = pick_bn(args.M, args.N, args.batch);
+  d->two_cta = use_1cta() ? 0 : 1;
+  d->bn = d->two_cta ? pick_bn_2cta(args.M, args.N, args.batch) : pick_bn_1cta(args.N);
   const char* e = encode_map(&d->tmA, A, args.K, args.M, args.batch, lda, a_bs, GEMM_BM);
   if (e) return e;
-  return encode_map(&d->tmB, B, args.K, args.N, args.batch, ldb, b_bs, d->bn);
+  return encode_map(&d->tmB, B, args.K, args.N, args.batch, ldb, b_bs, d->two_cta ? d->bn / 2 : d->bn);
 }
 
 template <int BN, int STAGES>
@@ -76,7 +99,30 @@ static void launch_t(const GemmDesc& d, cudaStream_t s) {
   gemm_tn_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, s>>>(d.tmA, d.tmB, d.a);
 }
 
+template <int BN, int STAGES>
+static void launch_2cta(const GemmDesc& d, cudaStream_t s) {
+  using L = Gemm2Smem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tn_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    attr_set = true;
+  }
+  const int mtiles = (d.a.M + GEMM_BM - 1) / GEMM_BM;
+  dim3 grid(((mtiles + 1) / 2) * 2, (d.a.N + BN - 1) / BN, d.a.batch);     // grid.x even: CTA pairs along M
+  gemm_tn_2cta_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, s>>>(d.tmA, d.tmB, d.a);
+}
+
 void launch_gemm(const GemmDesc& d, cudaStream_t s) {
+  if (d.two_cta) {
+    switch (d.bn) {
+      case 64: launch_2cta<64, 4>(d, s); break;
+      case 96: launch_2cta<96, 4>(d, s); break;
+      case 192: launch_2cta<192, 3>(d, s); break;
+      case 256: launch_2cta<256, 3>(d, s); break;
+      default: launch_2cta<128, 4>(d, s); break;
+    }
+    return;
+  }
   switch (d.bn) {
     case 64: launch_t<64, 4>(d, s); break;
     case 96: launch_t<96, 3>(d, s); break;

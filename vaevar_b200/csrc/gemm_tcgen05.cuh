@@ -48,6 +48,80 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;  // +1024: manual alignment slack
 };
 
+// Epilogue of one 128-row accumulator tile held in this CTA's TMEM: executed by warps 2..5 (warp w may touch TMEM lanes
+// [(w%4)*32, +32)); thread = row, 32 fp32 columns per tcgen05.ld, fused bias / GELU / GELU' / residual, direct global stores.
+template <int BN>
+VV_DEVINL void gemm_epilogue(const GemmArgs& p, uint32_t tmem_base, uint64_t* tmem_full_bar, int warp, int lane, int m0, int n0, int b) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int m = m0 + row;
+  const bool row_ok = m < p.M;
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
+  const float* res = p.res ? p.res + (long long)b * p.res_bs + (long long)m * p.ld_res : nullptr;
+  const __nv_bfloat16* aux_in = p.aux_in ? p.aux_in + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
+  __nv_bfloat16* aux_out = p.aux_out ? p.aux_out + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
+  float* of = p.out_f32 ? p.out_f32 + (long long)b * p.f32_bs + (long long)m * p.ld_f32 : nullptr;
+  __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)b * p.bf16_bs + (long long)m * p.ld_bf16 : nullptr;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    __syncwarp();
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {            // 4 groups of 8 columns
+      const int n = n0 + c0 + g * 8;
+      if (!row_ok || n + 8 > p.N) continue;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+      if (bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.epi == EPI_GELU) {
+        if (aux_out) {
+          uint4 w;
+          w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+          w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(aux_out + n) = w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+      } else if (p.epi == EPI_DGELU) {
+        const uint4 w = *reinterpret_cast<const uint4*>(aux_in + n);
+        const float2 u0 = unpack_bf16(w.x), u1 = unpack_bf16(w.y), u2 = unpack_bf16(w.z), u3 = unpack_bf16(w.w);
+        v[0] *= gelu_erf_grad(u0.x); v[1] *= gelu_erf_grad(u0.y);
+        v[2] *= gelu_erf_grad(u1.x); v[3] *= gelu_erf_grad(u1.y);
+        v[4] *= gelu_erf_grad(u2.x); v[5] *= gelu_erf_grad(u2.y);
+        v[6] *= gelu_erf_grad(u3.x); v[7] *= gelu_erf_grad(u3.y);
+      }
+      if (res) {
+        const float4 r0 = *reinterpret_cast<const float4*>(res + n);
+        const float4 r1 = *reinterpret_cast<const float4*>(res + n + 4);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+        v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+      }
+      if (of) {
+        *reinterpret_cast<float4*>(of + n) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(of + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (ob) {
+        uint4 w;
+        w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+        w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
+        long long off = n;
+        if (p.split_n > 0) off = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
+        *reinterpret_cast<uint4*>(ob + off) = w;
+      }
+    }
+  }
+  }
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
@@ -124,81 +198,114 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       umma_commit(tmem_full_bar);            // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [(w%4)*32, +32) =====
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
-    const float* res = p.res ? p.res + (long long)b * p.res_bs + (long long)m * p.ld_res : nullptr;
-    const __nv_bfloat16* aux_in = p.aux_in ? p.aux_in + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
-    __nv_bfloat16* aux_out = p.aux_out ? p.aux_out + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
-    float* of = p.out_f32 ? p.out_f32 + (long long)b * p.f32_bs + (long long)m * p.ld_f32 : nullptr;
-    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)b * p.bf16_bs + (long long)m * p.ld_bf16 : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {            // 4 groups of 8 columns
-        const int n = n0 + c0 + g * 8;
-        if (!row_ok || n + 8 > p.N) continue;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-        if (bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (p.epi == EPI_GELU) {
-          if (aux_out) {
-            uint4 w;
-            w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
-            w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
-            *reinterpret_cast<uint4*>(aux_out + n) = w;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-        } else if (p.epi == EPI_DGELU) {
-          const uint4 w = *reinterpret_cast<const uint4*>(aux_in + n);
-          const float2 u0 = unpack_bf16(w.x), u1 = unpack_bf16(w.y), u2 = unpack_bf16(w.z), u3 = unpack_bf16(w.w);
-          v[0] *= gelu_erf_grad(u0.x); v[1] *= gelu_erf_grad(u0.y);
-          v[2] *= gelu_erf_grad(u1.x); v[3] *= gelu_erf_grad(u1.y);
-          v[4] *= gelu_erf_grad(u2.x); v[5] *= gelu_erf_grad(u2.y);
-          v[6] *= gelu_erf_grad(u3.x); v[7] *= gelu_erf_grad(u3.y);
-        }
-        if (res) {
-          const float4 r0 = *reinterpret_cast<const float4*>(res + n);
-          const float4 r1 = *reinterpret_cast<const float4*>(res + n + 4);
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        if (of) {
-          *reinterpret_cast<float4*>(of + n) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(of + n + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (ob) {
-          uint4 w;
-          w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
-          w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
-          long long off = n;
-          if (p.split_n > 0) off = (long long)(n / p.split_n) * p.split_stride + (n % p.split_n);
-          *reinterpret_cast<uint4*>(ob + off) = w;
-        }
-      }
-    }
+    gemm_epilogue<BN>(p, tmem_base, tmem_full_bar, warp, lane, m0, n0, b);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant: two CTAs of a (2,1,1) cluster compute one 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so the L2 -> shared-memory traffic per MAC drops to
+// (128 + BN/2) / (128 * BN) of an operand row (BN = 256: half of the single-CTA 128 x 128 tile).  The leader CTA (rank 0)
+// issues the MMAs; both CTAs' TMA loads credit the leader's "full" barrier; tcgen05.commit multicasts the "slot free"
+// and "accumulator ready" arrivals to both CTAs; each CTA drains its own 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN");
+  using L = Gemm2Smem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
+  const int n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * GEMM_BM;              // this CTA's 128 rows (pair = blockIdx.x >> 1)
+  const int b = blockIdx.z;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();                               // barriers of both CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);     // bytes of both CTAs land on the leader's barrier
+        const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        tma_load_3d_2cta(sa, &tmA, leader_full, kb * GEMM_BK, m0, b);
+        tma_load_3d_2cta(sa + L::A_BYTES, &tmB, leader_full, kb * GEMM_BK, n0 + (int)rank * (BN / 2), b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t da = make_smem_desc_sw128(sa);
+        const uint64_t db = make_smem_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_2cta(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit_2cta(&empty_bar[s], 3);         // frees this slot in BOTH CTAs
+      }
+      umma_commit_2cta(tmem_full_bar, 3);           // accumulator complete in both CTAs
+    }
+  } else {
+    gemm_epilogue<BN>(p, tmem_base, tmem_full_bar, warp, lane, m0, n0, b);
+  }
+  tc_fence_before();
+  cluster_sync_all();                               // neither CTA may retire while its peer can still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
   }
 }
 

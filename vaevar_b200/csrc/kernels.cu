@@ -26,8 +26,45 @@ VV_DEVINL long long ln_elem_off(int r, int c, int C, int gw, long long ld) {
   }
 }
 
-template <int NPL, int MAP>
+// Each lane owns NPL = C/32 elements of the row as NPL/VEC vectors of VEC consecutive floats:
+// element (k, v) = column VEC*(lane + 32*k) + v, so every warp-wide access is one contiguous 128*VEC-byte segment.
+template <int VEC> struct VecT;
+template <> struct VecT<1> { typedef float T; };
+template <> struct VecT<2> { typedef float2 T; };
+template <> struct VecT<4> { typedef float4 T; };
+
+template <int VEC>
+VV_DEVINL void ldv(float* dst, const float* src) {
+  typename VecT<VEC>::T t = *reinterpret_cast<const typename VecT<VEC>::T*>(src);
+  const float* f = reinterpret_cast<const float*>(&t);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) dst[v] = f[v];
+}
+template <int VEC>
+VV_DEVINL void stv(float* dst, const float* src) {
+  typename VecT<VEC>::T t;
+  float* f = reinterpret_cast<float*>(&t);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) f[v] = src[v];
+  *reinterpret_cast<typename VecT<VEC>::T*>(dst) = t;
+}
+template <int VEC>
+VV_DEVINL void stv_bf16(bf16* dst, const float* src) {
+  if (VEC == 1) {
+    dst[0] = __float2bfloat16(src[0]);
+  } else if (VEC == 2) {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16(src[0], src[1]);
+  } else {
+    uint2 w;
+    w.x = pack_bf16(src[0], src[1]);
+    w.y = pack_bf16(src[2], src[3]);
+    *reinterpret_cast<uint2*>(dst) = w;
+  }
+}
+
+template <int NPL, int VEC, int MAP>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
+  constexpr int NV = NPL / VEC;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = blockIdx.y;
@@ -36,9 +73,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   float v[NPL];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    v[k] = x[ln_elem_off<MAP>(r, lane + 32 * k, a.C, a.gw, a.ld_x)];
-    s += v[k];
+  for (int k = 0; k < NV; ++k) {
+    ldv<VEC>(v + k * VEC, x + ln_elem_off<MAP>(r, VEC * (lane + 32 * k), a.C, a.gw, a.ld_x));
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += v[k * VEC + i];
   }
   const float mean = warp_sum(s) / a.C;
   float q = 0.f;
@@ -51,16 +89,21 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   const float* g = a.gamma + (long long)b * a.gb_bs;
   const float* be = a.beta + (long long)b * a.gb_bs;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    const int c = lane + 32 * k;
-    const float y = (v[k] - mean) * rstd * g[c] + be[c];
-    if (a.out_bf16) a.out_bf16[(long long)b * a.ob_bs + (long long)r * a.ld_ob + c] = __float2bfloat16(y);
-    if (a.out_f32) a.out_f32[(long long)b * a.of_bs + (long long)r * a.ld_of + c] = y;
+  for (int k = 0; k < NV; ++k) {
+    const int c = VEC * (lane + 32 * k);
+    float gg[VEC], bb[VEC], y[VEC];
+    ldv<VEC>(gg, g + c);
+    ldv<VEC>(bb, be + c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) y[i] = (v[k * VEC + i] - mean) * rstd * gg[i] + bb[i];
+    if (a.out_bf16) stv_bf16<VEC>(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + c, y);
+    if (a.out_f32) stv<VEC>(a.out_f32 + (long long)b * a.of_bs + (long long)r * a.ld_of + c, y);
   }
 }
 
-template <int NPL, int MAP>
+template <int NPL, int VEC, int MAP>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  constexpr int NV = NPL / VEC;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = blockIdx.y;
@@ -71,9 +114,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   float v[NPL], gd[NPL];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    v[k] = x[ln_elem_off<MAP>(r, lane + 32 * k, a.C, a.gw, a.ld_x)];
-    s += v[k];
+  for (int k = 0; k < NV; ++k) {
+    ldv<VEC>(v + k * VEC, x + ln_elem_off<MAP>(r, VEC * (lane + 32 * k), a.C, a.gw, a.ld_x));
+    ldv<VEC>(gd + k * VEC, dy + VEC * (lane + 32 * k));
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += v[k * VEC + i];
   }
   const float mean = warp_sum(s) / a.C;
   float q = 0.f;
@@ -85,22 +130,34 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   const float rstd = rsqrtf(warp_sum(q) / a.C + a.eps);
   float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    const int c = lane + 32 * k;
-    v[k] *= rstd;                     // xhat
-    gd[k] = dy[c] * g[c];
-    m1 += gd[k];
-    m2 += gd[k] * v[k];
+  for (int k = 0; k < NV; ++k) {
+    float gg[VEC];
+    ldv<VEC>(gg, g + VEC * (lane + 32 * k));
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int e = k * VEC + i;
+      v[e] *= rstd;                     // xhat
+      gd[e] *= gg[i];
+      m1 += gd[e];
+      m2 += gd[e] * v[e];
+    }
   }
   m1 = warp_sum(m1) / a.C;
   m2 = warp_sum(m2) / a.C;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    const int c = lane + 32 * k;
-    float d = (gd[k] - m1 - v[k] * m2) * rstd;
-    if (a.dres) d += a.dres[(long long)b * a.dres_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dres)];
-    a.dx[(long long)b * a.dx_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dx)] = d;
-    if (a.dx_bf16) a.dx_bf16[(long long)b * a.dxb_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dxb)] = __float2bfloat16(d);
+  for (int k = 0; k < NV; ++k) {
+    const int c = VEC * (lane + 32 * k);
+    float d[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) d[i] = (gd[k * VEC + i] - m1 - v[k * VEC + i] * m2) * rstd;
+    if (a.dres) {
+      float rr[VEC];
+      ldv<VEC>(rr, a.dres + (long long)b * a.dres_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dres));
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) d[i] += rr[i];
+    }
+    stv<VEC>(a.dx + (long long)b * a.dx_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dx), d);
+    if (a.dx_bf16) stv_bf16<VEC>(a.dx_bf16 + (long long)b * a.dxb_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dxb), d);
   }
 }
 
@@ -109,16 +166,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     const int npl = ARGS.C / 32;                                                         \
     dim3 grid((ARGS.rows + 7) / 8, ARGS.batch);                                          \
     switch (ARGS.map * 100 + npl) {                                                      \
-      case 2: KERNEL<2, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                    \
-      case 3: KERNEL<3, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                    \
-      case 4: KERNEL<4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                    \
-      case 6: KERNEL<6, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                    \
-      case 12: KERNEL<12, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                  \
-      case 36: KERNEL<36, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                  \
-      case 108: KERNEL<8, MAP_MERGE><<<grid, 256, 0, s>>>(ARGS); break;                  \
-      case 112: KERNEL<12, MAP_MERGE><<<grid, 256, 0, s>>>(ARGS); break;                 \
-      case 202: KERNEL<2, MAP_EXPAND><<<grid, 256, 0, s>>>(ARGS); break;                 \
-      case 203: KERNEL<3, MAP_EXPAND><<<grid, 256, 0, s>>>(ARGS); break;                 \
+      case 2: KERNEL<2, 2, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
+      case 3: KERNEL<3, 1, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
+      case 4: KERNEL<4, 4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
+      case 6: KERNEL<6, 2, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
+      case 12: KERNEL<12, 4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;               \
+      case 36: KERNEL<36, 4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;               \
+      case 108: KERNEL<8, 4, MAP_MERGE><<<grid, 256, 0, s>>>(ARGS); break;               \
+      case 112: KERNEL<12, 4, MAP_MERGE><<<grid, 256, 0, s>>>(ARGS); break;              \
+      case 202: KERNEL<2, 2, MAP_EXPAND><<<grid, 256, 0, s>>>(ARGS); break;              \
+      case 203: KERNEL<3, 1, MAP_EXPAND><<<grid, 256, 0, s>>>(ARGS); break;              \
       default: break;                                                                    \
     }                                                                                    \
   }
@@ -141,7 +198,7 @@ void launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) { VV_LN_DISPATCH(ln_bwd_k
 template <int HD, bool BWD>
 struct AttnSmem {
   static constexpr int W2 = HD / 2;             // 32-bit words (bf16 pairs) per token row
-  static constexpr int RS = W2 + 1;             // padded row stride -> conflict-free row-parallel reads
+  static constexpr int RS = W2 + 2;             // padded row stride (even: 8-byte cp.async rows; 2i+w banks: conflict-free)
   static constexpr int MAT = 16 * RS;           // one 16 x HD operand
   static constexpr int WORDS = (BWD ? 4 : 3) * MAT + (BWD ? 2 : 1) * 16 * 17;
   static constexpr int BYTES = 4 * WORDS * 4;   // 4 warps per CTA
@@ -175,19 +232,21 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
     return row * a.gw + col;
   };
 
+  // Stage Q, K, V (and dO) with 8-byte cp.async: every copy of the warp is in flight before the single wait.
   const bf16* qkv = a.qkv + (long long)b * a.qkv_bs;
-#pragma unroll 1
-  for (int t = 0; t < 16; ++t) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(qkv + (long long)tok_of(t) * a.ld_qkv + h * HD);
-    for (int w = lane; w < W2; w += 32) {
-      Qs[t * RS + w] = src[w];
-      Ks[t * RS + w] = src[w + d / 2];
-      Vs[t * RS + w] = src[w + d];
+  {
+    constexpr int CH = W2 / 2;                                   // 8-byte chunks per operand row
+    constexpr int NMAT = BWD ? 4 : 3;
+    for (int idx = lane; idx < 16 * 4 * CH; idx += 32) {
+      const int ch = idx % CH, rowm = idx / CH, m = rowm & 3, t = rowm >> 2;     // m: 0 Q, 1 K, 2 V, 3 dO
+      if (m >= NMAT) continue;
+      const bf16* src = m < 3 ? qkv + (long long)tok_of(t) * a.ld_qkv + m * d + h * HD
+                              : a.dout + (long long)b * a.o_bs + (long long)tok_of(t) * a.ld_o + h * HD;
+      uint32_t* dst = Qs + m * L::MAT + t * RS + 2 * ch;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src + 4 * ch) : "memory");
     }
-    if (BWD) {
-      const uint32_t* dsrc = reinterpret_cast<const uint32_t*>(a.dout + (long long)b * a.o_bs + (long long)tok_of(t) * a.ld_o + h * HD);
-      for (int w = lane; w < W2; w += 32) dOs[t * RS + w] = dsrc[w];
-    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncwarp();
 

@@ -6,14 +6,21 @@
 #include <math.h>
 
 #include <algorithm>
+#include <functional>
 #include <vector>
 
 #include "engine.h"
 
 using namespace vv;
 
+// closure(z, Jdev[>=1], grad_out, stream): enqueue J(z) -> Jdev[0] and dJ/dz -> grad_out on `stream`
+typedef std::function<int(const float*, double*, float*, cudaStream_t)> Closure;
+
 struct vv_lbfgs {
   vv_engine* e = nullptr;
+  Closure closure;
+  cudaStream_t own_stream = nullptr;     // test-function optimisers have no engine stream
+  std::vector<double> hist_loss, hist_t; // every closure evaluation: loss and trial step
   int hist = 10, max_iter = 10, max_eval = 12;
   double lr = 1.0, tol_grad = 1e-7, tol_change = 1e-9;
   long long n = 0;
@@ -77,7 +84,7 @@ int absmax_l1_host(vv_lbfgs* o, const float* x, double* mx, double* l1, cudaStre
 }
 // closure at z: loss -> *f, gradient -> gout, and gout . dvec -> *gtd (when dvec != null), one read-back
 int eval(vv_lbfgs* o, const float* z, float* gout, const float* dvec, double* f, double* gtd, cudaStream_t s) {
-  int rc = engine_cost_grad(o->e, z, o->Jdev, gout, s);
+  int rc = o->closure(z, o->Jdev, gout, s);
   if (rc) return rc;
   if (dvec) {
     DotPairs p{}; p.a[0] = gout; p.b[0] = dvec; p.n_pairs = 1;
@@ -87,6 +94,7 @@ int eval(vv_lbfgs* o, const float* z, float* gout, const float* dvec, double* f,
   *f = o->pinned[0];
   if (gtd) *gtd = o->pinned[3];
   o->func_evals++;
+  o->hist_loss.push_back(*f);
   return 0;
 }
 
@@ -112,6 +120,7 @@ int strong_wolfe(vv_lbfgs* o, float* z, double t, double f, double gtd, int max_
   auto trial = [&](double tt, double* fn, double* gn) -> int {        // _directional_evaluate, lbfgs.py:325-331
     if (copy_vec(o, z, o->x_init, s)) return -1;
     launch_axpby(z, o->d, nullptr, tt, nullptr, 1.0, o->n, s);
+    o->hist_t.push_back(tt);
     return eval(o, z, o->g_new, o->d, fn, gn, s);
   };
   double f_new, gtd_new;
@@ -202,11 +211,62 @@ int strong_wolfe(vv_lbfgs* o, float* z, double t, double f, double gtd, int max_
 
 extern "C" {
 
+static int lbfgs_alloc(vv_lbfgs* o, long long nn, int history_size, int max_iter, vv_lbfgs** out);
+
 VV_API int vv_lbfgs_create(vv_engine* e, int history_size, int max_iter, vv_lbfgs** out) {
   if (!e || !out || history_size < 1 || max_iter < 1) { set_error("vv_lbfgs_create: bad argument"); return -2; }
   vv_lbfgs* o = new vv_lbfgs();
-  o->e = e; o->hist = history_size; o->max_iter = max_iter; o->max_eval = max_iter * 5 / 4;
-  o->n = (long long)e->Zc * e->HW;
+  o->e = e;
+  o->closure = [e](const float* z, double* Jdev, float* g, cudaStream_t s) { return engine_cost_grad(e, z, Jdev, g, s); };
+  return lbfgs_alloc(o, (long long)e->Zc * e->HW, history_size, max_iter, out);
+}
+
+// Analytic closure for testing the controller against torch.optim.LBFGS on the same function:
+//   f(x) = sum_i [ 100 (x_{2i+1} - x_{2i}^2)^2 + (1 - x_{2i})^2 ]   (pairwise Rosenbrock), evaluated in fp32 on the device.
+__global__ void rosenbrock_kernel(const float* x, long long n, float* g, double* partial) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += (long long)gridDim.x * blockDim.x) {
+    const float a = x[2 * i], b = x[2 * i + 1];
+    const float r = b - a * a, q = 1.0f - a;
+    acc += (double)(100.0f * r * r + q * q);
+    g[2 * i] = -400.0f * a * r - 2.0f * q;
+    g[2 * i + 1] = 200.0f * r;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, vv_lbfgs** out) {
+  if (!out || n < 2 || (n & 1) || history_size < 1 || max_iter < 1) { set_error("vv_lbfgs_create_testfn: bad argument"); return -2; }
+  vv_lbfgs* o = new vv_lbfgs();
+  if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete o; set_error("stream"); return -1; }
+  double* part = nullptr;
+  if (cudaMalloc(&part, 64 * sizeof(double)) != cudaSuccess) { delete o; set_error("oom"); return -1; }
+  o->allocs.push_back(part);
+  o->closure = [n, part](const float* z, double* Jdev, float* g, cudaStream_t s) {
+    rosenbrock_kernel<<<64, 256, 0, s>>>(z, n, g, part);
+    launch_reduce_partials(part, 64, Jdev, s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  };
+  return lbfgs_alloc(o, n, history_size, max_iter, out);
+}
+
+VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out, int cap) {
+  if (!o) return 0;
+  const int k = (int)std::min<size_t>(o->hist_loss.size(), (size_t)cap);
+  for (int i = 0; i < k && loss_out; ++i) loss_out[i] = o->hist_loss[i];
+  return (int)o->hist_loss.size();
+}
+
+static int lbfgs_alloc(vv_lbfgs* o, long long nn, int history_size, int max_iter, vv_lbfgs** out) {
+  o->hist = history_size; o->max_iter = max_iter; o->max_eval = max_iter * 5 / 4;
+  o->n = nn;
   const size_t n = (size_t)o->n;
   float** vecs[] = {&o->g, &o->g_prev, &o->d, &o->x_init, &o->g_new, &o->bg[0], &o->bg[1], &o->ls_gprev};
   bool ok = true;
@@ -230,14 +290,16 @@ VV_API void vv_lbfgs_destroy(vv_lbfgs* o) {
   cudaDeviceSynchronize();
   for (void* p : o->allocs) cudaFree(p);
   if (o->pinned) cudaFreeHost(o->pinned);
+  if (o->own_stream) cudaStreamDestroy(o->own_stream);
   delete o;
 }
 
 VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   if (!o || !z) { set_error("vv_lbfgs_step: null argument"); return -2; }
   cudaStream_t user = (cudaStream_t)stream;
-  cudaStream_t s = o->e->stream;               // everything runs on the engine's capturable stream
-  if (fence_in(o->e, user)) return -1;
+  cudaStream_t s = o->e ? o->e->stream : o->own_stream;   // everything runs on a private capturable stream
+  if (o->e) { if (fence_in(o->e, user)) return -1; }
+  else LB_CUDA(cudaStreamSynchronize(user));
   const long long n = o->n;
   double loss, gmax, gl1;
   int rc = eval(o, z, o->g, nullptr, &loss, nullptr, s);             // lbfgs.py:361-366

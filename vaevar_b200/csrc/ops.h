@@ -18,6 +18,7 @@ struct GemmDesc {
   CUtensorMap tmA, tmB;
   GemmArgs a;
   int bn;
+  int two_cta;   // 1: CTA-pair kernel (256 x bn tile, tcgen05 cta_group::2); 0: single-CTA 128 x bn
 };
 // A: [batch][M][K] bf16 with row stride lda / batch stride a_bs (elements); B: [batch][N][K] likewise.
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,

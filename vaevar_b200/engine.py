@@ -144,6 +144,16 @@ class Engine:
         _lib.check(self.lib.vv_test_obs(self._h, _ptr(xn.contiguous()), _ptr(J), _ptr(g), _stream()))
         return J, g
 
+    def profile_ops(self, app: int, bwd: bool, reps: int = 20):
+        """Steady-state CUDA-event time of every launch of one application plan: list of dicts."""
+        cap = 4096
+        ms = (C.c_float * cap)(); kind = (C.c_int * cap)(); fl = (C.c_double * cap)(); mnk = (C.c_int * (4 * cap))()
+        n = self.lib.vv_profile_ops(self._h, app, int(bwd), reps, ms, kind, fl, mnk, cap)
+        if n < 0:
+            _lib.check(n)
+        names = ["gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "p2t", "t2p"]
+        return [dict(kind=names[kind[i]], ms=ms[i], flop=fl[i], shape=tuple(mnk[4 * i:4 * i + 4])) for i in range(min(n, cap))]
+
     @property
     def last_launch_count(self) -> int:
         return self.lib.vv_last_launch_count(self._h)
@@ -163,20 +173,30 @@ class Engine:
 class LBFGS:
     """torch.optim.LBFGS(history_size, max_iter, line_search_fn='strong_wolfe') bound to an Engine (da_4dvar.py:1240)."""
 
-    def __init__(self, engine: Engine, history_size: int = 10, max_iter: int = 10):
+    def __init__(self, engine: Optional[Engine], history_size: int = 10, max_iter: int = 10, testfn_n: int = 0):
         self.engine = engine
+        self.lib = _lib.load()
         self._h = C.c_void_p()
-        _lib.check(engine.lib.vv_lbfgs_create(engine._h, history_size, max_iter, C.byref(self._h)))
+        if engine is None:      # analytic pairwise-Rosenbrock closure on the device (controller tests)
+            _lib.check(self.lib.vv_lbfgs_create_testfn(testfn_n, history_size, max_iter, C.byref(self._h)))
+        else:
+            _lib.check(self.lib.vv_lbfgs_create(engine._h, history_size, max_iter, C.byref(self._h)))
+
+    def history(self):
+        n = self.lib.vv_lbfgs_history(self._h, None, 0)
+        buf = (C.c_double * max(n, 1))()
+        self.lib.vv_lbfgs_history(self._h, buf, n)
+        return [buf[i] for i in range(n)]
 
     def step(self, z: torch.Tensor):
         info = (C.c_double * 8)()
-        _lib.check(self.engine.lib.vv_lbfgs_step(self._h, _ptr(z), info, _stream()))
+        _lib.check(self.lib.vv_lbfgs_step(self._h, _ptr(z), info, _stream()))
         return dict(loss0=info[0], loss=info[1], n_evals=int(info[2]), n_iter=int(info[3]), t=info[4], gmax=info[5],
                     func_evals=int(info[6]))
 
     def close(self):
         if self._h:
-            self.engine.lib.vv_lbfgs_destroy(self._h)
+            self.lib.vv_lbfgs_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
