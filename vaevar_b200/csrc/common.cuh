@@ -65,6 +65,15 @@ VV_DEVINL void tma_load_3d(void* smem_dst, const void* desc, uint64_t* bar, int 
       : "memory");
 }
 
+// 3-D tiled store shared -> global (bulk async-group completion); rows / columns beyond the tensor extent are clipped.
+VV_DEVINL void tma_store_3d(const void* desc, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+VV_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+VV_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- clusters / CTA pairs -------------------------------------------------------------------
 VV_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
@@ -167,11 +176,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 // ---- math -----------------------------------------------------------------------------------
-VV_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (swinblock.py:14 nn.GELU) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+// bf16 rounding of the result): one MUFU.EX2, one MUFU.RCP and ~10 FMAs instead of erff's two-branch polynomial.
+// e = exp(-x^2/2) is shared between erf's exp(-(x/sqrt2)^2) and the Gaussian pdf of the derivative.
+VV_DEVINL float gelu_cdf_pdf(float x, float* pdf_times_sqrt2pi) {
+  const float e = __expf(-0.5f * x * x);
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;            // erf(|x|/sqrt2)
+  *pdf_times_sqrt2pi = e;
+  return 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+VV_DEVINL float gelu_erf(float x) {
+  float e;
+  return x * gelu_cdf_pdf(x, &e);
+}
 VV_DEVINL float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float cdf = gelu_cdf_pdf(x, &e);
+  return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 VV_DEVINL float warp_sum(float v) {
 #pragma unroll

@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "ops.h"
 
 namespace vv {
@@ -22,18 +24,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 3-D map over a [batch][rows][K] bf16 tensor, box = (64 x box_rows x 1), 128B swizzle, OOB -> zeros.
-static const char* encode_map(CUtensorMap* tm, const bf16* base, long long K, long long rows, long long batch, long long ld,
-                              long long bs, int box_rows) {
+// 3-D map over a [batch][rows][cols] tensor (bf16 or fp32), box = (box_cols x box_rows x 1) with 128-byte rows,
+// 128B swizzle, OOB -> zeros on loads / clipped on stores.
+static const char* encode_map_t(CUtensorMap* tm, const void* base, bool f32, long long K, long long rows, long long batch,
+                                long long ld, long long bs, int box_cols, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return "cuTensorMapEncodeTiled entry point not available";
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 7) || (batch > 1 && (bs & 7))) return "GEMM operand not 16-byte aligned";
+  const int es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * es) & 15) || (batch > 1 && ((bs * es) & 15))) return "GEMM operand not 16-byte aligned";
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bs : ld * rows) * 2};
-  cuuint32_t box[3] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows, 1};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * es, (cuuint64_t)(batch > 1 ? bs : ld * rows) * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[160];
@@ -42,6 +46,20 @@ static const char* encode_map(CUtensorMap* tm, const bf16* base, long long K, lo
     return buf;
   }
   return nullptr;
+}
+static const char* encode_map(CUtensorMap* tm, const bf16* base, long long K, long long rows, long long batch, long long ld,
+                              long long bs, int box_rows) {
+  return encode_map_t(tm, base, false, K, rows, batch, ld, bs, GEMM_BK, box_rows);
+}
+
+static bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+static bool use_direct_epilogue() {
+  static int v = -1;
+  if (v < 0) v = env_flag("VV_GEMM_DIRECT_EPI") ? 1 : 0;
+  return v == 1;
 }
 
 static bool use_1cta() {
@@ -58,16 +76,20 @@ static int pick_bn_1cta(int N) {
   if (N % 64 == 0 && N < 256) return 64;
   return 128;
 }
-// CTA-pair kernel: 256 x BN tiles.  Largest BN dividing N that still yields about one CTA per SM; otherwise the
-// dividing BN with the most CTAs.
+// CTA-pair kernel: 256 x BN tiles, BN a multiple of 64 (the TMA-store epilogue works on 64-column slabs; tiles may overhang N,
+// TMA zero-fills the loads and clips the stores).  Least column padding first; then the largest BN that still gives about
+// one CTA per SM, otherwise the BN with the most CTAs.
 static int pick_bn_2cta(int M, int N, int batch) {
-  static const int cand[5] = {256, 192, 128, 96, 64};
+  static const int cand[4] = {256, 192, 128, 64};
   const long long pair_rows = (M + 255) / 256;
+  int min_waste = 1 << 30;
+  for (int i = 0; i < 4; ++i) min_waste = std::min(min_waste, (N + cand[i] - 1) / cand[i] * cand[i] - N);
   int best = 0; long long best_ctas = -1;
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
-    if (N % bn) continue;
-    const long long ctas = 2 * pair_rows * (N / bn) * batch;
+    const int tiles = (N + bn - 1) / bn;
+    if (tiles * bn - N != min_waste) continue;
+    const long long ctas = 2 * pair_rows * tiles * batch;
     if (ctas >= 140) return bn;
     if (ctas > best_ctas) { best_ctas = ctas; best = bn; }
   }
@@ -82,9 +104,27 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   d->a = args;
   d->two_cta = use_1cta() ? 0 : 1;
   d->bn = d->two_cta ? pick_bn_2cta(args.M, args.N, args.batch) : pick_bn_1cta(args.N);
+  d->a.tma_store = (d->two_cta && !use_direct_epilogue()) ? 1 : 0;
+  if (args.split_n > 0 && args.split_n % 64) d->a.tma_store = 0;
   const char* e = encode_map(&d->tmA, A, args.K, args.M, args.batch, lda, a_bs, GEMM_BM);
   if (e) return e;
-  return encode_map(&d->tmB, B, args.K, args.N, args.batch, ldb, b_bs, d->two_cta ? d->bn / 2 : d->bn);
+  e = encode_map(&d->tmB, B, args.K, args.N, args.batch, ldb, b_bs, d->two_cta ? d->bn / 2 : d->bn);
+  if (e) return e;
+  memset(&d->sm, 0, sizeof d->sm);
+  if (d->a.tma_store) {
+    if (args.out_f32 && (e = encode_map_t(&d->sm.f32, args.out_f32, true, args.N, args.M, args.batch, args.ld_f32, args.f32_bs, 32, 32))) return e;
+    if (args.out_bf16) {
+      if (args.split_n > 0)
+        e = encode_map_t(&d->sm.bf16, args.out_bf16, false, args.split_n, args.M, args.N / args.split_n, args.ld_bf16, args.split_stride, 64, 32);
+      else
+        e = encode_map_t(&d->sm.bf16, args.out_bf16, false, args.N, args.M, args.batch, args.ld_bf16, args.bf16_bs, 64, 32);
+      if (e) return e;
+    }
+    if (args.epi == EPI_GELU && args.aux_out &&
+        (e = encode_map_t(&d->sm.aux, args.aux_out, false, args.N, args.M, args.batch, args.ld_aux, args.aux_bs, 64, 32)))
+      return e;
+  }
+  return nullptr;
 }
 
 template <int BN, int STAGES>
@@ -109,14 +149,13 @@ static void launch_2cta(const GemmDesc& d, cudaStream_t s) {
   }
   const int mtiles = (d.a.M + GEMM_BM - 1) / GEMM_BM;
   dim3 grid(((mtiles + 1) / 2) * 2, (d.a.N + BN - 1) / BN, d.a.batch);     // grid.x even: CTA pairs along M
-  gemm_tn_2cta_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, s>>>(d.tmA, d.tmB, d.a);
+  gemm_tn_2cta_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, s>>>(d.tmA, d.tmB, d.sm, d.a);
 }
 
 void launch_gemm(const GemmDesc& d, cudaStream_t s) {
   if (d.two_cta) {
     switch (d.bn) {
       case 64: launch_2cta<64, 4>(d, s); break;
-      case 96: launch_2cta<96, 4>(d, s); break;
       case 192: launch_2cta<192, 3>(d, s); break;
       case 256: launch_2cta<256, 3>(d, s); break;
       default: launch_2cta<128, 4>(d, s); break;

@@ -33,6 +33,13 @@ struct GemmArgs {
   long long ld_bf16, bf16_bs;
   int split_n;                // >0: bf16 output column n goes to block n / split_n (stride split_stride), column n % split_n
   long long split_stride;
+  int tma_store;              // CTA-pair kernel: 1 = TMA-store epilogue, 0 = direct per-thread stores
+};
+
+// Output tensor maps of the TMA-store epilogue (CTA-pair kernel): fp32 boxes are 32 cols x 32 rows, bf16 boxes 64 cols x
+// 32 rows, both 128-byte rows with the 128B swizzle.  A map whose pointer in GemmArgs is null is unused.
+struct alignas(64) GemmStoreMaps {
+  CUtensorMap f32, bf16, aux;
 };
 
 constexpr int GEMM_BM = 128;
@@ -208,6 +215,125 @@ gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// TMA-store epilogue: every epilogue warp owns 32 accumulator rows.  Per 64 output columns it loads the fp32 accumulators
+// from TMEM, applies the fused bias / GELU / GELU' / residual, stages fp32 / bf16 / aux results in 128B-swizzled 4 KB slabs
+// (the main-loop stage buffers, idle once the accumulator is complete) and lets one elected lane issue bulk tensor
+// stores: fully coalesced writes, clipping at the tensor edge for free, stores of slab set i overlap the TMEM load and
+// math of set i+1.
+template <int BN>
+VV_DEVINL void gemm_epilogue_tma(const GemmArgs& p, const GemmStoreMaps& sm, uint8_t* smem, uint32_t tmem_base,
+                                 uint64_t* tmem_full_bar, int warp, int lane, int m0, int n0, int b) {
+  static_assert(BN % 64 == 0, "TMA-store epilogue works on 64-column slabs");
+  const int q = warp & 3;
+  const int m = m0 + q * 32 + lane;
+  const bool row_ok = m < p.M;
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  uint8_t* slab = smem + q * 16384;                       // 4 slabs of 4 KB per warp
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);    // 128B swizzle: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+  const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
+  const float* res = (p.res && row_ok) ? p.res + (long long)b * p.res_bs + (long long)m * p.ld_res : nullptr;
+  const __nv_bfloat16* aux_in = (p.aux_in && row_ok) ? p.aux_in + (long long)b * p.aux_bs + (long long)m * p.ld_aux : nullptr;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 64) {
+    const int nb = n0 + c0;
+    if (nb >= p.N) break;                                  // warp-uniform: nothing of this slab is inside the tensor
+    uint32_t r[64];
+    __syncwarp();
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+    tmem_ld_wait();
+    uint32_t ub[32];                                       // bf16 copy of the pre-activation (EPI_GELU)
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int n = nb + g * 8;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+      if (n + 8 <= p.N) {
+        if (bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (p.epi == EPI_GELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ub[g * 4 + i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        } else if (p.epi == EPI_DGELU) {
+          if (aux_in) {
+            const uint4 w = *reinterpret_cast<const uint4*>(aux_in + n);
+            const float2 u0 = unpack_bf16(w.x), u1 = unpack_bf16(w.y), u2 = unpack_bf16(w.z), u3 = unpack_bf16(w.w);
+            v[0] *= gelu_erf_grad(u0.x); v[1] *= gelu_erf_grad(u0.y);
+            v[2] *= gelu_erf_grad(u1.x); v[3] *= gelu_erf_grad(u1.y);
+            v[4] *= gelu_erf_grad(u2.x); v[5] *= gelu_erf_grad(u2.y);
+            v[6] *= gelu_erf_grad(u3.x); v[7] *= gelu_erf_grad(u3.y);
+          }
+        }
+        if (res) {
+          const float4 r0 = *reinterpret_cast<const float4*>(res + n);
+          const float4 r1 = *reinterpret_cast<const float4*>(res + n + 4);
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[g * 8 + i] = __float_as_uint(v[i]);
+    }
+    // the previous slab set must have been read by the TMA engine before it is overwritten
+    if (lane == 0) tma_store_wait_read0();
+    __syncwarp();
+    const uint32_t rowoff = static_cast<uint32_t>(lane) * 128;
+    if (p.out_f32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                         // two fp32 slabs of 32 columns
+        uint8_t* s = slab + h * 4096 + rowoff;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(s + ((c ^ sw) << 4)) =
+              make_uint4(r[h * 32 + c * 4], r[h * 32 + c * 4 + 1], r[h * 32 + c * 4 + 2], r[h * 32 + c * 4 + 3]);
+      }
+    }
+    if (p.out_bf16) {
+      uint8_t* s = slab + 2 * 4096 + rowoff;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(r[c * 8]), __uint_as_float(r[c * 8 + 1]));
+        w.y = pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
+        w.z = pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
+        w.w = pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
+        *reinterpret_cast<uint4*>(s + ((c ^ sw) << 4)) = w;
+      }
+    }
+    if (p.epi == EPI_GELU && p.aux_out) {
+      uint8_t* s = slab + 3 * 4096 + rowoff;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(s + ((c ^ sw) << 4)) = make_uint4(ub[c * 4], ub[c * 4 + 1], ub[c * 4 + 2], ub[c * 4 + 3]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      const int mrow = m0 + q * 32;
+      if (p.out_f32) {
+        tma_store_3d(&sm.f32, slab, nb, mrow, b);
+        if (nb + 32 < p.N) tma_store_3d(&sm.f32, slab + 4096, nb + 32, mrow, b);
+      }
+      if (p.out_bf16) {
+        if (p.split_n > 0) tma_store_3d(&sm.bf16, slab + 2 * 4096, nb % p.split_n, mrow, nb / p.split_n);
+        else tma_store_3d(&sm.bf16, slab + 2 * 4096, nb, mrow, b);
+      }
+      if (p.epi == EPI_GELU && p.aux_out) tma_store_3d(&sm.aux, slab + 3 * 4096, nb, mrow, b);
+      tma_store_commit();
+    }
+  }
+  if (lane == 0) tma_store_wait_read0();
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CTA-pair variant: two CTAs of a (2,1,1) cluster compute one 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA
 // stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so the L2 -> shared-memory traffic per MAC drops to
@@ -226,9 +352,11 @@ struct Gemm2Smem {
 
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-  static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN");
+gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ GemmStoreMaps sm, const GemmArgs p) {
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "BN");
   using L = Gemm2Smem<BN, STAGES>;
+  static_assert(STAGES * L::STAGE_BYTES >= 4 * 16384, "epilogue slabs live in the stage buffers");
   constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
 
   extern __shared__ uint8_t smem_raw[];
@@ -299,7 +427,8 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       umma_commit_2cta(tmem_full_bar, 3);           // accumulator complete in both CTAs
     }
   } else {
-    gemm_epilogue<BN>(p, tmem_base, tmem_full_bar, warp, lane, m0, n0, b);
+    if (p.tma_store) gemm_epilogue_tma<BN>(p, sm, smem, tmem_base, tmem_full_bar, warp, lane, m0, n0, b);
+    else gemm_epilogue<BN>(p, tmem_base, tmem_full_bar, warp, lane, m0, n0, b);
   }
   tc_fence_before();
   cluster_sync_all();                               // neither CTA may retire while its peer can still touch its smem / TMEM

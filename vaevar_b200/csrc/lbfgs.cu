@@ -31,6 +31,7 @@ struct vv_lbfgs {
   std::vector<float*> free_vecs;
   std::vector<double> ro;
   double H_diag = 1.0, t = 1.0, prev_loss = 0.0;
+  bool t_is_tensor = false;
   bool have_prev = false;
   long long n_iter_total = 0, func_evals = 0;
   // device scalars + pinned read-back
@@ -91,68 +92,111 @@ int eval(vv_lbfgs* o, const float* z, float* gout, const float* dvec, double* f,
     launch_multi_dot(p, o->n, o->Jdev + 3, o->dscratch, s);
   }
   if (readback(o, o->Jdev, 4, s)) return -1;
-  *f = o->pinned[0];
+  *f = (double)(float)o->pinned[0];          // float(closure()): the reference's loss is a float32 tensor
   if (gtd) *gtd = o->pinned[3];
   o->func_evals++;
   o->hist_loss.push_back(*f);
   return 0;
 }
 
-double cubic_interpolate(double x1, double f1, double g1, double x2, double f2, double g2, bool has_bounds, double lo, double hi) {
-  double xmin = has_bounds ? lo : std::min(x1, x2), xmax = has_bounds ? hi : std::max(x1, x2);
-  const double d1 = g1 + g2 - 3.0 * (f1 - f2) / (x1 - x2);
-  const double d2sq = d1 * d1 - g1 * g2;
-  if (d2sq >= 0.0) {
-    const double d2 = sqrt(d2sq);
-    const double mp = x1 <= x2 ? x2 - (x2 - x1) * ((g2 + d2 - d1) / (g2 - g1 + 2.0 * d2))
-                               : x1 - (x1 - x2) * ((g1 + d2 - d1) / (g1 - g2 + 2.0 * d2));
-    return std::min(std::max(mp, xmin), xmax);
+// ---- scalar arithmetic exactly as the reference performs it -------------------------------------------------------
+// In torch.optim.LBFGS the step length t, the directional derivatives gtd and everything derived from them are 0-dim
+// float32 tensors (flat_grad.dot(d), 1/flat_grad.abs().sum(), ...) while the losses are Python floats.  A binary op
+// with a tensor operand is carried out in float32 and yields a tensor; Python-float-only ops stay double.  The line
+// search is sensitive to this (d1^2 - g1 g2 cancels catastrophically in float32), so the controller mirrors it.
+struct Sc {
+  double v;
+  bool t;   // true: 0-dim float32 tensor
+};
+inline Sc py(double v) { return Sc{v, false}; }
+inline Sc tn(double v) { return Sc{(double)(float)v, true}; }
+inline Sc op(Sc a, char o, Sc b) {
+  if (a.t || b.t) {
+    const float x = (float)a.v, y = (float)b.v;
+    float r = 0.f;
+    switch (o) { case '+': r = x + y; break; case '-': r = x - y; break; case '*': r = x * y; break; default: r = x / y; }
+    return Sc{(double)r, true};
   }
-  return (xmin + xmax) / 2.0;
+  double r = 0.0;
+  switch (o) { case '+': r = a.v + b.v; break; case '-': r = a.v - b.v; break; case '*': r = a.v * b.v; break; default: r = a.v / b.v; }
+  return Sc{r, false};
+}
+inline bool lt(Sc a, Sc b) { return (a.t || b.t) ? (float)a.v < (float)b.v : a.v < b.v; }
+inline bool le(Sc a, Sc b) { return (a.t || b.t) ? (float)a.v <= (float)b.v : a.v <= b.v; }
+inline bool gt(Sc a, Sc b) { return lt(b, a); }
+inline bool ge(Sc a, Sc b) { return le(b, a); }
+inline Sc sabs(Sc a) { return Sc{fabs(a.v), a.t}; }
+inline Sc pymin(Sc a, Sc b) { return lt(b, a) ? b : a; }   // Python's min(a, b)
+inline Sc pymax(Sc a, Sc b) { return gt(b, a) ? b : a; }   // Python's max(a, b)
+
+// lbfgs.py:12-37
+Sc cubic_interpolate(Sc x1, double f1, Sc g1, Sc x2, double f2, Sc g2, bool has_bounds, Sc lo, Sc hi) {
+  Sc xmin = lo, xmax = hi;
+  if (!has_bounds) {
+    if (le(x1, x2)) { xmin = x1; xmax = x2; } else { xmin = x2; xmax = x1; }
+  }
+  const Sc d1 = op(op(g1, '+', g2), '-', op(py(3.0 * (f1 - f2)), '/', op(x1, '-', x2)));
+  const Sc d2sq = op(op(d1, '*', d1), '-', op(g1, '*', g2));
+  if (ge(d2sq, py(0.0))) {
+    const Sc d2 = d2sq.t ? Sc{(double)sqrtf((float)d2sq.v), true} : Sc{sqrt(d2sq.v), false};
+    Sc mp;
+    if (le(x1, x2))
+      mp = op(x2, '-', op(op(x2, '-', x1), '*', op(op(op(g2, '+', d2), '-', d1), '/', op(op(g2, '-', g1), '+', op(py(2.0), '*', d2)))));
+    else
+      mp = op(x1, '-', op(op(x1, '-', x2), '*', op(op(op(g1, '+', d2), '-', d1), '/', op(op(g1, '-', g2), '+', op(py(2.0), '*', d2)))));
+    return pymin(pymax(mp, xmin), xmax);
+  }
+  return op(op(xmin, '+', xmax), '/', py(2.0));
 }
 
 // lbfgs.py:40-209.  On return: *f_out / o->g hold the loss / gradient of the lowest bracket end, *t_out its step.
-int strong_wolfe(vv_lbfgs* o, float* z, double t, double f, double gtd, int max_ls, double* f_out, double* t_out, int* evals,
-                 cudaStream_t s) {
-  const double c1 = 1e-4, c2 = 0.9;
-  double d_norm;
-  if (absmax_l1_host(o, o->d, &d_norm, nullptr, s)) return -1;
-  auto trial = [&](double tt, double* fn, double* gn) -> int {        // _directional_evaluate, lbfgs.py:325-331
+int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, double* f_out, Sc* t_out, int* evals, cudaStream_t s) {
+  const Sc c1 = py(1e-4), mc2 = py(-0.9);
+  double dn;
+  if (absmax_l1_host(o, o->d, &dn, nullptr, s)) return -1;
+  const Sc d_norm = tn(dn);
+  auto trial = [&](Sc tt, double* fn, Sc* gn) -> int {                // _directional_evaluate, lbfgs.py:325-331
     if (copy_vec(o, z, o->x_init, s)) return -1;
-    launch_axpby(z, o->d, nullptr, tt, nullptr, 1.0, o->n, s);
-    o->hist_t.push_back(tt);
-    return eval(o, z, o->g_new, o->d, fn, gn, s);
+    launch_axpby(z, o->d, nullptr, tt.v, nullptr, 1.0, o->n, s);
+    o->hist_t.push_back(tt.v);
+    double g = 0.0;
+    int rc = eval(o, z, o->g_new, o->d, fn, &g, s);
+    *gn = tn(g);
+    return rc;
   };
-  double f_new, gtd_new;
+  auto armijo_fails = [&](double fnew, Sc tt) { return gt(py(fnew), op(py(f), '+', op(op(c1, '*', tt), '*', gtd))); };
+  double f_new; Sc gtd_new;
   if (trial(t, &f_new, &gtd_new)) return -1;
   int ls_evals = 1;
-  double t_prev = 0.0, f_prev = f, gtd_prev = gtd;
+  Sc t_prev = py(0.0), gtd_prev = gtd;
+  double f_prev = f;
   if (copy_vec(o, o->ls_gprev, o->g, s)) return -1;                   // g_prev = g
-  bool done = false;
+  bool done = false, single = false, have_bracket = false;
   int ls_iter = 0;
-  double br[2] = {0, 0}, br_f[2] = {0, 0}, br_gtd[2] = {0, 0};
-  bool single = false;   // bracket collapsed to one point (Wolfe satisfied in the bracketing phase)
-  bool have_bracket = false;
+  Sc br[2] = {py(0), py(0)}, br_gtd[2] = {py(0), py(0)};
+  double br_f[2] = {0, 0};
   while (ls_iter < max_ls) {
-    if (f_new > (f + c1 * t * gtd) || (ls_iter > 1 && f_new >= f_prev)) {
+    if (armijo_fails(f_new, t) || (ls_iter > 1 && f_new >= f_prev)) {
       br[0] = t_prev; br[1] = t; br_f[0] = f_prev; br_f[1] = f_new; br_gtd[0] = gtd_prev; br_gtd[1] = gtd_new;
       if (copy_vec(o, o->bg[0], o->ls_gprev, s) || copy_vec(o, o->bg[1], o->g_new, s)) return -1;
       have_bracket = true;
       break;
     }
-    if (fabs(gtd_new) <= -c2 * gtd) {
+    if (le(sabs(gtd_new), op(mc2, '*', gtd))) {
       br[0] = t; br_f[0] = f_new;
       if (copy_vec(o, o->bg[0], o->g_new, s)) return -1;
       single = true; done = true; have_bracket = true;
       break;
     }
-    if (gtd_new >= 0) {
+    if (ge(gtd_new, py(0.0))) {
       br[0] = t_prev; br[1] = t; br_f[0] = f_prev; br_f[1] = f_new; br_gtd[0] = gtd_prev; br_gtd[1] = gtd_new;
       if (copy_vec(o, o->bg[0], o->ls_gprev, s) || copy_vec(o, o->bg[1], o->g_new, s)) return -1;
       have_bracket = true;
       break;
     }
-    const double min_step = t + 0.01 * (t - t_prev), max_step = t * 10.0, tmp = t;
+    const Sc min_step = op(t, '+', op(py(0.01), '*', op(t, '-', t_prev)));
+    const Sc max_step = op(t, '*', py(10.0));
+    const Sc tmp = t;
     t = cubic_interpolate(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, true, min_step, max_step);
     t_prev = tmp; f_prev = f_new; gtd_prev = gtd_new;
     if (copy_vec(o, o->ls_gprev, o->g_new, s)) return -1;
@@ -160,21 +204,21 @@ int strong_wolfe(vv_lbfgs* o, float* z, double t, double f, double gtd, int max_
     ++ls_evals; ++ls_iter;
   }
   if (!have_bracket) {                                                // reached max_ls (lbfgs.py:96-100)
-    br[0] = 0.0; br[1] = t; br_f[0] = f; br_f[1] = f_new;
+    br[0] = py(0.0); br[1] = t; br_f[0] = f; br_f[1] = f_new;
     if (copy_vec(o, o->bg[0], o->g, s) || copy_vec(o, o->bg[1], o->g_new, s)) return -1;
     br_gtd[0] = gtd; br_gtd[1] = gtd_new;
   }
   bool insuf = false;
   int low = 0, high = 1;
-  if (!single) { if (!(br_f[0] <= br_f[1])) { low = 1; high = 0; } }
+  if (!single && !(br_f[0] <= br_f[1])) { low = 1; high = 0; }
   while (!done && ls_iter < max_ls) {
-    if (fabs(br[1] - br[0]) * d_norm < o->tol_change) break;
-    t = cubic_interpolate(br[0], br_f[0], br_gtd[0], br[1], br_f[1], br_gtd[1], false, 0, 0);
-    const double bmax = std::max(br[0], br[1]), bmin = std::min(br[0], br[1]);
-    const double eps = 0.1 * (bmax - bmin);
-    if (std::min(bmax - t, t - bmin) < eps) {
-      if (insuf || t >= bmax || t <= bmin) {
-        t = fabs(t - bmax) < fabs(t - bmin) ? bmax - eps : bmin + eps;
+    if (lt(op(sabs(op(br[1], '-', br[0])), '*', d_norm), py(o->tol_change))) break;
+    t = cubic_interpolate(br[0], br_f[0], br_gtd[0], br[1], br_f[1], br_gtd[1], false, py(0), py(0));
+    const Sc bmax = pymax(br[0], br[1]), bmin = pymin(br[0], br[1]);
+    const Sc eps = op(py(0.1), '*', op(bmax, '-', bmin));
+    if (lt(pymin(op(bmax, '-', t), op(t, '-', bmin)), eps)) {
+      if (insuf || ge(t, bmax) || le(t, bmin)) {
+        t = lt(sabs(op(t, '-', bmax)), sabs(op(t, '-', bmin))) ? op(bmax, '-', eps) : op(bmin, '+', eps);
         insuf = false;
       } else {
         insuf = true;
@@ -184,14 +228,14 @@ int strong_wolfe(vv_lbfgs* o, float* z, double t, double f, double gtd, int max_
     }
     if (trial(t, &f_new, &gtd_new)) return -1;
     ++ls_evals; ++ls_iter;
-    if (f_new > (f + c1 * t * gtd) || f_new >= br_f[low]) {
+    if (armijo_fails(f_new, t) || f_new >= br_f[low]) {
       br[high] = t; br_f[high] = f_new; br_gtd[high] = gtd_new;
       if (copy_vec(o, o->bg[high], o->g_new, s)) return -1;
       if (br_f[0] <= br_f[1]) { low = 0; high = 1; } else { low = 1; high = 0; }
     } else {
-      if (fabs(gtd_new) <= -c2 * gtd) {
+      if (le(sabs(gtd_new), op(mc2, '*', gtd))) {
         done = true;
-      } else if (gtd_new * (br[high] - br[low]) >= 0) {
+      } else if (ge(op(gtd_new, '*', op(br[high], '-', br[low])), py(0.0))) {
         br[high] = br[low]; br_f[high] = br_f[low]; br_gtd[high] = br_gtd[low];
         if (copy_vec(o, o->bg[high], o->bg[low], s)) return -1;
       }
@@ -326,14 +370,14 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
         DotPairs p{}; p.a[0] = y; p.b[0] = sv; p.a[1] = y; p.b[1] = y; p.n_pairs = 2;
         launch_multi_dot(p, n, o->dsc, o->dscratch, s);
         if (readback(o, o->dsc, 2, s)) return -1;
-        const double ys = o->pinned[0], yy = o->pinned[1];
+        const double ys = (double)(float)o->pinned[0], yy = (double)(float)o->pinned[1];
         if (ys > 1e-10) {                                                             // lbfgs.py:407-421
           if ((int)o->old_y.size() == o->hist) {
             o->free_vecs.push_back(o->old_y.front()); o->free_vecs.push_back(o->old_s.front());
             o->old_y.erase(o->old_y.begin()); o->old_s.erase(o->old_s.begin()); o->ro.erase(o->ro.begin());
           }
-          o->old_y.push_back(y); o->old_s.push_back(sv); o->ro.push_back(1.0 / ys);
-          o->H_diag = ys / yy;
+          o->old_y.push_back(y); o->old_s.push_back(sv); o->ro.push_back((double)(1.0f / (float)ys));
+          o->H_diag = (double)((float)ys / (float)yy);
         } else {
           o->free_vecs.push_back(y); o->free_vecs.push_back(sv);
         }
@@ -356,20 +400,23 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
       if (copy_vec(o, o->g_prev, o->g, s)) return -1;
       o->have_prev = true;
       o->prev_loss = loss;
+      Sc t0;
       if (o->n_iter_total == 1) {
         if (absmax_l1_host(o, o->g, &gmax, &gl1, s)) return -1;
-        o->t = std::min(1.0, 1.0 / gl1) * o->lr;                                      // lbfgs.py:454-457
+        const Sc inv = op(py(1.0), '/', tn(gl1));                                     // 1. / flat_grad.abs().sum(): a tensor
+        t0 = op(pymin(py(1.0), inv), '*', py(o->lr));                                 // lbfgs.py:454-457
       } else {
-        o->t = o->lr;
+        t0 = py(o->lr);
       }
-      double gtd;
-      if (dot_host(o, o->g, o->d, &gtd, s)) return -1;
-      if (gtd > -o->tol_change) break;                                                // lbfgs.py:460-464
+      double gtd_d;
+      if (dot_host(o, o->g, o->d, &gtd_d, s)) return -1;
+      const Sc gtd = tn(gtd_d);
+      if (gt(gtd, py(-o->tol_change))) break;                                         // lbfgs.py:460-464
       if (copy_vec(o, o->x_init, z, s)) return -1;
       int ls_evals = 0;
-      double t_new, f_new;
-      if (strong_wolfe(o, z, o->t, loss, gtd, o->max_eval - current_evals, &f_new, &t_new, &ls_evals, s)) return -1;
-      loss = f_new; o->t = t_new;
+      Sc t_new; double f_new;
+      if (strong_wolfe(o, z, t0, loss, gtd, o->max_eval - current_evals, &f_new, &t_new, &ls_evals, s)) return -1;
+      loss = f_new; o->t = t_new.v; o->t_is_tensor = t_new.t;
       if (copy_vec(o, z, o->x_init, s)) return -1;
       launch_axpby(z, o->d, nullptr, o->t, nullptr, 1.0, n, s);                       // z += t d  (lbfgs.py:488)
       if (absmax_l1_host(o, o->g, &gmax, nullptr, s)) return -1;

@@ -16,6 +16,7 @@ typedef __nv_bfloat16 bf16;
 // ---- GEMM -----------------------------------------------------------------------------------
 struct GemmDesc {
   CUtensorMap tmA, tmB;
+  GemmStoreMaps sm;
   GemmArgs a;
   int bn;
   int two_cta;   // 1: CTA-pair kernel (256 x bn tile, tcgen05 cta_group::2); 0: single-CTA 128 x bn
