@@ -23,7 +23,7 @@ def chk():
     return gpu_check
 
 
-@pytest.mark.parametrize("stage", ["gemm", "ln", "attn", "obs", "net_small", "cost_small", "lbfgs_small"])
+@pytest.mark.parametrize("stage", ["gemm", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small"])
 def test_stage(chk, stage):
     assert getattr(chk, "stage_" + stage)(), f"stage {stage} has failing checks (see stdout)"
 
@@ -63,23 +63,30 @@ def test_full_size_cost_grad_against_reference_golden(chk, gold, tag, T, recompu
 
 
 def test_full_size_lbfgs_analysis_wrmse(chk, gold):
-    """Config 1: 3D-Var (T=1), one LBFGS.step(max_iter=10): analysis WRMSE within 1 % of the reference run."""
+    """Config 1 (3D-Var, T=1) with the shipped script's Nit=4 x LBFGS.step(max_iter=10): analysis WRMSE of all 69
+    channels within 1 % of the run of the REAL reference modules + torch.optim.LBFGS (fixture cost_full_T1.npz)."""
     from vaevar_b200.config import era5_stats
     from vaevar_b200.da import wrmse
     from vaevar_b200.engine import LBFGS
     g = gold("cost_full_T1.npz")
+    if "ana_wrmse_nit4" not in g:
+        pytest.skip("fixture without the Nit=4 run")
     e, case = _full_engine(1, int(g["seed"]))
     z = torch.zeros(1, 32, 128, 256, device="cuda")
-    info = LBFGS(e, 10, 10).step(z)
+    opt = LBFGS(e, 10, 10)
+    for _ in range(4):
+        info = opt.step(z)
     xa = e.decode(z)
     mean, std, _ = era5_stats()
     m = torch.from_numpy(mean).float().cuda().reshape(-1, 1, 1)
     s = torch.from_numpy(std).float().cuda().reshape(-1, 1, 1)
     gt = torch.from_numpy(case["gt"][0]).cuda()
     w = wrmse(((xa - m) / s).unsqueeze(0), ((gt - m) / s).unsqueeze(0), torch.from_numpy(std).cuda()).cpu().numpy()
-    assert info["n_evals"] == int(g["n_evals"])
-    np.testing.assert_allclose(w, g["ana_wrmse"], rtol=1e-2)
-    assert abs(info["loss"] / float(g["J_history"].min()) - 1) < 1e-2
+    h = opt.history()
+    print("engine J:", h[0], min(h), "reference J:", g["J_history_nit4"][0], g["J_history_nit4"].min(), "evals", len(h), int(g["n_evals_nit4"]))
+    assert abs(h[0] / float(g["J_history_nit4"][0]) - 1) < 1e-3
+    np.testing.assert_allclose(w, g["ana_wrmse_nit4"], rtol=1e-2)
+    assert abs(min(h) / float(g["J_history_nit4"].min()) - 1) < 2e-2
     e.close()
 
 

@@ -182,7 +182,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 VV_DEVINL float gelu_cdf_pdf(float x, float* pdf_times_sqrt2pi) {
   const float e = __expf(-0.5f * x * x);
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;                                               // rcp.approx: no IEEE fix-up subroutine, keeps the epilogue branch-free
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -193,26 +193,44 @@ void launch_ln_fwd(const LnArgs& a, cudaStream_t s) { VV_LN_DISPATCH(ln_fwd_kern
 void launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s) { VV_LN_DISPATCH(ln_bwd_kernel, a) }
 
 // =============================================================================================
-// Window attention: one warp per (window, head); N = 16 tokens per window.
+// Window attention: one warp per (window, head); N = 16 tokens per window, so Q K^T, P V and the four products of the
+// backward are single m16n8k16 tensor-core tiles (mma.sync, bf16 in / fp32 accumulate -- the 16-token problem is far
+// below a tcgen05 tile).  Operands are staged once with 16-byte cp.async into padded shared-memory rows (conflict-free
+// for both the 32-bit fragment loads and ldmatrix); softmax, bias, the latitude mask and dS stay in fp32 registers;
+// results are staged back through the operand buffers and written with 16-byte coalesced stores.
 // =============================================================================================
+VV_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+VV_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row_ptr)));
+}
+
 template <int HD, bool BWD>
 struct AttnSmem {
   static constexpr int W2 = HD / 2;             // 32-bit words (bf16 pairs) per token row
-  static constexpr int RS = W2 + 2;             // padded row stride (even: 8-byte cp.async rows; 2i+w banks: conflict-free)
+  static constexpr int RS = W2 + 4;             // padded row stride in words: 16-byte aligned rows, 4g+t / ldmatrix conflict-free
   static constexpr int MAT = 16 * RS;           // one 16 x HD operand
-  static constexpr int WORDS = (BWD ? 4 : 3) * MAT + (BWD ? 2 : 1) * 16 * 17;
+  static constexpr int PW = 12;                 // words per row of the 16 x 16 bf16 P / dS tiles (24 bf16 = 48 B)
+  static constexpr int WORDS = (BWD ? 4 : 3) * MAT + (BWD ? 2 * 16 * PW : 0);
   static constexpr int BYTES = 4 * WORDS * 4;   // 4 warps per CTA
 };
 
 template <int HD, bool BWD>
 __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   using L = AttnSmem<HD, BWD>;
-  constexpr int W2 = L::W2, RS = L::RS;
-  extern __shared__ uint32_t attn_sm[];
+  constexpr int W2 = L::W2, RS = L::RS, PW = L::PW;
+  constexpr int CH = HD / 8;                     // 16-byte chunks per operand row
+  extern __shared__ __align__(16) uint32_t attn_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int nww = a.gw >> 2, nwh = a.gh >> 2;
   const int item = blockIdx.x * 4 + warp;
-  if (item >= nww * nwh * a.heads) return;      // warp-uniform; only __syncwarp below
+  if (item >= nww * nwh * a.heads) return;      // warp-uniform; only warp-level sync below
   const int b = blockIdx.y;
   const int win = item / a.heads, h = item - win * a.heads;
   const int wi = win / nww, wj = win - wi * nww;
@@ -222,171 +240,179 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   uint32_t* Ks = Qs + L::MAT;
   uint32_t* Vs = Ks + L::MAT;
   uint32_t* dOs = Vs + L::MAT;                                   // BWD only
-  float* P = reinterpret_cast<float*>(Qs + (BWD ? 4 : 3) * L::MAT);
-  float* dS = P + 16 * 17;                                       // BWD only
+  uint32_t* Ps = Qs + 4 * L::MAT;                                // BWD only: bf16 P
+  uint32_t* dSs = Ps + 16 * PW;                                  // BWD only: bf16 dS
 
-  // original-grid token index of window-local token t (roll by -shift folded in; swinblock.py:275, 297)
-  auto tok_of = [&](int t) {
-    int row = 4 * wi + (t >> 2) + a.shift; if (row >= a.gh) row -= a.gh;
-    int col = 4 * wj + (t & 3) + a.shift;  if (col >= a.gw) col -= a.gw;
+  // original-grid token index of window-local token tk (roll by -shift folded in; swinblock.py:275, 297)
+  auto tok_of = [&](int tk) {
+    int row = 4 * wi + (tk >> 2) + a.shift; if (row >= a.gh) row -= a.gh;
+    int col = 4 * wj + (tk & 3) + a.shift;  if (col >= a.gw) col -= a.gw;
     return row * a.gw + col;
   };
 
-  // Stage Q, K, V (and dO) with 8-byte cp.async: every copy of the warp is in flight before the single wait.
   const bf16* qkv = a.qkv + (long long)b * a.qkv_bs;
   {
-    constexpr int CH = W2 / 2;                                   // 8-byte chunks per operand row
     constexpr int NMAT = BWD ? 4 : 3;
     for (int idx = lane; idx < 16 * 4 * CH; idx += 32) {
-      const int ch = idx % CH, rowm = idx / CH, m = rowm & 3, t = rowm >> 2;     // m: 0 Q, 1 K, 2 V, 3 dO
+      const int ch = idx % CH, rowm = idx / CH, m = rowm & 3, tk = rowm >> 2;     // m: 0 Q, 1 K, 2 V, 3 dO
       if (m >= NMAT) continue;
-      const bf16* src = m < 3 ? qkv + (long long)tok_of(t) * a.ld_qkv + m * d + h * HD
-                              : a.dout + (long long)b * a.o_bs + (long long)tok_of(t) * a.ld_o + h * HD;
-      uint32_t* dst = Qs + m * L::MAT + t * RS + 2 * ch;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src + 4 * ch) : "memory");
+      const bf16* src = m < 3 ? qkv + (long long)tok_of(tk) * a.ld_qkv + m * d + h * HD
+                              : a.dout + (long long)b * a.o_bs + (long long)tok_of(tk) * a.ld_o + h * HD;
+      uint32_t* dst = Qs + m * L::MAT + tk * RS + 4 * ch;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + 8 * ch) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncwarp();
 
-  // ---- S = scale * Q K^T + bias + mask ; P = softmax(S) : lane -> row i, 8 columns ----
-  const int i = lane >> 1, jh = lane & 1;
+  // ---- S = Q K^T : two m16n8 tiles (key tokens 0-7 and 8-15), k over the head dimension ----
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    const int w = ks * 8 + t;
+    const uint32_t af[4] = {Qs[g * RS + w], Qs[(g + 8) * RS + w], Qs[g * RS + w + 4], Qs[(g + 8) * RS + w + 4]};
+    mma_bf16_16816(s0, af, Ks[g * RS + w], Ks[g * RS + w + 4]);
+    mma_bf16_16816(s1, af, Ks[(g + 8) * RS + w], Ks[(g + 8) * RS + w + 4]);
+  }
+  // ---- P = softmax(scale S + bias + mask); this thread owns rows g and g+8, columns {2t,2t+1} and {8+2t,9+2t} ----
   const float scale = rsqrtf((float)HD);
-  float sc[8];
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) sc[jj] = 0.f;
-#pragma unroll 4
-  for (int w = 0; w < W2; ++w) {
-    const float2 q2 = unpack_bf16(Qs[i * RS + w]);
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const float2 k2 = unpack_bf16(Ks[(jh * 8 + jj) * RS + w]);
-      sc[jj] = fmaf(q2.x, k2.x, fmaf(q2.y, k2.y, sc[jj]));
-    }
-  }
-  const float* rb = a.relbias + (long long)b * a.relbias_bs + (h * 16 + i) * 16 + jh * 8;
   const bool masked_win = a.shift > 0 && wi == nwh - 1;          // swinblock.py:236-260: latitude bands only
-  float mx = -3.0e38f;
+  const float* rb = a.relbias + (long long)b * a.relbias_bs + h * 256;
+  float p0[4], p1[4];
 #pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const int j = jh * 8 + jj;
-    float sv = sc[jj] * scale + rb[jj];
-    if (masked_win && ((i >> 2) < 2) != ((j >> 2) < 2)) sv += -100.0f;
-    sc[jj] = sv;
-    mx = fmaxf(mx, sv);
+  for (int hh = 0; hh < 2; ++hh) {                               // hh = 0: row g, hh = 1: row g + 8
+    const int i = g + 8 * hh;
+    const float2 b0 = *reinterpret_cast<const float2*>(rb + i * 16 + 2 * t);
+    const float2 b1 = *reinterpret_cast<const float2*>(rb + i * 16 + 8 + 2 * t);
+    float v0 = s0[2 * hh] * scale + b0.x, v1 = s0[2 * hh + 1] * scale + b0.y;
+    float v2 = s1[2 * hh] * scale + b1.x, v3 = s1[2 * hh + 1] * scale + b1.y;
+    if (masked_win) {
+      // window rows {0,1} and {2,3} lie in different latitude bands: key columns 0..7 (this thread's v0,v1) are rows 0,1,
+      // key columns 8..15 (v2,v3) are rows 2,3; query row i is in the upper band iff (i >> 2) < 2.
+      if ((i >> 2) < 2) { v2 += -100.0f; v3 += -100.0f; }
+      else { v0 += -100.0f; v1 += -100.0f; }
+    }
+    float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    v0 = expf(v0 - mx); v1 = expf(v1 - mx); v2 = expf(v2 - mx); v3 = expf(v3 - mx);
+    float sum = v0 + v1 + v2 + v3;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.0f / sum;
+    p0[2 * hh] = v0 * inv; p0[2 * hh + 1] = v1 * inv;
+    p1[2 * hh] = v2 * inv; p1[2 * hh + 1] = v3 * inv;
   }
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  float sum = 0.f;
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    sc[jj] = expf(sc[jj] - mx);
-    sum += sc[jj];
-  }
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  const float inv = 1.0f / sum;
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    sc[jj] *= inv;
-    P[i * 17 + jh * 8 + jj] = sc[jj];
-  }
+
+  // lane -> row address of the ldmatrix.x4.trans that yields the B fragments (k = token, n = channel) of two
+  // adjacent 8-channel tiles of a token-major 16 x HD operand
+  const int lm = lane >> 3, lr = lane & 7;
+  auto bfrag_ptr = [&](const uint32_t* M, int c0) { return M + ((lm & 1) * 8 + lr) * RS + (c0 >> 1) + (lm >> 1) * 4; };
+  // staged 16 x HD result (bf16 pairs) -> global rows tok_of(r), 16-byte coalesced
+  auto copy_out = [&](const uint32_t* M, bf16* gbase, long long ld, int coloff) {
+    for (int idx = lane; idx < 16 * CH; idx += 32) {
+      const int r = idx / CH, ch = idx - r * CH;
+      *reinterpret_cast<uint4*>(gbase + (long long)tok_of(r) * ld + coloff + 8 * ch) = *reinterpret_cast<const uint4*>(M + r * RS + 4 * ch);
+    }
+  };
 
   if (!BWD) {
-    __syncwarp();
-    // ---- O = P V : lane -> channel pair, all 16 rows ----
-    bf16* out = a.out + (long long)b * a.o_bs;
-    for (int w = lane; w < W2; w += 32) {
-      float2 o[16];
+    // ---- O = P V ----
+    const uint32_t pa[4] = {pack_bf16(p0[0], p0[1]), pack_bf16(p0[2], p0[3]), pack_bf16(p1[0], p1[1]), pack_bf16(p1[2], p1[3])};
+    __syncwarp();                                                 // every lane is done reading Qs before it is reused for O
 #pragma unroll
-      for (int r = 0; r < 16; ++r) o[r] = make_float2(0.f, 0.f);
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const float2 v2 = unpack_bf16(Vs[j * RS + w]);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const float p = P[r * 17 + j];
-          o[r].x = fmaf(p, v2.x, o[r].x);
-          o[r].y = fmaf(p, v2.y, o[r].y);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 16; ++r)
-        reinterpret_cast<uint32_t*>(out + (long long)tok_of(r) * a.ld_o + h * HD)[w] = pack_bf16(o[r].x, o[r].y);
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, bfrag_ptr(Vs, c0));
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o0, pa, vb[0], vb[1]);
+      mma_bf16_16816(o1, pa, vb[2], vb[3]);
+      Qs[g * RS + (c0 >> 1) + t] = pack_bf16(o0[0], o0[1]);
+      Qs[(g + 8) * RS + (c0 >> 1) + t] = pack_bf16(o0[2], o0[3]);
+      Qs[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0], o1[1]);
+      Qs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2], o1[3]);
     }
+    __syncwarp();
+    copy_out(Qs, a.out + (long long)b * a.o_bs, a.ld_o, h * HD);
   } else {
-    // ---- dP = dO V^T ; dS = P o (dP - rowsum(dP o P)) ----
-    float dp[8];
+    // ---- dP = dO V^T ----
+    float dp0[4] = {0.f, 0.f, 0.f, 0.f}, dp1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) dp[jj] = 0.f;
-#pragma unroll 4
-    for (int w = 0; w < W2; ++w) {
-      const float2 o2 = unpack_bf16(dOs[i * RS + w]);
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const float2 v2 = unpack_bf16(Vs[(jh * 8 + jj) * RS + w]);
-        dp[jj] = fmaf(o2.x, v2.x, fmaf(o2.y, v2.y, dp[jj]));
-      }
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      const int w = ks * 8 + t;
+      const uint32_t af[4] = {dOs[g * RS + w], dOs[(g + 8) * RS + w], dOs[g * RS + w + 4], dOs[(g + 8) * RS + w + 4]};
+      mma_bf16_16816(dp0, af, Vs[g * RS + w], Vs[g * RS + w + 4]);
+      mma_bf16_16816(dp1, af, Vs[(g + 8) * RS + w], Vs[(g + 8) * RS + w + 4]);
     }
-    float rs = 0.f;
+    // ---- dS = P o (dP - rowsum(dP o P)) ----
+    float ds0[4], ds1[4];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) rs = fmaf(dp[jj], sc[jj], rs);
-    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) dS[i * 17 + jh * 8 + jj] = sc[jj] * (dp[jj] - rs);
+    for (int hh = 0; hh < 2; ++hh) {
+      float rs = dp0[2 * hh] * p0[2 * hh] + dp0[2 * hh + 1] * p0[2 * hh + 1] + dp1[2 * hh] * p1[2 * hh] + dp1[2 * hh + 1] * p1[2 * hh + 1];
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      ds0[2 * hh] = p0[2 * hh] * (dp0[2 * hh] - rs); ds0[2 * hh + 1] = p0[2 * hh + 1] * (dp0[2 * hh + 1] - rs);
+      ds1[2 * hh] = p1[2 * hh] * (dp1[2 * hh] - rs); ds1[2 * hh + 1] = p1[2 * hh + 1] * (dp1[2 * hh + 1] - rs);
+    }
+    // bf16 copies of P and dS for the transposed (ldmatrix.trans) A fragments
+    Ps[g * PW + t] = pack_bf16(p0[0], p0[1]);        Ps[(g + 8) * PW + t] = pack_bf16(p0[2], p0[3]);
+    Ps[g * PW + 4 + t] = pack_bf16(p1[0], p1[1]);    Ps[(g + 8) * PW + 4 + t] = pack_bf16(p1[2], p1[3]);
+    dSs[g * PW + t] = pack_bf16(ds0[0], ds0[1]);     dSs[(g + 8) * PW + t] = pack_bf16(ds0[2], ds0[3]);
+    dSs[g * PW + 4 + t] = pack_bf16(ds1[0], ds1[1]); dSs[(g + 8) * PW + 4 + t] = pack_bf16(ds1[2], ds1[3]);
     __syncwarp();
+    // A fragments of P^T and dS^T: matrix mi of the x4 load = block (rows (mi>>1)*8.., cols (mi&1)*8..) of the stored tile
+    uint32_t pT[4], dsT[4];
+    ldmatrix_x4_trans(pT, Ps + ((lm >> 1) * 8 + lr) * PW + (lm & 1) * 4);
+    ldmatrix_x4_trans(dsT, dSs + ((lm >> 1) * 8 + lr) * PW + (lm & 1) * 4);
+    const uint32_t dsA[4] = {pack_bf16(ds0[0], ds0[1]), pack_bf16(ds0[2], ds0[3]), pack_bf16(ds1[0], ds1[1]), pack_bf16(ds1[2], ds1[3])};
 
-    bf16* dqkv = a.dqkv + (long long)b * a.qkv_bs;
-    for (int w = lane; w < W2; w += 32) {
-      float2 acc[16];
-      // dV[j] = sum_i P[i][j] dO[i]
+    // ---- dV = P^T dO  -> staged in the V buffer (V is dead after dP) ----
 #pragma unroll
-      for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll 4
-      for (int ii = 0; ii < 16; ++ii) {
-        const float2 o2 = unpack_bf16(dOs[ii * RS + w]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float p = P[ii * 17 + j];
-          acc[j].x = fmaf(p, o2.x, acc[j].x);
-          acc[j].y = fmaf(p, o2.y, acc[j].y);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        reinterpret_cast<uint32_t*>(dqkv + (long long)tok_of(j) * a.ld_qkv + 2 * d + h * HD)[w] = pack_bf16(acc[j].x, acc[j].y);
-      // dQ[i] = scale * sum_j dS[i][j] K[j]
-#pragma unroll
-      for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll 4
-      for (int j = 0; j < 16; ++j) {
-        const float2 k2 = unpack_bf16(Ks[j * RS + w]);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const float g = dS[r * 17 + j];
-          acc[r].x = fmaf(g, k2.x, acc[r].x);
-          acc[r].y = fmaf(g, k2.y, acc[r].y);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 16; ++r)
-        reinterpret_cast<uint32_t*>(dqkv + (long long)tok_of(r) * a.ld_qkv + h * HD)[w] = pack_bf16(acc[r].x * scale, acc[r].y * scale);
-      // dK[j] = scale * sum_i dS[i][j] Q[i]
-#pragma unroll
-      for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll 4
-      for (int ii = 0; ii < 16; ++ii) {
-        const float2 q2 = unpack_bf16(Qs[ii * RS + w]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float g = dS[ii * 17 + j];
-          acc[j].x = fmaf(g, q2.x, acc[j].x);
-          acc[j].y = fmaf(g, q2.y, acc[j].y);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        reinterpret_cast<uint32_t*>(dqkv + (long long)tok_of(j) * a.ld_qkv + d + h * HD)[w] = pack_bf16(acc[j].x * scale, acc[j].y * scale);
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, bfrag_ptr(dOs, c0));
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o0, pT, bb[0], bb[1]);
+      mma_bf16_16816(o1, pT, bb[2], bb[3]);
+      Vs[g * RS + (c0 >> 1) + t] = pack_bf16(o0[0], o0[1]);
+      Vs[(g + 8) * RS + (c0 >> 1) + t] = pack_bf16(o0[2], o0[3]);
+      Vs[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0], o1[1]);
+      Vs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2], o1[3]);
     }
+    __syncwarp();                                                 // dO fully consumed -> its buffer takes dQ
+    // ---- dQ = scale dS K -> staged in the dO buffer ----
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, bfrag_ptr(Ks, c0));
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o0, dsA, bb[0], bb[1]);
+      mma_bf16_16816(o1, dsA, bb[2], bb[3]);
+      dOs[g * RS + (c0 >> 1) + t] = pack_bf16(o0[0] * scale, o0[1] * scale);
+      dOs[(g + 8) * RS + (c0 >> 1) + t] = pack_bf16(o0[2] * scale, o0[3] * scale);
+      dOs[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0] * scale, o1[1] * scale);
+      dOs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2] * scale, o1[3] * scale);
+    }
+    __syncwarp();                                                 // K fully consumed -> its buffer takes dK
+    // ---- dK = scale dS^T Q -> staged in the K buffer ----
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t bb[4];
+      ldmatrix_x4_trans(bb, bfrag_ptr(Qs, c0));
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_bf16_16816(o0, dsT, bb[0], bb[1]);
+      mma_bf16_16816(o1, dsT, bb[2], bb[3]);
+      Ks[g * RS + (c0 >> 1) + t] = pack_bf16(o0[0] * scale, o0[1] * scale);
+      Ks[(g + 8) * RS + (c0 >> 1) + t] = pack_bf16(o0[2] * scale, o0[3] * scale);
+      Ks[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0] * scale, o1[1] * scale);
+      Ks[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2] * scale, o1[3] * scale);
+    }
+    __syncwarp();
+    bf16* dqkv = a.dqkv + (long long)b * a.qkv_bs;
+    copy_out(dOs, dqkv, a.ld_qkv, h * HD);              // dQ
+    copy_out(Ks, dqkv, a.ld_qkv, d + h * HD);           // dK
+    copy_out(Vs, dqkv, a.ld_qkv, 2 * d + h * HD);       // dV
   }
 }
 
