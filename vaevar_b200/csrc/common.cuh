@@ -98,6 +98,24 @@ VV_DEVINL void tma_load_3d_2cta(void* smem_dst, const void* desc, uint32_t mbar_
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Arrive on the mbarrier at the same offset in CTA `rank` of the cluster (release at cluster scope).
+VV_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  const uint32_t addr = mapa_shared(smem_u32(bar), rank);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// Cluster-scope acquire wait (pairs with mbar_arrive_remote).
+VV_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
 VV_DEVINL void tmem_alloc_2cta(uint32_t* smem_out, uint32_t ncols) {   // one warp in EACH CTA of the pair, collectively
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
 }

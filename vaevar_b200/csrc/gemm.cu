@@ -62,6 +62,21 @@ static bool use_direct_epilogue() {
   return v == 1;
 }
 
+static bool use_nonpersistent() {
+  static int v = -1;
+  if (v < 0) v = env_flag("VV_GEMM_NONPERSISTENT") ? 1 : 0;
+  return v == 1;
+}
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 static bool use_1cta() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VV_GEMM_1CTA"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -105,6 +120,7 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   d->two_cta = use_1cta() ? 0 : 1;
   d->bn = d->two_cta ? pick_bn_2cta(args.M, args.N, args.batch) : pick_bn_1cta(args.N);
   d->a.tma_store = (d->two_cta && !use_direct_epilogue()) ? 1 : 0;
+  d->persist = 0;
   if (args.split_n > 0 && args.split_n % 64) d->a.tma_store = 0;
   const char* e = encode_map(&d->tmA, A, args.K, args.M, args.batch, lda, a_bs, GEMM_BM);
   if (e) return e;
@@ -123,6 +139,13 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
     if (args.epi == EPI_GELU && args.aux_out &&
         (e = encode_map_t(&d->sm.aux, args.aux_out, false, args.N, args.M, args.batch, args.ld_aux, args.aux_bs, 64, 32)))
       return e;
+    d->persist = use_nonpersistent() ? 0 : 1;
+    if (d->persist) {
+      if (args.res && (e = encode_map_t(&d->sm.res, args.res, true, args.N, args.M, args.batch, args.ld_res, args.res_bs, 32, 32))) return e;
+      if (args.epi == EPI_DGELU && args.aux_in &&
+          (e = encode_map_t(&d->sm.aux_in, args.aux_in, false, args.N, args.M, args.batch, args.ld_aux, args.aux_bs, 64, 32)))
+        return e;
+    }
   }
   return nullptr;
 }
@@ -152,7 +175,29 @@ static void launch_2cta(const GemmDesc& d, cudaStream_t s) {
   gemm_tn_2cta_kernel<BN, STAGES><<<grid, GEMM_THREADS, L::TOTAL, s>>>(d.tmA, d.tmB, d.sm, d.a);
 }
 
+template <int BN, int STAGES>
+static void launch_persist(const GemmDesc& d, cudaStream_t s) {
+  using L = GemmPSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tn_persist_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    attr_set = true;
+  }
+  const long long tiles = (long long)((d.a.N + BN - 1) / BN) * ((d.a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * d.a.batch;
+  const int pairs = (int)std::min<long long>(tiles, num_sms() / 2);
+  gemm_tn_persist_kernel<BN, STAGES><<<2 * pairs, GEMMP_THREADS, L::TOTAL, s>>>(d.tmA, d.tmB, d.sm, d.a);
+}
+
 void launch_gemm(const GemmDesc& d, cudaStream_t s) {
+  if (d.persist) {
+    switch (d.bn) {
+      case 64: launch_persist<64, 6>(d, s); break;
+      case 192: launch_persist<192, 4>(d, s); break;
+      case 256: launch_persist<256, 4>(d, s); break;
+      default: launch_persist<128, 5>(d, s); break;
+    }
+    return;
+  }
   if (d.two_cta) {
     switch (d.bn) {
       case 64: launch_2cta<64, 4>(d, s); break;

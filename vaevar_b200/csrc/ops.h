@@ -20,6 +20,7 @@ struct GemmDesc {
   GemmArgs a;
   int bn;
   int two_cta;   // 1: CTA-pair kernel (256 x bn tile, tcgen05 cta_group::2); 0: single-CTA 128 x bn
+  int persist;   // 1: persistent CTA-pair kernel with double-buffered TMEM accumulators and TMA-fed epilogue
 };
 // A: [batch][M][K] bf16 with row stride lda / batch stride a_bs (elements); B: [batch][N][K] likewise.
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,
