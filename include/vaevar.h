@@ -49,6 +49,8 @@ typedef struct {
   int recompute; /* 0 = stash every application's activations; 1 = keep each application's input only and
                     recompute its forward inside the backward sweep */
   int use_graph; /* 1 = capture cost+grad into a CUDA graph on first use */
+  int forward_fp16; /* 1 = forward activations and weights in IEEE fp16 (11-bit significand: 8x less rounding noise in
+                       J(z) than bf16, which the strong-Wolfe line search needs), gradients in bf16; 0 = bf16 throughout */
 } vv_config;
 
 typedef struct vv_engine vv_engine;
@@ -112,12 +114,15 @@ VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out_host, int cap);
 VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, vv_lbfgs** out);
 
 /* Kernel-level hooks used by tests/ and bench.py (roofline of the dominant kernel). */
-VV_API int vv_test_gemm(const void* A_bf16_dev, const void* B_bf16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
-                 void* out_bf16_dev, void* aux_bf16_dev, int M, int N, int K, int batch, int epi, void* stream);
+/* epi: 0 linear, 1 GELU (aux = saved pre-activation, out), 2 GELU' (aux = pre-activation, in); | 16: operands, 16-bit outputs
+ * and aux are fp16 instead of bf16. */
+VV_API int vv_test_gemm(const void* A_16_dev, const void* B_16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
+                 void* out_16_dev, void* aux_16_dev, int M, int N, int K, int batch, int epi, void* stream);
 VV_API int vv_test_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, float* y_dev, const float* dy_dev,
                       float* dx_dev, int rows, int C, float eps, void* stream);
-VV_API int vv_test_winattn(const void* qkv_bf16_dev, const float* relbias_dev, void* out_bf16_dev, const void* dout_bf16_dev,
-                    void* dqkv_bf16_dev, int gh, int gw, int heads, int hd, int shift, void* stream);
+/* f16 = 1: qkv and out are fp16 (dout / dqkv stay bf16). */
+VV_API int vv_test_winattn(const void* qkv_16_dev, const float* relbias_dev, void* out_16_dev, const void* dout_bf16_dev,
+                    void* dqkv_bf16_dev, int gh, int gw, int heads, int hd, int shift, int f16, void* stream);
 /* J_obs and residuals for a given normalised trajectory xn (T,C,H,W) with the case already set. */
 VV_API int vv_test_obs(vv_engine* e, const float* xn_dev, double* J_obs_dev, float* grad_xn_dev, void* stream);
 /* Steady-state time of every launch of one application plan (app 0 = decoder, >= 1 = flow; bwd = 0/1): each op is run

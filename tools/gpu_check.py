@@ -12,7 +12,7 @@ import time
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
-STAGES = ["gemm", "gemm_1cta", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
+STAGES = ["gemm", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
 
 
 def rel(a, b):
@@ -37,31 +37,38 @@ def stage_gemm():
     P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     for (M, N, K, B) in [(128, 128, 64, 1), (256, 128, 128, 1), (2048, 1152, 1152, 1), (2048, 3456, 1152, 1), (2048, 1152, 4608, 1),
                          (8192, 288, 96, 6), (8192, 96, 384, 6), (2048, 192, 768, 6), (512, 192, 64, 6), (128, 1536, 384, 1),
-                         (2048, 4608, 1152, 1)]:
-        g = torch.Generator(device=dev).manual_seed(M + N + K)
-        A = (torch.randn(B, M, K, device=dev, generator=g)).bfloat16()
-        W = (torch.randn(B, N, K, device=dev, generator=g) * 0.05).bfloat16()
-        bias = torch.randn(B, N, device=dev, generator=g)
-        res = torch.randn(B, M, N, device=dev, generator=g)
-        ref = torch.einsum("bmk,bnk->bmn", A.float(), W.float()) + bias[:, None, :]
-        of = torch.empty(B, M, N, device=dev)
-        ob = torch.empty(B, M, N, device=dev, dtype=torch.bfloat16)
-        _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), P(res), P(of), P(ob), None, M, N, K, B, 0, st))
-        torch.cuda.synchronize()
-        ok &= report("gemm", f"linear+bias+res {M}x{N}x{K}x{B} f32", rel(of, ref + res), 2e-5)
-        ok &= report("gemm", f"linear+bias+res {M}x{N}x{K}x{B} bf16", rel(ob.float(), ref + res), 4e-3)
-        # GELU epilogue: saves u, returns gelu(u)
-        aux = torch.empty(B, M, N, device=dev, dtype=torch.bfloat16)
-        _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), None, P(of), None, P(aux), M, N, K, B, 1, st))
-        torch.cuda.synchronize()
-        ok &= report("gemm", f"gelu {M}x{N}x{K}x{B}", rel(of, torch.nn.functional.gelu(ref)), 2e-5)
-        ok &= report("gemm", f"gelu-aux {M}x{N}x{K}x{B}", rel(aux.float(), ref), 4e-3)
-        # DGELU epilogue: acc * gelu'(u)
-        u = aux.float().requires_grad_(True)
-        torch.nn.functional.gelu(u).sum().backward()
-        _lib.check(lib.vv_test_gemm(P(A), P(W), None, None, P(of), None, P(aux), M, N, K, B, 2, st))
-        torch.cuda.synchronize()
-        ok &= report("gemm", f"dgelu {M}x{N}x{K}x{B}", rel(of, (ref - bias[:, None, :]) * u.grad), 5e-5)
+                         (2048, 4608, 1152, 1), (384, 72, 40, 2)]:
+        for f16 in (0, 1):
+            dt = torch.float16 if f16 else torch.bfloat16
+            tol16 = 6e-4 if f16 else 4e-3           # rounding of the 16-bit output: 2^-12 / 2^-9 relative
+            tag = f"{M}x{N}x{K}x{B} {'f16' if f16 else 'bf16'}"
+            g = torch.Generator(device=dev).manual_seed(M + N + K)
+            A = (torch.randn(B, M, K, device=dev, generator=g)).to(dt)
+            W = (torch.randn(B, N, K, device=dev, generator=g) * 0.05).to(dt)
+            bias = torch.randn(B, N, device=dev, generator=g)
+            res = torch.randn(B, M, N, device=dev, generator=g)
+            ref = torch.einsum("bmk,bnk->bmn", A.float(), W.float()) + bias[:, None, :]
+            of = torch.empty(B, M, N, device=dev)
+            ob = torch.empty(B, M, N, device=dev, dtype=dt)
+            _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), P(res), P(of), P(ob), None, M, N, K, B, 0 | 16 * f16, st))
+            torch.cuda.synchronize()
+            ok &= report("gemm", f"linear+bias+res {tag} f32", rel(of, ref + res), 2e-5)
+            ok &= report("gemm", f"linear+bias+res {tag} 16-bit", rel(ob.float(), ref + res), tol16)
+            # GELU epilogue: fp32 result without the saved pre-activation, then 16-bit result + saved u (the engine's use)
+            _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), None, P(of), None, None, M, N, K, B, 1 | 16 * f16, st))
+            torch.cuda.synchronize()
+            ok &= report("gemm", f"gelu {tag} f32", rel(of, torch.nn.functional.gelu(ref)), 2e-5)
+            aux = torch.empty(B, M, N, device=dev, dtype=dt)
+            _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), None, None, P(ob), P(aux), M, N, K, B, 1 | 16 * f16, st))
+            torch.cuda.synchronize()
+            ok &= report("gemm", f"gelu {tag} 16-bit", rel(ob.float(), torch.nn.functional.gelu(ref)), tol16)
+            ok &= report("gemm", f"gelu-aux {tag}", rel(aux.float(), ref), tol16)
+            # DGELU epilogue: acc * gelu'(u)
+            u = aux.float().requires_grad_(True)
+            torch.nn.functional.gelu(u).sum().backward()
+            _lib.check(lib.vv_test_gemm(P(A), P(W), None, None, P(of), None, P(aux), M, N, K, B, 2 | 16 * f16, st))
+            torch.cuda.synchronize()
+            ok &= report("gemm", f"dgelu {tag}", rel(of, (ref - bias[:, None, :]) * u.grad), 5e-5)
     # timing of the dominant shapes
     for (M, N, K) in [(2048, 1152, 1152), (2048, 3456, 1152), (2048, 4608, 1152), (2048, 1152, 4608)]:
         A = torch.randn(1, M, K, device=dev).bfloat16(); W = torch.randn(1, N, K, device=dev).bfloat16()
@@ -103,11 +110,6 @@ def stage_gemm():
             line.append(f"{name} {e0.elapsed_time(e1)/30*1e3:.1f}us")
         print(f"[gemm] time epilogues {M}x{N}x{K}x{B}: " + " | ".join(line), flush=True)
     return ok
-
-
-def stage_gemm_1cta():
-    os.environ["VV_GEMM_1CTA"] = "1"
-    return stage_gemm()
 
 
 def stage_ln():
@@ -167,18 +169,21 @@ def stage_attn():
     for (gh, gw, heads, hd) in [(8, 16, 2, 32), (64, 128, 3, 32), (32, 64, 6, 32), (32, 64, 6, 192), (8, 16, 2, 192)]:
         for shift in (0, 2):
             d = heads * hd
-            qkv = (torch.randn(gh * gw, 3 * d, device=dev) * 1.5).bfloat16()
-            rb = torch.randn(heads, 16, 16, device=dev)
-            dout = torch.randn(gh * gw, d, device=dev).bfloat16()
-            out = torch.empty(gh * gw, d, device=dev, dtype=torch.bfloat16)
-            dqkv = torch.empty_like(qkv)
-            _lib.check(lib.vv_test_winattn(P(qkv), P(rb), P(out), P(dout), P(dqkv), gh, gw, heads, hd, shift, st))
-            q32 = qkv.float().requires_grad_(True)
-            o = attn_ref(q32, rb, gh, gw, heads, hd, shift)
-            (o * dout.float()).sum().backward()
-            torch.cuda.synchronize()
-            ok &= report("attn", f"fwd {gh}x{gw} h{heads} hd{hd} s{shift}", rel(out.float(), o.detach()), 4e-3)
-            ok &= report("attn", f"bwd {gh}x{gw} h{heads} hd{hd} s{shift}", rel(dqkv.float(), q32.grad), 5e-3)
+            for f16 in (0, 1):
+                dt = torch.float16 if f16 else torch.bfloat16
+                qkv = (torch.randn(gh * gw, 3 * d, device=dev) * 1.5).to(dt)
+                rb = torch.randn(heads, 16, 16, device=dev)
+                dout = torch.randn(gh * gw, d, device=dev).bfloat16()
+                out = torch.empty(gh * gw, d, device=dev, dtype=dt)
+                dqkv = torch.empty(gh * gw, 3 * d, device=dev, dtype=torch.bfloat16)
+                _lib.check(lib.vv_test_winattn(P(qkv), P(rb), P(out), P(dout), P(dqkv), gh, gw, heads, hd, shift, f16, st))
+                q32 = qkv.float().requires_grad_(True)
+                o = attn_ref(q32, rb, gh, gw, heads, hd, shift)
+                (o * dout.float()).sum().backward()
+                torch.cuda.synchronize()
+                tag = f"{gh}x{gw} h{heads} hd{hd} s{shift} {'f16' if f16 else 'bf16'}"
+                ok &= report("attn", f"fwd {tag}", rel(out.float(), o.detach()), 6e-4 if f16 else 4e-3)
+                ok &= report("attn", f"bwd {tag}", rel(dqkv.float(), q32.grad), 5e-3)
     return ok
 
 

@@ -21,7 +21,7 @@ class NetConfigC(C.Structure):
 
 class ConfigC(C.Structure):
     _fields_ = [("dec", NetConfigC), ("flow", NetConfigC), ("has_flow", C.c_int), ("T", C.c_int),
-                ("recompute", C.c_int), ("use_graph", C.c_int)]
+                ("recompute", C.c_int), ("use_graph", C.c_int), ("forward_fp16", C.c_int)]
 
 
 _P = C.c_void_p
@@ -50,7 +50,7 @@ _SIGS = {
     "vv_profile_ops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int]),
     "vv_test_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vv_test_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
-    "vv_test_winattn": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vv_test_winattn": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vv_test_obs": (C.c_int, [_P, _P, _P, _P, _P]),
     "vv_last_launch_count": (C.c_int, [_P]),
 }

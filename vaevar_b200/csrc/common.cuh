@@ -73,6 +73,14 @@ VV_DEVINL void tma_store_3d(const void* desc, const void* smem_src, int c0, int 
 }
 VV_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 VV_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+VV_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+// Every kernel of the engine is launched with programmatic stream serialization: its prologue may overlap the tail of the
+// kernel before it; pdl_wait() blocks until that kernel has completed and its writes are visible.  Both are no-ops when the
+// kernel is launched without the attribute.
+VV_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+VV_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- clusters / CTA pairs -------------------------------------------------------------------
 VV_DEVINL uint32_t cluster_ctarank() {
@@ -98,23 +106,11 @@ VV_DEVINL void tma_load_3d_2cta(void* smem_dst, const void* desc, uint32_t mbar_
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// Arrive on the mbarrier at the same offset in CTA `rank` of the cluster (release at cluster scope).
-VV_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+// Arrive on the mbarrier at the same offset in CTA `rank` of the cluster.  Default (CTA-scope release) semantics: what the
+// arrival orders is TMEM traffic, which the tcgen05 fences around it cover; a cluster-scope release would cost a MEMBAR.GPU.
+VV_DEVINL void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   const uint32_t addr = mapa_shared(smem_u32(bar), rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-// Cluster-scope acquire wait (pairs with mbar_arrive_remote).
-VV_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) __trap();
-  }
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 VV_DEVINL void tmem_alloc_2cta(uint32_t* smem_out, uint32_t ncols) {   // one warp in EACH CTA of the pair, collectively
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
@@ -124,7 +120,7 @@ VV_DEVINL void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem of both CTAs] (+)= A (128 rows from each CTA) * B^T (N/2 rows from each CTA); issued by ONE thread of the leader CTA.
-VV_DEVINL void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+VV_DEVINL void umma_16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -188,35 +184,47 @@ VV_DEVINL uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16: A,B bf16 K-major, D fp32, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+// Instruction descriptor for kind::f16: A,B both fp16 (format 0) or both bf16 (format 1), K-major, D fp32, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---- math -----------------------------------------------------------------------------------
-// Exact-erf GELU (swinblock.py:14 nn.GELU) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
-// bf16 rounding of the result): one MUFU.EX2, one MUFU.RCP and ~10 FMAs instead of erff's two-branch polynomial.
-// e = exp(-x^2/2) is shared between erf's exp(-(x/sqrt2)^2) and the Gaussian pdf of the derivative.
-VV_DEVINL float gelu_cdf_pdf(float x, float* pdf_times_sqrt2pi) {
-  const float e = __expf(-0.5f * x * x);
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;                                               // rcp.approx: no IEEE fix-up subroutine, keeps the epilogue branch-free
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+// Exact-erf GELU (swinblock.py:14 nn.GELU) with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
+// 16-bit rounding of the result).  With e = exp(-x^2/2), t = 1/(1 + p|x|/sqrt2) and q = t*poly(t)*e = erfc(|x|/sqrt2):
+//   Phi(x) = 1 - q/2 (x >= 0),  q/2 (x < 0)   =>   gelu(x) = x Phi(x) = max(x, 0) - |x| q / 2
+//   gelu'(x) = Phi(x) + x e / sqrt(2 pi)
+// One MUFU.EX2, one MUFU.RCP and ~12 FMA-pipe instructions per element, branch-free.
+VV_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+VV_DEVINL float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erfc(|x|/sqrt2); *e_out = exp(-x^2/2)
+VV_DEVINL float gelu_erfc_abs(float x, float* e_out) {
+  const float e = ex2_approx(x * (x * -0.72134752044448170f));          // -0.5 * log2(e)
+  const float t = rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * e;            // erf(|x|/sqrt2)
-  *pdf_times_sqrt2pi = e;
-  return 0.5f * (1.0f + copysignf(erf_abs, x));
+  *e_out = e;
+  return poly * (t * e);
 }
 VV_DEVINL float gelu_erf(float x) {
   float e;
-  return x * gelu_cdf_pdf(x, &e);
+  const float q = gelu_erfc_abs(x, &e);
+  return fmaf(fabsf(x) * -0.5f, q, fmaxf(x, 0.0f));
 }
 VV_DEVINL float gelu_erf_grad(float x) {
   float e;
-  const float cdf = gelu_cdf_pdf(x, &e);
+  const float q = gelu_erfc_abs(x, &e);
+  const float cdf = 0.5f + copysignf(fmaf(-0.5f, q, 0.5f), x);
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 VV_DEVINL float warp_sum(float v) {

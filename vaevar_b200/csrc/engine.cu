@@ -40,13 +40,16 @@ void set_error(const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_w_kernel(bf16* dst, bf16* dstT, const float* src, int rows, int cols) {
+// dst: the forward operand (fp16 when the forward pass runs in fp16, else bf16); dstT: its transpose for the
+// input-gradient GEMMs, always bf16 (gradients need bf16's range).
+__global__ void pack_w_kernel(bf16* dst, bf16* dstT, const float* src, int rows, int cols, int f16) {
   const long long n = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
-    const bf16 v = __float2bfloat16(src[i]);
-    dst[i] = v;
-    if (dstT) dstT[(long long)c * rows + r] = v;
+    const float w = src[i];
+    if (f16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(w);
+    else dst[i] = __float2bfloat16(w);
+    if (dstT) dstT[(long long)c * rows + r] = __float2bfloat16(w);
   }
 }
 __global__ void finalize_J_kernel(const double* dots, const double* jobs, float coeff, double* out) {
@@ -145,9 +148,10 @@ struct WeightReader {
   }
 };
 
+static int g_pack_f16 = 0;   // set by finalize_net from the engine configuration
 static void pack_matrix(bf16* dst, bf16* dstT, const float* src, int rows, int cols) {
   if (!src) return;
-  pack_w_kernel<<<592, 256>>>(dst, dstT, src, rows, cols);
+  pack_w_kernel<<<592, 256>>>(dst, dstT, src, rows, cols, g_pack_f16);
 }
 
 // Gather the (2ws-1)^2 x heads table into dense [heads][16][16] (swinblock.py:88-103, 154-157).
@@ -200,6 +204,7 @@ static int build_blocks(vv_engine* e, WeightReader& R, std::vector<BlockW>& out,
 
 static int finalize_net(vv_engine* e, Net& n) {
   WeightReader R{e, &n};
+  g_pack_f16 = e->cfg.forward_fp16 ? 1 : 0;
   const int G = n.G, D = n.D, E = n.E;
   std::vector<std::string> pe0, pe1, pu0, pu1;
   for (int g = 0; g < G; ++g) {
@@ -342,6 +347,7 @@ struct Temps {
 
 struct Builder {
   vv_engine* e; Net* n; Temps t; const char* err = nullptr;
+  int f16 = 0;        // forward activations / weights in fp16 (gradients always bf16)
 
   void gemm(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g) {
     Op o{}; o.kind = Op::GEMM;
@@ -349,13 +355,17 @@ struct Builder {
     if (er && !err) err = er;
     P.ops.push_back(o);
   }
-  static GemmArgs ga(int M, int N, int K, int batch) {
-    GemmArgs g{}; g.M = M; g.N = N; g.K = K; g.batch = batch; g.epi = EPI_LINEAR; return g;
+  // forward GEMM (operands in the forward format) / gradient GEMM (bf16 operands; the saved pre-activation keeps the forward format)
+  GemmArgs ga(int M, int N, int K, int batch) const {
+    GemmArgs g{}; g.M = M; g.N = N; g.K = K; g.batch = batch; g.epi = EPI_LINEAR; g.f16 = f16; g.aux_f16 = f16; return g;
+  }
+  GemmArgs gb(int M, int N, int K, int batch) const {
+    GemmArgs g = ga(M, N, K, batch); g.f16 = 0; return g;
   }
   void ln_f(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
             const float* gamma, const float* beta, bf16* ob, long long ld_ob, long long ob_bs, float* of, long long ld_of, long long of_bs) {
     Op o{}; o.kind = Op::LN_F;
-    o.lnf = LnArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, beta, (long long)C, ob, ld_ob, ob_bs, of, ld_of, of_bs};
+    o.lnf = LnArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, beta, (long long)C, ob, ld_ob, ob_bs, of, ld_of, of_bs, f16};
     P.ops.push_back(o);
   }
   void ln_b(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
@@ -377,7 +387,7 @@ struct Builder {
     g.bias = w.bqkv; g.bias_bs = 3 * d; g.out_bf16 = st.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd;
     gemm(P, t.h, d, rd, w.Wqkv, d, 3LL * d * d, g);
     Op o{}; o.kind = Op::ATT_F;
-    o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, t.ao, d, rd, nullptr, nullptr};
+    o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, t.ao, d, rd, nullptr, nullptr, f16};
     P.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = st.x1; g.ld_f32 = d; g.f32_bs = rd;
@@ -396,20 +406,20 @@ struct Builder {
   void block_bwd(Plan& P, const BlockW& w, int gh, int gw, int shift, const float* x, BlkStash& st, float* g32, bf16* g16) {
     const int G = w.G, d = w.d, rows = gh * gw;
     const long long rd = (long long)rows * d;
-    GemmArgs g = ga(rows, 4 * d, d, G);                       // d(gelu out) = dy W2 ; du = . * gelu'(u)
+    GemmArgs g = gb(rows, 4 * d, d, G);                       // d(gelu out) = dy W2 ; du = . * gelu'(u)
     g.epi = EPI_DGELU; g.aux_in = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd; g.out_bf16 = t.du; g.ld_bf16 = 4 * d; g.bf16_bs = 4 * rd;
     gemm(P, g16, d, rd, w.W2T, d, 4LL * d * d, g);
-    g = ga(rows, d, 4 * d, G);                                // d(LN2 out) = du W1
+    g = gb(rows, d, 4 * d, G);                                // d(LN2 out) = du W1
     g.out_f32 = t.dh; g.ld_f32 = d; g.f32_bs = rd;
     gemm(P, t.du, 4 * d, 4 * rd, w.W1T, 4 * d, 4LL * d * d, g);
     ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, t.dh, d, rd, g32, d, rd, t.dx1, d, rd, t.dx1b, d, rd);
-    g = ga(rows, d, d, G);                                    // d(attn out) = dx1 Wproj
+    g = gb(rows, d, d, G);                                    // d(attn out) = dx1 Wproj
     g.out_bf16 = t.dao; g.ld_bf16 = d; g.bf16_bs = rd;
     gemm(P, t.dx1b, d, rd, w.WprojT, d, (long long)d * d, g);
     Op o{}; o.kind = Op::ATT_B;
-    o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, nullptr, d, rd, t.dao, t.dqkv};
+    o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, nullptr, d, rd, t.dao, t.dqkv, f16};
     P.ops.push_back(o);
-    g = ga(rows, d, 3 * d, G);                                // d(LN1 out) = dqkv Wqkv
+    g = gb(rows, d, 3 * d, G);                                // d(LN1 out) = dqkv Wqkv
     g.out_f32 = t.dh; g.ld_f32 = d; g.f32_bs = rd;
     gemm(P, t.dqkv, 3 * d, 3 * rd, w.WqkvT, 3 * d, 3LL * d * d, g);
     ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, t.dh, d, rd, t.dx1, d, rd, g32, d, rd, g16, d, rd);
@@ -491,36 +501,36 @@ struct Builder {
          t.gU1, D, (long long)L0 * D, t.gU1b, D, (long long)L0 * D);
     stage_bwd(P, N.u1, N.h0, N.w0, S.u1, t.gU1, t.gU1b);
     // concat_back_dim[1]^T: first D input columns -> PatchExpand norm output, last D -> skip 0
-    GemmArgs g = ga(L0, D, D, G);
+    GemmArgs g = gb(L0, D, D, G);
     g.out_f32 = t.dC1a; g.ld_f32 = D; g.f32_bs = (long long)L0 * D;
     gemm(P, t.gU1b, D, (long long)L0 * D, N.Wc1T, D, 2LL * D * D, g);
-    g = ga(L0, D, D, G);
+    g = gb(L0, D, D, G);
     g.out_f32 = t.dSK0; g.ld_f32 = D; g.f32_bs = (long long)L0 * D;
     gemm(P, t.gU1b, D, (long long)L0 * D, N.Wc1T + (long long)D * D, D, 2LL * D * D, g);
     ln_b(P, L0, D, G, MAP_EXPAND, N.h0, N.w0, 1e-6f, S.EX, 4 * D, (long long)L1 * 4 * D, N.ex_g, t.dC1a, D, (long long)L0 * D, nullptr, 0, 0,
          t.dEX, 4 * D, (long long)L1 * 4 * D, t.dEXb, 4 * D, (long long)L1 * 4 * D);
-    g = ga(L1, 2 * D, 4 * D, G);                                                                  // expand^T
+    g = gb(L1, 2 * D, 4 * D, G);                                                                  // expand^T
     g.out_f32 = t.gU0; g.ld_f32 = 2 * D; g.f32_bs = (long long)L1 * 2 * D; g.out_bf16 = t.gU0b; g.ld_bf16 = 2 * D; g.bf16_bs = (long long)L1 * 2 * D;
     gemm(P, t.dEXb, 4 * D, (long long)L1 * 4 * D, N.WexT, 4 * D, 8LL * D * D, g);
     stage_bwd(P, N.u0, N.h1, N.w1, S.u0, t.gU0, t.gU0b);
     // concat_back_dim[0]^T: first 2D columns -> Dec_net.proj output slice of tower g, last 2D -> skip 1
-    g = ga(L1, 2 * D, 2 * D, G);
+    g = gb(L1, 2 * D, 2 * D, G);
     g.out_bf16 = t.DPb; g.ld_bf16 = (long long)G * 2 * D; g.bf16_bs = 2 * D;
     gemm(P, t.gU0b, 2 * D, (long long)L1 * 2 * D, N.Wc0T, 2 * D, 8LL * D * D, g);
-    g = ga(L1, 2 * D, 2 * D, G);
+    g = gb(L1, 2 * D, 2 * D, G);
     g.out_f32 = t.dSK1; g.ld_f32 = 2 * D; g.f32_bs = (long long)L1 * 2 * D;
     gemm(P, t.gU0b, 2 * D, (long long)L1 * 2 * D, N.Wc0T + 4LL * D * D, 2 * D, 8LL * D * D, g);
-    g = ga(L1, E, G * 2 * D, 1);                                                                  // Dec_net.proj^T
+    g = gb(L1, E, G * 2 * D, 1);                                                                  // Dec_net.proj^T
     g.out_f32 = t.gT; g.ld_f32 = E; g.out_bf16 = t.gTb; g.ld_bf16 = E;
     gemm(P, t.DPb, (long long)G * 2 * D, 0, N.WdpT, (long long)G * 2 * D, 0, g);
     for (int b = (int)N.lg.size() - 1; b >= 0; --b) block_bwd(P, N.lg[b], N.h1, N.w1, shift_of_trunk(b), S.lg.x[b], S.lg.b[b], t.gT, t.gTb);
-    g = ga(L1, G * 2 * D, E, 1);                                                                  // Enc_net.proj^T
+    g = gb(L1, G * 2 * D, E, 1);                                                                  // Enc_net.proj^T
     g.out_f32 = t.dEP; g.ld_f32 = (long long)G * 2 * D;
     gemm(P, t.gTb, E, 0, N.WepT, E, 0, g);
     ln_b(P, L1, 2 * D, G, MAP_PLAIN, N.h1, N.w1, 1e-6f, S.e1.x.back(), 2 * D, (long long)L1 * 2 * D, N.en_g, t.dEP, (long long)G * 2 * D, 2 * D,
          t.dSK1, 2 * D, (long long)L1 * 2 * D, t.gE1, 2 * D, (long long)L1 * 2 * D, t.gE1b, 2 * D, (long long)L1 * 2 * D);
     stage_bwd(P, N.e1, N.h1, N.w1, S.e1, t.gE1, t.gE1b);
-    g = ga(L1, 4 * D, 2 * D, G);                                                                  // reduction^T
+    g = gb(L1, 4 * D, 2 * D, G);                                                                  // reduction^T
     g.out_f32 = t.dMB; g.ld_f32 = 4 * D; g.f32_bs = (long long)L1 * 4 * D;
     gemm(P, t.gE1b, 2 * D, (long long)L1 * 2 * D, N.WredT, 2 * D, 8LL * D * D, g);
     ln_b(P, L1, 4 * D, G, MAP_MERGE, N.h0, N.w0, 1e-6f, S.e0.x.back(), D, (long long)L0 * D, N.mg_g, t.dMB, 4 * D, (long long)L1 * 4 * D,
@@ -606,6 +616,7 @@ static int build_plans(vv_engine* e) {
     if (share && a >= 2) e->stash[a] = e->stash[1];
     else if (alloc_stash(e, n, e->stash[a])) return -1;
     Builder B{e, &n, t};
+    B.f16 = e->cfg.forward_fp16 ? 1 : 0;
     if (a == 0) {
       B.net_fwd(e->fwd[a], e->stash[a], e->Z, e->DOUT);
       B.net_bwd(e->bwd[a], e->stash[a], e->GD, e->GZ);
@@ -1013,6 +1024,9 @@ VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_ou
 VV_API int vv_test_gemm(const void* A, const void* B, const float* bias, const float* res, float* out_f32, void* out_bf16, void* aux, int M,
                  int N, int K, int batch, int epi, void* stream) {
   GemmArgs g{};
+  g.f16 = (epi >> 4) & 1;          // bit 4: operands, 16-bit outputs and the saved pre-activation are fp16
+  g.aux_f16 = g.f16;
+  epi &= 15;
   g.M = M; g.N = N; g.K = K; g.batch = batch; g.epi = epi;
   g.bias = bias; g.bias_bs = N;
   g.res = res; g.ld_res = N; g.res_bs = (long long)M * N;
@@ -1033,7 +1047,7 @@ VV_API int vv_test_layernorm(const float* x, const float* gamma, const float* be
                       float eps, void* stream) {
   VV_CHECK(ln_supported(MAP_PLAIN, C), "LayerNorm width %d not instantiated", C);
   if (y) {
-    LnArgs a{rows, C, 1, MAP_PLAIN, 0, 0, eps, x, C, 0, gamma, beta, 0, nullptr, 0, 0, y, C, 0};
+    LnArgs a{rows, C, 1, MAP_PLAIN, 0, 0, eps, x, C, 0, gamma, beta, 0, nullptr, 0, 0, y, C, 0, 0};
     launch_ln_fwd(a, (cudaStream_t)stream);
   }
   if (dy && dx) {
@@ -1045,10 +1059,10 @@ VV_API int vv_test_layernorm(const float* x, const float* gamma, const float* be
 }
 
 VV_API int vv_test_winattn(const void* qkv, const float* relbias, void* out, const void* dout, void* dqkv, int gh, int gw, int heads, int hd,
-                    int shift, void* stream) {
+                    int shift, int f16, void* stream) {
   VV_CHECK(hd == 32 || hd == 192, "head_dim %d not instantiated", hd);
   const long long d = (long long)heads * hd;
-  AttnArgs a{gh, gw, heads, hd, shift, 1, (const bf16*)qkv, 3 * d, 0, relbias, 0, (bf16*)out, d, 0, (const bf16*)dout, (bf16*)dqkv};
+  AttnArgs a{gh, gw, heads, hd, shift, 1, (const bf16*)qkv, 3 * d, 0, relbias, 0, (bf16*)out, d, 0, (const bf16*)dout, (bf16*)dqkv, f16};
   if (out) launch_attn_fwd(a, (cudaStream_t)stream);
   if (dout && dqkv) launch_attn_bwd(a, (cudaStream_t)stream);
   VV_CUDA(cudaGetLastError());

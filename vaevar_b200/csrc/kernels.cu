@@ -2,9 +2,20 @@
 // LayerNorm fwd/bwd (with the PatchMerging gather / PatchExpand pixel-shuffle folded into the addressing),
 // 4x4-window attention fwd/bwd (roll + window partition/reverse folded into the addressing, P recomputed in
 // the backward), the 2x2/stride-2 patch operators, and the per-channel affine seams.
+#include <stdlib.h>
+
 #include "ops.h"
 
 namespace vv {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VV_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // =============================================================================================
 // LayerNorm
@@ -48,16 +59,18 @@ VV_DEVINL void stv(float* dst, const float* src) {
   for (int v = 0; v < VEC; ++v) f[v] = src[v];
   *reinterpret_cast<typename VecT<VEC>::T*>(dst) = t;
 }
+VV_DEVINL uint32_t pack16_rt(float a, float b, bool f16) { return f16 ? pack16<true>(a, b) : pack16<false>(a, b); }
 template <int VEC>
-VV_DEVINL void stv_bf16(bf16* dst, const float* src) {
+VV_DEVINL void stv_16(bf16* dst, const float* src, bool f16) {
   if (VEC == 1) {
-    dst[0] = __float2bfloat16(src[0]);
+    if (f16) *reinterpret_cast<__half*>(dst) = __float2half_rn(src[0]);
+    else dst[0] = __float2bfloat16(src[0]);
   } else if (VEC == 2) {
-    *reinterpret_cast<uint32_t*>(dst) = pack_bf16(src[0], src[1]);
+    *reinterpret_cast<uint32_t*>(dst) = pack16_rt(src[0], src[1], f16);
   } else {
     uint2 w;
-    w.x = pack_bf16(src[0], src[1]);
-    w.y = pack_bf16(src[2], src[3]);
+    w.x = pack16_rt(src[0], src[1], f16);
+    w.y = pack16_rt(src[2], src[3], f16);
     *reinterpret_cast<uint2*>(dst) = w;
   }
 }
@@ -68,6 +81,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   if (r >= a.rows) return;
   const float* x = a.x + (long long)b * a.x_bs;
   float v[NPL];
@@ -96,7 +111,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
     ldv<VEC>(bb, be + c);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) y[i] = (v[k * VEC + i] - mean) * rstd * gg[i] + bb[i];
-    if (a.out_bf16) stv_bf16<VEC>(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + c, y);
+    if (a.out_bf16) stv_16<VEC>(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + c, y, a.out_f16 != 0);
     if (a.out_f32) stv<VEC>(a.out_f32 + (long long)b * a.of_bs + (long long)r * a.ld_of + c, y);
   }
 }
@@ -107,6 +122,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int b = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   if (r >= a.rows) return;
   const float* x = a.x + (long long)b * a.x_bs;
   const float* dy = a.dy + (long long)b * a.dy_bs + (long long)r * a.ld_dy;
@@ -157,7 +174,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       for (int i = 0; i < VEC; ++i) d[i] += rr[i];
     }
     stv<VEC>(a.dx + (long long)b * a.dx_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dx), d);
-    if (a.dx_bf16) stv_bf16<VEC>(a.dx_bf16 + (long long)b * a.dxb_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dxb), d);
+    if (a.dx_bf16) stv_16<VEC>(a.dx_bf16 + (long long)b * a.dxb_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dxb), d, false);
   }
 }
 
@@ -166,16 +183,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     const int npl = ARGS.C / 32;                                                         \
     dim3 grid((ARGS.rows + 7) / 8, ARGS.batch);                                          \
     switch (ARGS.map * 100 + npl) {                                                      \
-      case 2: KERNEL<2, 2, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
-      case 3: KERNEL<3, 1, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
-      case 4: KERNEL<4, 4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
-      case 6: KERNEL<6, 2, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;                 \
-      case 12: KERNEL<12, 4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;               \
-      case 36: KERNEL<36, 4, MAP_PLAIN><<<grid, 256, 0, s>>>(ARGS); break;               \
-      case 108: KERNEL<8, 4, MAP_MERGE><<<grid, 256, 0, s>>>(ARGS); break;               \
-      case 112: KERNEL<12, 4, MAP_MERGE><<<grid, 256, 0, s>>>(ARGS); break;              \
-      case 202: KERNEL<2, 2, MAP_EXPAND><<<grid, 256, 0, s>>>(ARGS); break;              \
-      case 203: KERNEL<3, 1, MAP_EXPAND><<<grid, 256, 0, s>>>(ARGS); break;              \
+      case 2: launch_kernel(KERNEL<2, 2, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
+      case 3: launch_kernel(KERNEL<3, 1, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
+      case 4: launch_kernel(KERNEL<4, 4, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
+      case 6: launch_kernel(KERNEL<6, 2, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
+      case 12: launch_kernel(KERNEL<12, 4, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;               \
+      case 36: launch_kernel(KERNEL<36, 4, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;               \
+      case 108: launch_kernel(KERNEL<8, 4, MAP_MERGE>, grid, dim3(256), 0, s, ARGS); break;               \
+      case 112: launch_kernel(KERNEL<12, 4, MAP_MERGE>, grid, dim3(256), 0, s, ARGS); break;              \
+      case 202: launch_kernel(KERNEL<2, 2, MAP_EXPAND>, grid, dim3(256), 0, s, ARGS); break;              \
+      case 203: launch_kernel(KERNEL<3, 1, MAP_EXPAND>, grid, dim3(256), 0, s, ARGS); break;              \
       default: break;                                                                    \
     }                                                                                    \
   }
@@ -204,6 +221,21 @@ VV_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+VV_DEVINL void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 16-bit operand format of the forward pass: IEEE fp16 (F16) or bf16
+template <bool F16>
+VV_DEVINL void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (F16) mma_f16_16816(d, a, b0, b1);
+  else mma_bf16_16816(d, a, b0, b1);
+}
+VV_DEVINL uint32_t half2_to_bf162(uint32_t w) {
+  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&w));
+  return pack_bf16(f.x, f.y);
+}
 VV_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row_ptr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -220,7 +252,9 @@ struct AttnSmem {
   static constexpr int BYTES = 4 * WORDS * 4;   // 4 warps per CTA
 };
 
-template <int HD, bool BWD>
+// F16: qkv (and the forward output) are fp16.  The backward pass recomputes P from the fp16 Q, K exactly as the forward did,
+// then converts Q, K, V to bf16 in shared memory: its products pair them with bf16 gradients whose range fp16 cannot hold.
+template <int HD, bool BWD, bool F16>
 __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   using L = AttnSmem<HD, BWD>;
   constexpr int W2 = L::W2, RS = L::RS, PW = L::PW;
@@ -230,6 +264,8 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   const int g = lane >> 2, t = lane & 3;
   const int nww = a.gw >> 2, nwh = a.gh >> 2;
   const int item = blockIdx.x * 4 + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (item >= nww * nwh * a.heads) return;      // warp-uniform; only warp-level sync below
   const int b = blockIdx.y;
   const int win = item / a.heads, h = item - win * a.heads;
@@ -272,8 +308,19 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   for (int ks = 0; ks < HD / 16; ++ks) {
     const int w = ks * 8 + t;
     const uint32_t af[4] = {Qs[g * RS + w], Qs[(g + 8) * RS + w], Qs[g * RS + w + 4], Qs[(g + 8) * RS + w + 4]};
-    mma_bf16_16816(s0, af, Ks[g * RS + w], Ks[g * RS + w + 4]);
-    mma_bf16_16816(s1, af, Ks[(g + 8) * RS + w], Ks[(g + 8) * RS + w + 4]);
+    mma_16816<F16>(s0, af, Ks[g * RS + w], Ks[g * RS + w + 4]);
+    mma_16816<F16>(s1, af, Ks[(g + 8) * RS + w], Ks[(g + 8) * RS + w + 4]);
+  }
+  if (BWD && F16) {                                              // Q, K, V -> bf16 in place (the gradient products are bf16)
+    __syncwarp();
+    for (int idx = lane; idx < 3 * 16 * CH; idx += 32) {
+      const int ch = idx % CH, rowm = idx / CH;                  // rowm = matrix * 16 + token
+      uint4* ptr = reinterpret_cast<uint4*>(Qs + (rowm >> 4) * L::MAT + (rowm & 15) * RS + 4 * ch);
+      uint4 w = *ptr;
+      w.x = half2_to_bf162(w.x); w.y = half2_to_bf162(w.y); w.z = half2_to_bf162(w.z); w.w = half2_to_bf162(w.w);
+      *ptr = w;
+    }
+    __syncwarp();
   }
   // ---- P = softmax(scale S + bias + mask); this thread owns rows g and g+8, columns {2t,2t+1} and {8+2t,9+2t} ----
   const float scale = rsqrtf((float)HD);
@@ -319,19 +366,19 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
 
   if (!BWD) {
     // ---- O = P V ----
-    const uint32_t pa[4] = {pack_bf16(p0[0], p0[1]), pack_bf16(p0[2], p0[3]), pack_bf16(p1[0], p1[1]), pack_bf16(p1[2], p1[3])};
+    const uint32_t pa[4] = {pack16<F16>(p0[0], p0[1]), pack16<F16>(p0[2], p0[3]), pack16<F16>(p1[0], p1[1]), pack16<F16>(p1[2], p1[3])};
     __syncwarp();                                                 // every lane is done reading Qs before it is reused for O
 #pragma unroll
     for (int c0 = 0; c0 < HD; c0 += 16) {
       uint32_t vb[4];
       ldmatrix_x4_trans(vb, bfrag_ptr(Vs, c0));
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-      mma_bf16_16816(o0, pa, vb[0], vb[1]);
-      mma_bf16_16816(o1, pa, vb[2], vb[3]);
-      Qs[g * RS + (c0 >> 1) + t] = pack_bf16(o0[0], o0[1]);
-      Qs[(g + 8) * RS + (c0 >> 1) + t] = pack_bf16(o0[2], o0[3]);
-      Qs[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0], o1[1]);
-      Qs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2], o1[3]);
+      mma_16816<F16>(o0, pa, vb[0], vb[1]);
+      mma_16816<F16>(o1, pa, vb[2], vb[3]);
+      Qs[g * RS + (c0 >> 1) + t] = pack16<F16>(o0[0], o0[1]);
+      Qs[(g + 8) * RS + (c0 >> 1) + t] = pack16<F16>(o0[2], o0[3]);
+      Qs[g * RS + (c0 >> 1) + 4 + t] = pack16<F16>(o1[0], o1[1]);
+      Qs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack16<F16>(o1[2], o1[3]);
     }
     __syncwarp();
     copy_out(Qs, a.out + (long long)b * a.o_bs, a.ld_o, h * HD);
@@ -416,26 +463,25 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   }
 }
 
-template <int HD, bool BWD>
+template <int HD, bool BWD, bool F16>
 static void launch_attn_t(const AttnArgs& a, cudaStream_t s) {
   using L = AttnSmem<HD, BWD>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn_kernel<HD, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    cudaFuncSetAttribute(attn_kernel<HD, BWD, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     attr_set = true;
   }
   const int items = (a.gh / 4) * (a.gw / 4) * a.heads;
   dim3 grid((items + 3) / 4, a.batch);
-  attn_kernel<HD, BWD><<<grid, 128, L::BYTES, s>>>(a);
+  launch_kernel(attn_kernel<HD, BWD, F16>, grid, dim3(128), L::BYTES, s, a);
 }
-void launch_attn_fwd(const AttnArgs& a, cudaStream_t s) {
-  if (a.hd == 32) launch_attn_t<32, false>(a, s);
-  else if (a.hd == 192) launch_attn_t<192, false>(a, s);
+template <bool BWD>
+static void launch_attn_d(const AttnArgs& a, cudaStream_t s) {
+  if (a.hd == 32) { if (a.f16) launch_attn_t<32, BWD, true>(a, s); else launch_attn_t<32, BWD, false>(a, s); }
+  else if (a.hd == 192) { if (a.f16) launch_attn_t<192, BWD, true>(a, s); else launch_attn_t<192, BWD, false>(a, s); }
 }
-void launch_attn_bwd(const AttnArgs& a, cudaStream_t s) {
-  if (a.hd == 32) launch_attn_t<32, true>(a, s);
-  else if (a.hd == 192) launch_attn_t<192, true>(a, s);
-}
+void launch_attn_fwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<false>(a, s); }
+void launch_attn_bwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<true>(a, s); }
 
 // =============================================================================================
 // Patch operators
@@ -449,6 +495,8 @@ __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
   const int t0 = blockIdx.x * P2T_TOK;
+  pdl_launch_dependents();
+  pdl_wait();
   const int K = a.kcnt[g] * 4;
   const int cb = a.cbase[g];
   const long long HW = (long long)a.H * a.W;
@@ -482,7 +530,7 @@ __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
 void launch_p2t(const PatchArgs& a, cudaStream_t s) {
   const int L0 = (a.H / 2) * (a.W / 2);
   dim3 grid(L0 / P2T_TOK, a.G);
-  p2t_kernel<<<grid, ((a.D + 31) / 32) * 32, 0, s>>>(a);
+  launch_kernel(p2t_kernel, grid, dim3(((a.D + 31) / 32) * 32), 0, s, a);
 }
 
 constexpr int T2P_TOK = 32;
@@ -495,6 +543,8 @@ __global__ void __launch_bounds__(128) t2p_kernel(const PatchArgs a) {
   const int i = blockIdx.y;
   const int j0 = blockIdx.x * T2P_TOK;
   const int D = a.D, RS = D + 1;
+  pdl_launch_dependents();
+  pdl_wait();
   const float* src = a.tok_in + ((long long)g * L0 + (long long)i * W0 + j0) * D;
   for (int idx = threadIdx.x; idx < T2P_TOK * D; idx += blockDim.x) {
     const int jj = idx / D, c = idx - jj * D;
@@ -517,7 +567,7 @@ __global__ void __launch_bounds__(128) t2p_kernel(const PatchArgs a) {
 
 void launch_t2p(const PatchArgs& a, cudaStream_t s) {
   dim3 grid((a.W / 2) / T2P_TOK, a.H / 2, a.G);
-  t2p_kernel<<<grid, 128, T2P_TOK * (a.D + 1) * sizeof(float), s>>>(a);
+  launch_kernel(t2p_kernel, grid, dim3(128), T2P_TOK * (a.D + 1) * sizeof(float), s, a);
 }
 
 // =============================================================================================
@@ -526,6 +576,8 @@ void launch_t2p(const PatchArgs& a, cudaStream_t s) {
 __global__ void chan_affine_kernel(float* out, const float* a, const float* sa, const float* b, const float* sb, const float* t,
                                    int C, long long HW) {
   const int c = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   const float fa = sa ? sa[c] : 1.f, fb = sb ? sb[c] : 1.f, ft = t ? t[c] : 0.f;
   const long long base = (long long)c * HW;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
@@ -537,7 +589,7 @@ __global__ void chan_affine_kernel(float* out, const float* a, const float* sa, 
 void launch_chan_affine(float* out, const float* a, const float* sa, const float* b, const float* sb, const float* t, int C,
                         long long HW, cudaStream_t s) {
   dim3 grid((unsigned)((HW + 1023) / 1024 < 64 ? (HW + 1023) / 1024 : 64), C);
-  chan_affine_kernel<<<grid, 256, 0, s>>>(out, a, sa, b, sb, t, C, HW);
+  launch_kernel(chan_affine_kernel, grid, dim3(256), 0, s, out, a, sa, b, sb, t, C, HW);
 }
 
 }  // namespace vv

@@ -7,22 +7,37 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "gemm_tcgen05.cuh"
 
 namespace vv {
 
-typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat16 bf16;   // also used as the STORAGE type of fp16 activations (the format is a per-launch flag)
+
+// Every kernel of the engine goes through this launcher: programmatic stream serialization lets the prologue of a kernel
+// (barrier init, TMEM allocation, descriptor prefetch, index math) overlap the tail of the kernel before it; each kernel
+// calls pdl_wait() before its first global access.  VV_NO_PDL=1 turns the attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- GEMM -----------------------------------------------------------------------------------
 struct GemmDesc {
   CUtensorMap tmA, tmB;
   GemmStoreMaps sm;
   GemmArgs a;
-  int bn;
-  int two_cta;   // 1: CTA-pair kernel (256 x bn tile, tcgen05 cta_group::2); 0: single-CTA 128 x bn
-  int persist;   // 1: persistent CTA-pair kernel with double-buffered TMEM accumulators and TMA-fed epilogue
+  int bn;        // tile = 256 rows (one CTA pair) x bn columns
 };
-// A: [batch][M][K] bf16 with row stride lda / batch stride a_bs (elements); B: [batch][N][K] likewise.
+// A: [batch][M][K] 16-bit with row stride lda / batch stride a_bs (elements); B: [batch][N][K] likewise.
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,
                            long long b_bs, const GemmArgs& args);
 void launch_gemm(const GemmDesc& d, cudaStream_t s);
@@ -40,6 +55,7 @@ struct LnArgs {
   const float *gamma, *beta; long long gb_bs;
   bf16* out_bf16; long long ld_ob, ob_bs;          // outputs are plain rows
   float* out_f32; long long ld_of, of_bs;
+  int out_f16;                                     // 1: the 16-bit output is IEEE fp16 (forward pass), 0: bf16
 };
 struct LnBwdArgs {
   int rows, C, batch, map, gh, gw;
@@ -60,8 +76,9 @@ struct AttnArgs {
   const bf16* qkv; long long ld_qkv, qkv_bs;       // [batch][gh*gw][3*heads*hd], token order = original grid
   const float* relbias; long long relbias_bs;      // [batch][heads][16][16] (table gathered at pack time)
   bf16* out; long long ld_o, o_bs;                 // forward: attention output [batch][tokens][heads*hd]
-  const bf16* dout;                                // backward: gradient of `out` (same strides as out)
-  bf16* dqkv;                                      // backward: gradient of qkv (same strides as qkv)
+  const bf16* dout;                                // backward: gradient of `out` (same strides as out), bf16
+  bf16* dqkv;                                      // backward: gradient of qkv (same strides as qkv), bf16
+  int f16;                                         // 1: qkv (and the forward output) are IEEE fp16, 0: bf16
 };
 void launch_attn_fwd(const AttnArgs& a, cudaStream_t s);
 void launch_attn_bwd(const AttnArgs& a, cudaStream_t s);

@@ -48,7 +48,8 @@ class Engine:
     """cost J(z) and grad_z J of da_4dvar.py:1183-1208 / 1242-1246 on one B200."""
 
     def __init__(self, dec: NetConfig, flow: Optional[NetConfig] = None, T: int = 1, recompute: bool = False,
-                 use_graph: bool = True, device: str = "cuda:0", flow_keep: int = 69, dec_keep: int = 0):
+                 use_graph: bool = True, device: str = "cuda:0", flow_keep: int = 69, dec_keep: int = 0,
+                 forward_fp16: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("vaevar_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -63,6 +64,7 @@ class Engine:
             cfg.flow = _net_c(flow, flow_keep)
         cfg.has_flow = int(flow is not None)
         cfg.T, cfg.recompute, cfg.use_graph = T, int(recompute), int(use_graph)
+        cfg.forward_fp16 = int(forward_fp16)     # fp16 forward / bf16 gradients (include/vaevar.h: vv_config.forward_fp16)
         self._h = C.c_void_p()
         _lib.check(self.lib.vv_engine_create(C.byref(cfg), C.byref(self._h)))
         self.n_state = dec_keep or dec.out_chans
