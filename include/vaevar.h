@@ -109,6 +109,13 @@ VV_API void vv_lbfgs_destroy(vv_lbfgs* o);
 VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z_dev, double* info_host, void* stream);
 /* Losses of every closure evaluation so far (returns the total count; copies at most cap). */
 VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out_host, int cap);
+/* Relative rounding noise of the closure's loss that the line search tolerates in its "loss went up" tests (relaxed Armijo
+ * condition f(t) <= f(0) + c1 t g'd + f_noise_rel |f(0)|).  Engine-bound optimisers default to 5e-5 (fp16 forward) / 4e-4
+ * (bf16 forward); 0 reproduces torch.optim.LBFGS decision for decision. */
+VV_API int vv_lbfgs_set_noise(vv_lbfgs* o, double f_noise_rel);
+/* Trial step length t of every closure evaluation so far, aligned with vv_lbfgs_history (0 for the evaluation that opens a
+ * step()). */
+VV_API int vv_lbfgs_steps(vv_lbfgs* o, double* t_out_host, int cap);
 /* Same controller on an analytic device function (pairwise Rosenbrock over n floats) -- lets tests compare the
  * optimiser's decisions with torch.optim.LBFGS on an identical objective. */
 VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, vv_lbfgs** out);

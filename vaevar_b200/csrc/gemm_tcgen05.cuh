@@ -76,11 +76,15 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFF + NBAR * 8 + 16 + 1024;   // +1024: manual alignment slack
 };
 
+// Two fp32 -> packed 16-bit pair (a in the low half).  fp16 conversions saturate to +-65504 instead of producing inf: an
+// activation that leaves fp16's range (a line-search trial far outside the basin) then yields a large finite J the line
+// search backs away from, as the fp32 reference would, instead of NaN.
 template <bool F16>
 VV_DEVINL uint32_t pack16(float a, float b) {
   if (F16) {
-    __half2 t = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
   return pack_bf16(a, b);
 }

@@ -63,7 +63,7 @@ VV_DEVINL uint32_t pack16_rt(float a, float b, bool f16) { return f16 ? pack16<t
 template <int VEC>
 VV_DEVINL void stv_16(bf16* dst, const float* src, bool f16) {
   if (VEC == 1) {
-    if (f16) *reinterpret_cast<__half*>(dst) = __float2half_rn(src[0]);
+    if (f16) *reinterpret_cast<uint16_t*>(dst) = static_cast<uint16_t>(pack16<true>(src[0], 0.f));
     else dst[0] = __float2bfloat16(src[0]);
   } else if (VEC == 2) {
     *reinterpret_cast<uint32_t*>(dst) = pack16_rt(src[0], src[1], f16);

@@ -23,6 +23,7 @@ struct vv_lbfgs {
   std::vector<double> hist_loss, hist_t; // every closure evaluation: loss and trial step
   int hist = 10, max_iter = 10, max_eval = 12;
   double lr = 1.0, tol_grad = 1e-7, tol_change = 1e-9;
+  double f_noise_rel = 0.0;              // relative rounding noise of the closure's loss (0 = exact torch.optim.LBFGS tests)
   long long n = 0;
   // device vectors
   float *g = nullptr, *g_prev = nullptr, *d = nullptr, *x_init = nullptr, *g_new = nullptr, *bg[2] = {nullptr, nullptr}, *ls_gprev = nullptr;
@@ -129,13 +130,17 @@ inline Sc sabs(Sc a) { return Sc{fabs(a.v), a.t}; }
 inline Sc pymin(Sc a, Sc b) { return lt(b, a) ? b : a; }   // Python's min(a, b)
 inline Sc pymax(Sc a, Sc b) { return gt(b, a) ? b : a; }   // Python's max(a, b)
 
-// lbfgs.py:12-37
-Sc cubic_interpolate(Sc x1, double f1, Sc g1, Sc x2, double f2, Sc g2, bool has_bounds, Sc lo, Sc hi) {
+// lbfgs.py:12-37.  eps_f > 0: when the two function values differ by less than the closure's rounding noise, their difference
+// carries no information; it is replaced by the trapezoid rule (f1 - f2 = (x1 - x2)(g1 + g2)/2, exact for a quadratic), which
+// turns the cubic step into the secant step on the directional derivative.
+Sc cubic_interpolate(Sc x1, double f1, Sc g1, Sc x2, double f2, Sc g2, bool has_bounds, Sc lo, Sc hi, double eps_f) {
   Sc xmin = lo, xmax = hi;
   if (!has_bounds) {
     if (le(x1, x2)) { xmin = x1; xmax = x2; } else { xmin = x2; xmax = x1; }
   }
-  const Sc d1 = op(op(g1, '+', g2), '-', op(py(3.0 * (f1 - f2)), '/', op(x1, '-', x2)));
+  const bool noisy = eps_f > 0.0 && fabs(f1 - f2) <= 2.0 * eps_f;
+  const Sc slope3 = noisy ? op(py(1.5), '*', op(g1, '+', g2)) : op(py(3.0 * (f1 - f2)), '/', op(x1, '-', x2));
+  const Sc d1 = op(op(g1, '+', g2), '-', slope3);
   const Sc d2sq = op(op(d1, '*', d1), '-', op(g1, '*', g2));
   if (ge(d2sq, py(0.0))) {
     const Sc d2 = d2sq.t ? Sc{(double)sqrtf((float)d2sq.v), true} : Sc{sqrt(d2sq.v), false};
@@ -164,7 +169,14 @@ int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, doub
     *gn = tn(g);
     return rc;
   };
-  auto armijo_fails = [&](double fnew, Sc tt) { return gt(py(fnew), op(py(f), '+', op(op(c1, '*', tt), '*', gtd))); };
+  // Noise-tolerant sufficient-decrease test: the closure's loss carries relative rounding noise eps (16-bit activations), and
+  // the first trial steps of a cycle (t ~ 1/|g|_1, lbfgs.py:454-457) change J by less than that.  Every "did the loss go up"
+  // decision therefore gets the slack eps_f = f_noise_rel |f(0)| (relaxed Armijo of noise-tolerant quasi-Newton methods);
+  // the curvature test uses gradients only and is unchanged.  f_noise_rel = 0 is torch.optim.LBFGS to the letter.
+  const double eps_f = o->f_noise_rel * fabs(f);
+  auto armijo_fails = [&](double fnew, Sc tt) {
+    return gt(py(fnew), op(op(py(f), '+', op(op(c1, '*', tt), '*', gtd)), '+', py(eps_f)));
+  };
   double f_new; Sc gtd_new;
   if (trial(t, &f_new, &gtd_new)) return -1;
   int ls_evals = 1;
@@ -176,7 +188,7 @@ int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, doub
   Sc br[2] = {py(0), py(0)}, br_gtd[2] = {py(0), py(0)};
   double br_f[2] = {0, 0};
   while (ls_iter < max_ls) {
-    if (armijo_fails(f_new, t) || (ls_iter > 1 && f_new >= f_prev)) {
+    if (armijo_fails(f_new, t) || (ls_iter > 1 && f_new >= f_prev + eps_f)) {
       br[0] = t_prev; br[1] = t; br_f[0] = f_prev; br_f[1] = f_new; br_gtd[0] = gtd_prev; br_gtd[1] = gtd_new;
       if (copy_vec(o, o->bg[0], o->ls_gprev, s) || copy_vec(o, o->bg[1], o->g_new, s)) return -1;
       have_bracket = true;
@@ -197,7 +209,7 @@ int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, doub
     const Sc min_step = op(t, '+', op(py(0.01), '*', op(t, '-', t_prev)));
     const Sc max_step = op(t, '*', py(10.0));
     const Sc tmp = t;
-    t = cubic_interpolate(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, true, min_step, max_step);
+    t = cubic_interpolate(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, true, min_step, max_step, eps_f);
     t_prev = tmp; f_prev = f_new; gtd_prev = gtd_new;
     if (copy_vec(o, o->ls_gprev, o->g_new, s)) return -1;
     if (trial(t, &f_new, &gtd_new)) return -1;
@@ -213,7 +225,7 @@ int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, doub
   if (!single && !(br_f[0] <= br_f[1])) { low = 1; high = 0; }
   while (!done && ls_iter < max_ls) {
     if (lt(op(sabs(op(br[1], '-', br[0])), '*', d_norm), py(o->tol_change))) break;
-    t = cubic_interpolate(br[0], br_f[0], br_gtd[0], br[1], br_f[1], br_gtd[1], false, py(0), py(0));
+    t = cubic_interpolate(br[0], br_f[0], br_gtd[0], br[1], br_f[1], br_gtd[1], false, py(0), py(0), eps_f);
     const Sc bmax = pymax(br[0], br[1]), bmin = pymin(br[0], br[1]);
     const Sc eps = op(py(0.1), '*', op(bmax, '-', bmin));
     if (lt(pymin(op(bmax, '-', t), op(t, '-', bmin)), eps)) {
@@ -228,7 +240,7 @@ int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, doub
     }
     if (trial(t, &f_new, &gtd_new)) return -1;
     ++ls_evals; ++ls_iter;
-    if (armijo_fails(f_new, t) || f_new >= br_f[low]) {
+    if (armijo_fails(f_new, t) || f_new >= br_f[low] + eps_f) {
       br[high] = t; br_f[high] = f_new; br_gtd[high] = gtd_new;
       if (copy_vec(o, o->bg[high], o->g_new, s)) return -1;
       if (br_f[0] <= br_f[1]) { low = 0; high = 1; } else { low = 1; high = 0; }
@@ -262,6 +274,7 @@ VV_API int vv_lbfgs_create(vv_engine* e, int history_size, int max_iter, vv_lbfg
   vv_lbfgs* o = new vv_lbfgs();
   o->e = e;
   o->closure = [e](const float* z, double* Jdev, float* g, cudaStream_t s) { return engine_cost_grad(e, z, Jdev, g, s); };
+  o->f_noise_rel = e->cfg.forward_fp16 ? 5e-5 : 4e-4;   // ~ measured |J_engine(z + dz) - J_engine(z) - dJ| / J for tiny dz
   return lbfgs_alloc(o, (long long)e->Zc * e->HW, history_size, max_iter, out);
 }
 
@@ -308,6 +321,19 @@ VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out, int cap) {
   return (int)o->hist_loss.size();
 }
 
+VV_API int vv_lbfgs_set_noise(vv_lbfgs* o, double f_noise_rel) {
+  if (!o || !(f_noise_rel >= 0.0)) { set_error("vv_lbfgs_set_noise: bad argument"); return -2; }
+  o->f_noise_rel = f_noise_rel;
+  return 0;
+}
+
+VV_API int vv_lbfgs_steps(vv_lbfgs* o, double* t_out, int cap) {
+  if (!o) return 0;
+  const int k = (int)std::min<size_t>(o->hist_t.size(), (size_t)cap);
+  for (int i = 0; i < k && t_out; ++i) t_out[i] = o->hist_t[i];
+  return (int)o->hist_t.size();
+}
+
 static int lbfgs_alloc(vv_lbfgs* o, long long nn, int history_size, int max_iter, vv_lbfgs** out) {
   o->hist = history_size; o->max_iter = max_iter; o->max_eval = max_iter * 5 / 4;
   o->n = nn;
@@ -346,6 +372,7 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   else LB_CUDA(cudaStreamSynchronize(user));
   const long long n = o->n;
   double loss, gmax, gl1;
+  o->hist_t.push_back(0.0);
   int rc = eval(o, z, o->g, nullptr, &loss, nullptr, s);             // lbfgs.py:361-366
   if (rc) return rc;
   const double orig_loss = loss;

@@ -175,7 +175,8 @@ class Engine:
 class LBFGS:
     """torch.optim.LBFGS(history_size, max_iter, line_search_fn='strong_wolfe') bound to an Engine (da_4dvar.py:1240)."""
 
-    def __init__(self, engine: Optional[Engine], history_size: int = 10, max_iter: int = 10, testfn_n: int = 0):
+    def __init__(self, engine: Optional[Engine], history_size: int = 10, max_iter: int = 10, testfn_n: int = 0,
+                 f_noise_rel: Optional[float] = None):
         self.engine = engine
         self.lib = _lib.load()
         self._h = C.c_void_p()
@@ -183,11 +184,20 @@ class LBFGS:
             _lib.check(self.lib.vv_lbfgs_create_testfn(testfn_n, history_size, max_iter, C.byref(self._h)))
         else:
             _lib.check(self.lib.vv_lbfgs_create(engine._h, history_size, max_iter, C.byref(self._h)))
+        if f_noise_rel is not None:     # line-search tolerance to rounding noise in J (include/vaevar.h: vv_lbfgs_set_noise)
+            _lib.check(self.lib.vv_lbfgs_set_noise(self._h, float(f_noise_rel)))
 
     def history(self):
         n = self.lib.vv_lbfgs_history(self._h, None, 0)
         buf = (C.c_double * max(n, 1))()
         self.lib.vv_lbfgs_history(self._h, buf, n)
+        return [buf[i] for i in range(n)]
+
+    def steps(self):
+        """Trial step length of every closure evaluation (aligned with history(); 0 = evaluation opening a step())."""
+        n = self.lib.vv_lbfgs_steps(self._h, None, 0)
+        buf = (C.c_double * max(n, 1))()
+        self.lib.vv_lbfgs_steps(self._h, buf, n)
         return [buf[i] for i in range(n)]
 
     def step(self, z: torch.Tensor):
