@@ -125,6 +125,12 @@ VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, v
  * and aux are fp16 instead of bf16. */
 VV_API int vv_test_gemm(const void* A_16_dev, const void* B_16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
                  void* out_16_dev, void* aux_16_dev, int M, int N, int K, int batch, int epi, void* stream);
+/* Debug: GEMM launches built after this call stamp per-CTA clock64 values into trace_dev (64 x uint64 per CTA; layout in
+ * tools/gemm_trace.py); null switches tracing off. */
+VV_API int vv_debug_gemm_trace(void* trace_dev);
+/* Debug: 1 = GEMMs issue their MMAs without loading operands, 2 = GEMMs load operands without issuing MMAs (results are
+ * garbage; isolates the tensor-pipe and the TMA-feed rates), 0 = normal. */
+VV_API int vv_debug_gemm_mode(int mode);
 VV_API int vv_test_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, float* y_dev, const float* dy_dev,
                       float* dx_dev, int rows, int C, float eps, void* stream);
 /* f16 = 1: qkv and out are fp16 (dout / dqkv stay bf16). */

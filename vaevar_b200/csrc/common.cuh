@@ -82,6 +82,12 @@ VV_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.r
 VV_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 VV_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+VV_DEVINL unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---- clusters / CTA pairs -------------------------------------------------------------------
 VV_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;

@@ -248,6 +248,7 @@ static int finalize_net(vv_engine* e, Net& n) {
     }
     n.embed.kcnt = dupload(e, kcnt); n.embed.cbase = dupload(e, cbase); n.embed.chan = dupload(e, chan);
     n.embed.Wp = dupload(e, Wp); n.embed.bias = dupload(e, bias); n.embed.nslots = c0;
+    n.embed.max_cnt = *std::max_element(kcnt.begin(), kcnt.end());
   }
   // ---- final projection (ConvTranspose2d k2 s2, transformer.py:593-594) with the mean/std half shuffle (:616-623) ----
   {
@@ -277,6 +278,7 @@ static int finalize_net(vv_engine* e, Net& n) {
     VV_CHECK(slots == n.ckeep, "keep_out=%d does not align with the mean/std channel layout (%d slots)", n.ckeep, slots);
     n.fin.kcnt = dupload(e, kcnt); n.fin.cbase = dupload(e, cbase); n.fin.chan = dupload(e, chan);
     n.fin.Wp = dupload(e, Wp); n.fin.bias = dupload(e, bias); n.fin.nslots = slots;
+    n.fin.max_cnt = *std::max_element(kcnt.begin(), kcnt.end());
   }
   // ---- stacked per-group seams ----
   auto stack_vec = [&](const char* fmt_suffix, const std::vector<std::string>& prefixes, long long numel) {
@@ -471,7 +473,7 @@ struct Builder {
     stage_fwd(P, N.u1, N.h0, N.w0, S.u1, nullptr, 0, 0);
     ln_f(P, L0, D, G, MAP_PLAIN, N.h0, N.w0, 1e-6f, S.u1.x.back(), D, (long long)L0 * D, N.nu_g, N.nu_b, nullptr, 0, 0, t.NU, D, (long long)L0 * D);
     o = Op{}; o.kind = Op::T2P;
-    o.patch = PatchArgs{N.H, N.W, G, D, N.fin.kcnt, N.fin.cbase, N.fin.chan, N.fin.Wp, N.fin.bias, nullptr, nullptr, nullptr, t.NU, out};
+    o.patch = PatchArgs{N.H, N.W, G, D, N.fin.kcnt, N.fin.cbase, N.fin.chan, N.fin.Wp, N.fin.bias, nullptr, nullptr, nullptr, t.NU, out, N.fin.max_cnt};
     P.ops.push_back(o);
   }
   void stage_fwd_trunk(Plan& P, Stash& S) {
@@ -537,7 +539,7 @@ struct Builder {
          t.dSK0, D, (long long)L0 * D, t.gE0, D, (long long)L0 * D, t.gE0b, D, (long long)L0 * D);
     stage_bwd(P, N.e0, N.h0, N.w0, S.e0, t.gE0, t.gE0b);
     o = Op{}; o.kind = Op::T2P;                                                                   // Conv2d^T
-    o.patch = PatchArgs{N.H, N.W, G, D, N.embed.kcnt, N.embed.cbase, N.embed.chan, N.embed.Wp, nullptr, nullptr, nullptr, nullptr, t.gE0, din};
+    o.patch = PatchArgs{N.H, N.W, G, D, N.embed.kcnt, N.embed.cbase, N.embed.chan, N.embed.Wp, nullptr, nullptr, nullptr, nullptr, t.gE0, din, N.embed.max_cnt};
     P.ops.push_back(o);
   }
 };
@@ -1040,6 +1042,15 @@ VV_API int vv_test_gemm(const void* A, const void* B, const float* bias, const f
   VV_CHECK(!er, "%s", er);
   launch_gemm(d, (cudaStream_t)stream);
   VV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+VV_API int vv_debug_gemm_trace(void* dev_ptr) {
+  set_gemm_trace((unsigned long long*)dev_ptr);
+  return 0;
+}
+VV_API int vv_debug_gemm_mode(int mode) {
+  set_gemm_debug_mode(mode);
   return 0;
 }
 

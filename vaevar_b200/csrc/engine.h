@@ -47,6 +47,7 @@ struct PatchPack {
   int* kcnt = nullptr; int* cbase = nullptr; int* chan = nullptr;   // device
   float* Wp = nullptr; float* bias = nullptr;
   int nslots = 0;
+  int max_cnt = 0;             // largest kcnt[g]
 };
 
 struct Net {

@@ -81,6 +81,11 @@ static int pick_bn(int M, int N, int batch) {
   return best;
 }
 
+static unsigned long long* g_gemm_trace = nullptr;
+static int g_gemm_debug_mode = 0;
+void set_gemm_trace(unsigned long long* dev_ptr) { g_gemm_trace = dev_ptr; }
+void set_gemm_debug_mode(int mode) { g_gemm_debug_mode = mode; }
+
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs,
                            const GemmArgs& args) {
   if (args.N % 8) return "GEMM N must be a multiple of 8";
@@ -89,6 +94,8 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   if (args.epi == EPI_GELU && args.aux_out && args.out_f32) return "GEMM: fp32 output together with a saved pre-activation is not supported";
   if (args.epi == EPI_DGELU && args.res) return "GEMM: GELU' epilogue with a residual is not supported";
   d->a = args;
+  d->a.trace = g_gemm_trace;
+  d->a.debug_mode = g_gemm_debug_mode;
   d->bn = pick_bn(args.M, args.N, args.batch);
   const char* e = encode_map_t(&d->tmA, A, false, args.K, args.M, args.batch, lda, a_bs, GEMM_BK, GEMM_BM);
   if (e) return e;

@@ -46,6 +46,8 @@ struct GemmArgs {
   long long ld_bf16, bf16_bs;
   int split_n;                // >0: 16-bit output column n goes to block n / split_n (stride split_stride), column n % split_n
   long long split_stride;
+  int debug_mode;             // debug: 0 normal; 1 MMA only (no TMA, operands = whatever is in smem); 2 TMA only (no MMA)
+  unsigned long long* trace;  // debug: per-CTA clock64 stamps (64 slots per CTA, see tools/gemm_trace.py); null in production
 };
 
 // Tensor maps of the epilogue: fp32 boxes are 32 cols x 32 rows (128-byte rows, 128B swizzle), 16-bit boxes 32 cols x 32 rows
@@ -166,7 +168,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* epi_ld_bar = tmem_empty_bar + 2;         // [8 warps][2 buffers]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(epi_ld_bar + 2 * GEMM_EPI_WARPS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for the compiler (uniform datapath)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
@@ -204,10 +206,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // may touch global memory before the previous kernel has completed.
   pdl_launch_dependents();
   pdl_wait();
+  unsigned long long* trc = p.trace ? p.trace + (size_t)blockIdx.x * 64 : nullptr;
+  if (trc && threadIdx.x == 0) { trc[0] = clock64(); trc[10] = globaltimer_ns(); }
 
+  // The producer and the MMA warp run their loops WARP-UNIFORMLY (all 32 lanes take the same path; one elected lane issues
+  // the TMA / tcgen05 instructions): descriptors, coordinates and barrier addresses then live in uniform registers.  Under a
+  // divergent `lane == 0` branch the compiler has to wrap every TMA / MMA instruction in an ELECT + R2UR waterfall loop, which
+  // alone costs ~170 cycles per tcgen05.mma (measured) -- more than the MMA itself.
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (p.debug_mode != 1) {
       uint32_t it = 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         const int nt = tile % n_tiles, rest = tile / n_tiles, mp = rest % pair_rows, b = rest / pair_rows;
@@ -216,39 +224,64 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
+          if (trc && it < 24 && lane == 0) trc[16 + it] = clock64();
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          tma_load_3d_2cta(sa, &tmA, leader_full, kb * GEMM_BK, m0, b);
-          tma_load_3d_2cta(sa + L::A_BYTES, &tmB, leader_full, kb * GEMM_BK, n0, b);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);   // bytes of both CTAs land on the leader's barrier
+            tma_load_3d_2cta(sa, &tmA, leader_full, kb * GEMM_BK, m0, b);
+            tma_load_3d_2cta(sa + L::A_BYTES, &tmB, leader_full, kb * GEMM_BK, n0, b);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA) =====
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_16(2 * GEMM_BM, BN, F16);
+      const uint32_t smem_base = smem_u32(smem);
       uint32_t it = 0, ti = 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs, ++ti) {
         const uint32_t acc = ti & 1;
         mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);          // both CTAs drained this accumulator stage
         tc_fence_after();
+        if (trc && ti < 2 && lane == 0) trc[2 + ti] = clock64();
         const uint32_t tacc = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (p.debug_mode != 1) mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          if (trc && it < 24 && lane == 0) trc[40 + it] = clock64();
+          if (p.debug_mode == 2) {                                       // feed only: hand the slot straight back
+            if (elect_one()) {
+              mbar_arrive(&empty_bar[s]);
+              mbar_arrive_cluster(&empty_bar[s], 1);
+            }
+            __syncwarp();
+            continue;
+          }
+          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + L::A_BYTES);
           const int krem = p.K - kb * GEMM_BK;                           // a short last block issues only the MMAs it needs
           const int nk = krem >= GEMM_BK ? GEMM_BK / 16 : (krem + 15) / 16;
-          // advance 16 elements = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          for (int k = 0; k < nk; ++k) umma_16_2cta(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          umma_commit_2cta(&empty_bar[s], 3);         // frees this slot in BOTH CTAs once these MMAs retire
+          if (elect_one()) {
+            // advance 16 elements = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            if (nk == GEMM_BK / 16) {
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k) umma_16_2cta(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            } else {
+              for (int k = 0; k < nk; ++k) umma_16_2cta(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty_bar[s], 3);       // frees this slot in BOTH CTAs once these MMAs retire
+          }
+          __syncwarp();
         }
-        umma_commit_2cta(&tmem_full_bar[acc], 3);     // accumulator complete in both CTAs
+        if (elect_one()) umma_commit_2cta(&tmem_full_bar[acc], 3);     // accumulator complete in both CTAs
+        __syncwarp();
+        if (trc && ti < 2 && lane == 0) trc[4 + ti] = clock64();
       }
     }
   } else {
@@ -273,7 +306,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int ncol = min(BN, p.N - n0);
       nch = mrow < p.M ? (ncol + GEMM_EC - 1) / GEMM_EC : 0;
     };
-    auto issue_loads = [&](int col, int mrow, int b, int buf) {        // lane 0 only
+    auto issue_loads = [&](int col, int mrow, int b, int buf) {        // the elected lane only
       tma_store_wait_read0();                                          // the store that last read this buffer is done with it
       mbar_expect_tx(&ldbar[buf], load_bytes);
       if (has_res) tma_load_3d(slab + buf * GEMM_BUF, &io.res, &ldbar[buf], col, mrow, b);
@@ -290,9 +323,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
 
     uint32_t it = 0;
-    if (has_loads && lane == 0) {
+    if (has_loads) {
       int n0, mrow, b;
-      if (first_chunk_from(pair, n0, mrow, b) >= 0) issue_loads(n0 + half * GEMM_EC, mrow, b, 0);
+      if (first_chunk_from(pair, n0, mrow, b) >= 0 && elect_one()) issue_loads(n0 + half * GEMM_EC, mrow, b, 0);
+      __syncwarp();
     }
     uint32_t ti = 0;
     for (int tile = pair; tile < total_tiles; tile += num_pairs, ++ti) {
@@ -302,6 +336,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
+      if (trc && ew == 0 && lane == 0 && ti < 2) trc[6 + ti] = clock64();
 #pragma unroll 1
       for (int c = half; c < nch; c += 2, ++it) {
         const int buf = it & 1;
@@ -322,16 +357,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         // (3) prefetch the residual / pre-activation of this warp's NEXT chunk into the other buffer
         if (has_loads) {
-          if (lane == 0) {
-            if (c + 2 < nch) {
-              issue_loads(col + 2 * GEMM_EC, mrow, b, buf ^ 1);
-            } else {
-              int n0x, mrowx, bx;
-              if (first_chunk_from(tile + num_pairs, n0x, mrowx, bx) >= 0) issue_loads(n0x + half * GEMM_EC, mrowx, bx, buf ^ 1);
-            }
+          if (c + 2 < nch) {
+            if (elect_one()) issue_loads(col + 2 * GEMM_EC, mrow, b, buf ^ 1);
+          } else {
+            int n0x, mrowx, bx;
+            if (first_chunk_from(tile + num_pairs, n0x, mrowx, bx) >= 0 && elect_one()) issue_loads(n0x + half * GEMM_EC, mrowx, bx, buf ^ 1);
           }
         } else {
-          if (lane == 0) tma_store_wait_read1();                       // the store issued two chunks ago has read this buffer
+          if (elect_one()) tma_store_wait_read1();                     // the store issued two chunks ago has read this buffer
         }
         __syncwarp();
         tmem_ld_wait();
@@ -348,7 +381,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // (5) bulk stores
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           if (p.out_f32) tma_store_3d(&io.f32, SA, col, mrow, b);
           if (p.out_bf16) {
             if (p.split_n > 0) tma_store_3d(&io.bf16, SB, col % p.split_n, mrow, col / p.split_n);
@@ -361,11 +394,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // this warp no longer needs accumulator stage `acc`: tell the leader's MMA thread
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      if (elect_one()) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      if (trc && ew == 0 && lane == 0 && ti < 2) trc[8 + ti] = clock64();
     }
-    if (lane == 0) tma_store_wait_read0();            // the staging slabs must outlive the bulk stores that read them
+    if (elect_one()) tma_store_wait_read0();          // the staging slabs must outlive the bulk stores that read them
     __syncwarp();
   }
+  if (trc && threadIdx.x == 0) trc[1] = clock64();
   tc_fence_before();
   cluster_sync_all();                                 // neither CTA may retire while its peer can still touch its smem / TMEM
   if (warp == 1) {

@@ -486,26 +486,28 @@ void launch_attn_bwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<true>(a,
 // =============================================================================================
 // Patch operators
 // =============================================================================================
-constexpr int P2T_TOK = 16;
+constexpr int P2T_TOK = 32;         // tokens per CTA: 32 consecutive tokens of one token row
 constexpr int P2T_KMAX = 128;
 
+// Thread c owns output channel c of the 32 tokens: per k one coalesced weight load, eight broadcast LDS.128 of the
+// transposed patch tile and 32 FMAs.
 __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
-  __shared__ float patch[P2T_TOK][P2T_KMAX];
+  __shared__ __align__(16) float patch[P2T_KMAX][P2T_TOK];            // [k = ci*4 + rowpar*2 + colpar][token]
   const int g = blockIdx.y;
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
   const int t0 = blockIdx.x * P2T_TOK;
+  const int i = t0 / W0, j0 = t0 - i * W0;
   pdl_launch_dependents();
   pdl_wait();
-  const int K = a.kcnt[g] * 4;
+  const int cnt = a.kcnt[g];
+  const int K = cnt * 4;
   const int cb = a.cbase[g];
   const long long HW = (long long)a.H * a.W;
-  for (int idx = threadIdx.x; idx < P2T_TOK * K; idx += blockDim.x) {
-    const int tt = idx / K, k = idx - tt * K;
-    const int tok = t0 + tt;
-    const int i = tok / W0, j = tok - i * W0;
-    const int ch = a.chan[cb + (k >> 2)];
-    patch[tt][k] = a.img_in[ch * HW + (long long)(2 * i + ((k >> 1) & 1)) * a.W + 2 * j + (k & 1)];
+  for (int idx = threadIdx.x; idx < cnt * 2 * 64; idx += blockDim.x) {
+    const int e = idx & 63, r = idx >> 6, ci = r >> 1, rp = r & 1;    // 64 consecutive pixels of image row 2i+rp, channel ci
+    const int ch = a.chan[cb + ci];
+    patch[ci * 4 + rp * 2 + (e & 1)][e >> 1] = a.img_in[ch * HW + (long long)(2 * i + rp) * a.W + 2 * j0 + e];
   }
   __syncthreads();
   const int c = threadIdx.x;
@@ -515,15 +517,22 @@ __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
 #pragma unroll
   for (int tt = 0; tt < P2T_TOK; ++tt) acc[tt] = b0;
   const float* w = a.Wp + (long long)cb * 4 * a.D + c;
+#pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    const float wv = w[(long long)k * a.D];
+    const float wv = __ldg(w + (long long)k * a.D);
 #pragma unroll
-    for (int tt = 0; tt < P2T_TOK; ++tt) acc[tt] = fmaf(patch[tt][k], wv, acc[tt]);
+    for (int q = 0; q < P2T_TOK / 4; ++q) {
+      const float4 pv = *reinterpret_cast<const float4*>(&patch[k][4 * q]);
+      acc[4 * q] = fmaf(pv.x, wv, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(pv.y, wv, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(pv.z, wv, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(pv.w, wv, acc[4 * q + 3]);
+    }
   }
 #pragma unroll
   for (int tt = 0; tt < P2T_TOK; ++tt) {
     const long long o = ((long long)g * L0 + t0 + tt) * a.D + c;
-    a.tok_out[o] = acc[tt] + (a.ape ? a.ape[o] : 0.f);
+    a.tok_out[o] = acc[tt] + (a.ape ? __ldg(a.ape + o) : 0.f);
   }
 }
 
@@ -533,41 +542,74 @@ void launch_p2t(const PatchArgs& a, cudaStream_t s) {
   launch_kernel(p2t_kernel, grid, dim3(((a.D + 31) / 32) * 32), 0, s, a);
 }
 
-constexpr int T2P_TOK = 32;
+constexpr int T2P_TOK = 64;         // tokens per CTA (consecutive tokens of one token row)
+constexpr int T2P_SC = 7;           // output channels accumulated per pass
 
-__global__ void __launch_bounds__(128) t2p_kernel(const PatchArgs a) {
-  extern __shared__ float Xs[];                       // [32][D+1]
-  const int g = blockIdx.z;
+// Thread (p1, jj, p2) owns pixel (2i+p1, 2(j0+jj)+p2) of every output channel of the group.  The group's weights and the
+// 64-token tile live in shared memory (rows padded by 4 floats: conflict-free LDS.128); per 4 input channels one x load and
+// T2P_SC weight loads feed 4*T2P_SC FMAs.
+__global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
+  extern __shared__ __align__(16) float t2p_sm[];
+  const int g = blockIdx.y;
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
-  const int i = blockIdx.y;
-  const int j0 = blockIdx.x * T2P_TOK;
-  const int D = a.D, RS = D + 1;
+  const int t0 = blockIdx.x * T2P_TOK;                 // the tile may span token rows when W0 < 64
+  const int D = a.D, RS = D + 4, D4 = D >> 2;
+  float* Xs = t2p_sm;                                  // [64][RS]
+  float* Ws = t2p_sm + T2P_TOK * RS;                   // [cnt*4][RS]
   pdl_launch_dependents();
   pdl_wait();
-  const float* src = a.tok_in + ((long long)g * L0 + (long long)i * W0 + j0) * D;
-  for (int idx = threadIdx.x; idx < T2P_TOK * D; idx += blockDim.x) {
-    const int jj = idx / D, c = idx - jj * D;
-    Xs[jj * RS + c] = src[idx];
+  const int cb = a.cbase[g], cnt = a.kcnt[g];
+  const float4* src = reinterpret_cast<const float4*>(a.tok_in + ((long long)g * L0 + t0) * D);
+  for (int idx = threadIdx.x; idx < T2P_TOK * D4; idx += blockDim.x) {
+    const int jj = idx / D4, c4 = idx - jj * D4;
+    *reinterpret_cast<float4*>(Xs + jj * RS + 4 * c4) = __ldg(src + idx);
+  }
+  const float4* wsrc = reinterpret_cast<const float4*>(a.Wp + (long long)cb * 4 * D);
+  for (int idx = threadIdx.x; idx < cnt * 4 * D4; idx += blockDim.x) {
+    const int row = idx / D4, c4 = idx - row * D4;
+    *reinterpret_cast<float4*>(Ws + row * RS + 4 * c4) = __ldg(wsrc + idx);
   }
   __syncthreads();
-  const int p1 = threadIdx.x >> 6, xx = threadIdx.x & 63, jj = xx >> 1, p2 = xx & 1;
-  const int cb = a.cbase[g], cnt = a.kcnt[g];
+  const int p1 = threadIdx.x >> 7, xx = threadIdx.x & 127, jj = xx >> 1, p2 = xx & 1;
+  const int tok = t0 + jj, i = tok / W0, j = tok - i * W0;
   const long long HW = (long long)a.H * a.W;
   const float* xr = Xs + jj * RS;
-  for (int slot = 0; slot < cnt; ++slot) {
-    const float* w = a.Wp + ((long long)(cb + slot) * 4 + p1 * 2 + p2) * D;
-    float acc = a.bias ? a.bias[cb + slot] : 0.f;
-#pragma unroll 8
-    for (int c = 0; c < D; ++c) acc = fmaf(xr[c], __ldg(w + c), acc);
-    const int ch = a.chan[cb + slot];
-    a.img_out[ch * HW + (long long)(2 * i + p1) * a.W + 2 * j0 + xx] = acc;
+  for (int s0 = 0; s0 < cnt; s0 += T2P_SC) {
+    float acc[T2P_SC];
+#pragma unroll
+    for (int q = 0; q < T2P_SC; ++q) acc[q] = 0.f;
+    const float* wr = Ws + ((s0 * 4) + p1 * 2 + p2) * RS;
+    for (int c4 = 0; c4 < D4; ++c4) {
+      const float4 x = *reinterpret_cast<const float4*>(xr + 4 * c4);
+#pragma unroll
+      for (int q = 0; q < T2P_SC; ++q) {
+        if (s0 + q < cnt) {                              // block-uniform
+          const float4 w = *reinterpret_cast<const float4*>(wr + q * 4 * RS + 4 * c4);
+          acc[q] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[q]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < T2P_SC; ++q) {
+      if (s0 + q < cnt) {
+        const int slot = cb + s0 + q;
+        a.img_out[a.chan[slot] * HW + (long long)(2 * i + p1) * a.W + 2 * j + p2] = acc[q] + (a.bias ? a.bias[slot] : 0.f);
+      }
+    }
   }
 }
 
 void launch_t2p(const PatchArgs& a, cudaStream_t s) {
-  dim3 grid((a.W / 2) / T2P_TOK, a.H / 2, a.G);
-  launch_kernel(t2p_kernel, grid, dim3(128), T2P_TOK * (a.D + 1) * sizeof(float), s, a);
+  const int max_cnt = a.max_cnt > 0 ? a.max_cnt : 32;
+  const size_t smem = (size_t)(T2P_TOK + max_cnt * 4) * (a.D + 4) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(t2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  dim3 grid((a.H / 2) * (a.W / 2) / T2P_TOK, a.G);
+  launch_kernel(t2p_kernel, grid, dim3(256), smem, s, a);
 }
 
 // =============================================================================================

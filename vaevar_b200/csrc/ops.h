@@ -41,6 +41,8 @@ struct GemmDesc {
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,
                            long long b_bs, const GemmArgs& args);
 void launch_gemm(const GemmDesc& d, cudaStream_t s);
+void set_gemm_debug_mode(int mode);                 // debug: 1 = MMA only, 2 = TMA feed only (results are garbage)
+void set_gemm_trace(unsigned long long* dev_ptr);   // debug: GEMM descriptors built afterwards stamp clocks into dev_ptr (null = off)
 
 // ---- LayerNorm (one warp per row, fp32 statistics) -------------------------------------------
 enum RowMap : int {
@@ -98,6 +100,7 @@ struct PatchArgs {
   float* tok_out;              // P2T: [G][L0][D]
   const float* tok_in;         // T2P: [G][L0][D]
   float* img_out;              // T2P: NCHW image
+  int max_cnt;                 // largest kcnt[g] (host copy; sizes the T2P weight tile); 0 = assume the maximum (32)
 };
 void launch_p2t(const PatchArgs& a, cudaStream_t s);
 void launch_t2p(const PatchArgs& a, cudaStream_t s);
