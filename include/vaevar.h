@@ -121,10 +121,18 @@ VV_API int vv_lbfgs_steps(vv_lbfgs* o, double* t_out_host, int cap);
 VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, vv_lbfgs** out);
 
 /* Kernel-level hooks used by tests/ and bench.py (roofline of the dominant kernel). */
-/* epi: 0 linear, 1 GELU (aux = saved pre-activation, out), 2 GELU' (aux = pre-activation, in); | 16: operands, 16-bit outputs
+/* epi: 0 linear, 1 GELU (aux out = saved gelu'(u)), 2 multiply by aux (aux in = the saved gelu'(u)); | 16: operands, 16-bit outputs
  * and aux are fp16 instead of bf16. */
 VV_API int vv_test_gemm(const void* A_16_dev, const void* B_16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
                  void* out_16_dev, void* aux_16_dev, int M, int N, int K, int batch, int epi, void* stream);
+/* GEMM with a LayerNorm folded into it (the forward pass's norm1 -> qkv and norm2 -> fc1, swinblock.py:268,305):
+ * out = epi(LN(x) W^T + b) evaluated as rstd (x W'^T - mean s) + c, with A = the raw 16-bit rows of x, B = W' = W o gamma,
+ * cbias = c = b + W beta, colsum = s = W' 1, stats = per-row (sum, sumsq) partials [batch][parts][M] float2, C = row length.
+ * If stats_out is given the GEMM also emits the partials of the rows of its fp32 output ([batch][*parts_out][M] float2), as
+ * the proj / fc2 GEMMs do for the LayerNorm that follows them. */
+VV_API int vv_test_gemm_ln(const void* A_16_dev, const void* B_16_dev, const float* cbias_dev, const float* colsum_dev, const float* stats_dev,
+                    int parts, int C, float eps, void* out_16_dev, void* aux_16_dev, float* out_f32_dev, float* stats_out_dev,
+                    int* parts_out_host, int M, int N, int K, int batch, int epi, void* stream);
 /* Debug: GEMM launches built after this call stamp per-CTA clock64 values into trace_dev (64 x uint64 per CTA; layout in
  * tools/gemm_trace.py); null switches tracing off. */
 VV_API int vv_debug_gemm_trace(void* trace_dev);

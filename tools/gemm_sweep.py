@@ -67,6 +67,16 @@ for shp in a.shapes.split(";"):
         else:
             os.environ.pop("VV_GEMM_BN", None)
         for name in a.variants.split(","):
+            if name.startswith("ln_"):                      # folded-LayerNorm consumer (statistics with 2 partials per row)
+                epi = 1 if "gelu" in name else 0
+                stats = torch.rand(B * 2 * M * 2, device=dev) + 1.0
+                colsum = torch.randn(B, N, device=dev)
+                largs = (P(A), P(W), P(bias), P(colsum), P(stats), 2, K, 1e-5, P(ob), P(aux) if "aux" in name else None, None, None, None,
+                         M, N, K, B, epi | (16 if a.f16 else 0), st)
+                _lib.check(lib.vv_test_gemm_ln(*largs))
+                med, mn = timeit(lambda: lib.vv_test_gemm_ln(*largs))
+                print(f"{M}x{N}x{K}x{B} BN={bn:>3s} {name:14s}: median {med*1e3:7.1f} us (min {mn*1e3:7.1f}) = {fl/med/1e9:6.0f} TFLOP/s", flush=True)
+                continue
             b_, r_, f_, o_, a_, epi = variants[name]
             args = (P(A), P(W), P(b_), P(r_), P(f_), P(o_), P(a_), M, N, K, B, epi | (16 if a.f16 else 0), st)
             _lib.check(lib.vv_test_gemm(*args))

@@ -62,13 +62,50 @@ def stage_gemm():
             _lib.check(lib.vv_test_gemm(P(A), P(W), P(bias), None, None, P(ob), P(aux), M, N, K, B, 1 | 16 * f16, st))
             torch.cuda.synchronize()
             ok &= report("gemm", f"gelu {tag} 16-bit", rel(ob.float(), torch.nn.functional.gelu(ref)), tol16)
-            ok &= report("gemm", f"gelu-aux {tag}", rel(aux.float(), ref), tol16)
-            # DGELU epilogue: acc * gelu'(u)
-            u = aux.float().requires_grad_(True)
+            # the GELU epilogue saves gelu'(u) (what the gradient GEMM multiplies by), not u
+            u = ref.clone().requires_grad_(True)
             torch.nn.functional.gelu(u).sum().backward()
+            ok &= report("gemm", f"gelu-aux {tag}", rel(aux.float(), u.grad), tol16)
+            # DGELU epilogue: acc * aux
             _lib.check(lib.vv_test_gemm(P(A), P(W), None, None, P(of), None, P(aux), M, N, K, B, 2 | 16 * f16, st))
             torch.cuda.synchronize()
-            ok &= report("gemm", f"dgelu {tag}", rel(of, (ref - bias[:, None, :]) * u.grad), 5e-5)
+            ok &= report("gemm", f"dgelu {tag}", rel(of, (ref - bias[:, None, :]) * aux.float()), 5e-5)
+    # LayerNorm folded into the GEMM (norm1 -> qkv, norm2 -> fc1): producer statistics + consumer epilogue vs torch
+    for (M, N, K, B) in [(2048, 3456, 1152, 1), (2048, 4608, 1152, 1), (8192, 288, 96, 6), (8192, 384, 96, 6), (2048, 768, 192, 6), (256, 160, 64, 2)]:
+        for f16 in (0, 1):
+            dt = torch.float16 if f16 else torch.bfloat16
+            tol16 = 1.5e-3 if f16 else 8e-3
+            tag = f"{M}x{N}x{K}x{B} {'f16' if f16 else 'bf16'}"
+            g = torch.Generator(device=dev).manual_seed(M + N + K + 7)
+            # producer: x = A0 W0^T + res (fp32) with its raw 16-bit copy and (sum, sumsq) partials
+            A0 = torch.randn(B, M, 64, device=dev, generator=g).to(dt); W0 = (torch.randn(B, K, 64, device=dev, generator=g) * 0.2).to(dt)
+            res = torch.randn(B, M, K, device=dev, generator=g) * 2 + 0.7
+            x32 = torch.empty(B, M, K, device=dev); x16 = torch.empty(B, M, K, device=dev, dtype=dt)
+            st_buf = torch.zeros(B * 64 * M * 2, device=dev)
+            po = C.c_int(0)
+            lib.vv_test_gemm_ln.restype = C.c_int
+            _lib.check(lib.vv_test_gemm_ln(P(A0), P(W0), None, None, None, 0, K, 0.0, P(x16), None, P(x32), P(st_buf), C.byref(po), M, K, 64, B,
+                                           0 | 16 * f16, st))
+            torch.cuda.synchronize()
+            parts = po.value
+            xr = torch.einsum("bmk,bnk->bmn", A0.float(), W0.float())
+            # the hook has no residual input: compare against the plain product
+            ok &= report("gemm", f"ln-producer x {tag}", rel(x32, xr), 2e-5)
+            stv = st_buf[: B * parts * M * 2].view(B, parts, M, 2).sum(1)
+            ok &= report("gemm", f"ln-producer sum {tag}", rel(stv[..., 0], x32.sum(-1)), 2e-5)
+            ok &= report("gemm", f"ln-producer sumsq {tag}", rel(stv[..., 1], (x32 * x32).sum(-1)), 2e-5)
+            # consumer: LN(x) W^T + b from the raw copy, folded weights and the partials
+            gamma = torch.rand(B, K, device=dev, generator=g) + 0.5; beta = torch.randn(B, K, device=dev, generator=g) * 0.3
+            W = torch.randn(B, N, K, device=dev, generator=g) * 0.05; bias = torch.randn(B, N, device=dev, generator=g)
+            Wf = (W * gamma[:, None, :]).to(dt)
+            colsum = Wf.float().sum(-1).contiguous(); cb = (bias + torch.einsum("bnk,bk->bn", W, beta)).contiguous()
+            ob = torch.empty(B, M, N, device=dev, dtype=dt)
+            _lib.check(lib.vv_test_gemm_ln(P(x16), P(Wf), P(cb), P(colsum), P(st_buf), parts, K, 1e-5, P(ob), None, None, None, None, M, N, K, B,
+                                           0 | 16 * f16, st))
+            torch.cuda.synchronize()
+            h = torch.nn.functional.layer_norm(x32, (K,), eps=1e-5) * gamma[:, None, :] + beta[:, None, :]
+            yref = torch.einsum("bmk,bnk->bmn", h, W) + bias[:, None, :]
+            ok &= report("gemm", f"ln-consumer {tag}", rel(ob.float(), yref), 3 * tol16)
     # timing of the dominant shapes
     for (M, N, K) in [(2048, 1152, 1152), (2048, 3456, 1152), (2048, 4608, 1152), (2048, 1152, 4608)]:
         A = torch.randn(1, M, K, device=dev).bfloat16(); W = torch.randn(1, N, K, device=dev).bfloat16()

@@ -51,6 +51,8 @@ _SIGS = {
     "vv_lbfgs_create_testfn": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(_P)]),
     "vv_profile_ops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int]),
     "vv_test_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vv_test_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, _P]),
     "vv_debug_gemm_trace": (C.c_int, [_P]),
     "vv_debug_gemm_mode": (C.c_int, [C.c_int]),
     "vv_test_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),

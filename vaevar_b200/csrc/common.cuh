@@ -75,6 +75,11 @@ VV_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" :
 VV_DEVINL void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 VV_DEVINL void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
+// Asynchronous prefetch of `bytes` (multiple of 16, 16-byte aligned address) of global memory into L2.
+VV_DEVINL void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // ---- programmatic dependent launch ------------------------------------------------------------
 // Every kernel of the engine is launched with programmatic stream serialization: its prologue may overlap the tail of the
 // kernel before it; pdl_wait() blocks until that kernel has completed and its writes are visible.  Both are no-ops when the
@@ -232,6 +237,16 @@ VV_DEVINL float gelu_erf_grad(float x) {
   const float q = gelu_erfc_abs(x, &e);
   const float cdf = 0.5f + copysignf(fmaf(-0.5f, q, 0.5f), x);
   return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+// gelu(x) and gelu'(x) together (they share the exponential and the erfc polynomial): the forward GEMM saves gelu'(u) instead
+// of the pre-activation u, so the gradient GEMM's epilogue is a plain multiply.
+VV_DEVINL void gelu_erf_both(float x, float* y, float* dy) {
+  float e;
+  const float q = gelu_erfc_abs(x, &e);
+  const float sh = copysignf(0.5f, x);                   // Phi(x) = 1/2 + sign(x) (1/2 - q/2)
+  const float cdf = fmaf(-sh, q, 0.5f + sh);
+  *y = x * cdf;
+  *dy = fmaf(x * 0.39894228040143268f, e, cdf);
 }
 VV_DEVINL float warp_sum(float v) {
 #pragma unroll

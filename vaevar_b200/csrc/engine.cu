@@ -3,6 +3,7 @@
 // da_4dvar.py:1183-1208 / 1242-1246, and the C ABI of include/vaevar.h.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,6 +52,27 @@ __global__ void pack_w_kernel(bf16* dst, bf16* dstT, const float* src, int rows,
     else dst[i] = __float2bfloat16(w);
     if (dstT) dstT[(long long)c * rows + r] = __float2bfloat16(w);
   }
+}
+// LayerNorm folded into the following Linear (see GemmArgs::ln_stats): one warp per output row n of W (N x K, fp32).
+//   dst[n,k]  = 16bit(W[n,k] gamma[k])            (forward operand; the gradient GEMMs keep the unfolded W^T)
+//   colsum[n] = sum_k float(dst[n,k])             (of the ROUNDED values: the mean term must cancel what the MMA summed)
+//   cbias[n]  = bias[n] + sum_k beta[k] W[n,k]
+__global__ void fold_ln_kernel(bf16* dst, float* colsum, float* cbias, const float* W, const float* gamma, const float* beta,
+                               const float* bias, int rows, int cols, int f16) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= rows) return;
+  float s = 0.f, c = 0.f;
+  for (int k = lane; k < cols; k += 32) {
+    const float w = W[(long long)n * cols + k];
+    const float wf = w * gamma[k];
+    float r;
+    if (f16) { const __half h = __float2half_rn(wf); reinterpret_cast<__half*>(dst)[(long long)n * cols + k] = h; r = __half2float(h); }
+    else { const bf16 h = __float2bfloat16(wf); dst[(long long)n * cols + k] = h; r = __bfloat162float(h); }
+    s += r;
+    c = fmaf(beta[k], w, c);
+  }
+  s = warp_sum(s); c = warp_sum(c);
+  if (lane == 0) { colsum[n] = s; cbias[n] = bias[n] + c; }
 }
 __global__ void finalize_J_kernel(const double* dots, const double* jobs, float coeff, double* out) {
   const double jr = 0.5 * dots[0];
@@ -198,6 +220,20 @@ static int build_blocks(vv_engine* e, WeightReader& R, std::vector<BlockW>& out,
     w.bqkv = dupload(e, bqkv); w.bproj = dupload(e, bproj); w.b1 = dupload(e, b1); w.b2 = dupload(e, b2);
     w.g1 = dupload(e, g1); w.be1 = dupload(e, be1); w.g2 = dupload(e, g2); w.be2 = dupload(e, be2);
     w.relbias = dupload(e, rb);
+    // norm1 folded into qkv, norm2 into fc1 (forward operands only)
+    w.sqkv = dalloc<float>(e, (size_t)G * 3 * d); w.cqkv = dalloc<float>(e, (size_t)G * 3 * d);
+    w.s1 = dalloc<float>(e, (size_t)G * 4 * d); w.c1 = dalloc<float>(e, (size_t)G * 4 * d);
+    if (!w.sqkv || !w.cqkv || !w.s1 || !w.c1) return -1;
+    for (int g = 0; g < G; ++g) {
+      const std::string p = stage_prefix[g] + ".blocks." + std::to_string(b);
+      const float* wq = R.dev(p + ".attn.qkv.weight", 3 * dd);
+      const float* w1 = R.dev(p + ".mlp.fc1.weight", 4 * dd);
+      if (!R.ok) return -2;
+      fold_ln_kernel<<<(3 * d + 7) / 8, 256>>>(w.Wqkv + g * 3 * dd, w.sqkv + (size_t)g * 3 * d, w.cqkv + (size_t)g * 3 * d, wq, w.g1 + (size_t)g * d,
+                                                w.be1 + (size_t)g * d, w.bqkv + (size_t)g * 3 * d, 3 * d, d, g_pack_f16);
+      fold_ln_kernel<<<(4 * d + 7) / 8, 256>>>(w.W1 + g * 4 * dd, w.s1 + (size_t)g * 4 * d, w.c1 + (size_t)g * 4 * d, w1, w.g2 + (size_t)g * d,
+                                                w.be2 + (size_t)g * d, w.b1 + (size_t)g * 4 * d, 4 * d, d, g_pack_f16);
+    }
   }
   return 0;
 }
@@ -339,6 +375,7 @@ static int finalize_net(vv_engine* e, Net& n) {
 struct Temps {
   bf16 *h, *ao, *a, *du, *dao, *dqkv, *dx1b;
   float *dh, *dx1;
+  float* lnst; size_t lnst_cap;      // LayerNorm statistics partials: float2 [batch][parts][rows]; capacity in float2
   // seams (forward)
   bf16 *MB, *EPIN, *TB, *CAT0, *CAT1, *U1B;
   float* NU;
@@ -367,7 +404,14 @@ struct Builder {
   void ln_f(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
             const float* gamma, const float* beta, bf16* ob, long long ld_ob, long long ob_bs, float* of, long long ld_of, long long of_bs) {
     Op o{}; o.kind = Op::LN_F;
-    o.lnf = LnArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, beta, (long long)C, ob, ld_ob, ob_bs, of, ld_of, of_bs, f16};
+    o.lnf = LnArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, beta, (long long)C, ob, ld_ob, ob_bs, of, ld_of, of_bs, f16, nullptr};
+    P.ops.push_back(o);
+  }
+  // statistics-only LayerNorm pass (raw 16-bit copy of x into t.h + (sum, sumsq) per row) for a stage input no GEMM produced
+  void ln_stats(Plan& P, int rows, int C, int batch, const float* x) {
+    const long long rd = (long long)rows * C;
+    Op o{}; o.kind = Op::LN_F;
+    o.lnf = LnArgs{rows, C, batch, MAP_PLAIN, 0, 0, 0.f, x, (long long)C, rd, nullptr, nullptr, 0, t.h, (long long)C, rd, nullptr, 0, 0, f16, t.lnst};
     P.ops.push_back(o);
   }
   void ln_b(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
@@ -378,31 +422,59 @@ struct Builder {
                       dx, ld_dx, dx_bs, dxb, ld_dxb, dxb_bs};
     P.ops.push_back(o);
   }
+  // GEMM whose fp32 output is the input of a LayerNorm folded into the NEXT GEMM: it also writes the raw 16-bit copy of its
+  // output rows (width C) into t.h and their (sum, sumsq) partials into t.lnst.  Returns the number of partials per row.
+  int gemm_with_stats(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g, int C) {
+    const char* dbg = getenv("VV_DBG");
+    if (!(dbg && strchr(dbg, 'c'))) { g.out_bf16 = t.h; g.ld_bf16 = C; g.bf16_bs = (long long)g.M * C; }
+    if (!(dbg && strchr(dbg, 's'))) g.stats_out = t.lnst;
+    gemm(P, A, lda, a_bs, B, ldb, b_bs, g);
+    GemmDesc& d = P.ops.back().gemm;
+    const int parts = 2 * ((g.N + d.bn - 1) / d.bn);
+    d.a.stats_out_bs = (long long)parts * g.M * 2;
+    if ((size_t)parts * g.M * g.batch > t.lnst_cap && !err) err = "LayerNorm statistics buffer too small";
+    return parts;
+  }
+  void fold_ln(GemmArgs& g, int parts, const float* colsum, int C, float eps) const {
+    const char* dbg = getenv("VV_DBG");
+    if (dbg && strchr(dbg, 'l')) return;
+    g.ln_stats = t.lnst; g.ln_parts = parts; g.ln_stats_bs = (long long)parts * g.M * 2; g.ln_colsum = colsum;
+    g.ln_inv_c = 1.0f / (float)C; g.ln_eps = eps;
+  }
 
   // SwinTransformerBlock.forward, swinblock.py:265-309
+  // norm1 / norm2 are folded into the qkv / fc1 GEMMs (GemmArgs::ln_stats): no LayerNorm launches inside a stage.
+  // parts: in = number of statistics partials already in t.lnst for `x` (0: none -- a statistics pass is issued);
+  //        out = partials for x_out if emit_next (the next block's norm1), else 0.
   void block_fwd(Plan& P, const BlockW& w, int gh, int gw, int shift, const float* x, float* x_out, BlkStash& st,
-                 bf16* copy_b, long long ld_c, long long bs_c) {
+                 bf16* copy_b, long long ld_c, long long bs_c, int& parts, bool emit_next) {
     const int G = w.G, d = w.d, rows = gh * gw;
     const long long rd = (long long)rows * d;
-    ln_f(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, w.be1, t.h, d, rd, nullptr, 0, 0);
+    if (parts == 0) { ln_stats(P, rows, d, G, x); parts = 1; }
     GemmArgs g = ga(rows, 3 * d, d, G);
-    g.bias = w.bqkv; g.bias_bs = 3 * d; g.out_bf16 = st.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd;
+    g.bias = w.cqkv; g.bias_bs = 3 * d; g.out_bf16 = st.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd;
+    fold_ln(g, parts, w.sqkv, d, 1e-5f);
     gemm(P, t.h, d, rd, w.Wqkv, d, 3LL * d * d, g);
     Op o{}; o.kind = Op::ATT_F;
     o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, t.ao, d, rd, nullptr, nullptr, f16};
     P.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = st.x1; g.ld_f32 = d; g.f32_bs = rd;
-    gemm(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g);
-    ln_f(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, w.be2, t.h, d, rd, nullptr, 0, 0);
+    const int parts2 = gemm_with_stats(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g, d);
     g = ga(rows, 4 * d, d, G);
-    g.epi = EPI_GELU; g.bias = w.b1; g.bias_bs = 4 * d; g.aux_out = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd;
+    g.epi = EPI_GELU; g.bias = w.c1; g.bias_bs = 4 * d; g.aux_out = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd;
     g.out_bf16 = t.a; g.ld_bf16 = 4 * d; g.bf16_bs = 4 * rd;
+    fold_ln(g, parts2, w.s1, d, 1e-5f);
     gemm(P, t.h, d, rd, w.W1, d, 4LL * d * d, g);
     g = ga(rows, d, 4 * d, G);
     g.bias = w.b2; g.bias_bs = d; g.res = st.x1; g.ld_res = d; g.res_bs = rd; g.out_f32 = x_out; g.ld_f32 = d; g.f32_bs = rd;
-    if (copy_b) { g.out_bf16 = copy_b; g.ld_bf16 = ld_c; g.bf16_bs = bs_c; }
-    gemm(P, t.a, 4 * d, 4 * rd, w.W2, 4 * d, 4LL * d * d, g);
+    if (emit_next) {
+      parts = gemm_with_stats(P, t.a, 4 * d, 4 * rd, w.W2, 4 * d, 4LL * d * d, g, d);
+    } else {
+      if (copy_b) { g.out_bf16 = copy_b; g.ld_bf16 = ld_c; g.bf16_bs = bs_c; }
+      gemm(P, t.a, 4 * d, 4 * rd, w.W2, 4 * d, 4LL * d * d, g);
+      parts = 0;
+    }
   }
   // Input-VJP of the block; the gradient (g32 fp32 + g16 bf16, [G][rows][d]) is updated in place.
   void block_bwd(Plan& P, const BlockW& w, int gh, int gw, int shift, const float* x, BlkStash& st, float* g32, bf16* g16) {
@@ -427,9 +499,10 @@ struct Builder {
     ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, t.dh, d, rd, t.dx1, d, rd, g32, d, rd, g16, d, rd);
   }
   void stage_fwd(Plan& P, const std::vector<BlockW>& ws, int gh, int gw, StageStash& st, bf16* copy_b, long long ld_c, long long bs_c) {
+    int parts = 0;
     for (size_t b = 0; b < ws.size(); ++b) {
       const bool last = b + 1 == ws.size();
-      block_fwd(P, ws[b], gh, gw, (b % 2) ? 2 : 0, st.x[b], st.x[b + 1], st.b[b], last ? copy_b : nullptr, ld_c, bs_c);
+      block_fwd(P, ws[b], gh, gw, (b % 2) ? 2 : 0, st.x[b], st.x[b + 1], st.b[b], last ? copy_b : nullptr, ld_c, bs_c, parts, !last);
     }
   }
   void stage_bwd(Plan& P, const std::vector<BlockW>& ws, int gh, int gw, StageStash& st, float* g32, bf16* g16) {
@@ -478,9 +551,10 @@ struct Builder {
   }
   void stage_fwd_trunk(Plan& P, Stash& S) {
     Net& N = *n;
+    int parts = 0;
     for (size_t b = 0; b < N.lg.size(); ++b) {
       const bool last = b + 1 == N.lg.size();
-      block_fwd(P, N.lg[b], N.h1, N.w1, shift_of_trunk(b), S.lg.x[b], S.lg.x[b + 1], S.lg.b[b], last ? t.TB : nullptr, N.E, 0);
+      block_fwd(P, N.lg[b], N.h1, N.w1, shift_of_trunk(b), S.lg.x[b], S.lg.x[b + 1], S.lg.b[b], last ? t.TB : nullptr, N.E, 0, parts, !last);
     }
   }
   int shift_of_trunk(size_t b) const {          // block index inside its Layer decides the shift (transformer.py:502)
@@ -583,6 +657,14 @@ static int alloc_temps(vv_engine* e, Temps& t) {
   t.MB = dalloc<bf16>(e, 4 * m_l1d); t.EPIN = dalloc<bf16>(e, m_l1gd); t.TB = dalloc<bf16>(e, m_l1e);
   t.CAT0 = dalloc<bf16>(e, 4 * m_l1d); t.CAT1 = dalloc<bf16>(e, 2 * m_l0d); t.U1B = dalloc<bf16>(e, 2 * m_l1d);
   t.NU = dalloc<float>(e, m_l0d);
+  {
+    size_t tower_rows = 0, trunk_rows = 0;
+    for (int k = 0; k < 2; ++k)
+      if (e->net[k].finalized) { tower_rows = std::max(tower_rows, (size_t)e->net[k].G * e->net[k].L0); trunk_rows = std::max(trunk_rows, (size_t)e->net[k].L1); }
+    t.lnst_cap = std::max(8 * tower_rows, 40 * trunk_rows);
+    t.lnst = dalloc<float>(e, 2 * t.lnst_cap);
+    if (!t.lnst) return -1;
+  }
   t.gU1 = dalloc<float>(e, m_l0d); t.gU1b = dalloc<bf16>(e, m_l0d);
   t.gU0 = dalloc<float>(e, 2 * m_l1d); t.gU0b = dalloc<bf16>(e, 2 * m_l1d);
   t.gT = dalloc<float>(e, m_l1e); t.gTb = dalloc<bf16>(e, m_l1e);
@@ -627,6 +709,20 @@ static int build_plans(vv_engine* e) {
       B.net_bwd(e->bwd[a], e->stash[a], e->Gb[a % 2], e->Gb[(a - 1) % 2]);
     }
     VV_CHECK(!B.err, "plan construction failed: %s", B.err);
+  }
+  // Chain the GEMMs in execution order (fwd[0..napp-1], then bwd[napp-1..0], wrapping around to the next evaluation): each
+  // one prefetches the weights of its successor into L2 while its own epilogue drains.
+  if (!getenv("VV_NO_WEIGHT_PREFETCH")) {
+    std::vector<GemmDesc*> chain;
+    for (int a = 0; a < napp; ++a)
+      for (Op& o : e->fwd[a].ops) if (o.kind == Op::GEMM) chain.push_back(&o.gemm);
+    for (int a = napp - 1; a >= 0; --a)
+      for (Op& o : e->bwd[a].ops) if (o.kind == Op::GEMM) chain.push_back(&o.gemm);
+    for (size_t i = 0; i < chain.size(); ++i) {
+      const GemmDesc* nx = chain[(i + 1) % chain.size()];
+      chain[i]->a.pf_ptr = nx->b_ptr;
+      chain[i]->a.pf_bytes = nx->b_ptr ? nx->b_bytes : 0;
+    }
   }
   e->plans_built = true;
   return 0;
@@ -1040,6 +1136,37 @@ VV_API int vv_test_gemm(const void* A, const void* B, const float* bias, const f
   GemmDesc d;
   const char* er = make_gemm_desc(&d, (const bf16*)A, K, (long long)M * K, (const bf16*)B, K, (long long)N * K, g);
   VV_CHECK(!er, "%s", er);
+  launch_gemm(d, (cudaStream_t)stream);
+  VV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Folded-LayerNorm GEMM hook: out = epi( LN(x) W^T + b ) computed as rstd (x W'^T - mean s) + c from the raw 16-bit x (A),
+// the folded operand W' (B), c (bias), s (colsum) and per-row (sum, sumsq) statistics [batch][parts][M] float2.  stats_out /
+// out_f32: when given, the GEMM also acts as a statistics producer for its fp32 output (partials [batch][2*n_tiles][M]).
+VV_API int vv_test_gemm_ln(const void* A, const void* B, const float* cbias, const float* colsum, const float* stats, int parts, int C,
+                    float eps, void* out_16, void* aux_16, float* out_f32, float* stats_out, int* parts_out, int M, int N, int K,
+                    int batch, int epi, void* stream) {
+  GemmArgs g{};
+  g.f16 = (epi >> 4) & 1; g.aux_f16 = g.f16;
+  epi &= 15;
+  g.M = M; g.N = N; g.K = K; g.batch = batch; g.epi = epi;
+  g.bias = cbias; g.bias_bs = N;
+  if (stats) {
+    g.ln_stats = stats; g.ln_parts = parts; g.ln_stats_bs = (long long)parts * M * 2; g.ln_colsum = colsum;
+    g.ln_inv_c = 1.0f / (float)C; g.ln_eps = eps;
+  }
+  if (epi == EPI_GELU) g.aux_out = (bf16*)aux_16;
+  g.ld_aux = N; g.aux_bs = (long long)M * N;
+  g.out_bf16 = (bf16*)out_16; g.ld_bf16 = N; g.bf16_bs = (long long)M * N;
+  g.out_f32 = out_f32; g.ld_f32 = N; g.f32_bs = (long long)M * N;
+  g.stats_out = stats_out;
+  GemmDesc d;
+  const char* er = make_gemm_desc(&d, (const bf16*)A, K, (long long)M * K, (const bf16*)B, K, (long long)N * K, g);
+  VV_CHECK(!er, "%s", er);
+  const int po = 2 * ((N + d.bn - 1) / d.bn);
+  d.a.stats_out_bs = (long long)po * M * 2;
+  if (parts_out) *parts_out = po;
   launch_gemm(d, (cudaStream_t)stream);
   VV_CUDA(cudaGetLastError());
   return 0;

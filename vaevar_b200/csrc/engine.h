@@ -30,6 +30,7 @@ struct BlockW {
   bf16 *Wqkv = nullptr, *WqkvT = nullptr, *Wproj = nullptr, *WprojT = nullptr, *W1 = nullptr, *W1T = nullptr, *W2 = nullptr, *W2T = nullptr;
   float *bqkv = nullptr, *bproj = nullptr, *b1 = nullptr, *b2 = nullptr, *g1 = nullptr, *be1 = nullptr, *g2 = nullptr, *be2 = nullptr;
   float* relbias = nullptr;
+  float *sqkv = nullptr, *cqkv = nullptr, *s1 = nullptr, *c1 = nullptr;   // LayerNorm folded into qkv / fc1: column sums, folded biases
 };
 struct BlkStash {
   bf16* qkv; float* x1; bf16* u;

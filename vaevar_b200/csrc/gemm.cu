@@ -93,7 +93,12 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   if (args.split_n > 0 && args.split_n % GEMM_EC) return "GEMM split_n must be a multiple of 32";
   if (args.epi == EPI_GELU && args.aux_out && args.out_f32) return "GEMM: fp32 output together with a saved pre-activation is not supported";
   if (args.epi == EPI_DGELU && args.res) return "GEMM: GELU' epilogue with a residual is not supported";
+  if (args.epi == EPI_DGELU && (args.ln_stats || args.stats_out)) return "GEMM: GELU' epilogue with LayerNorm folding is not supported";
   d->a = args;
+  const bool b_contig = ldb == args.K && (args.batch == 1 || b_bs == (long long)args.N * args.K);
+  d->b_ptr = b_contig ? B : nullptr;
+  d->b_bytes = b_contig ? (unsigned long long)args.N * args.K * args.batch * 2 : 0;
+  d->a.pf_ptr = nullptr; d->a.pf_bytes = 0;
   d->a.trace = g_gemm_trace;
   d->a.debug_mode = g_gemm_debug_mode;
   d->bn = pick_bn(args.M, args.N, args.batch);
@@ -120,32 +125,33 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   return nullptr;
 }
 
-template <int BN, int STAGES, bool F16>
+template <int BN, int STAGES, bool F16, bool LNX>
 static void launch_pair(const GemmDesc& d, cudaStream_t s) {
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_pair_kernel<BN, STAGES, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaFuncSetAttribute(gemm_pair_kernel<BN, STAGES, F16, LNX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     attr_set = true;
   }
   const long long tiles = (long long)((d.a.N + BN - 1) / BN) * ((d.a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * d.a.batch;
   const int pairs = (int)std::min<long long>(tiles, num_sms() / 2);
-  launch_kernel(gemm_pair_kernel<BN, STAGES, F16>, dim3(2 * pairs), dim3(GEMM_THREADS), L::TOTAL, s, d.tmA, d.tmB, d.sm, d.a);
+  launch_kernel(gemm_pair_kernel<BN, STAGES, F16, LNX>, dim3(2 * pairs), dim3(GEMM_THREADS), L::TOTAL, s, d.tmA, d.tmB, d.sm, d.a);
 }
 
-template <bool F16>
+template <bool F16, bool LNX>
 static void launch_f(const GemmDesc& d, cudaStream_t s) {
   switch (d.bn) {
-    case 64: launch_pair<64, 6, F16>(d, s); break;
-    case 192: launch_pair<192, 4, F16>(d, s); break;
-    case 256: launch_pair<256, 4, F16>(d, s); break;
-    default: launch_pair<128, 5, F16>(d, s); break;
+    case 64: launch_pair<64, 6, F16, LNX>(d, s); break;
+    case 192: launch_pair<192, 4, F16, LNX>(d, s); break;
+    case 256: launch_pair<256, 4, F16, LNX>(d, s); break;
+    default: launch_pair<128, 5, F16, LNX>(d, s); break;
   }
 }
 
 void launch_gemm(const GemmDesc& d, cudaStream_t s) {
-  if (d.a.f16) launch_f<true>(d, s);
-  else launch_f<false>(d, s);
+  const bool lnx = d.a.ln_stats != nullptr || d.a.stats_out != nullptr;     // forward pass only (DGELU is never combined with it)
+  if (d.a.f16) { if (lnx) launch_f<true, true>(d, s); else launch_f<true, false>(d, s); }
+  else { if (lnx) launch_f<false, true>(d, s); else launch_f<false, false>(d, s); }
 }
 
 }  // namespace vv

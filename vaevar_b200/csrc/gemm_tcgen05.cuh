@@ -24,8 +24,8 @@ namespace vv {
 
 enum GemmEpi : int {
   EPI_LINEAR = 0,  // v = acc + bias
-  EPI_GELU = 1,    // u = acc + bias ; aux_out = 16bit(u) ; v = gelu(u)
-  EPI_DGELU = 2,   // v = acc * gelu'(aux_in)
+  EPI_GELU = 1,    // u = acc + bias ; aux_out = 16bit(gelu'(u)) ; v = gelu(u)
+  EPI_DGELU = 2,   // v = acc * aux_in   (aux_in = the gelu'(u) the forward GEMM saved)
 };
 
 struct GemmArgs {
@@ -37,8 +37,8 @@ struct GemmArgs {
   long long bias_bs;
   const float* res;           // fp32 residual added to v, [batch][M][ld_res] or null
   long long ld_res, res_bs;
-  const __nv_bfloat16* aux_in;  // EPI_DGELU: saved pre-activation u (16-bit storage, format aux_f16)
-  __nv_bfloat16* aux_out;       // EPI_GELU: where to save u (16-bit storage, format f16)
+  const __nv_bfloat16* aux_in;  // EPI_DGELU: saved gelu'(u) (16-bit storage, format aux_f16)
+  __nv_bfloat16* aux_out;       // EPI_GELU: where to save gelu'(u) (16-bit storage, format f16)
   long long ld_aux, aux_bs;
   float* out_f32;             // optional fp32 output
   long long ld_f32, f32_bs;
@@ -46,6 +46,19 @@ struct GemmArgs {
   long long ld_bf16, bf16_bs;
   int split_n;                // >0: 16-bit output column n goes to block n / split_n (stride split_stride), column n % split_n
   long long split_stride;
+  // LayerNorm folded into the GEMM (forward pass).  With W' = W o gamma, s_n = sum_k W'[n,k], c_n = b_n + sum_k beta_k W[n,k]:
+  //   LN(x) W^T + b = rstd_r (x W'^T - mean_r s_n) + c_n
+  // so the GEMM runs on the RAW 16-bit copy of x and the epilogue applies the per-row (mean, rstd) it derives from the
+  // (sum, sum of squares) partials a PRODUCER GEMM (or the stats kernel) left in ln_stats; c_n travels as `bias`.
+  const float* ln_stats;      // consumer: [batch][ln_parts][M] float2 (sum, sumsq) partials of the A rows; null = plain GEMM
+  int ln_parts;
+  long long ln_stats_bs;      // batch stride in floats
+  const float* ln_colsum;     // consumer: s_n, [batch][N] (batch stride = bias_bs)
+  float ln_inv_c, ln_eps;     // 1 / row length of the normalised rows, epsilon
+  float* stats_out;           // producer: [batch][2 * n_tiles][M] float2 partials of the rows of the fp32 output; null = none
+  long long stats_out_bs;     // batch stride in floats
+  const void* pf_ptr;         // weights of the NEXT GEMM in the plan: prefetched into L2 by the idle producer warp (null = none)
+  unsigned long long pf_bytes;
   int debug_mode;             // debug: 0 normal; 1 MMA only (no TMA, operands = whatever is in smem); 2 TMA only (no MMA)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (64 slots per CTA, see tools/gemm_trace.py); null in production
 };
@@ -97,9 +110,11 @@ VV_DEVINL float2 unpack16(uint32_t w, bool f16) {
 
 // One 32-row x 32-column chunk of the epilogue, executed by one warp (thread = row).  r[] holds the fp32 accumulators,
 // bv[] the bias of the 32 columns; slot A / slot B are this warp's staging slabs (see GEMM_SLOT_*).
-template <int EPI, bool F16>
+// ln_a scales the accumulator (the row's rstd when a LayerNorm is folded into this GEMM, else 1); rs / rq accumulate the
+// row's sum and sum of squares of the final fp32 values when this GEMM produces LayerNorm statistics for its consumer.
+template <int EPI, bool F16, bool LNX>
 VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float (&bv)[32], uint8_t* SA, uint8_t* SB, int lane,
-                              bool has_res, bool has_auxin, bool has_auxout) {
+                              bool has_res, bool has_auxin, bool has_auxout, float ln_a, float& rs, float& rq) {
   const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // 128B swizzle: 16-byte chunk c of row r lives at c ^ (r & 7)
   const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);    // 64B swizzle: chunk c of row r lives at c ^ ((r >> 1) & 3)
   uint8_t* rowA = SA + lane * 128;
@@ -109,24 +124,27 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
   for (int g = 0; g < 4; ++g) {                                    // 4 groups of 8 columns
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) + bv[g * 8 + i];
+    for (int i = 0; i < 8; ++i)
+      v[i] = LNX ? fmaf(ln_a, __uint_as_float(r[g * 8 + i]), bv[g * 8 + i]) : __uint_as_float(r[g * 8 + i]) + bv[g * 8 + i];
     uint4 u16 = make_uint4(0, 0, 0, 0);
     if (EPI == EPI_GELU) {
-      if (has_auxout) {
-        u16.x = pack16<F16>(v[0], v[1]); u16.y = pack16<F16>(v[2], v[3]);
-        u16.z = pack16<F16>(v[4], v[5]); u16.w = pack16<F16>(v[6], v[7]);
-      }
+      if (has_auxout) {                      // gelu and gelu' share their transcendental work; the backward pass needs only gelu'(u)
+        float d[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 8; ++i) gelu_erf_both(v[i], &v[i], &d[i]);
+        u16.x = pack16<F16>(d[0], d[1]); u16.y = pack16<F16>(d[2], d[3]);
+        u16.z = pack16<F16>(d[4], d[5]); u16.w = pack16<F16>(d[6], d[7]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+      }
     } else if (EPI == EPI_DGELU) {
-      if (has_auxin) {
+      if (has_auxin) {                       // aux = gelu'(u) saved by the forward GEMM
         const uint4 w = *reinterpret_cast<const uint4*>(rowB + ((static_cast<uint32_t>(g) ^ sw64) << 4));
         const bool af = p.aux_f16 != 0;
         const float2 u0 = unpack16(w.x, af), u1 = unpack16(w.y, af), u2 = unpack16(w.z, af), u3 = unpack16(w.w, af);
-        v[0] *= gelu_erf_grad(u0.x); v[1] *= gelu_erf_grad(u0.y);
-        v[2] *= gelu_erf_grad(u1.x); v[3] *= gelu_erf_grad(u1.y);
-        v[4] *= gelu_erf_grad(u2.x); v[5] *= gelu_erf_grad(u2.y);
-        v[6] *= gelu_erf_grad(u3.x); v[7] *= gelu_erf_grad(u3.y);
+        v[0] *= u0.x; v[1] *= u0.y; v[2] *= u1.x; v[3] *= u1.y;
+        v[4] *= u2.x; v[5] *= u2.y; v[6] *= u3.x; v[7] *= u3.y;
       }
     }
     const uint32_t cA0 = (static_cast<uint32_t>(2 * g) ^ sw128) << 4, cA1 = (static_cast<uint32_t>(2 * g + 1) ^ sw128) << 4;
@@ -135,6 +153,10 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
       const float4 r1 = *reinterpret_cast<const float4*>(rowA + cA1);
       v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
       v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+    if (LNX && p.stats_out) {                 // two independent partial chains per statistic
+      rs += (v[0] + v[1]) + (v[2] + v[3]) + ((v[4] + v[5]) + (v[6] + v[7]));
+      rq += fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3]) + (fmaf(v[4], v[4], v[5] * v[5]) + fmaf(v[6], v[6], v[7] * v[7]));
     }
     if (p.out_f32) {
       *reinterpret_cast<float4*>(rowA + cA0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -150,7 +172,9 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
   }
 }
 
-template <int BN, int STAGES, bool F16>
+// LNX: the instantiation that can fold a LayerNorm into the epilogue (consumer: ln_stats) and / or emit LayerNorm statistics of
+// its fp32 output (producer: stats_out); the plain instantiation carries none of that code.
+template <int BN, int STAGES, bool F16, bool LNX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GemmStoreMaps io, const GemmArgs p) {
@@ -236,6 +260,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    // All operand loads of this CTA are in flight: use the idle producer warp to pull this CTA's slice of the NEXT GEMM's
+    // weights from HBM into L2 (the 0.43 GB of weights per network never stay in the 126 MB L2 from one evaluation to the
+    // next, so without this every GEMM starts on a DRAM-latency-bound pipeline fill).
+    if (p.pf_ptr) {
+      constexpr unsigned long long CH = 4096;
+      const unsigned long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
+      const unsigned long long beg = (unsigned long long)blockIdx.x * per;
+      const unsigned long long end = beg + per < p.pf_bytes ? beg + per : p.pf_bytes;
+      for (unsigned long long o = beg + lane * CH; o < end; o += 32 * CH) {
+        const unsigned long long n = end - o < CH ? (end - o) & ~15ull : CH;
+        if (n) l2_prefetch_bulk(static_cast<const uint8_t*>(p.pf_ptr) + o, (uint32_t)n);
+      }
+    }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA) =====
     if (rank == 0) {
@@ -297,14 +334,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_loads = has_res || has_auxin;
     const uint32_t load_bytes = (has_res ? GEMM_SLOT_A : 0) + (has_auxin ? GEMM_SLOT_B : 0);
 
-    // (tile, chunk) -> coordinates; nch = number of chunks of the tile this warp's rows take part in
-    auto tile_geom = [&](int tile, int& n0, int& mrow, int& b, int& nch) {
-      const int nt = tile % n_tiles, rest = tile / n_tiles, mp = rest % pair_rows;
-      b = rest / pair_rows;
-      mrow = (2 * mp + (int)rank) * GEMM_BM + q * 32;
-      n0 = nt * BN;
-      const int ncol = min(BN, p.N - n0);
-      nch = mrow < p.M ? (ncol + GEMM_EC - 1) / GEMM_EC : 0;
+    // Tile coordinates advance incrementally (the persistent stride num_pairs decomposed once into (nt, mp, b) steps): no
+    // integer divisions per tile -- the small-K tower GEMMs run ~13 tiles of ~1 us per CTA, where they were a visible cost.
+    struct Coord { int tile, nt, mp, b; };
+    const int step_nt = num_pairs % n_tiles, step_mp = (num_pairs / n_tiles) % pair_rows, step_b = num_pairs / (n_tiles * pair_rows);
+    auto advance = [&](Coord& c) {
+      c.tile += num_pairs;
+      c.nt += step_nt;
+      int carry = 0;
+      if (c.nt >= n_tiles) { c.nt -= n_tiles; carry = 1; }
+      c.mp += step_mp + carry;
+      carry = 0;
+      if (c.mp >= pair_rows) { c.mp -= pair_rows; carry = 1; }
+      c.b += step_b + carry;
+    };
+    auto row0_of = [&](const Coord& c) { return (2 * c.mp + (int)rank) * GEMM_BM + q * 32; };
+    // number of 32-column chunks of the tile this warp's rows take part in
+    auto nch_of = [&](const Coord& c) {
+      const int ncol = min(BN, p.N - c.nt * BN);
+      return row0_of(c) < p.M ? (ncol + GEMM_EC - 1) / GEMM_EC : 0;
     };
     auto issue_loads = [&](int col, int mrow, int b, int buf) {        // the elected lane only
       tma_store_wait_read0();                                          // the store that last read this buffer is done with it
@@ -312,28 +360,62 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (has_res) tma_load_3d(slab + buf * GEMM_BUF, &io.res, &ldbar[buf], col, mrow, b);
       if (has_auxin) tma_load_3d(slab + buf * GEMM_BUF + GEMM_SLOT_A, &io.aux_in, &ldbar[buf], col, mrow, b);
     };
-    // first chunk of this warp at or after `tile` (chunks of a tile: half, half+2, ...)
-    auto first_chunk_from = [&](int tile, int& n0, int& mrow, int& b) -> int {
-      for (; tile < total_tiles; tile += num_pairs) {
-        int nch;
-        tile_geom(tile, n0, mrow, b, nch);
-        if (half < nch) return tile;
-      }
-      return -1;
-    };
 
+    // folded LayerNorm: the first six (sum, sumsq) partials of this thread's row, fetched one tile ahead (a dependent global
+    // round trip per tile would dominate the small-K tower GEMMs)
+    float2 stat_nx[6];
+    const float2* stats2 = reinterpret_cast<const float2*>(p.ln_stats);
+    const long long stats_bs2 = p.ln_stats_bs >> 1;
+    auto load_stats = [&](const Coord& c) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) stat_nx[j] = make_float2(0.f, 0.f);
+      if (c.tile >= total_tiles) return;
+      const int row = row0_of(c) + lane;
+      if (row >= p.M) return;
+      const float2* st = stats2 + c.b * stats_bs2 + row;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        if (j < p.ln_parts) stat_nx[j] = __ldg(st + j * p.M);
+    };
+    Coord cur{pair, pair % n_tiles, (pair / n_tiles) % pair_rows, pair / (n_tiles * pair_rows)};
+    const bool ln_on = LNX && p.ln_stats != nullptr;
+    if (ln_on) load_stats(cur);
     uint32_t it = 0;
-    if (has_loads) {
-      int n0, mrow, b;
-      if (first_chunk_from(pair, n0, mrow, b) >= 0 && elect_one()) issue_loads(n0 + half * GEMM_EC, mrow, b, 0);
+    bool pre_issued = false;                                 // the loads of this warp's first chunk of the coming tile are in flight
+    if (has_loads && cur.tile < total_tiles && half < nch_of(cur)) {
+      if (elect_one()) issue_loads(cur.nt * BN + half * GEMM_EC, row0_of(cur), cur.b, 0);
       __syncwarp();
+      pre_issued = true;
     }
     uint32_t ti = 0;
-    for (int tile = pair; tile < total_tiles; tile += num_pairs, ++ti) {
-      int n0, mrow, b, nch;
-      tile_geom(tile, n0, mrow, b, nch);
+    for (; cur.tile < total_tiles; ++ti) {
+      const int tile = cur.tile, b = cur.b, n0 = cur.nt * BN, mrow = row0_of(cur), nch = nch_of(cur);
+      Coord nxt = cur;
+      advance(nxt);
       const uint32_t acc = ti & 1;
       const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
+      const float* colsum = ln_on ? p.ln_colsum + (long long)b * p.bias_bs : nullptr;
+      float ln_a = 1.f, ln_b = 0.f, rs = 0.f, rq = 0.f;
+      if (ln_on) {                                 // this thread's row: mean / rstd from the producer's partial sums
+        float sm = 0.f, sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { sm += stat_nx[j].x; sq += stat_nx[j].y; }
+        if (p.ln_parts > 6 && nch > 0 && mrow + lane < p.M) {
+          const float2* st = stats2 + b * stats_bs2 + mrow + lane;
+          for (int q0 = 6; q0 < p.ln_parts; q0 += 6) {                     // six independent loads in flight per round trip
+            float2 t2[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) t2[j] = q0 + j < p.ln_parts ? __ldg(st + (q0 + j) * p.M) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { sm += t2[j].x; sq += t2[j].y; }
+          }
+        }
+        load_stats(nxt);                           // the next tile's partials travel while this tile is processed
+        const float mean = sm * p.ln_inv_c;
+        const float var = fmaxf(fmaf(sq, p.ln_inv_c, -mean * mean), 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = ln_a * mean;
+      }
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
       if (trc && ew == 0 && lane == 0 && ti < 2) trc[6 + ti] = clock64();
@@ -347,37 +429,52 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[32];
         __syncwarp();
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * GEMM_EC, r);
-        // (2) bias of the 32 columns (warp-uniform addresses; in flight together with the TMEM load)
+        // (2) bias (and, for a folded LayerNorm, the column sums) of the 32 columns: warp-uniform addresses, every load into its
+        //     own registers and all of them in flight together with the TMEM load
         float bv[32];
+        float4 svv[LNX ? 8 : 1];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias && col + 4 * j < p.N) t = __ldg(reinterpret_cast<const float4*>(bias + col + 4 * j));
           bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+          if (LNX) {
+            svv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (colsum && col + 4 * j < p.N) svv[j] = __ldg(reinterpret_cast<const float4*>(colsum + col + 4 * j));
+          }
         }
         // (3) prefetch the residual / pre-activation of this warp's NEXT chunk into the other buffer
         if (has_loads) {
+          if (c == half && !pre_issued) {                              // (rare) nobody prefetched this tile's first chunk
+            if (elect_one()) issue_loads(col, mrow, b, buf);
+          }
+          pre_issued = false;
           if (c + 2 < nch) {
             if (elect_one()) issue_loads(col + 2 * GEMM_EC, mrow, b, buf ^ 1);
-          } else {
-            int n0x, mrowx, bx;
-            if (first_chunk_from(tile + num_pairs, n0x, mrowx, bx) >= 0 && elect_one()) issue_loads(n0x + half * GEMM_EC, mrowx, bx, buf ^ 1);
+          } else if (nxt.tile < total_tiles && half < nch_of(nxt)) {
+            if (elect_one()) issue_loads(nxt.nt * BN + half * GEMM_EC, row0_of(nxt), nxt.b, buf ^ 1);
+            pre_issued = true;
           }
         } else {
           if (elect_one()) tma_store_wait_read1();                     // the store issued two chunks ago has read this buffer
         }
         __syncwarp();
         tmem_ld_wait();
+        if (LNX && colsum) {                                             // folded LayerNorm: c_n - rstd mean s_n
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            bv[4 * j] = fmaf(-ln_b, svv[j].x, bv[4 * j]); bv[4 * j + 1] = fmaf(-ln_b, svv[j].y, bv[4 * j + 1]);
+            bv[4 * j + 2] = fmaf(-ln_b, svv[j].z, bv[4 * j + 2]); bv[4 * j + 3] = fmaf(-ln_b, svv[j].w, bv[4 * j + 3]);
+          }
+        }
         if (has_loads) {
           mbar_wait(&ldbar[buf], (ld_phase >> buf) & 1);
           ld_phase ^= 1u << buf;
         }
         // (4) fused math, results staged in place
-        switch (p.epi) {
-          case EPI_GELU: epilogue_chunk<EPI_GELU, F16>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout); break;
-          case EPI_DGELU: epilogue_chunk<EPI_DGELU, F16>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout); break;
-          default: epilogue_chunk<EPI_LINEAR, F16>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout); break;
-        }
+        if (p.epi == EPI_GELU) epilogue_chunk<EPI_GELU, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
+        else if (!LNX && p.epi == EPI_DGELU) epilogue_chunk<EPI_DGELU, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
+        else epilogue_chunk<EPI_LINEAR, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
         // (5) bulk stores
         fence_proxy_async();
         __syncwarp();
@@ -391,11 +488,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
+      if (LNX && p.stats_out && mrow + lane < p.M) {      // partial (sum, sumsq) of this warp's columns of the row; zeros if it had none
+        float2* so = reinterpret_cast<float2*>(p.stats_out + (long long)b * p.stats_out_bs);
+        so[(long long)(2 * cur.nt + half) * p.M + mrow + lane] = make_float2(rs, rq);
+      }
       // this warp no longer needs accumulator stage `acc`: tell the leader's MMA thread
       tc_fence_before();
       __syncwarp();
       if (elect_one()) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
       if (trc && ew == 0 && lane == 0 && ti < 2) trc[8 + ti] = clock64();
+      (void)tile;
+      cur = nxt;
     }
     if (elect_one()) tma_store_wait_read0();          // the staging slabs must outlive the bulk stores that read them
     __syncwarp();

@@ -37,171 +37,152 @@ VV_DEVINL long long ln_elem_off(int r, int c, int C, int gw, long long ld) {
   }
 }
 
-// Each lane owns NPL = C/32 elements of the row as NPL/VEC vectors of VEC consecutive floats:
-// element (k, v) = column VEC*(lane + 32*k) + v, so every warp-wide access is one contiguous 128*VEC-byte segment.
-template <int VEC> struct VecT;
-template <> struct VecT<1> { typedef float T; };
-template <> struct VecT<2> { typedef float2 T; };
-template <> struct VecT<4> { typedef float4 T; };
-
-template <int VEC>
-VV_DEVINL void ldv(float* dst, const float* src) {
-  typename VecT<VEC>::T t = *reinterpret_cast<const typename VecT<VEC>::T*>(src);
-  const float* f = reinterpret_cast<const float*>(&t);
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) dst[v] = f[v];
-}
-template <int VEC>
-VV_DEVINL void stv(float* dst, const float* src) {
-  typename VecT<VEC>::T t;
-  float* f = reinterpret_cast<float*>(&t);
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) f[v] = src[v];
-  *reinterpret_cast<typename VecT<VEC>::T*>(dst) = t;
-}
+// A row of C floats is owned by LANES lanes (8, 16 or 32: 4, 2 or 1 rows per warp); each lane holds NV float4 vectors,
+// vector k of lane l = columns 4*(l + LANES*k) .. +3, so every access of the sub-warp is one contiguous 16*LANES-byte segment.
+// Narrow rows (C = 96 / 192 of the towers) thus still move 16 bytes per lane per access instead of 4.
 VV_DEVINL uint32_t pack16_rt(float a, float b, bool f16) { return f16 ? pack16<true>(a, b) : pack16<false>(a, b); }
-template <int VEC>
-VV_DEVINL void stv_16(bf16* dst, const float* src, bool f16) {
-  if (VEC == 1) {
-    if (f16) *reinterpret_cast<uint16_t*>(dst) = static_cast<uint16_t>(pack16<true>(src[0], 0.f));
-    else dst[0] = __float2bfloat16(src[0]);
-  } else if (VEC == 2) {
-    *reinterpret_cast<uint32_t*>(dst) = pack16_rt(src[0], src[1], f16);
-  } else {
-    uint2 w;
-    w.x = pack16_rt(src[0], src[1], f16);
-    w.y = pack16_rt(src[2], src[3], f16);
-    *reinterpret_cast<uint2*>(dst) = w;
-  }
+VV_DEVINL void st4_16(bf16* dst, const float4& v, bool f16) {
+  uint2 w;
+  w.x = pack16_rt(v.x, v.y, f16);
+  w.y = pack16_rt(v.z, v.w, f16);
+  *reinterpret_cast<uint2*>(dst) = w;
+}
+template <int LANES>
+VV_DEVINL float row_sum(float v) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-template <int NPL, int VEC, int MAP>
+template <int LANES, int NV, int MAP>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
-  constexpr int NV = NPL / VEC;
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31, sl = lane % LANES;
+  const int r = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LANES;
   const int b = blockIdx.y;
   pdl_launch_dependents();
   pdl_wait();
-  if (r >= a.rows) return;
+  const bool live = r < a.rows;                    // dead rows still take part in the shuffles
+  const int rr = live ? r : a.rows - 1;
   const float* x = a.x + (long long)b * a.x_bs;
-  float v[NPL];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    ldv<VEC>(v + k * VEC, x + ln_elem_off<MAP>(r, VEC * (lane + 32 * k), a.C, a.gw, a.ld_x));
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s += v[k * VEC + i];
+    v[k] = *reinterpret_cast<const float4*>(x + ln_elem_off<MAP>(rr, 4 * (sl + LANES * k), a.C, a.gw, a.ld_x));
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
   }
-  const float mean = warp_sum(s) / a.C;
+  const float mean = row_sum<LANES>(s) / a.C;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    const float d = v[k] - mean;
-    q += d * d;
+  for (int k = 0; k < NV; ++k) {
+    const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+    q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
   }
-  const float rstd = rsqrtf(warp_sum(q) / a.C + a.eps);
+  const float qc = row_sum<LANES>(q);
+  if (!live) return;
+  if (a.stats_out) {                               // statistics-only mode: raw 16-bit copy + (sum, sumsq) of the row
+    if (sl == 0)
+      reinterpret_cast<float2*>(a.stats_out)[(long long)b * a.rows + r] = make_float2(mean * a.C, fmaf(mean * a.C, mean, qc));
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      st4_16(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + 4 * (sl + LANES * k), v[k], a.out_f16 != 0);
+    return;
+  }
+  const float rstd = rsqrtf(qc / a.C + a.eps);
   const float* g = a.gamma + (long long)b * a.gb_bs;
   const float* be = a.beta + (long long)b * a.gb_bs;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const int c = VEC * (lane + 32 * k);
-    float gg[VEC], bb[VEC], y[VEC];
-    ldv<VEC>(gg, g + c);
-    ldv<VEC>(bb, be + c);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) y[i] = (v[k * VEC + i] - mean) * rstd * gg[i] + bb[i];
-    if (a.out_bf16) stv_16<VEC>(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + c, y, a.out_f16 != 0);
-    if (a.out_f32) stv<VEC>(a.out_f32 + (long long)b * a.of_bs + (long long)r * a.ld_of + c, y);
+    const int c = 4 * (sl + LANES * k);
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c)), bb = __ldg(reinterpret_cast<const float4*>(be + c));
+    float4 y;
+    y.x = (v[k].x - mean) * rstd * gg.x + bb.x; y.y = (v[k].y - mean) * rstd * gg.y + bb.y;
+    y.z = (v[k].z - mean) * rstd * gg.z + bb.z; y.w = (v[k].w - mean) * rstd * gg.w + bb.w;
+    if (a.out_bf16) st4_16(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + c, y, a.out_f16 != 0);
+    if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + (long long)b * a.of_bs + (long long)r * a.ld_of + c) = y;
   }
 }
 
-template <int NPL, int VEC, int MAP>
+template <int LANES, int NV, int MAP>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
-  constexpr int NV = NPL / VEC;
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31, sl = lane % LANES;
+  const int r = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LANES;
   const int b = blockIdx.y;
   pdl_launch_dependents();
   pdl_wait();
-  if (r >= a.rows) return;
+  const bool live = r < a.rows;
+  const int rr = live ? r : a.rows - 1;
   const float* x = a.x + (long long)b * a.x_bs;
-  const float* dy = a.dy + (long long)b * a.dy_bs + (long long)r * a.ld_dy;
+  const float* dy = a.dy + (long long)b * a.dy_bs + (long long)rr * a.ld_dy;
   const float* g = a.gamma + (long long)b * a.gb_bs;
-  float v[NPL], gd[NPL];
+  float4 v[NV], gd[NV], rs[NV];
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    ldv<VEC>(v + k * VEC, x + ln_elem_off<MAP>(r, VEC * (lane + 32 * k), a.C, a.gw, a.ld_x));
-    ldv<VEC>(gd + k * VEC, dy + VEC * (lane + 32 * k));
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s += v[k * VEC + i];
+    const int c = 4 * (sl + LANES * k);
+    v[k] = *reinterpret_cast<const float4*>(x + ln_elem_off<MAP>(rr, c, a.C, a.gw, a.ld_x));
+    gd[k] = *reinterpret_cast<const float4*>(dy + c);
+    if (a.dres) rs[k] = *reinterpret_cast<const float4*>(a.dres + (long long)b * a.dres_bs + ln_elem_off<MAP>(rr, c, a.C, a.gw, a.ld_dres));
+    else rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
   }
-  const float mean = warp_sum(s) / a.C;
+  const float mean = row_sum<LANES>(s) / a.C;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < NPL; ++k) {
-    v[k] -= mean;
-    q += v[k] * v[k];
+  for (int k = 0; k < NV; ++k) {
+    v[k].x -= mean; v[k].y -= mean; v[k].z -= mean; v[k].w -= mean;
+    q += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
   }
-  const float rstd = rsqrtf(warp_sum(q) / a.C + a.eps);
+  const float rstd = rsqrtf(row_sum<LANES>(q) / a.C + a.eps);
   float m1 = 0.f, m2 = 0.f;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    float gg[VEC];
-    ldv<VEC>(gg, g + VEC * (lane + 32 * k));
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const int e = k * VEC + i;
-      v[e] *= rstd;                     // xhat
-      gd[e] *= gg[i];
-      m1 += gd[e];
-      m2 += gd[e] * v[e];
-    }
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + 4 * (sl + LANES * k)));
+    v[k].x *= rstd; v[k].y *= rstd; v[k].z *= rstd; v[k].w *= rstd;                  // xhat
+    gd[k].x *= gg.x; gd[k].y *= gg.y; gd[k].z *= gg.z; gd[k].w *= gg.w;
+    m1 += (gd[k].x + gd[k].y) + (gd[k].z + gd[k].w);
+    m2 += gd[k].x * v[k].x + gd[k].y * v[k].y + gd[k].z * v[k].z + gd[k].w * v[k].w;
   }
-  m1 = warp_sum(m1) / a.C;
-  m2 = warp_sum(m2) / a.C;
+  m1 = row_sum<LANES>(m1) / a.C;
+  m2 = row_sum<LANES>(m2) / a.C;
+  if (!live) return;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const int c = VEC * (lane + 32 * k);
-    float d[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) d[i] = (gd[k * VEC + i] - m1 - v[k * VEC + i] * m2) * rstd;
-    if (a.dres) {
-      float rr[VEC];
-      ldv<VEC>(rr, a.dres + (long long)b * a.dres_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dres));
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) d[i] += rr[i];
-    }
-    stv<VEC>(a.dx + (long long)b * a.dx_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dx), d);
-    if (a.dx_bf16) stv_16<VEC>(a.dx_bf16 + (long long)b * a.dxb_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dxb), d, false);
+    const int c = 4 * (sl + LANES * k);
+    float4 d;
+    d.x = (gd[k].x - m1 - v[k].x * m2) * rstd + rs[k].x; d.y = (gd[k].y - m1 - v[k].y * m2) * rstd + rs[k].y;
+    d.z = (gd[k].z - m1 - v[k].z * m2) * rstd + rs[k].z; d.w = (gd[k].w - m1 - v[k].w * m2) * rstd + rs[k].w;
+    *reinterpret_cast<float4*>(a.dx + (long long)b * a.dx_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dx)) = d;
+    if (a.dx_bf16) st4_16(a.dx_bf16 + (long long)b * a.dxb_bs + ln_elem_off<MAP>(r, c, a.C, a.gw, a.ld_dxb), d, false);
   }
 }
 
+// key = map * 1000 + C / 4 (float4 vectors per row)
+#define VV_LN_CASE(KERNEL, ARGS, LANES, NV, MAP)                                                          \
+  launch_kernel(KERNEL<LANES, NV, MAP>, dim3((ARGS.rows + 8 * (32 / LANES) - 1) / (8 * (32 / LANES)), ARGS.batch), dim3(256), 0, s, ARGS)
 #define VV_LN_DISPATCH(KERNEL, ARGS)                                                     \
   {                                                                                      \
-    const int npl = ARGS.C / 32;                                                         \
-    dim3 grid((ARGS.rows + 7) / 8, ARGS.batch);                                          \
-    switch (ARGS.map * 100 + npl) {                                                      \
-      case 2: launch_kernel(KERNEL<2, 2, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
-      case 3: launch_kernel(KERNEL<3, 1, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
-      case 4: launch_kernel(KERNEL<4, 4, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
-      case 6: launch_kernel(KERNEL<6, 2, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;                 \
-      case 12: launch_kernel(KERNEL<12, 4, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;               \
-      case 36: launch_kernel(KERNEL<36, 4, MAP_PLAIN>, grid, dim3(256), 0, s, ARGS); break;               \
-      case 108: launch_kernel(KERNEL<8, 4, MAP_MERGE>, grid, dim3(256), 0, s, ARGS); break;               \
-      case 112: launch_kernel(KERNEL<12, 4, MAP_MERGE>, grid, dim3(256), 0, s, ARGS); break;              \
-      case 202: launch_kernel(KERNEL<2, 2, MAP_EXPAND>, grid, dim3(256), 0, s, ARGS); break;              \
-      case 203: launch_kernel(KERNEL<3, 1, MAP_EXPAND>, grid, dim3(256), 0, s, ARGS); break;              \
+    switch (ARGS.map * 1000 + ARGS.C / 4) {                                              \
+      case 16: VV_LN_CASE(KERNEL, ARGS, 8, 2, MAP_PLAIN); break;      /* C = 64   */     \
+      case 24: VV_LN_CASE(KERNEL, ARGS, 8, 3, MAP_PLAIN); break;      /* C = 96   */     \
+      case 32: VV_LN_CASE(KERNEL, ARGS, 16, 2, MAP_PLAIN); break;     /* C = 128  */     \
+      case 48: VV_LN_CASE(KERNEL, ARGS, 16, 3, MAP_PLAIN); break;     /* C = 192  */     \
+      case 96: VV_LN_CASE(KERNEL, ARGS, 32, 3, MAP_PLAIN); break;     /* C = 384  */     \
+      case 288: VV_LN_CASE(KERNEL, ARGS, 32, 9, MAP_PLAIN); break;    /* C = 1152 */     \
+      case 1064: VV_LN_CASE(KERNEL, ARGS, 32, 2, MAP_MERGE); break;   /* C = 256  */     \
+      case 1096: VV_LN_CASE(KERNEL, ARGS, 32, 3, MAP_MERGE); break;   /* C = 384  */     \
+      case 2016: VV_LN_CASE(KERNEL, ARGS, 8, 2, MAP_EXPAND); break;   /* C = 64   */     \
+      case 2024: VV_LN_CASE(KERNEL, ARGS, 8, 3, MAP_EXPAND); break;   /* C = 96   */     \
       default: break;                                                                    \
     }                                                                                    \
   }
 
 bool ln_supported(int map, int C) {
   if (C % 32) return false;
-  const int key = map * 100 + C / 32;
-  switch (key) {
-    case 2: case 3: case 4: case 6: case 12: case 36: case 108: case 112: case 202: case 203: return true;
+  switch (map * 1000 + C / 4) {
+    case 16: case 24: case 32: case 48: case 96: case 288: case 1064: case 1096: case 2016: case 2024: return true;
     default: return false;
   }
 }

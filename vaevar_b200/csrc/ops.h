@@ -36,6 +36,8 @@ struct GemmDesc {
   GemmStoreMaps sm;
   GemmArgs a;
   int bn;        // tile = 256 rows (one CTA pair) x bn columns
+  const void* b_ptr;            // B operand as one contiguous block (null if it is a strided slice): what a previous GEMM prefetches
+  unsigned long long b_bytes;
 };
 // A: [batch][M][K] 16-bit with row stride lda / batch stride a_bs (elements); B: [batch][N][K] likewise.
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,
@@ -58,6 +60,8 @@ struct LnArgs {
   bf16* out_bf16; long long ld_ob, ob_bs;          // outputs are plain rows
   float* out_f32; long long ld_of, of_bs;
   int out_f16;                                     // 1: the 16-bit output is IEEE fp16 (forward pass), 0: bf16
+  float* stats_out;                                // non-null: "statistics only" mode for a LayerNorm folded into the next GEMM --
+                                                   // out_bf16 receives the RAW row, stats_out[batch][rows] float2 = (sum, sumsq)
 };
 struct LnBwdArgs {
   int rows, C, batch, map, gh, gw;
