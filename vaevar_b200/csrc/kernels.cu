@@ -223,42 +223,57 @@ VV_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row_ptr) {
                : "r"(smem_u32(smem_row_ptr)));
 }
 
-template <int HD, bool BWD>
+// SPLIT warps share one (window, head): warp `sl` owns the head-dimension slice [sl*HD/SPLIT, (sl+1)*HD/SPLIT) -- its third of
+// the loads, of the K-reduction of S = Q K^T (and dP = dO V^T), and of the output columns; the 16x16 partial products are
+// summed across the SPLIT warps through shared memory (one block barrier).  SPLIT = 3 for the d=1152 trunk (head_dim 192):
+// 768 (window, head) items are too few warps to keep 148 SMs busy, and a warp's 18-24 KB of loads and ~50 MMAs is a long
+// serial chain; SPLIT = 1 (four independent items per CTA) for the head_dim-32 towers.
+template <int HD, bool BWD, int SPLIT>
 struct AttnSmem {
-  static constexpr int W2 = HD / 2;             // 32-bit words (bf16 pairs) per token row
+  static constexpr int WARPS = SPLIT == 1 ? 4 : SPLIT;
+  static constexpr int ITEMS = WARPS / SPLIT;    // (window, head) items per CTA
+  static constexpr int W2 = HD / 2;             // 32-bit words (16-bit pairs) per token row
   static constexpr int RS = W2 + 4;             // padded row stride in words: 16-byte aligned rows, 4g+t / ldmatrix conflict-free
   static constexpr int MAT = 16 * RS;           // one 16 x HD operand
   static constexpr int PW = 12;                 // words per row of the 16 x 16 bf16 P / dS tiles (24 bf16 = 48 B)
-  static constexpr int WORDS = (BWD ? 4 : 3) * MAT + (BWD ? 2 * 16 * PW : 0);
-  static constexpr int BYTES = 4 * WORDS * 4;   // 4 warps per CTA
+  static constexpr int ITEM_WORDS = (BWD ? 4 : 3) * MAT;                      // Q, K, V (, dO) of one item
+  static constexpr int WARP_WORDS = BWD ? 2 * 16 * PW : 0;                    // per-warp P / dS scratch
+  static constexpr int RED_WORDS = SPLIT == 1 ? 0 : SPLIT * 32 * (BWD ? 16 : 8);   // partial S (and dP) fragments
+  static constexpr int WORDS = ITEMS * ITEM_WORDS + WARPS * WARP_WORDS + RED_WORDS;
+  static constexpr int BYTES = WORDS * 4;
 };
 
 // F16: qkv (and the forward output) are fp16.  The backward pass recomputes P from the fp16 Q, K exactly as the forward did,
 // then converts Q, K, V to bf16 in shared memory: its products pair them with bf16 gradients whose range fp16 cannot hold.
-template <int HD, bool BWD, bool F16>
-__global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
-  using L = AttnSmem<HD, BWD>;
-  constexpr int W2 = L::W2, RS = L::RS, PW = L::PW;
-  constexpr int CH = HD / 8;                     // 16-byte chunks per operand row
+template <int HD, bool BWD, bool F16, int SPLIT>
+__global__ void __launch_bounds__(AttnSmem<HD, BWD, SPLIT>::WARPS * 32) attn_kernel(const AttnArgs a) {
+  using L = AttnSmem<HD, BWD, SPLIT>;
+  constexpr int RS = L::RS, PW = L::PW;
+  constexpr int HDS = HD / SPLIT;                // head-dimension columns this warp owns
+  constexpr int CHS = HDS / 8;                   // 16-byte chunks per row of the slice
+  static_assert(HDS % 16 == 0, "slice must be a multiple of the MMA k step");
   extern __shared__ __align__(16) uint32_t attn_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nww = a.gw >> 2, nwh = a.gh >> 2;
-  const int item = blockIdx.x * 4 + warp;
+  const int li = warp / SPLIT, sl = warp - li * SPLIT;           // item within the CTA, slice within the item
+  const int item = blockIdx.x * L::ITEMS + li;
   pdl_launch_dependents();
   pdl_wait();
-  if (item >= nww * nwh * a.heads) return;      // warp-uniform; only warp-level sync below
+  if (item >= nww * nwh * a.heads) return;      // uniform over the SPLIT warps of an item (SPLIT > 1: over the CTA)
   const int b = blockIdx.y;
   const int win = item / a.heads, h = item - win * a.heads;
   const int wi = win / nww, wj = win - wi * nww;
   const int d = a.heads * HD;
+  const int c_lo = sl * HDS;                     // first column of the slice
 
-  uint32_t* Qs = attn_sm + warp * L::WORDS;
+  uint32_t* Qs = attn_sm + li * L::ITEM_WORDS;
   uint32_t* Ks = Qs + L::MAT;
   uint32_t* Vs = Ks + L::MAT;
   uint32_t* dOs = Vs + L::MAT;                                   // BWD only
-  uint32_t* Ps = Qs + 4 * L::MAT;                                // BWD only: bf16 P
-  uint32_t* dSs = Ps + 16 * PW;                                  // BWD only: bf16 dS
+  uint32_t* Ps = attn_sm + L::ITEMS * L::ITEM_WORDS + warp * L::WARP_WORDS;   // BWD only: this warp's bf16 P
+  uint32_t* dSs = Ps + 16 * PW;                                  // BWD only: this warp's bf16 dS
+  float* red = reinterpret_cast<float*>(attn_sm + L::ITEMS * L::ITEM_WORDS + L::WARPS * L::WARP_WORDS);   // SPLIT > 1
 
   // original-grid token index of window-local token tk (roll by -shift folded in; swinblock.py:275, 297)
   auto tok_of = [&](int tk) {
@@ -270,38 +285,72 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   const bf16* qkv = a.qkv + (long long)b * a.qkv_bs;
   {
     constexpr int NMAT = BWD ? 4 : 3;
-    for (int idx = lane; idx < 16 * 4 * CH; idx += 32) {
-      const int ch = idx % CH, rowm = idx / CH, m = rowm & 3, tk = rowm >> 2;     // m: 0 Q, 1 K, 2 V, 3 dO
+    for (int idx = lane; idx < 16 * 4 * CHS; idx += 32) {
+      const int ch = idx % CHS, rowm = idx / CHS, m = rowm & 3, tk = rowm >> 2;   // m: 0 Q, 1 K, 2 V, 3 dO
       if (m >= NMAT) continue;
       const bf16* src = m < 3 ? qkv + (long long)tok_of(tk) * a.ld_qkv + m * d + h * HD
                               : a.dout + (long long)b * a.o_bs + (long long)tok_of(tk) * a.ld_o + h * HD;
-      uint32_t* dst = Qs + m * L::MAT + tk * RS + 4 * ch;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + 8 * ch) : "memory");
+      uint32_t* dst = Qs + m * L::MAT + tk * RS + (c_lo >> 1) + 4 * ch;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + c_lo + 8 * ch) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncwarp();
 
-  // ---- S = Q K^T : two m16n8 tiles (key tokens 0-7 and 8-15), k over the head dimension ----
+  // ---- S = Q K^T : two m16n8 tiles (key tokens 0-7 and 8-15), k over this warp's slice of the head dimension ----
   float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int ks = 0; ks < HD / 16; ++ks) {
-    const int w = ks * 8 + t;
+  for (int ks = 0; ks < HDS / 16; ++ks) {
+    const int w = (c_lo >> 1) + ks * 8 + t;
     const uint32_t af[4] = {Qs[g * RS + w], Qs[(g + 8) * RS + w], Qs[g * RS + w + 4], Qs[(g + 8) * RS + w + 4]};
     mma_16816<F16>(s0, af, Ks[g * RS + w], Ks[g * RS + w + 4]);
     mma_16816<F16>(s1, af, Ks[(g + 8) * RS + w], Ks[(g + 8) * RS + w + 4]);
   }
-  if (BWD && F16) {                                              // Q, K, V -> bf16 in place (the gradient products are bf16)
+  if (BWD && F16) {                                              // own slice of Q, K, V -> bf16 in place (the gradient products are bf16)
     __syncwarp();
-    for (int idx = lane; idx < 3 * 16 * CH; idx += 32) {
-      const int ch = idx % CH, rowm = idx / CH;                  // rowm = matrix * 16 + token
-      uint4* ptr = reinterpret_cast<uint4*>(Qs + (rowm >> 4) * L::MAT + (rowm & 15) * RS + 4 * ch);
+    for (int idx = lane; idx < 3 * 16 * CHS; idx += 32) {
+      const int ch = idx % CHS, rowm = idx / CHS;                // rowm = matrix * 16 + token
+      uint4* ptr = reinterpret_cast<uint4*>(Qs + (rowm >> 4) * L::MAT + (rowm & 15) * RS + (c_lo >> 1) + 4 * ch);
       uint4 w = *ptr;
       w.x = half2_to_bf162(w.x); w.y = half2_to_bf162(w.y); w.z = half2_to_bf162(w.z); w.w = half2_to_bf162(w.w);
       *ptr = w;
     }
     __syncwarp();
+  }
+  // BWD: dP = dO V^T over the same slice (its K-reduction is shared with S's through one exchange)
+  float dp0[4] = {0.f, 0.f, 0.f, 0.f}, dp1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (BWD) {
+#pragma unroll
+    for (int ks = 0; ks < HDS / 16; ++ks) {
+      const int w = (c_lo >> 1) + ks * 8 + t;
+      const uint32_t af[4] = {dOs[g * RS + w], dOs[(g + 8) * RS + w], dOs[g * RS + w + 4], dOs[(g + 8) * RS + w + 4]};
+      mma_bf16_16816(dp0, af, Vs[g * RS + w], Vs[g * RS + w + 4]);
+      mma_bf16_16816(dp1, af, Vs[(g + 8) * RS + w], Vs[(g + 8) * RS + w + 4]);
+    }
+  }
+  if (SPLIT > 1) {                                               // sum the partial fragments over the SPLIT warps
+    constexpr int FR = BWD ? 16 : 8;
+    float* mine = red + (sl * 32 + lane) * FR;
+    *reinterpret_cast<float4*>(mine) = make_float4(s0[0], s0[1], s0[2], s0[3]);
+    *reinterpret_cast<float4*>(mine + 4) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    if (BWD) {
+      *reinterpret_cast<float4*>(mine + 8) = make_float4(dp0[0], dp0[1], dp0[2], dp0[3]);
+      *reinterpret_cast<float4*>(mine + 12) = make_float4(dp1[0], dp1[1], dp1[2], dp1[3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 1; o < SPLIT; ++o) {
+      const float* oth = red + (((sl + o) % SPLIT) * 32 + lane) * FR;
+      const float4 x0 = *reinterpret_cast<const float4*>(oth), x1 = *reinterpret_cast<const float4*>(oth + 4);
+      s0[0] += x0.x; s0[1] += x0.y; s0[2] += x0.z; s0[3] += x0.w;
+      s1[0] += x1.x; s1[1] += x1.y; s1[2] += x1.z; s1[3] += x1.w;
+      if (BWD) {
+        const float4 y0 = *reinterpret_cast<const float4*>(oth + 8), y1 = *reinterpret_cast<const float4*>(oth + 12);
+        dp0[0] += y0.x; dp0[1] += y0.y; dp0[2] += y0.z; dp0[3] += y0.w;
+        dp1[0] += y1.x; dp1[1] += y1.y; dp1[2] += y1.z; dp1[3] += y1.w;
+      }
+    }
   }
   // ---- P = softmax(scale S + bias + mask); this thread owns rows g and g+8, columns {2t,2t+1} and {8+2t,9+2t} ----
   const float scale = rsqrtf((float)HD);
@@ -337,20 +386,21 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   // adjacent 8-channel tiles of a token-major 16 x HD operand
   const int lm = lane >> 3, lr = lane & 7;
   auto bfrag_ptr = [&](const uint32_t* M, int c0) { return M + ((lm & 1) * 8 + lr) * RS + (c0 >> 1) + (lm >> 1) * 4; };
-  // staged 16 x HD result (bf16 pairs) -> global rows tok_of(r), 16-byte coalesced
+  // this warp's slice of a staged 16 x HD result (16-bit pairs) -> global rows tok_of(r), 16-byte coalesced
   auto copy_out = [&](const uint32_t* M, bf16* gbase, long long ld, int coloff) {
-    for (int idx = lane; idx < 16 * CH; idx += 32) {
-      const int r = idx / CH, ch = idx - r * CH;
-      *reinterpret_cast<uint4*>(gbase + (long long)tok_of(r) * ld + coloff + 8 * ch) = *reinterpret_cast<const uint4*>(M + r * RS + 4 * ch);
+    for (int idx = lane; idx < 16 * CHS; idx += 32) {
+      const int r = idx / CHS, ch = idx - r * CHS;
+      *reinterpret_cast<uint4*>(gbase + (long long)tok_of(r) * ld + coloff + c_lo + 8 * ch) =
+          *reinterpret_cast<const uint4*>(M + r * RS + (c_lo >> 1) + 4 * ch);
     }
   };
 
   if (!BWD) {
-    // ---- O = P V ----
+    // ---- O = P V (this warp's columns) ----
     const uint32_t pa[4] = {pack16<F16>(p0[0], p0[1]), pack16<F16>(p0[2], p0[3]), pack16<F16>(p1[0], p1[1]), pack16<F16>(p1[2], p1[3])};
-    __syncwarp();                                                 // every lane is done reading Qs before it is reused for O
+    __syncwarp();                                                 // every lane is done reading its Q slice before it is reused for O
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
+    for (int c0 = c_lo; c0 < c_lo + HDS; c0 += 16) {
       uint32_t vb[4];
       ldmatrix_x4_trans(vb, bfrag_ptr(Vs, c0));
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -364,15 +414,6 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
     __syncwarp();
     copy_out(Qs, a.out + (long long)b * a.o_bs, a.ld_o, h * HD);
   } else {
-    // ---- dP = dO V^T ----
-    float dp0[4] = {0.f, 0.f, 0.f, 0.f}, dp1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const int w = ks * 8 + t;
-      const uint32_t af[4] = {dOs[g * RS + w], dOs[(g + 8) * RS + w], dOs[g * RS + w + 4], dOs[(g + 8) * RS + w + 4]};
-      mma_bf16_16816(dp0, af, Vs[g * RS + w], Vs[g * RS + w + 4]);
-      mma_bf16_16816(dp1, af, Vs[(g + 8) * RS + w], Vs[(g + 8) * RS + w + 4]);
-    }
     // ---- dS = P o (dP - rowsum(dP o P)) ----
     float ds0[4], ds1[4];
 #pragma unroll
@@ -395,9 +436,9 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
     ldmatrix_x4_trans(dsT, dSs + ((lm >> 1) * 8 + lr) * PW + (lm & 1) * 4);
     const uint32_t dsA[4] = {pack_bf16(ds0[0], ds0[1]), pack_bf16(ds0[2], ds0[3]), pack_bf16(ds1[0], ds1[1]), pack_bf16(ds1[2], ds1[3])};
 
-    // ---- dV = P^T dO  -> staged in the V buffer (V is dead after dP) ----
+    // ---- dV = P^T dO  -> staged in the V buffer (this warp's V columns are dead after dP) ----
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
+    for (int c0 = c_lo; c0 < c_lo + HDS; c0 += 16) {
       uint32_t bb[4];
       ldmatrix_x4_trans(bb, bfrag_ptr(dOs, c0));
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -408,10 +449,10 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
       Vs[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0], o1[1]);
       Vs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2], o1[3]);
     }
-    __syncwarp();                                                 // dO fully consumed -> its buffer takes dQ
+    __syncwarp();                                                 // dO slice fully consumed -> it takes dQ
     // ---- dQ = scale dS K -> staged in the dO buffer ----
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
+    for (int c0 = c_lo; c0 < c_lo + HDS; c0 += 16) {
       uint32_t bb[4];
       ldmatrix_x4_trans(bb, bfrag_ptr(Ks, c0));
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -422,10 +463,10 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
       dOs[g * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[0] * scale, o1[1] * scale);
       dOs[(g + 8) * RS + (c0 >> 1) + 4 + t] = pack_bf16(o1[2] * scale, o1[3] * scale);
     }
-    __syncwarp();                                                 // K fully consumed -> its buffer takes dK
+    __syncwarp();                                                 // K slice fully consumed -> it takes dK
     // ---- dK = scale dS^T Q -> staged in the K buffer ----
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 16) {
+    for (int c0 = c_lo; c0 < c_lo + HDS; c0 += 16) {
       uint32_t bb[4];
       ldmatrix_x4_trans(bb, bfrag_ptr(Qs, c0));
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -444,22 +485,22 @@ __global__ void __launch_bounds__(128) attn_kernel(const AttnArgs a) {
   }
 }
 
-template <int HD, bool BWD, bool F16>
+template <int HD, bool BWD, bool F16, int SPLIT>
 static void launch_attn_t(const AttnArgs& a, cudaStream_t s) {
-  using L = AttnSmem<HD, BWD>;
+  using L = AttnSmem<HD, BWD, SPLIT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn_kernel<HD, BWD, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    cudaFuncSetAttribute(attn_kernel<HD, BWD, F16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
     attr_set = true;
   }
   const int items = (a.gh / 4) * (a.gw / 4) * a.heads;
-  dim3 grid((items + 3) / 4, a.batch);
-  launch_kernel(attn_kernel<HD, BWD, F16>, grid, dim3(128), L::BYTES, s, a);
+  dim3 grid((items + L::ITEMS - 1) / L::ITEMS, a.batch);
+  launch_kernel(attn_kernel<HD, BWD, F16, SPLIT>, grid, dim3(L::WARPS * 32), L::BYTES, s, a);
 }
 template <bool BWD>
 static void launch_attn_d(const AttnArgs& a, cudaStream_t s) {
-  if (a.hd == 32) { if (a.f16) launch_attn_t<32, BWD, true>(a, s); else launch_attn_t<32, BWD, false>(a, s); }
-  else if (a.hd == 192) { if (a.f16) launch_attn_t<192, BWD, true>(a, s); else launch_attn_t<192, BWD, false>(a, s); }
+  if (a.hd == 32) { if (a.f16) launch_attn_t<32, BWD, true, 1>(a, s); else launch_attn_t<32, BWD, false, 1>(a, s); }
+  else if (a.hd == 192) { if (a.f16) launch_attn_t<192, BWD, true, 3>(a, s); else launch_attn_t<192, BWD, false, 3>(a, s); }
 }
 void launch_attn_fwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<false>(a, s); }
 void launch_attn_bwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<true>(a, s); }
