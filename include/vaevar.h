@@ -98,6 +98,12 @@ VV_API int vv_integrate(vv_engine* e, const float* x_phys_in_dev, float* x_phys_
 VV_API int vv_net_forward(vv_engine* e, int net, const float* in_dev, float* out_dev, void* stream);
 VV_API int vv_net_vjp(vv_engine* e, int net, const float* in_dev, const float* dout_dev, float* din_dev, void* stream);
 
+/* Per-channel diagnostics of the outer loop (da_4dvar.py:1260-1264): out[0..C) = Metrics.WRMSE, out[C..2C) = Metrics.Bias
+ * (utils/metrics.py:526-544, 473-474, 282-296, 65-82; latitude weights with the reference's literal 3.1416) of the PHYSICAL
+ * fields x and gt (C,H,W), which are normalised with the constants of vv_set_constants first, as the reference does.
+ * One fused pass on the device; out is a device array of 2*C doubles. */
+VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, double* out_dev, void* stream);
+
 /* torch.optim.LBFGS([z], history_size, max_iter, line_search_fn="strong_wolfe") + .step(closure)
  * (da_4dvar.py:1240, 1298-1299; torch/optim/lbfgs.py:333-537).  State persists across steps; the vectors never
  * leave the device, the controller reads back O(10) scalars per closure evaluation. */

@@ -138,3 +138,47 @@ def test_module_surface_forward_backward(chk):
     assert y.shape == yr.shape == (1, cfg.out_chans, *cfg.img_size)
     assert float((y.cpu() - yr).norm() / yr.norm()) < 1e-2
     assert float((xg.grad.cpu() - xr.grad).norm() / xr.grad.norm()) < 3e-2
+
+
+def test_fused_metrics_kernel_against_reference_golden(chk, gold):
+    """vv_metrics (WRMSE + Bias in one device pass) against utils/metrics.py run on the REAL reference (fixture metrics.npz)."""
+    from vaevar_b200.config import DECODER_FULL, era5_stats, small
+    from vaevar_b200.engine import Engine
+    from vaevar_b200.synth import make_state_dict
+    g = gold("metrics.npz")
+    cfg = small(DECODER_FULL)
+    assert tuple(cfg.img_size) == g["pred"].shape[2:]
+    e = Engine(cfg)
+    e.load_state_dict(0, make_state_dict(cfg, seed=0)); e.finalize()
+    mean, std, _ = era5_stats()
+    m = torch.from_numpy(mean).float().cuda().reshape(-1, 1, 1); s = torch.from_numpy(std).float().cuda().reshape(-1, 1, 1)
+    pred = torch.from_numpy(g["pred"][0]).cuda() * s + m
+    gt = torch.from_numpy(g["gt"][0]).cuda() * s + m
+    w, b = e.metrics(pred, gt)
+    # the physical round trip (x sigma + mu, then back) costs ~1e-6 relative of the normalised values
+    np.testing.assert_allclose(w.cpu().numpy(), g["wrmse"], rtol=2e-5)
+    np.testing.assert_allclose(b.cpu().numpy(), g["bias"], rtol=2e-3, atol=2e-6 * float(std.max()))
+    e.close()
+
+
+def test_cycled_da_two_cycles_small(chk, tmp_path):
+    """Cycle driver on the engine (small networks, T=2): the analysis improves on the background in every cycle and the
+    checkpoint / metric files of da_4dvar.py:698-722 appear."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, era5_stats, small
+    from vaevar_b200.cycle import CycledDA, TwinObs
+    from vaevar_b200.da import VaeVar4D
+    from vaevar_b200.synth import make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    agent = VaeVar4D(ds, fs, make_state_dict(ds, seed=0), make_state_dict(fs, seed=1), da_win=2, Nit=1, verbose=False)
+    mean, std, _ = era5_stats()
+    gen = torch.Generator().manual_seed(0)
+    m = torch.from_numpy(mean).float().reshape(-1, 1, 1); s = torch.from_numpy(std).float().reshape(-1, 1, 1)
+    truth0 = m + s * torch.randn(69, *ds.img_size, generator=gen)
+    xb0 = truth0 + 0.1 * s * torch.randn(69, *ds.img_size, generator=gen)
+    run = CycledDA(agent, TwinObs(agent, truth0, obs_frac=0.2), xb0, name="t", root=str(tmp_path), n_cycles=2, resume=False)
+    r = run.run_assimilation()
+    assert r["cycles"] == 2 and r["cycles_per_hour"] > 0
+    bg = torch.stack(agent.metrics_list["bg_wrmse"]); an = torch.stack(agent.metrics_list["ana_wrmse"])
+    assert bg.shape == an.shape == (2, 69)
+    assert float((an / bg).mean()) < 1.0
+    assert (tmp_path / "t" / "xb.npy").exists() and (tmp_path / "t" / "ana_wrmse.npy").exists()

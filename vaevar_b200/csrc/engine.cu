@@ -964,6 +964,20 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
   return 0;
 }
 
+VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, double* out_dev, void* stream) {
+  VV_CHECK(e && x_phys_dev && gt_phys_dev && out_dev, "null argument");
+  VV_CHECK(e->have_consts, "vv_set_constants has not been called");
+  if (!e->met_w) {
+    e->met_w = dalloc<float>(e, (size_t)e->net[0].H);
+    e->met_part = dalloc<double>(e, (size_t)metrics_scratch_doubles(e->C));
+    VV_CHECK(e->met_w && e->met_part, "out of memory for the metric scratch");
+  }
+  launch_metrics(x_phys_dev, gt_phys_dev, e->mean, e->sigma, e->C, e->net[0].H, e->net[0].W, e->met_w, e->met_part, out_dev,
+                 (cudaStream_t)stream);
+  VV_CUDA(cudaGetLastError());
+  return 0;
+}
+
 VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs) {
   VV_CHECK(e && n_obs, "null argument");
   *n_obs = e->n_obs;

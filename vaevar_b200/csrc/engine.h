@@ -93,6 +93,7 @@ struct vv_engine {
   float obs_coeff = 1.f;
   bool have_case = false;
   double *partials = nullptr, *dots = nullptr, *dot_scratch = nullptr, *Jbuf = nullptr;
+  float* met_w = nullptr; double* met_part = nullptr;     // diagnostics scratch (latitude weights, block partials)
   // plans: index 0 = decoder application, 1..T-1 = flow applications
   std::vector<vv::Stash> stash;
   std::vector<vv::Plan> fwd, bwd;

@@ -269,4 +269,71 @@ void launch_absmax_l1(const float* x, long long n, double* out, double* scratch,
   absmax_l1_final_kernel<<<1, 256, 0, s>>>(scratch, out);
 }
 
+// ---- diagnostics: latitude-weighted RMSE and bias of every channel in one pass -----------------------------------
+// utils/metrics.py:282-296 (weighted_rmse_torch_channels), :65-82 (type_weighted_bias_torch_channels, "all"),
+// Metrics.WRMSE / Metrics.Bias :526-544, :473-474, applied the way da_4dvar.py:1260-1264 does: both fields are
+// normalised with (mean, std) first, the per-channel result is multiplied by std.
+//   w_j = H cos(3.1416/180 lat_j) / sum_j cos(3.1416/180 lat_j),  lat_j = 90 - 180 j / (H - 1)     (metrics.py:5-10)
+constexpr int MET_SPLIT = 8;    // blocks per channel
+
+__global__ void lat_weight_kernel(float* w, int H) {           // one block
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const float lat = 90.0f - (float)j * 180.0f / (float)(H - 1);
+    const float c = cosf(3.1416f / 180.0f * lat);
+    w[j] = c;
+    s += c;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float tot = red[0];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) w[j] = (float)H * w[j] / tot;
+}
+
+__global__ void __launch_bounds__(256) metrics_partial_kernel(const float* x, const float* gt, const float* mean, const float* sigma,
+                                                              const float* w, int H, int W, double* partials) {
+  const int c = blockIdx.y;
+  const long long HW = (long long)H * W, base = (long long)c * HW;
+  const float mu = mean[c], sd = sigma[c];
+  double s1 = 0.0, s2 = 0.0;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    const float d = (x[base + p] - mu) / sd - (gt[base + p] - mu) / sd;     // the reference subtracts the NORMALISED fields
+    const float wj = w[p / W];
+    s1 += (double)(wj * d);
+    s2 += (double)(wj * (d * d));
+  }
+  s1 = block_sum_d(s1);
+  __syncthreads();
+  s2 = block_sum_d(s2);
+  if (threadIdx.x == 0) {
+    partials[((long long)c * gridDim.x + blockIdx.x) * 2] = s1;
+    partials[((long long)c * gridDim.x + blockIdx.x) * 2 + 1] = s2;
+  }
+}
+
+__global__ void metrics_final_kernel(const double* partials, const float* sigma, int C, int nsplit, double inv_hw, double* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nsplit; ++k) { s1 += partials[((long long)c * nsplit + k) * 2]; s2 += partials[((long long)c * nsplit + k) * 2 + 1]; }
+  out[c] = sqrt(s2 * inv_hw) * (double)sigma[c];           // WRMSE
+  out[C + c] = s1 * inv_hw * (double)sigma[c];              // Bias
+}
+
+int metrics_scratch_doubles(int C) { return C * MET_SPLIT * 2; }
+void launch_metrics(const float* x, const float* gt, const float* mean, const float* sigma, int C, int H, int W, float* w_scratch,
+                    double* partials, double* out, cudaStream_t s) {
+  lat_weight_kernel<<<1, 256, 0, s>>>(w_scratch, H);
+  metrics_partial_kernel<<<dim3(MET_SPLIT, C), 256, 0, s>>>(x, gt, mean, sigma, w_scratch, H, W, partials);
+  metrics_final_kernel<<<(C + 127) / 128, 128, 0, s>>>(partials, sigma, C, MET_SPLIT, 1.0 / ((double)H * W), out);
+}
+
 }  // namespace vv

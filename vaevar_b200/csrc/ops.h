@@ -144,6 +144,12 @@ void launch_axpy_diff(float* y, const float* x, const double* a1_dev, const doub
 // max-abs and L1 norm of a vector: out[0]=max|x|, out[1]=sum|x|
 void launch_absmax_l1(const float* x, long long n, double* out, double* scratch, cudaStream_t s);
 
+// Latitude-weighted RMSE and bias of every channel (utils/metrics.py WRMSE / Bias as da_4dvar.py:1260-1264 applies them):
+// x, gt physical (C,H,W); out[0..C) = WRMSE, out[C..2C) = Bias.  w_scratch: H floats, partials: metrics_scratch_doubles(C).
+int metrics_scratch_doubles(int C);
+void launch_metrics(const float* x, const float* gt, const float* mean, const float* sigma, int C, int H, int W, float* w_scratch,
+                    double* partials, double* out, cudaStream_t s);
+
 int reduce_blocks();  // number of blocks the reduction kernels use (size of scratch in doubles * 4)
 
 }  // namespace vv

@@ -44,14 +44,18 @@ class VaeVar4D:
 
     def __init__(self, dec_cfg: NetConfig, flow_cfg: Optional[NetConfig], dec_sd: Dict, flow_sd: Optional[Dict],
                  da_win: int = 1, Nit: int = 4, obs_coeff: float = 1.0, device: str = "cuda:0",
-                 recompute: bool = False, use_graph: bool = True, verbose: bool = True):
+                 recompute: bool = False, use_graph: bool = True, verbose: bool = True, engine: Optional[Engine] = None):
         self.da_win, self.Nit, self.obs_coeff, self.verbose = da_win, Nit, obs_coeff, verbose
         self.device = torch.device(device)
-        self.engine = Engine(dec_cfg, flow_cfg, T=da_win, recompute=recompute, use_graph=use_graph, device=device)
-        self.engine.load_state_dict(0, dec_sd)
-        if flow_cfg is not None:
-            self.engine.load_state_dict(1, flow_sd)
-        self.engine.finalize()
+        if engine is not None:                       # an already loaded engine (same networks, same window length)
+            assert engine.T == da_win, "engine was built for another window length"
+            self.engine = engine
+        else:
+            self.engine = Engine(dec_cfg, flow_cfg, T=da_win, recompute=recompute, use_graph=use_graph, device=device)
+            self.engine.load_state_dict(0, dec_sd)
+            if flow_cfg is not None:
+                self.engine.load_state_dict(1, flow_sd)
+            self.engine.finalize()
         mean, std, _ = era5_stats()
         self.model_mean, self.model_std = mean, std                        # float64, da_4dvar.py:645-646
         self.model_mean_gpu = torch.from_numpy(mean).float().to(self.device)
@@ -66,24 +70,22 @@ class VaeVar4D:
         """(69,nlat,nlon) physical -> physical after `step` applications of the flow model (da_4dvar.py:666-681)."""
         return self.engine.integrate(xa.to(self.device, torch.float32), step)
 
-    def _diagnostics(self, z, gt_norm):
-        xhat = self.engine.decode(z)
-        xn = ((xhat - self.model_mean_gpu.reshape(-1, 1, 1)) / self.model_std_gpu.reshape(-1, 1, 1)).unsqueeze(0)
-        std = torch.from_numpy(self.model_std).to(self.device)
-        return wrmse(xn, gt_norm, std), bias(xn, gt_norm, std)
+    def _diagnostics(self, z, gt0):
+        """WRMSE / Bias of the current analysis (da_4dvar.py:1256-1264) without leaving the device: the fused metric
+        kernel normalises both fields and applies utils/metrics.py's latitude weighting in one pass."""
+        return self.engine.metrics(self.engine.decode(z), gt0)
 
     def one_step_DA(self, gt, xb, yo, H, R, mode: str = "vae4dvar"):
         if mode != "vae4dvar":
             raise NotImplementedError("not implemented da mode")            # da_4dvar.py:1308-1309
         dev = self.device
         gt0 = torch.as_tensor(gt[0]).to(dev, torch.float32)
-        gt_norm = ((gt0 - self.model_mean_gpu.reshape(-1, 1, 1)) / self.model_std_gpu.reshape(-1, 1, 1)).unsqueeze(0)
         self.engine.set_case(xb, yo, H, R, self.obs_coeff)
         z = torch.zeros(1, self.latent, self.nlat, self.nlon, device=dev)   # da_4dvar.py:1238
         opt = LBFGS(self.engine, history_size=10, max_iter=10)              # da_4dvar.py:1240
         t0 = time.time()
         for kk in range(self.Nit + 1):
-            w, b = self._diagnostics(z, gt_norm)
+            w, b = self._diagnostics(z, gt0)
             J = self.engine.cost(z).cpu()                                   # cal_loss, da_4dvar.py:1265
             if self.verbose:
                 print("iter: %d, RMSE (z500): %.4g Bias (z500): %.4g q500: %.4g, t2m: %.4g t850: %.4g u500: %.4g, v500: %.4g, "

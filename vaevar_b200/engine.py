@@ -123,6 +123,13 @@ class Engine:
         _lib.check(self.lib.vv_decode(self._h, _ptr(z.contiguous()), _ptr(out), _stream()))
         return out
 
+    def metrics(self, x_phys: torch.Tensor, gt_phys: torch.Tensor):
+        """(Metrics.WRMSE, Metrics.Bias) per channel of two PHYSICAL (C,H,W) fields, as da_4dvar.py:1260-1264 computes them
+        (utils/metrics.py:526-544, 473-474): one fused device pass, float64 device tensors of length C."""
+        out = torch.empty(2 * self.n_state, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.vv_metrics(self._h, _ptr(x_phys.contiguous()), _ptr(gt_phys.contiguous()), _ptr(out), _stream()))
+        return out[: self.n_state], out[self.n_state:]
+
     def integrate(self, x: torch.Tensor, steps: int = 1) -> torch.Tensor:
         out = torch.empty_like(x)
         _lib.check(self.lib.vv_integrate(self._h, _ptr(x.contiguous()), _ptr(out), steps, _stream()))
