@@ -4,6 +4,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <tuple>
 
 #include "ops.h"
 
@@ -86,8 +88,70 @@ static int g_gemm_debug_mode = 0;
 void set_gemm_trace(unsigned long long* dev_ptr) { g_gemm_trace = dev_ptr; }
 void set_gemm_debug_mode(int mode) { g_gemm_debug_mode = mode; }
 
+static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs,
+                                     const GemmArgs& args, int force_bn);
+
+// Tile width by measurement: the first time a (shape, epilogue) signature is seen, every candidate BN is timed on the real
+// operands (5 launches each, CUDA events) and the fastest is cached.  The cost model of pick_bn cannot see the epilogue's
+// instruction cost or the L2 feed limit, which decide the small-K tower GEMMs and the N = 1152 trunk GEMMs.
+struct TuneKey {
+  int M, N, K, batch, epi, f16, flags;
+  bool operator<(const TuneKey& o) const {
+    return std::tie(M, N, K, batch, epi, f16, flags) < std::tie(o.M, o.N, o.K, o.batch, o.epi, o.f16, o.flags);
+  }
+};
+static std::map<TuneKey, int> g_tuned;
+static bool autotune_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VV_GEMM_AUTOTUNE");      // opt-in: on B200 it confirmed pick_bn's choices (tools: VV_GEMM_AUTOTUNE_LOG=1),
+    v = (e && e[0] == '1') ? 1 : 0;                   // and a measured choice would make the kernel selection run-dependent
+  }
+  return v == 1 && !getenv("VV_GEMM_BN");
+}
+static int tuned_bn(const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, const GemmArgs& args) {
+  const int flags = (args.res ? 1 : 0) | (args.out_f32 ? 2 : 0) | (args.out_bf16 ? 4 : 0) | (args.aux_out ? 8 : 0) | (args.aux_in ? 16 : 0) |
+                    (args.ln_stats ? 32 : 0) | (args.stats_out ? 64 : 0) | (args.split_n > 0 ? 128 : 0) | (args.bias ? 256 : 0);
+  const TuneKey key{args.M, args.N, args.K, args.batch, args.epi, args.f16, flags};
+  auto it = g_tuned.find(key);
+  if (it != g_tuned.end()) return it->second;
+  static const int cand[4] = {64, 128, 192, 256};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int best = 0; float best_ms = 1e30f;
+  for (int i = 0; i < 4; ++i) {
+    GemmDesc d;
+    GemmArgs a2 = args;
+    if (a2.stats_out) a2.stats_out_bs = 2LL * 2 * ((a2.N + cand[i] - 1) / cand[i]) * a2.M;
+    if (make_gemm_desc_bn(&d, A, lda, a_bs, B, ldb, b_bs, a2, cand[i])) continue;
+    d.a.pf_ptr = nullptr; d.a.pf_bytes = 0; d.a.trace = nullptr; d.a.debug_mode = 0;
+    d.a.stats_out_bs = a2.stats_out_bs;
+    launch_gemm(d, 0); launch_gemm(d, 0);
+    cudaEventRecord(e0, 0);
+    for (int r = 0; r < 5; ++r) launch_gemm(d, 0);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); continue; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best_ms) { best_ms = ms; best = cand[i]; }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (getenv("VV_GEMM_AUTOTUNE_LOG"))
+    fprintf(stderr, "[vaevar] gemm %dx%dx%dx%d epi %d f16 %d flags 0x%x -> BN %d (%.1f us)\n", args.M, args.N, args.K, args.batch, args.epi,
+            args.f16, flags, best, best_ms * 200.f);
+  g_tuned[key] = best;
+  return best;
+}
+
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs,
                            const GemmArgs& args) {
+  int bn = 0;
+  if (autotune_enabled() && args.M >= 1024) bn = tuned_bn(A, lda, a_bs, B, ldb, b_bs, args);
+  return make_gemm_desc_bn(d, A, lda, a_bs, B, ldb, b_bs, args, bn);
+}
+
+static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs,
+                                     const GemmArgs& args, int force_bn) {
   if (args.N % 8) return "GEMM N must be a multiple of 8";
   if (args.K % 8) return "GEMM K must be a multiple of 8";
   if (args.split_n > 0 && args.split_n % GEMM_EC) return "GEMM split_n must be a multiple of 32";
@@ -101,7 +165,7 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
   d->a.pf_ptr = nullptr; d->a.pf_bytes = 0;
   d->a.trace = g_gemm_trace;
   d->a.debug_mode = g_gemm_debug_mode;
-  d->bn = pick_bn(args.M, args.N, args.batch);
+  d->bn = force_bn > 0 ? force_bn : pick_bn(args.M, args.N, args.batch);
   const char* e = encode_map_t(&d->tmA, A, false, args.K, args.M, args.batch, lda, a_bs, GEMM_BK, GEMM_BM);
   if (e) return e;
   e = encode_map_t(&d->tmB, B, false, args.K, args.N, args.batch, ldb, b_bs, GEMM_BK, d->bn / 2);
