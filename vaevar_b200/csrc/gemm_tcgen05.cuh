@@ -185,6 +185,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 64 + 11] = globaltimer_ns();     // kernel entry
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
@@ -228,6 +229,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; nothing below
   // may touch global memory before the previous kernel has completed.
+  if (p.trace && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 64 + 12] = globaltimer_ns();     // prologue done
   pdl_launch_dependents();
   pdl_wait();
   unsigned long long* trc = p.trace ? p.trace + (size_t)blockIdx.x * 64 : nullptr;
@@ -503,13 +505,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) tma_store_wait_read0();          // the staging slabs must outlive the bulk stores that read them
     __syncwarp();
   }
-  if (trc && threadIdx.x == 0) trc[1] = clock64();
+  if (trc && threadIdx.x == 0) { trc[1] = clock64(); trc[13] = globaltimer_ns(); }
   tc_fence_before();
   cluster_sync_all();                                 // neither CTA may retire while its peer can still touch its smem / TMEM
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, TMEM_COLS);
   }
+  if (trc && threadIdx.x == 0) trc[14] = globaltimer_ns();                                       // about to exit
 }
 
 }  // namespace vv
