@@ -290,6 +290,7 @@ def main():
         "roofline_step": {"bound": "tensor", "achieved": step_tfs, "peak": sustained, "unit": "TFLOP/s", "frac": step_tfs / sustained,
                           "algorithmic_tflop": tflop, "peak_source": f"{src} sustained"},
         "J": [float(v) for v in Jb.cpu()],
+        "hbm_used_gb": round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 2**30, 2),
     }
     if not args.no_cpu_baseline:
         times, Jcpu, threads = cpu_oracle_eval(T, args.obs_frac, 0, repeats=1)
