@@ -124,21 +124,40 @@ void launch_compact_write(const float* H, const float* yo, const float* R, long 
 }
 
 // ---- misfit + adjoint -----------------------------------------------------------------------
+// Four consecutive observations per thread and iteration: idx / y / 1/R are read and the residuals written as 16-byte vectors
+// (coalesced), the four gathers of x are independent and in flight together (the gather chain idx -> x is the latency that
+// bounds this kernel), the channel comes from a 32-bit division.
 __global__ void __launch_bounds__(RED_THREADS) obs_misfit_kernel(const float* __restrict__ xn, const int* __restrict__ idx,
                                                                  const float* __restrict__ y, const float* __restrict__ rinv,
                                                                  const float* __restrict__ sigma, const float* __restrict__ mu,
                                                                  long long n_obs, long long HW, int C, float coeff,
                                                                  float* __restrict__ resid, double* __restrict__ partials) {
   double acc = 0.0;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_obs; k += (long long)gridDim.x * blockDim.x) {
+  const unsigned hw = (unsigned)HW, uc = (unsigned)C;
+  const long long n4 = n_obs >> 2;
+  for (long long k4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; k4 < n4; k4 += (long long)gridDim.x * blockDim.x) {
+    const int4 id = __ldg(reinterpret_cast<const int4*>(idx) + k4);
+    const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + k4);
+    const float4 ri = __ldg(reinterpret_cast<const float4*>(rinv) + k4);
+    const float x0 = __ldg(xn + id.x), x1 = __ldg(xn + id.y), x2 = __ldg(xn + id.z), x3 = __ldg(xn + id.w);
+    const unsigned c0 = ((unsigned)id.x / hw) % uc, c1 = ((unsigned)id.y / hw) % uc, c2 = ((unsigned)id.z / hw) % uc, c3 = ((unsigned)id.w / hw) % uc;
+    const float s0 = sigma[c0], s1 = sigma[c1], s2 = sigma[c2], s3 = sigma[c3];
+    const float r0 = fmaf(x0, s0, mu[c0]) - yy.x, r1 = fmaf(x1, s1, mu[c1]) - yy.y;     // de-normalise (da_4dvar.py:681), misfit
+    const float r2 = fmaf(x2, s2, mu[c2]) - yy.z, r3 = fmaf(x3, s3, mu[c3]) - yy.w;
+    float4 out;
+    out.x = coeff * s0 * ri.x * r0; out.y = coeff * s1 * ri.y * r1;                      // d(coeff*J_obs)/d(xn)
+    out.z = coeff * s2 * ri.z * r2; out.w = coeff * s3 * ri.w * r3;
+    reinterpret_cast<float4*>(resid)[k4] = out;
+    acc += 0.5 * ((double)(ri.x * r0 * r0) + (double)(ri.y * r1 * r1) + (double)(ri.z * r2 * r2) + (double)(ri.w * r3 * r3));
+  }
+  for (long long k = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n_obs; k += (long long)gridDim.x * blockDim.x) {
     const int id = idx[k];
-    const int c = (int)((id / HW) % C);
+    const unsigned c = ((unsigned)id / hw) % uc;
     const float sg = sigma[c];
-    const float x = fmaf(xn[id], sg, mu[c]);        // de-normalise (da_4dvar.py:681)
-    const float r = x - y[k];
-    const float ri = rinv[k];
-    resid[k] = coeff * sg * ri * r;                 // d(coeff*J_obs)/d(xn)
-    acc += 0.5 * (double)(ri * r * r);
+    const float r = fmaf(xn[id], sg, mu[c]) - y[k];
+    const float rr = rinv[k];
+    resid[k] = coeff * sg * rr * r;
+    acc += 0.5 * (double)(rr * r * r);
   }
   acc = block_sum_d(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = acc;
@@ -161,8 +180,16 @@ void launch_reduce_partials(const double* partials, int n, double* out, cudaStre
 
 __global__ void __launch_bounds__(256) obs_adjoint_kernel(float* G, const int* idx, const float* resid, long long k0, long long k1,
                                                           long long base) {
-  for (long long k = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += (long long)gridDim.x * blockDim.x)
-    G[idx[k] - base] += resid[k];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long k = k0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; k + stride < k1; k += 2 * stride) {               // indices are unique: plain read-modify-write, two in flight
+    const int i0 = idx[k], i1 = idx[k + stride];
+    const float a0 = resid[k], a1 = resid[k + stride];
+    float* g0 = G + (i0 - base); float* g1 = G + (i1 - base);
+    const float v0 = *g0, v1 = *g1;
+    *g0 = v0 + a0; *g1 = v1 + a1;
+  }
+  if (k < k1) G[idx[k] - base] += resid[k];
 }
 void launch_obs_adjoint(float* G, const int* idx, const float* resid, long long k0, long long k1, long long base, cudaStream_t s) {
   if (k1 <= k0) return;
