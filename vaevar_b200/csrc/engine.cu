@@ -425,9 +425,8 @@ struct Builder {
   // GEMM whose fp32 output is the input of a LayerNorm folded into the NEXT GEMM: it also writes the raw 16-bit copy of its
   // output rows (width C) into t.h and their (sum, sumsq) partials into t.lnst.  Returns the number of partials per row.
   int gemm_with_stats(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g, int C) {
-    const char* dbg = getenv("VV_DBG");
-    if (!(dbg && strchr(dbg, 'c'))) { g.out_bf16 = t.h; g.ld_bf16 = C; g.bf16_bs = (long long)g.M * C; }
-    if (!(dbg && strchr(dbg, 's'))) g.stats_out = t.lnst;
+    g.out_bf16 = t.h; g.ld_bf16 = C; g.bf16_bs = (long long)g.M * C;
+    g.stats_out = t.lnst;
     gemm(P, A, lda, a_bs, B, ldb, b_bs, g);
     GemmDesc& d = P.ops.back().gemm;
     const int parts = 2 * ((g.N + d.bn - 1) / d.bn);
@@ -436,8 +435,6 @@ struct Builder {
     return parts;
   }
   void fold_ln(GemmArgs& g, int parts, const float* colsum, int C, float eps) const {
-    const char* dbg = getenv("VV_DBG");
-    if (dbg && strchr(dbg, 'l')) return;
     g.ln_stats = t.lnst; g.ln_parts = parts; g.ln_stats_bs = (long long)parts * g.M * 2; g.ln_colsum = colsum;
     g.ln_inv_c = 1.0f / (float)C; g.ln_eps = eps;
   }
