@@ -83,6 +83,15 @@ def build_inputs(T, obs_frac, seed):
     return DECODER_FULL, FLOW_FULL, sd_d, sd_f, case
 
 
+def workload_config(T, obs_frac, n_obs, recompute, cuda_graph, world):
+    """The `config` object both arms print (the reference arm runs the same workload on the host cores)."""
+    return {"workload": f"4D-Var {T}-step window cost+grad (VAE decoder + {T-1} flow-model applications, fwd + hand-derived adjoint), "
+                        f"1 case per GPU, 69x128x256 state, {int(obs_frac*100)}% column obs",
+            "T": T, "obs_frac": obs_frac, "n_obs": n_obs, "recompute": int(recompute), "cuda_graph": cuda_graph,
+            "parallelism": f"replicas x{world} (independent cases)",
+            "l2": "per-eval working set (2 x 0.86 GB 16-bit weights + ~1.3 GB stash per application) >> 126 MB L2; no flush needed"}
+
+
 def cpu_oracle_eval(T, obs_frac, seed, repeats=1, budget_s=180.0):
     """Times the CPU oracle (oracle/: reference algorithm, fp32, torch CPU, all host threads) on closure() calls."""
     import torch
@@ -117,7 +126,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ms per 4D-Var cost+grad eval (69x128x256)", "value": ms, "unit": "ms",
             "n_gpus": args.gpus, "steps": len(timed), "warmup": len(times) - len(timed), "ms_per_step": ms,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"4D-Var {Ts}-step window cost+grad, 1 case, 69x128x256, {int(args.obs_frac*100)}% obs", "T": Ts},
+            "config": workload_config(Ts, args.obs_frac, int(69 * Ts * int(args.obs_frac * 128 * 256)), 0, False, 1),
             "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "J": J}
@@ -310,11 +319,7 @@ def main():
         "metric": "ms per 4D-Var cost+grad eval (69x128x256)", "value": total_ms / (args.steps * world), "unit": "ms",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eval, "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp16 forward / bf16 gradients, fp32 accumulate", "data": "synthetic",
-        "config": {"workload": f"4D-Var {T}-step window cost+grad (VAE decoder + {T-1} flow-model applications, fwd + hand-derived adjoint), "
-                               f"1 case per GPU, 69x128x256 state, {int(args.obs_frac*100)}% column obs",
-                   "T": T, "obs_frac": args.obs_frac, "n_obs": eng.n_obs, "recompute": int(args.recompute), "cuda_graph": not args.no_graph,
-                   "parallelism": f"replicas x{world} (independent cases)",
-                   "l2": "per-eval working set (2 x 0.86 GB bf16 weights + ~1 GB stash per application) >> 126 MB L2; no flush needed"},
+        "config": workload_config(T, args.obs_frac, eng.n_obs, args.recompute, not args.no_graph, world),
         "evals_per_s": 1e3 * args.steps * world / total_ms,
         "da_cycles_per_hour": (3600.0 * world / cyc_s) if cyc_s else 3600e3 * args.steps * world / total_ms / (12 * 4 + 5 + 1),
         "da_cycle": {"measured": bool(cyc_s), "seconds_per_cycle": cyc_s, "closure_evals": cyc_evals,
