@@ -198,7 +198,8 @@ static void launch_pair(const GemmDesc& d, cudaStream_t s) {
     attr_set = true;
   }
   const long long tiles = (long long)((d.a.N + BN - 1) / BN) * ((d.a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * d.a.batch;
-  const int pairs = (int)std::min<long long>(tiles, num_sms() / 2);
+  int pairs = (int)std::min<long long>(tiles, num_sms() / 2);
+  if (const char* cap = getenv("VV_GEMM_MAXPAIRS")) pairs = std::max(1, std::min(pairs, atoi(cap)));   // experiments only
   launch_kernel(gemm_pair_kernel<BN, STAGES, F16, LNX>, dim3(2 * pairs), dim3(GEMM_THREADS), L::TOTAL, s, d.tmA, d.tmB, d.sm, d.a);
 }
 
