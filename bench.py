@@ -239,7 +239,8 @@ def main():
         if world > 1:
             dist.all_reduce(cyc, op=dist.ReduceOp.MAX)
         cyc_s = float(cyc)
-        cyc_evals = int(sum(h["n_evals"] for h in agent.history[-4:]))
+        cyc_evals = int(sum(h["n_evals"] for h in agent.history[-4:]))       # as torch.optim.LBFGS counts them; 3 of them are served
+                                                                             # from the optimiser's own state (vv_lbfgs_set_reuse)
         eng.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)          # restore the benchmark case
 
     if rank != 0:

@@ -111,10 +111,15 @@ typedef struct vv_lbfgs vv_lbfgs;
 VV_API int vv_lbfgs_create(vv_engine* e, int history_size, int max_iter, vv_lbfgs** out);
 VV_API void vv_lbfgs_destroy(vv_lbfgs* o);
 /* One optimizer.step(closure) on z_dev (updated in place). info_host[8] = {loss at entry, final loss, n closure evals
- * this step, n_iter total, last step length, |g|_inf, 0, 0}. Synchronises. */
+ * this step, n_iter total, last step length, |g|_inf, closure evaluations so far, evaluations skipped so far}. Synchronises. */
 VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z_dev, double* info_host, void* stream);
 /* Losses of every closure evaluation so far (returns the total count; copies at most cap). */
 VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out_host, int cap);
+/* torch.optim.LBFGS.step() opens with a closure() at the point the previous step() ended on; its loss and gradient are already
+ * held by the optimiser.  With reuse on (the default) that evaluation is skipped when z is bit-identical to the z the previous
+ * step left (checked on the device): same iterates, one cost+gradient sweep less per step; it still counts against max_eval.
+ * info_host[7] of vv_lbfgs_step = evaluations skipped so far.  on = 0 restores an evaluation per step() entry. */
+VV_API int vv_lbfgs_set_reuse(vv_lbfgs* o, int on);
 /* Relative rounding noise of the closure's loss that the line search tolerates in its "loss went up" tests (relaxed Armijo
  * condition f(t) <= f(0) + c1 t g'd + f_noise_rel |f(0)|).  Engine-bound optimisers default to 5e-5 (fp16 forward) / 4e-4
  * (bf16 forward); 0 reproduces torch.optim.LBFGS decision for decision. */

@@ -185,3 +185,30 @@ def test_cycled_da_two_cycles_small(chk, tmp_path):
     assert bg.shape == an.shape == (2, 69)
     assert float((an / bg).mean()) < 1.0
     assert (tmp_path / "t" / "xb.npy").exists() and (tmp_path / "t" / "ana_wrmse.npy").exists()
+
+
+def test_lbfgs_entry_evaluation_reuse_keeps_the_trajectory(chk):
+    """The closure() a step() opens with is skipped when z is unchanged since the previous step (vv_lbfgs_set_reuse):
+    bit-identical iterates, one evaluation less per step after the first."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import LBFGS, Engine
+    from vaevar_b200.synth import make_case, make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    e = Engine(ds, fs, T=2)
+    e.load_state_dict(0, make_state_dict(ds, seed=0)); e.load_state_dict(1, make_state_dict(fs, seed=1)); e.finalize()
+    case = make_case(2, *ds.img_size, obs_frac=0.2, seed=3)
+    e.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+    out = []
+    for reuse in (True, False):
+        z = torch.zeros(1, 32, *ds.img_size, device="cuda")
+        opt = LBFGS(e, 10, 10)
+        opt.set_reuse(reuse)
+        infos = [opt.step(z) for _ in range(3)]
+        out.append((z.clone(), infos))
+        opt.close()
+    (z1, i1), (z0, i0) = out
+    assert torch.equal(z1, z0)
+    assert [i["n_evals"] for i in i1] == [i["n_evals"] for i in i0]           # logical count (max_eval budget) unchanged
+    assert i1[-1]["skipped_evals"] == 2 and i0[-1]["skipped_evals"] == 0
+    assert i0[-1]["func_evals"] - i1[-1]["func_evals"] == 2
+    e.close()

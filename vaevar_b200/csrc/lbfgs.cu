@@ -35,6 +35,14 @@ struct vv_lbfgs {
   bool t_is_tensor = false;
   bool have_prev = false;
   long long n_iter_total = 0, func_evals = 0;
+  // torch.optim.LBFGS.step() opens with closure() at the point the previous step() ended on (lbfgs.py:361-366) -- a point whose
+  // loss and gradient this object already holds (strong_wolfe leaves them in last_loss / g).  The engine is deterministic, so
+  // when z is bit-identical to the copy taken at the end of the previous step the evaluation is skipped and the stored values
+  // are used: same trajectory, one network sweep less per step.  The skipped evaluation still counts against max_eval.
+  bool reuse_entry = true, have_last = false;
+  double last_loss = 0.0;
+  long long skipped_evals = 0;
+  float* z_last = nullptr;
   // device scalars + pinned read-back
   double *dsc = nullptr, *dscratch = nullptr, *Jdev = nullptr;
   double* pinned = nullptr;
@@ -321,6 +329,12 @@ VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out, int cap) {
   return (int)o->hist_loss.size();
 }
 
+VV_API int vv_lbfgs_set_reuse(vv_lbfgs* o, int on) {
+  if (!o) { set_error("vv_lbfgs_set_reuse: null argument"); return -2; }
+  o->reuse_entry = on != 0;
+  return 0;
+}
+
 VV_API int vv_lbfgs_set_noise(vv_lbfgs* o, double f_noise_rel) {
   if (!o || !(f_noise_rel >= 0.0)) { set_error("vv_lbfgs_set_noise: bad argument"); return -2; }
   o->f_noise_rel = f_noise_rel;
@@ -338,7 +352,7 @@ static int lbfgs_alloc(vv_lbfgs* o, long long nn, int history_size, int max_iter
   o->hist = history_size; o->max_iter = max_iter; o->max_eval = max_iter * 5 / 4;
   o->n = nn;
   const size_t n = (size_t)o->n;
-  float** vecs[] = {&o->g, &o->g_prev, &o->d, &o->x_init, &o->g_new, &o->bg[0], &o->bg[1], &o->ls_gprev};
+  float** vecs[] = {&o->g, &o->g_prev, &o->d, &o->x_init, &o->g_new, &o->bg[0], &o->bg[1], &o->ls_gprev, &o->z_last};
   bool ok = true;
   for (auto v : vecs) ok = ok && (*v = lalloc<float>(o, n));
   for (int i = 0; i < 2 * history_size + 2 && ok; ++i) {
@@ -373,8 +387,18 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   const long long n = o->n;
   double loss, gmax, gl1;
   o->hist_t.push_back(0.0);
-  int rc = eval(o, z, o->g, nullptr, &loss, nullptr, s);             // lbfgs.py:361-366
-  if (rc) return rc;
+  bool reused = false;
+  if (o->reuse_entry && o->have_last) {
+    launch_axpby(o->x_init, z, nullptr, 1.0, nullptr, 0.0, n, s);                     // x_init is scratch here: z - z_last
+    launch_axpby(o->x_init, o->z_last, nullptr, -1.0, nullptr, 1.0, n, s);
+    double dmax0;
+    if (absmax_l1_host(o, o->x_init, &dmax0, nullptr, s)) return -1;
+    if (dmax0 == 0.0) { loss = o->last_loss; o->hist_loss.push_back(loss); o->skipped_evals++; reused = true; }
+  }
+  if (!reused) {
+    int rc = eval(o, z, o->g, nullptr, &loss, nullptr, s);           // lbfgs.py:361-366
+    if (rc) return rc;
+  }
   const double orig_loss = loss;
   int current_evals = 1;
   if (absmax_l1_host(o, o->g, &gmax, &gl1, s)) return -1;
@@ -457,10 +481,12 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
       if (fabs(loss - o->prev_loss) < o->tol_change) break;
     }
   }
+  if (copy_vec(o, o->z_last, z, s)) return -1;
+  o->last_loss = loss; o->have_last = true;
   LB_CUDA(cudaStreamSynchronize(s));
   if (info) {
     info[0] = orig_loss; info[1] = loss; info[2] = current_evals; info[3] = (double)o->n_iter_total;
-    info[4] = o->t; info[5] = gmax; info[6] = (double)o->func_evals; info[7] = 0;
+    info[4] = o->t; info[5] = gmax; info[6] = (double)o->func_evals; info[7] = (double)o->skipped_evals;
   }
   return 0;
 }

@@ -211,7 +211,11 @@ class LBFGS:
         info = (C.c_double * 8)()
         _lib.check(self.lib.vv_lbfgs_step(self._h, _ptr(z), info, _stream()))
         return dict(loss0=info[0], loss=info[1], n_evals=int(info[2]), n_iter=int(info[3]), t=info[4], gmax=info[5],
-                    func_evals=int(info[6]))
+                    func_evals=int(info[6]), skipped_evals=int(info[7]))
+
+    def set_reuse(self, on: bool):
+        """Skip the closure() a step() opens with when z is unchanged since the previous step (default on)."""
+        _lib.check(self.lib.vv_lbfgs_set_reuse(self._h, int(on)))
 
     def close(self):
         if self._h:
