@@ -110,11 +110,17 @@ VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phy
 typedef struct vv_lbfgs vv_lbfgs;
 VV_API int vv_lbfgs_create(vv_engine* e, int history_size, int max_iter, vv_lbfgs** out);
 VV_API void vv_lbfgs_destroy(vv_lbfgs* o);
+/* Forget history, step count and cached evaluations: the state of a new optimiser (one per DA cycle, da_4dvar.py:1240), keeping
+ * the device vectors. */
+VV_API int vv_lbfgs_reset(vv_lbfgs* o);
 /* One optimizer.step(closure) on z_dev (updated in place). info_host[8] = {loss at entry, final loss, n closure evals
  * this step, n_iter total, last step length, |g|_inf, closure evaluations so far, evaluations skipped so far}. Synchronises. */
 VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z_dev, double* info_host, void* stream);
 /* Losses of every closure evaluation so far (returns the total count; copies at most cap). */
 VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out_host, int cap);
+/* {J, J_reg, J_obs} at the point the last step() left z on -- what cal_loss(z) (da_4dvar.py:1210-1236, printed by the outer
+ * loop at :1265-1269) evaluates again; the optimiser already has it from the accepted line-search trial. */
+VV_API int vv_lbfgs_last_cost(vv_lbfgs* o, double* J3_host);
 /* torch.optim.LBFGS.step() opens with a closure() at the point the previous step() ended on; its loss and gradient are already
  * held by the optimiser.  With reuse on (the default) that evaluation is skipped when z is bit-identical to the z the previous
  * step left (checked on the device): same iterates, one cost+gradient sweep less per step; it still counts against max_eval.

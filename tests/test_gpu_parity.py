@@ -204,6 +204,8 @@ def test_lbfgs_entry_evaluation_reuse_keeps_the_trajectory(chk):
         opt = LBFGS(e, 10, 10)
         opt.set_reuse(reuse)
         infos = [opt.step(z) for _ in range(3)]
+        # the cost split the optimiser holds for the point it stopped on == cal_loss(z) evaluated afresh
+        np.testing.assert_allclose(opt.last_cost().numpy(), e.cost(z).cpu().numpy(), rtol=1e-12)
         out.append((z.clone(), infos))
         opt.close()
     (z1, i1), (z0, i0) = out

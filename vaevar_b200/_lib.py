@@ -45,8 +45,10 @@ _SIGS = {
     "vv_net_vjp": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "vv_lbfgs_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "vv_lbfgs_destroy": (None, [_P]),
+    "vv_lbfgs_reset": (C.c_int, [_P]),
     "vv_lbfgs_step": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     "vv_lbfgs_history": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
+    "vv_lbfgs_last_cost": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "vv_lbfgs_set_reuse": (C.c_int, [_P, C.c_int]),
     "vv_lbfgs_set_noise": (C.c_int, [_P, C.c_double]),
     "vv_lbfgs_steps": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),

@@ -6,6 +6,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <array>
 #include <functional>
 #include <vector>
 
@@ -39,6 +40,9 @@ struct vv_lbfgs {
   // loss and gradient this object already holds (strong_wolfe leaves them in last_loss / g).  The engine is deterministic, so
   // when z is bit-identical to the copy taken at the end of the previous step the evaluation is skipped and the stored values
   // are used: same trajectory, one network sweep less per step.  The skipped evaluation still counts against max_eval.
+  double eval_J3[3] = {0, 0, 0};          // {J, J_reg, J_obs} of the most recent closure evaluation (engine closures)
+  double acc_J3[3] = {0, 0, 0};           // ... of the point z currently sits on (what cal_loss(z) would return)
+  std::vector<std::array<double, 4>> ls_log;   // (t, J, J_reg, J_obs) of the current line search's trials
   bool reuse_entry = true, have_last = false;
   double last_loss = 0.0;
   long long skipped_evals = 0;
@@ -102,6 +106,7 @@ int eval(vv_lbfgs* o, const float* z, float* gout, const float* dvec, double* f,
   }
   if (readback(o, o->Jdev, 4, s)) return -1;
   *f = (double)(float)o->pinned[0];          // float(closure()): the reference's loss is a float32 tensor
+  o->eval_J3[0] = o->pinned[0]; o->eval_J3[1] = o->pinned[1]; o->eval_J3[2] = o->pinned[2];
   if (gtd) *gtd = o->pinned[3];
   o->func_evals++;
   o->hist_loss.push_back(*f);
@@ -175,6 +180,7 @@ int strong_wolfe(vv_lbfgs* o, float* z, Sc t, double f, Sc gtd, int max_ls, doub
     double g = 0.0;
     int rc = eval(o, z, o->g_new, o->d, fn, &g, s);
     *gn = tn(g);
+    o->ls_log.push_back({tt.v, o->eval_J3[0], o->eval_J3[1], o->eval_J3[2]});
     return rc;
   };
   // Noise-tolerant sufficient-decrease test: the closure's loss carries relative rounding noise eps (16-bit activations), and
@@ -329,6 +335,28 @@ VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out, int cap) {
   return (int)o->hist_loss.size();
 }
 
+// Back to the state of a freshly constructed optimiser (the reference builds a new torch.optim.LBFGS per cycle,
+// da_4dvar.py:1240) without giving back its ~30 device vectors and pinned buffer.
+VV_API int vv_lbfgs_reset(vv_lbfgs* o) {
+  if (!o) { set_error("vv_lbfgs_reset: null argument"); return -2; }
+  for (float* p : o->old_y) o->free_vecs.push_back(p);
+  for (float* p : o->old_s) o->free_vecs.push_back(p);
+  o->old_y.clear(); o->old_s.clear(); o->ro.clear();
+  o->hist_loss.clear(); o->hist_t.clear(); o->ls_log.clear();
+  o->H_diag = 1.0; o->t = 1.0; o->prev_loss = 0.0;
+  o->t_is_tensor = false; o->have_prev = false; o->have_last = false;
+  o->n_iter_total = 0; o->func_evals = 0; o->skipped_evals = 0; o->last_loss = 0.0;
+  for (int k = 0; k < 3; ++k) o->eval_J3[k] = o->acc_J3[k] = 0.0;
+  return 0;
+}
+
+VV_API int vv_lbfgs_last_cost(vv_lbfgs* o, double* J3_host) {
+  if (!o || !J3_host) { set_error("vv_lbfgs_last_cost: null argument"); return -2; }
+  if (!o->have_last) { set_error("vv_lbfgs_last_cost: no step has been taken yet"); return -2; }
+  for (int k = 0; k < 3; ++k) J3_host[k] = o->acc_J3[k];
+  return 0;
+}
+
 VV_API int vv_lbfgs_set_reuse(vv_lbfgs* o, int on) {
   if (!o) { set_error("vv_lbfgs_set_reuse: null argument"); return -2; }
   o->reuse_entry = on != 0;
@@ -398,6 +426,7 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   if (!reused) {
     int rc = eval(o, z, o->g, nullptr, &loss, nullptr, s);           // lbfgs.py:361-366
     if (rc) return rc;
+    for (int k = 0; k < 3; ++k) o->acc_J3[k] = o->eval_J3[k];
   }
   const double orig_loss = loss;
   int current_evals = 1;
@@ -466,7 +495,10 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
       if (copy_vec(o, o->x_init, z, s)) return -1;
       int ls_evals = 0;
       Sc t_new; double f_new;
+      o->ls_log.clear();
       if (strong_wolfe(o, z, t0, loss, gtd, o->max_eval - current_evals, &f_new, &t_new, &ls_evals, s)) return -1;
+      for (const auto& r : o->ls_log)                                                 // the trial the search settled on (t = 0: keep)
+        if (r[0] == t_new.v) { o->acc_J3[0] = r[1]; o->acc_J3[1] = r[2]; o->acc_J3[2] = r[3]; }
       loss = f_new; o->t = t_new.v; o->t_is_tensor = t_new.t;
       if (copy_vec(o, z, o->x_init, s)) return -1;
       launch_axpby(z, o->d, nullptr, o->t, nullptr, 1.0, n, s);                       // z += t d  (lbfgs.py:488)

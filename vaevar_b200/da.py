@@ -65,6 +65,7 @@ class VaeVar4D:
         self.latent = dec_cfg.in_chans
         self.metrics_list = {k: [] for k in ("bg_wrmse", "bg_bias", "ana_wrmse", "ana_bias")}
         self.history = []
+        self._opt = None
 
     def integrate(self, xa: torch.Tensor, model=None, step: int = 1, interpolation: bool = False, detach: bool = True):
         """(69,nlat,nlon) physical -> physical after `step` applications of the flow model (da_4dvar.py:666-681)."""
@@ -82,11 +83,15 @@ class VaeVar4D:
         gt0 = torch.as_tensor(gt[0]).to(dev, torch.float32)
         self.engine.set_case(xb, yo, H, R, self.obs_coeff)
         z = torch.zeros(1, self.latent, self.nlat, self.nlon, device=dev)   # da_4dvar.py:1238
-        opt = LBFGS(self.engine, history_size=10, max_iter=10)              # da_4dvar.py:1240
+        if self._opt is None:                                               # da_4dvar.py:1240: a new optimiser per cycle --
+            self._opt = LBFGS(self.engine, history_size=10, max_iter=10)    # here one object, reset (its 30 device vectors are kept)
+        opt = self._opt
+        opt.reset()
         t0 = time.time()
         for kk in range(self.Nit + 1):
             w, b = self._diagnostics(z, gt0)
-            J = self.engine.cost(z).cpu()                                   # cal_loss, da_4dvar.py:1265
+            # cal_loss(z), da_4dvar.py:1265: after a step the optimiser already holds the split of the point it stopped on
+            J = self.engine.cost(z).cpu() if kk == 0 else opt.last_cost()
             if self.verbose:
                 print("iter: %d, RMSE (z500): %.4g Bias (z500): %.4g q500: %.4g, t2m: %.4g t850: %.4g u500: %.4g, v500: %.4g, "
                       "loss reg: %.4g loss obs: %.4g loss: %.4g" % (kk, w[11], b[11], w[24], w[2], w[66], w[37], w[50],
@@ -103,6 +108,5 @@ class VaeVar4D:
         torch.cuda.synchronize()
         if self.verbose:
             print("DA finished. Time consumed: %.3f (s)" % (time.time() - t0), flush=True)
-        opt.close()
         self.z = z
         return xa

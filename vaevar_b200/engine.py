@@ -213,6 +213,16 @@ class LBFGS:
         return dict(loss0=info[0], loss=info[1], n_evals=int(info[2]), n_iter=int(info[3]), t=info[4], gmax=info[5],
                     func_evals=int(info[6]), skipped_evals=int(info[7]))
 
+    def reset(self):
+        """State of a freshly constructed optimiser (the reference builds one per cycle), device vectors kept."""
+        _lib.check(self.lib.vv_lbfgs_reset(self._h))
+
+    def last_cost(self):
+        """(J, J_reg, J_obs) at the point the last step() left z on (cal_loss(z) without another network sweep)."""
+        out = (C.c_double * 3)()
+        _lib.check(self.lib.vv_lbfgs_last_cost(self._h, out))
+        return torch.tensor([out[0], out[1], out[2]], dtype=torch.float64)
+
     def set_reuse(self, on: bool):
         """Skip the closure() a step() opens with when z is unchanged since the previous step (default on)."""
         _lib.check(self.lib.vv_lbfgs_set_reuse(self._h, int(on)))
