@@ -189,34 +189,46 @@ static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, 
   return nullptr;
 }
 
-template <int BN, int STAGES, bool F16, bool LNX>
+template <int BN, int STAGES, bool F16, bool LNX, int EPI>
 static void launch_pair(const GemmDesc& d, cudaStream_t s) {
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_pair_kernel<BN, STAGES, F16, LNX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaFuncSetAttribute(gemm_pair_kernel<BN, STAGES, F16, LNX, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     attr_set = true;
   }
   const long long tiles = (long long)((d.a.N + BN - 1) / BN) * ((d.a.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * d.a.batch;
   int pairs = (int)std::min<long long>(tiles, num_sms() / 2);
   if (const char* cap = getenv("VV_GEMM_MAXPAIRS")) pairs = std::max(1, std::min(pairs, atoi(cap)));   // experiments only
-  launch_kernel(gemm_pair_kernel<BN, STAGES, F16, LNX>, dim3(2 * pairs), dim3(GEMM_THREADS), L::TOTAL, s, d.tmA, d.tmB, d.sm, d.a);
+  launch_kernel(gemm_pair_kernel<BN, STAGES, F16, LNX, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), L::TOTAL, s, d.tmA, d.tmB, d.sm, d.a);
 }
 
-template <bool F16, bool LNX>
+template <bool F16, bool LNX, int EPI>
 static void launch_f(const GemmDesc& d, cudaStream_t s) {
   switch (d.bn) {
-    case 64: launch_pair<64, 6, F16, LNX>(d, s); break;
-    case 192: launch_pair<192, 4, F16, LNX>(d, s); break;
-    case 256: launch_pair<256, 4, F16, LNX>(d, s); break;
-    default: launch_pair<128, 5, F16, LNX>(d, s); break;
+    case 64: launch_pair<64, 6, F16, LNX, EPI>(d, s); break;
+    case 192: launch_pair<192, 4, F16, LNX, EPI>(d, s); break;
+    case 256: launch_pair<256, 4, F16, LNX, EPI>(d, s); break;
+    default: launch_pair<128, 5, F16, LNX, EPI>(d, s); break;
+  }
+}
+
+template <bool F16>
+static void launch_e(const GemmDesc& d, cudaStream_t s) {
+  const bool lnx = d.a.ln_stats != nullptr || d.a.stats_out != nullptr;     // forward pass only (GELU' is never combined with it)
+  if (lnx) {
+    if (d.a.epi == EPI_GELU) launch_f<F16, true, EPI_GELU>(d, s);
+    else launch_f<F16, true, EPI_LINEAR>(d, s);
+  } else {
+    if (d.a.epi == EPI_GELU) launch_f<F16, false, EPI_GELU>(d, s);
+    else if (d.a.epi == EPI_DGELU) launch_f<F16, false, EPI_DGELU>(d, s);
+    else launch_f<F16, false, EPI_LINEAR>(d, s);
   }
 }
 
 void launch_gemm(const GemmDesc& d, cudaStream_t s) {
-  const bool lnx = d.a.ln_stats != nullptr || d.a.stats_out != nullptr;     // forward pass only (DGELU is never combined with it)
-  if (d.a.f16) { if (lnx) launch_f<true, true>(d, s); else launch_f<true, false>(d, s); }
-  else { if (lnx) launch_f<false, true>(d, s); else launch_f<false, false>(d, s); }
+  if (d.a.f16) launch_e<true>(d, s);
+  else launch_e<false>(d, s);
 }
 
 }  // namespace vv

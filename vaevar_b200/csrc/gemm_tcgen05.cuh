@@ -174,7 +174,9 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
 
 // LNX: the instantiation that can fold a LayerNorm into the epilogue (consumer: ln_stats) and / or emit LayerNorm statistics of
 // its fp32 output (producer: stats_out); the plain instantiation carries none of that code.
-template <int BN, int STAGES, bool F16, bool LNX>
+// EPI is a compile-time parameter as well: one epilogue variant per instantiation keeps the kernel around 40 KB of SASS (the
+// three roles' code sits far apart and the all-variants kernel overflowed the instruction cache: "no instruction" stalls).
+template <int BN, int STAGES, bool F16, bool LNX, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GemmStoreMaps io, const GemmArgs p) {
@@ -331,8 +333,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* slab = smem + L::SLAB_OFF + ew * GEMM_WARP_SLAB;
     uint64_t* ldbar = &epi_ld_bar[2 * ew];
     uint32_t ld_phase = 0;                                   // bit b: phase of ldbar[b]
-    const bool has_res = p.res != nullptr, has_auxin = (p.epi == EPI_DGELU) && p.aux_in != nullptr;
-    const bool has_auxout = (p.epi == EPI_GELU) && p.aux_out != nullptr;
+    const bool has_res = p.res != nullptr, has_auxin = (EPI == EPI_DGELU) && p.aux_in != nullptr;
+    const bool has_auxout = (EPI == EPI_GELU) && p.aux_out != nullptr;
     const bool has_loads = has_res || has_auxin;
     const uint32_t load_bytes = (has_res ? GEMM_SLOT_A : 0) + (has_auxin ? GEMM_SLOT_B : 0);
 
@@ -474,9 +476,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ld_phase ^= 1u << buf;
         }
         // (4) fused math, results staged in place
-        if (p.epi == EPI_GELU) epilogue_chunk<EPI_GELU, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
-        else if (!LNX && p.epi == EPI_DGELU) epilogue_chunk<EPI_DGELU, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
-        else epilogue_chunk<EPI_LINEAR, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
+        epilogue_chunk<EPI, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
         // (5) bulk stores
         fence_proxy_async();
         __syncwarp();
