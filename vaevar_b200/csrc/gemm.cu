@@ -158,6 +158,8 @@ static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, 
   if (args.epi == EPI_GELU && args.aux_out && args.out_f32) return "GEMM: fp32 output together with a saved pre-activation is not supported";
   if (args.epi == EPI_DGELU && args.res) return "GEMM: GELU' epilogue with a residual is not supported";
   if (args.epi == EPI_DGELU && (args.ln_stats || args.stats_out)) return "GEMM: GELU' epilogue with LayerNorm folding is not supported";
+  if (args.ln_stats && args.stats_out) return "GEMM: a LayerNorm consumer cannot also be a statistics producer";
+  if (args.stats_out && args.epi != EPI_LINEAR) return "GEMM: statistics are produced by linear epilogues only";
   d->a = args;
   const bool b_contig = ldb == args.K && (args.batch == 1 || b_bs == (long long)args.N * args.K);
   d->b_ptr = b_contig ? B : nullptr;
@@ -189,7 +191,7 @@ static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, 
   return nullptr;
 }
 
-template <int BN, int STAGES, bool F16, bool LNX, int EPI>
+template <int BN, int STAGES, bool F16, int LNX, int EPI>
 static void launch_pair(const GemmDesc& d, cudaStream_t s) {
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
@@ -203,7 +205,7 @@ static void launch_pair(const GemmDesc& d, cudaStream_t s) {
   launch_kernel(gemm_pair_kernel<BN, STAGES, F16, LNX, EPI>, dim3(2 * pairs), dim3(GEMM_THREADS), L::TOTAL, s, d.tmA, d.tmB, d.sm, d.a);
 }
 
-template <bool F16, bool LNX, int EPI>
+template <bool F16, int LNX, int EPI>
 static void launch_f(const GemmDesc& d, cudaStream_t s) {
   switch (d.bn) {
     case 64: launch_pair<64, 6, F16, LNX, EPI>(d, s); break;
@@ -215,14 +217,16 @@ static void launch_f(const GemmDesc& d, cudaStream_t s) {
 
 template <bool F16>
 static void launch_e(const GemmDesc& d, cudaStream_t s) {
-  const bool lnx = d.a.ln_stats != nullptr || d.a.stats_out != nullptr;     // forward pass only (GELU' is never combined with it)
-  if (lnx) {
-    if (d.a.epi == EPI_GELU) launch_f<F16, true, EPI_GELU>(d, s);
-    else launch_f<F16, true, EPI_LINEAR>(d, s);
+  // forward pass only: a GEMM either applies a folded LayerNorm (qkv, fc1) or emits the statistics of its output (proj, fc2, seams)
+  if (d.a.ln_stats) {
+    if (d.a.epi == EPI_GELU) launch_f<F16, LN_CONSUME, EPI_GELU>(d, s);
+    else launch_f<F16, LN_CONSUME, EPI_LINEAR>(d, s);
+  } else if (d.a.stats_out) {
+    launch_f<F16, LN_PRODUCE, EPI_LINEAR>(d, s);
   } else {
-    if (d.a.epi == EPI_GELU) launch_f<F16, false, EPI_GELU>(d, s);
-    else if (d.a.epi == EPI_DGELU) launch_f<F16, false, EPI_DGELU>(d, s);
-    else launch_f<F16, false, EPI_LINEAR>(d, s);
+    if (d.a.epi == EPI_GELU) launch_f<F16, LN_NONE, EPI_GELU>(d, s);
+    else if (d.a.epi == EPI_DGELU) launch_f<F16, LN_NONE, EPI_DGELU>(d, s);
+    else launch_f<F16, LN_NONE, EPI_LINEAR>(d, s);
   }
 }
 

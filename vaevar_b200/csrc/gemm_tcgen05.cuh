@@ -22,6 +22,8 @@
 
 namespace vv {
 
+enum GemmLn : int { LN_NONE = 0, LN_CONSUME = 1, LN_PRODUCE = 2 };
+
 enum GemmEpi : int {
   EPI_LINEAR = 0,  // v = acc + bias
   EPI_GELU = 1,    // u = acc + bias ; aux_out = 16bit(gelu'(u)) ; v = gelu(u)
@@ -112,7 +114,7 @@ VV_DEVINL float2 unpack16(uint32_t w, bool f16) {
 // bv[] the bias of the 32 columns; slot A / slot B are this warp's staging slabs (see GEMM_SLOT_*).
 // ln_a scales the accumulator (the row's rstd when a LayerNorm is folded into this GEMM, else 1); rs / rq accumulate the
 // row's sum and sum of squares of the final fp32 values when this GEMM produces LayerNorm statistics for its consumer.
-template <int EPI, bool F16, bool LNX>
+template <int EPI, bool F16, int LNX>
 VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float (&bv)[32], uint8_t* SA, uint8_t* SB, int lane,
                               bool has_res, bool has_auxin, bool has_auxout, float ln_a, float& rs, float& rq) {
   const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // 128B swizzle: 16-byte chunk c of row r lives at c ^ (r & 7)
@@ -125,7 +127,7 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      v[i] = LNX ? fmaf(ln_a, __uint_as_float(r[g * 8 + i]), bv[g * 8 + i]) : __uint_as_float(r[g * 8 + i]) + bv[g * 8 + i];
+      v[i] = LNX == LN_CONSUME ? fmaf(ln_a, __uint_as_float(r[g * 8 + i]), bv[g * 8 + i]) : __uint_as_float(r[g * 8 + i]) + bv[g * 8 + i];
     uint4 u16 = make_uint4(0, 0, 0, 0);
     if (EPI == EPI_GELU) {
       if (has_auxout) {                      // gelu and gelu' share their transcendental work; the backward pass needs only gelu'(u)
@@ -154,7 +156,7 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
       v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
       v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
     }
-    if (LNX && p.stats_out) {                 // two independent partial chains per statistic
+    if (LNX == LN_PRODUCE && p.stats_out) {   // two independent partial chains per statistic
       rs += (v[0] + v[1]) + (v[2] + v[3]) + ((v[4] + v[5]) + (v[6] + v[7]));
       rq += fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3]) + (fmaf(v[4], v[4], v[5] * v[5]) + fmaf(v[6], v[6], v[7] * v[7]));
     }
@@ -172,11 +174,11 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
   }
 }
 
-// LNX: the instantiation that can fold a LayerNorm into the epilogue (consumer: ln_stats) and / or emit LayerNorm statistics of
+// LNX: LN_CONSUME = the instantiation that folds a LayerNorm into the epilogue (ln_stats), LN_PRODUCE = the one that emits the statistics of
 // its fp32 output (producer: stats_out); the plain instantiation carries none of that code.
 // EPI is a compile-time parameter as well: one epilogue variant per instantiation keeps the kernel around 40 KB of SASS (the
 // three roles' code sits far apart and the all-variants kernel overflowed the instruction cache: "no instruction" stalls).
-template <int BN, int STAGES, bool F16, bool LNX, int EPI>
+template <int BN, int STAGES, bool F16, int LNX, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ GemmStoreMaps io, const GemmArgs p) {
@@ -382,7 +384,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (j < p.ln_parts) stat_nx[j] = __ldg(st + j * p.M);
     };
     Coord cur{pair, pair % n_tiles, (pair / n_tiles) % pair_rows, pair / (n_tiles * pair_rows)};
-    const bool ln_on = LNX && p.ln_stats != nullptr;
+    const bool ln_on = LNX == LN_CONSUME && p.ln_stats != nullptr;
     if (ln_on) load_stats(cur);
     uint32_t it = 0;
     bool pre_issued = false;                                 // the loads of this warp's first chunk of the coming tile are in flight
@@ -436,13 +438,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // (2) bias (and, for a folded LayerNorm, the column sums) of the 32 columns: warp-uniform addresses, every load into its
         //     own registers and all of them in flight together with the TMEM load
         float bv[32];
-        float4 svv[LNX ? 8 : 1];
+        float4 svv[LNX == LN_CONSUME ? 8 : 1];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias && col + 4 * j < p.N) t = __ldg(reinterpret_cast<const float4*>(bias + col + 4 * j));
           bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
-          if (LNX) {
+          if (LNX == LN_CONSUME) {
             svv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (colsum && col + 4 * j < p.N) svv[j] = __ldg(reinterpret_cast<const float4*>(colsum + col + 4 * j));
           }
@@ -464,7 +466,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
         tmem_ld_wait();
-        if (LNX && colsum) {                                             // folded LayerNorm: c_n - rstd mean s_n
+        if (LNX == LN_CONSUME && colsum) {                                             // folded LayerNorm: c_n - rstd mean s_n
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             bv[4 * j] = fmaf(-ln_b, svv[j].x, bv[4 * j]); bv[4 * j + 1] = fmaf(-ln_b, svv[j].y, bv[4 * j + 1]);
@@ -490,7 +492,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
-      if (LNX && p.stats_out && mrow + lane < p.M) {      // partial (sum, sumsq) of this warp's columns of the row; zeros if it had none
+      if (LNX == LN_PRODUCE && p.stats_out && mrow + lane < p.M) {      // partial (sum, sumsq) of this warp's columns of the row; zeros if it had none
         float2* so = reinterpret_cast<float2*>(p.stats_out + (long long)b * p.stats_out_bs);
         so[(long long)(2 * cur.nt + half) * p.M + mrow + lane] = make_float2(rs, rq);
       }
