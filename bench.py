@@ -335,7 +335,8 @@ def main():
         "gpu_launches": launches * args.steps,
         "gpu_launches_per_step": launches,
         "roofline": {"bound": "tensor", "achieved": k_tfs, "peak": burst, "unit": "TFLOP/s", "frac": k_tfs / burst,
-                     "traffic": 17.26e6,   # dram__bytes_read + write of this launch, profiles/r1_ncu_fc1_gelu.csv (algorithmic reads: 15.3 MB)
+                     "traffic": 16.24e6,   # dram__bytes_read + write of this launch, profiles/r1_ncu_fc1_gelu.csv (algorithmic reads: 15.3 MB;
+                                           # the 37.7 MB of results stay in the write-back L2 past the end of the launch)
                      "kernel": "gemm_pair_kernel<256,4,fp16> 2048x4608x1152 + bias + GELU + saved pre-activation (fc1 of the d=1152 trunk blocks), timed alone, L2 flushed",
                      "peak_source": f"{src} burst"},
         "roofline_step": {"bound": "tensor", "achieved": step_tfs, "peak": sustained, "unit": "TFLOP/s", "frac": step_tfs / sustained,
