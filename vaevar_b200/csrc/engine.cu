@@ -373,7 +373,7 @@ static int finalize_net(vv_engine* e, Net& n) {
 // plan construction
 // ---------------------------------------------------------------------------------------------
 struct Temps {
-  bf16 *h, *ao, *a, *du, *dao, *dqkv, *dx1b;
+  bf16 *h, *ao, *a, *du, *dao, *dqkv, *dx1b, *dhb;
   float *dh, *dx1;
   float* lnst; size_t lnst_cap;      // LayerNorm statistics partials: float2 [batch][parts][rows]; capacity in float2
   // seams (forward)
@@ -416,10 +416,10 @@ struct Builder {
   }
   void ln_b(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
             const float* gamma, const float* dy, long long ld_dy, long long dy_bs, const float* dres, long long ld_dres, long long dres_bs,
-            float* dx, long long ld_dx, long long dx_bs, bf16* dxb, long long ld_dxb, long long dxb_bs) {
+            float* dx, long long ld_dx, long long dx_bs, bf16* dxb, long long ld_dxb, long long dxb_bs, const bf16* dy16 = nullptr) {
     Op o{}; o.kind = Op::LN_B;
     o.lnb = LnBwdArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, (long long)C, dy, ld_dy, dy_bs, dres, ld_dres, dres_bs,
-                      dx, ld_dx, dx_bs, dxb, ld_dxb, dxb_bs};
+                      dx, ld_dx, dx_bs, dxb, ld_dxb, dxb_bs, dy16};
     P.ops.push_back(o);
   }
   // GEMM whose fp32 output is the input of a LayerNorm folded into the NEXT GEMM: it also writes the raw 16-bit copy of its
@@ -481,9 +481,9 @@ struct Builder {
     g.epi = EPI_DGELU; g.aux_in = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd; g.out_bf16 = t.du; g.ld_bf16 = 4 * d; g.bf16_bs = 4 * rd;
     gemm(P, g16, d, rd, w.W2T, d, 4LL * d * d, g);
     g = gb(rows, d, 4 * d, G);                                // d(LN2 out) = du W1
-    g.out_f32 = t.dh; g.ld_f32 = d; g.f32_bs = rd;
+    g.out_bf16 = t.dhb; g.ld_bf16 = d; g.bf16_bs = rd;        // bf16 like every other gradient that enters a GEMM / LayerNorm adjoint
     gemm(P, t.du, 4 * d, 4 * rd, w.W1T, 4 * d, 4LL * d * d, g);
-    ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, t.dh, d, rd, g32, d, rd, t.dx1, d, rd, t.dx1b, d, rd);
+    ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, nullptr, d, rd, g32, d, rd, t.dx1, d, rd, t.dx1b, d, rd, t.dhb);
     g = gb(rows, d, d, G);                                    // d(attn out) = dx1 Wproj
     g.out_bf16 = t.dao; g.ld_bf16 = d; g.bf16_bs = rd;
     gemm(P, t.dx1b, d, rd, w.WprojT, d, (long long)d * d, g);
@@ -491,9 +491,9 @@ struct Builder {
     o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, nullptr, d, rd, t.dao, t.dqkv, f16};
     P.ops.push_back(o);
     g = gb(rows, d, 3 * d, G);                                // d(LN1 out) = dqkv Wqkv
-    g.out_f32 = t.dh; g.ld_f32 = d; g.f32_bs = rd;
+    g.out_bf16 = t.dhb; g.ld_bf16 = d; g.bf16_bs = rd;
     gemm(P, t.dqkv, 3 * d, 3 * rd, w.WqkvT, 3 * d, 3LL * d * d, g);
-    ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, t.dh, d, rd, t.dx1, d, rd, g32, d, rd, g16, d, rd);
+    ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, nullptr, d, rd, t.dx1, d, rd, g32, d, rd, g16, d, rd, t.dhb);
   }
   void stage_fwd(Plan& P, const std::vector<BlockW>& ws, int gh, int gw, StageStash& st, bf16* copy_b, long long ld_c, long long bs_c) {
     int parts = 0;
@@ -650,7 +650,7 @@ static int alloc_temps(vv_engine* e, Temps& t) {
   }
   t.h = dalloc<bf16>(e, m_rd); t.ao = dalloc<bf16>(e, m_rd); t.a = dalloc<bf16>(e, 4 * m_rd); t.du = dalloc<bf16>(e, 4 * m_rd);
   t.dao = dalloc<bf16>(e, m_rd); t.dqkv = dalloc<bf16>(e, 3 * m_rd); t.dx1b = dalloc<bf16>(e, m_rd);
-  t.dh = dalloc<float>(e, m_rd); t.dx1 = dalloc<float>(e, m_rd);
+  t.dh = dalloc<float>(e, m_rd); t.dx1 = dalloc<float>(e, m_rd); t.dhb = dalloc<bf16>(e, m_rd);
   t.MB = dalloc<bf16>(e, 4 * m_l1d); t.EPIN = dalloc<bf16>(e, m_l1gd); t.TB = dalloc<bf16>(e, m_l1e);
   t.CAT0 = dalloc<bf16>(e, 4 * m_l1d); t.CAT1 = dalloc<bf16>(e, 2 * m_l0d); t.U1B = dalloc<bf16>(e, 2 * m_l1d);
   t.NU = dalloc<float>(e, m_l0d);

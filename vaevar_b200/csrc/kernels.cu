@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   const int rr = live ? r : a.rows - 1;
   const float* x = a.x + (long long)b * a.x_bs;
   const float* dy = a.dy + (long long)b * a.dy_bs + (long long)rr * a.ld_dy;
+  const bf16* dy16 = a.dy16 ? a.dy16 + (long long)b * a.dy_bs + (long long)rr * a.ld_dy : nullptr;
   const float* g = a.gamma + (long long)b * a.gb_bs;
   float4 v[NV], gd[NV], rs[NV];
   float s = 0.f;
@@ -123,7 +124,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   for (int k = 0; k < NV; ++k) {
     const int c = 4 * (sl + LANES * k);
     v[k] = *reinterpret_cast<const float4*>(x + ln_elem_off<MAP>(rr, c, a.C, a.gw, a.ld_x));
-    gd[k] = *reinterpret_cast<const float4*>(dy + c);
+    if (dy16) {
+      const uint2 w = *reinterpret_cast<const uint2*>(dy16 + c);
+      const float2 lo = unpack_bf16(w.x), hi = unpack_bf16(w.y);
+      gd[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      gd[k] = *reinterpret_cast<const float4*>(dy + c);
+    }
     if (a.dres) rs[k] = *reinterpret_cast<const float4*>(a.dres + (long long)b * a.dres_bs + ln_elem_off<MAP>(rr, c, a.C, a.gw, a.ld_dres));
     else rs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     s += (v[k].x + v[k].y) + (v[k].z + v[k].w);

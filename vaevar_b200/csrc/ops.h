@@ -68,10 +68,11 @@ struct LnBwdArgs {
   float eps;
   const float* x; long long ld_x, x_bs;            // the forward input (same addressing as forward)
   const float* gamma; long long gb_bs;
-  const float* dy; long long ld_dy, dy_bs;         // gradient w.r.t. the LN output, plain rows, fp32
+  const float* dy; long long ld_dy, dy_bs;         // gradient w.r.t. the LN output, plain rows, fp32 (or, if dy16 is set, bf16 at dy16)
   const float* dres; long long ld_dres, dres_bs;   // optional extra gradient added to dx (addressed like x)
   float* dx; long long ld_dx, dx_bs;               // gradient w.r.t. the LN input (addressed like x)
   bf16* dx_bf16; long long ld_dxb, dxb_bs;         // optional bf16 copy of dx (addressed like x)
+  const bf16* dy16;                                // non-null: dy is read from here as bf16 (same ld_dy / dy_bs, in elements)
 };
 void launch_ln_fwd(const LnArgs& a, cudaStream_t s);
 void launch_ln_bwd(const LnBwdArgs& a, cudaStream_t s);
