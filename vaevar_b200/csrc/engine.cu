@@ -97,6 +97,7 @@ int Plan::run(cudaStream_t s) const {
 }
 
 bool ln_supported(int map, int C);
+bool p2t_supported(int D);
 
 }  // namespace vv
 
@@ -144,7 +145,7 @@ static int net_init(Net& n, const vv_net_config& c) {
   VV_CHECK(ln_supported(MAP_PLAIN, n.D) && ln_supported(MAP_PLAIN, 2 * n.D) && ln_supported(MAP_PLAIN, n.E) &&
                ln_supported(MAP_MERGE, 4 * n.D) && ln_supported(MAP_EXPAND, n.D),
            "LayerNorm width not instantiated for enc_dim=%d embed_dim=%d", n.D, n.E);
-  VV_CHECK(n.D <= 128, "enc_dim > 128 not supported by the patch kernels");
+  VV_CHECK(p2t_supported(n.D), "enc_dim %d not supported by the patch kernels (32, 64, 96, 128)", n.D);
   for (int g = 0; g < n.G; ++g) VV_CHECK(c.in_chans[g] * 4 <= 128 && c.out_chans[g] * 4 <= 128, "group has too many channels");
   return 0;
 }
@@ -511,7 +512,7 @@ struct Builder {
     Net& N = *n;
     const int G = N.G, D = N.D, E = N.E, L0 = N.L0, L1 = N.L1;
     Op o{}; o.kind = Op::P2T;
-    o.patch = PatchArgs{N.H, N.W, G, D, N.embed.kcnt, N.embed.cbase, N.embed.chan, N.embed.Wp, N.embed.bias, N.ape, in, S.e0.x[0], nullptr, nullptr};
+    o.patch = PatchArgs{N.H, N.W, G, D, N.embed.kcnt, N.embed.cbase, N.embed.chan, N.embed.Wp, N.embed.bias, N.ape, in, S.e0.x[0], nullptr, nullptr, N.embed.max_cnt};
     P.ops.push_back(o);
     stage_fwd(P, N.e0, N.h0, N.w0, S.e0, t.CAT1 + D, 2 * D, (long long)L0 * 2 * D);            // skip 0 -> CAT1[:, D:2D]
     float* S0 = S.e0.x.back();
@@ -568,7 +569,7 @@ struct Builder {
     Net& N = *n;
     const int G = N.G, D = N.D, E = N.E, L0 = N.L0, L1 = N.L1;
     Op o{}; o.kind = Op::P2T;                                                                     // ConvTranspose2d^T
-    o.patch = PatchArgs{N.H, N.W, G, D, N.fin.kcnt, N.fin.cbase, N.fin.chan, N.fin.Wp, nullptr, nullptr, dout, t.dNU, nullptr, nullptr};
+    o.patch = PatchArgs{N.H, N.W, G, D, N.fin.kcnt, N.fin.cbase, N.fin.chan, N.fin.Wp, nullptr, nullptr, dout, t.dNU, nullptr, nullptr, N.fin.max_cnt};
     P.ops.push_back(o);
     ln_b(P, L0, D, G, MAP_PLAIN, N.h0, N.w0, 1e-6f, S.u1.x.back(), D, (long long)L0 * D, N.nu_g, t.dNU, D, (long long)L0 * D, nullptr, 0, 0,
          t.gU1, D, (long long)L0 * D, t.gU1b, D, (long long)L0 * D);

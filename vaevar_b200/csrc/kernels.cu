@@ -515,115 +515,168 @@ void launch_attn_bwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<true>(a,
 // =============================================================================================
 // Patch operators
 // =============================================================================================
-constexpr int P2T_TOK = 32;         // tokens per CTA: 32 consecutive tokens of one token row
-constexpr int P2T_KMAX = 128;
+constexpr int P2T_TOK = 64;         // tokens per CTA: 64 consecutive tokens (the tile may span token rows)
 
-// Thread c owns output channel c of the 32 tokens: per k one coalesced weight load, eight broadcast LDS.128 of the
-// transposed patch tile and 32 FMAs.
+// 128 threads = 16 channel groups x 8 token groups; a thread owns CPT = D/16 consecutive channels of 8 consecutive tokens:
+// per k two LDS.128 of the transposed patch tile and CPT weights (shared memory, loaded once per CTA) feed 8*CPT FMAs.
+template <int CPT>
 __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
-  __shared__ __align__(16) float patch[P2T_KMAX][P2T_TOK];            // [k = ci*4 + rowpar*2 + colpar][token]
+  extern __shared__ __align__(16) float p2t_sm[];
   const int g = blockIdx.y;
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
   const int t0 = blockIdx.x * P2T_TOK;
-  const int i = t0 / W0, j0 = t0 - i * W0;
+  const int D = a.D;
   pdl_launch_dependents();
   pdl_wait();
   const int cnt = a.kcnt[g];
   const int K = cnt * 4;
   const int cb = a.cbase[g];
+  float* patch = p2t_sm;                               // [K][64]: k = ci*4 + rowpar*2 + colpar
+  float* Ws = p2t_sm + K * P2T_TOK;                    // [K][D]
   const long long HW = (long long)a.H * a.W;
-  for (int idx = threadIdx.x; idx < cnt * 2 * 64; idx += blockDim.x) {
-    const int e = idx & 63, r = idx >> 6, ci = r >> 1, rp = r & 1;    // 64 consecutive pixels of image row 2i+rp, channel ci
-    const int ch = a.chan[cb + ci];
-    patch[ci * 4 + rp * 2 + (e & 1)][e >> 1] = a.img_in[ch * HW + (long long)(2 * i + rp) * a.W + 2 * j0 + e];
-  }
+  __shared__ int s_chan[32];
+  if (threadIdx.x < cnt) s_chan[threadIdx.x] = a.chan[cb + threadIdx.x];
   __syncthreads();
-  const int c = threadIdx.x;
-  if (c >= a.D) return;
-  float acc[P2T_TOK];
-  const float b0 = a.bias ? a.bias[g * a.D + c] : 0.f;
+  for (int idx = threadIdx.x; idx < cnt * 2 * 128; idx += blockDim.x) {
+    const int e = idx & 127, r = idx >> 7, ci = r >> 1, rp = r & 1;     // 128 pixels (64 tokens x 2 columns) of pixel-row parity rp
+    const int tok = t0 + (e >> 1), i = tok / W0, j = tok - i * W0;
+    const int ch = s_chan[ci];
+    patch[(ci * 4 + rp * 2 + (e & 1)) * P2T_TOK + (e >> 1)] = a.img_in[ch * HW + (long long)(2 * i + rp) * a.W + 2 * j + (e & 1)];
+  }
+  const float4* wsrc = reinterpret_cast<const float4*>(a.Wp + (long long)cb * 4 * D);
+  for (int idx = threadIdx.x; idx < K * D / 4; idx += blockDim.x) reinterpret_cast<float4*>(Ws)[idx] = __ldg(wsrc + idx);
+  __syncthreads();
+  const int cq = threadIdx.x & 15, tq = threadIdx.x >> 4;
+  const int c0 = cq * CPT, tk0 = tq * 8;
+  float acc[8][CPT];
 #pragma unroll
-  for (int tt = 0; tt < P2T_TOK; ++tt) acc[tt] = b0;
-  const float* w = a.Wp + (long long)cb * 4 * a.D + c;
+  for (int q = 0; q < CPT; ++q) {
+    const float b0 = a.bias ? a.bias[g * D + c0 + q] : 0.f;
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt) acc[tt][q] = b0;
+  }
 #pragma unroll 2
   for (int k = 0; k < K; ++k) {
-    const float wv = __ldg(w + (long long)k * a.D);
+    const float4 pa = *reinterpret_cast<const float4*>(patch + k * P2T_TOK + tk0);
+    const float4 pb = *reinterpret_cast<const float4*>(patch + k * P2T_TOK + tk0 + 4);
+    const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+    float wv[CPT];
 #pragma unroll
-    for (int q = 0; q < P2T_TOK / 4; ++q) {
-      const float4 pv = *reinterpret_cast<const float4*>(&patch[k][4 * q]);
-      acc[4 * q] = fmaf(pv.x, wv, acc[4 * q]);
-      acc[4 * q + 1] = fmaf(pv.y, wv, acc[4 * q + 1]);
-      acc[4 * q + 2] = fmaf(pv.z, wv, acc[4 * q + 2]);
-      acc[4 * q + 3] = fmaf(pv.w, wv, acc[4 * q + 3]);
+    for (int q = 0; q < CPT; q += 2) {
+      const float2 w2 = *reinterpret_cast<const float2*>(Ws + k * D + c0 + q);
+      wv[q] = w2.x; wv[q + 1] = w2.y;
+    }
+#pragma unroll
+    for (int tt = 0; tt < 8; ++tt)
+#pragma unroll
+      for (int q = 0; q < CPT; ++q) acc[tt][q] = fmaf(pv[tt], wv[q], acc[tt][q]);
+  }
+#pragma unroll
+  for (int tt = 0; tt < 8; ++tt) {
+    const long long o = ((long long)g * L0 + t0 + tk0 + tt) * D + c0;
+#pragma unroll
+    for (int q = 0; q < CPT; q += 2) {
+      float2 v = make_float2(acc[tt][q], acc[tt][q + 1]);
+      if (a.ape) { const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.ape + o + q)); v.x += p2.x; v.y += p2.y; }
+      *reinterpret_cast<float2*>(a.tok_out + o + q) = v;
     }
   }
-#pragma unroll
-  for (int tt = 0; tt < P2T_TOK; ++tt) {
-    const long long o = ((long long)g * L0 + t0 + tt) * a.D + c;
-    a.tok_out[o] = acc[tt] + (a.ape ? __ldg(a.ape + o) : 0.f);
+}
+
+template <int CPT>
+static void launch_p2t_t(const PatchArgs& a, cudaStream_t s) {
+  const int max_cnt = a.max_cnt > 0 ? a.max_cnt : 32;
+  const size_t smem = (size_t)max_cnt * 4 * (P2T_TOK + a.D) * sizeof(float);
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(p2t_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  const int L0 = (a.H / 2) * (a.W / 2);
+  launch_kernel(p2t_kernel<CPT>, dim3(L0 / P2T_TOK, a.G), dim3(128), smem, s, a);
+}
+bool p2t_supported(int D) { return D == 32 || D == 64 || D == 96 || D == 128; }
+void launch_p2t(const PatchArgs& a, cudaStream_t s) {
+  switch (a.D / 16) {
+    case 2: launch_p2t_t<2>(a, s); break;
+    case 4: launch_p2t_t<4>(a, s); break;
+    case 6: launch_p2t_t<6>(a, s); break;
+    case 8: launch_p2t_t<8>(a, s); break;
+    default: break;
   }
 }
 
-void launch_p2t(const PatchArgs& a, cudaStream_t s) {
-  const int L0 = (a.H / 2) * (a.W / 2);
-  dim3 grid(L0 / P2T_TOK, a.G);
-  launch_kernel(p2t_kernel, grid, dim3(((a.D + 31) / 32) * 32), 0, s, a);
-}
-
-constexpr int T2P_TOK = 64;         // tokens per CTA (consecutive tokens of one token row)
+constexpr int T2P_TOK = 128;        // tokens per CTA (consecutive tokens; the tile may span token rows)
 constexpr int T2P_SC = 7;           // output channels accumulated per pass
 
-// Thread (p1, jj, p2) owns pixel (2i+p1, 2(j0+jj)+p2) of every output channel of the group.  The group's weights and the
-// 64-token tile live in shared memory (rows padded by 4 floats: conflict-free LDS.128); per 4 input channels one x load and
-// T2P_SC weight loads feed 4*T2P_SC FMAs.
+// Thread (p1, jj, p2) owns pixel (p1, p2) of tokens jj and jj + 64 for every output channel of the group: per 4 input channels
+// two x loads and T2P_SC weight loads (LDS.128, rows padded by 4 floats: conflict-free) feed 8*T2P_SC FMAs.  The group's
+// weights (zero-padded to a multiple of T2P_SC channels, so the inner loop is branch-free) and the 128-token tile live in
+// shared memory.
 __global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) float t2p_sm[];
   const int g = blockIdx.y;
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
-  const int t0 = blockIdx.x * T2P_TOK;                 // the tile may span token rows when W0 < 64
+  const int t0 = blockIdx.x * T2P_TOK;
   const int D = a.D, RS = D + 4, D4 = D >> 2;
-  float* Xs = t2p_sm;                                  // [64][RS]
-  float* Ws = t2p_sm + T2P_TOK * RS;                   // [cnt*4][RS]
+  float* Xs = t2p_sm;                                  // [128][RS]
+  float* Ws = t2p_sm + T2P_TOK * RS;                   // [cnt_pad*4][RS]
   pdl_launch_dependents();
   pdl_wait();
   const int cb = a.cbase[g], cnt = a.kcnt[g];
+  const int cnt_pad = (cnt + T2P_SC - 1) / T2P_SC * T2P_SC;
+  __shared__ int s_chan[32];                           // output channel and bias of every slot of the group: read once, not as a
+  __shared__ float s_bias[32];                         // dependent global round trip per slot inside the store loop
+  if (threadIdx.x < cnt) {
+    s_chan[threadIdx.x] = a.chan[cb + threadIdx.x];
+    s_bias[threadIdx.x] = a.bias ? a.bias[cb + threadIdx.x] : 0.f;
+  }
   const float4* src = reinterpret_cast<const float4*>(a.tok_in + ((long long)g * L0 + t0) * D);
   for (int idx = threadIdx.x; idx < T2P_TOK * D4; idx += blockDim.x) {
     const int jj = idx / D4, c4 = idx - jj * D4;
     *reinterpret_cast<float4*>(Xs + jj * RS + 4 * c4) = __ldg(src + idx);
   }
   const float4* wsrc = reinterpret_cast<const float4*>(a.Wp + (long long)cb * 4 * D);
-  for (int idx = threadIdx.x; idx < cnt * 4 * D4; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < cnt_pad * 4 * D4; idx += blockDim.x) {
     const int row = idx / D4, c4 = idx - row * D4;
-    *reinterpret_cast<float4*>(Ws + row * RS + 4 * c4) = __ldg(wsrc + idx);
+    *reinterpret_cast<float4*>(Ws + row * RS + 4 * c4) = row < cnt * 4 ? __ldg(wsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
   const int p1 = threadIdx.x >> 7, xx = threadIdx.x & 127, jj = xx >> 1, p2 = xx & 1;
-  const int tok = t0 + jj, i = tok / W0, j = tok - i * W0;
   const long long HW = (long long)a.H * a.W;
-  const float* xr = Xs + jj * RS;
-  for (int s0 = 0; s0 < cnt; s0 += T2P_SC) {
-    float acc[T2P_SC];
+  const float* xr0 = Xs + jj * RS;
+  const float* xr1 = Xs + (jj + 64) * RS;
+  long long pix[2];
 #pragma unroll
-    for (int q = 0; q < T2P_SC; ++q) acc[q] = 0.f;
+  for (int h = 0; h < 2; ++h) {
+    const int tok = t0 + jj + 64 * h, i = tok / W0, j = tok - i * W0;
+    pix[h] = (long long)(2 * i + p1) * a.W + 2 * j + p2;
+  }
+  for (int s0 = 0; s0 < cnt; s0 += T2P_SC) {
+    float acc0[T2P_SC], acc1[T2P_SC];
+#pragma unroll
+    for (int q = 0; q < T2P_SC; ++q) acc0[q] = acc1[q] = 0.f;
     const float* wr = Ws + ((s0 * 4) + p1 * 2 + p2) * RS;
+#pragma unroll 2
     for (int c4 = 0; c4 < D4; ++c4) {
-      const float4 x = *reinterpret_cast<const float4*>(xr + 4 * c4);
+      const float4 x0 = *reinterpret_cast<const float4*>(xr0 + 4 * c4);
+      const float4 x1 = *reinterpret_cast<const float4*>(xr1 + 4 * c4);
 #pragma unroll
       for (int q = 0; q < T2P_SC; ++q) {
-        if (s0 + q < cnt) {                              // block-uniform
-          const float4 w = *reinterpret_cast<const float4*>(wr + q * 4 * RS + 4 * c4);
-          acc[q] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[q]))));
-        }
+        const float4 w = *reinterpret_cast<const float4*>(wr + q * 4 * RS + 4 * c4);
+        acc0[q] = fmaf(x0.x, w.x, fmaf(x0.y, w.y, fmaf(x0.z, w.z, fmaf(x0.w, w.w, acc0[q]))));
+        acc1[q] = fmaf(x1.x, w.x, fmaf(x1.y, w.y, fmaf(x1.z, w.z, fmaf(x1.w, w.w, acc1[q]))));
       }
     }
 #pragma unroll
     for (int q = 0; q < T2P_SC; ++q) {
       if (s0 + q < cnt) {
-        const int slot = cb + s0 + q;
-        a.img_out[a.chan[slot] * HW + (long long)(2 * i + p1) * a.W + 2 * j + p2] = acc[q] + (a.bias ? a.bias[slot] : 0.f);
+        const float bb = s_bias[s0 + q];
+        float* dst = a.img_out + s_chan[s0 + q] * HW;
+        dst[pix[0]] = acc0[q] + bb;
+        dst[pix[1]] = acc1[q] + bb;
       }
     }
   }
@@ -631,7 +684,8 @@ __global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
 
 void launch_t2p(const PatchArgs& a, cudaStream_t s) {
   const int max_cnt = a.max_cnt > 0 ? a.max_cnt : 32;
-  const size_t smem = (size_t)(T2P_TOK + max_cnt * 4) * (a.D + 4) * sizeof(float);
+  const int cnt_pad = (max_cnt + T2P_SC - 1) / T2P_SC * T2P_SC;
+  const size_t smem = (size_t)(T2P_TOK + cnt_pad * 4) * (a.D + 4) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
     cudaFuncSetAttribute(t2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
