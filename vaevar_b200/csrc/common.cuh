@@ -248,6 +248,53 @@ VV_DEVINL void gelu_erf_both(float x, float* y, float* dy) {
   *y = x * cdf;
   *dy = fmaf(x * 0.39894228040143268f, e, cdf);
 }
+// ---- packed fp32 (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per instruction, bit-identical to the scalar
+// ones).  The CUDA-core epilogues of the GEMMs are bound by the FP32 pipe's issue rate; pairing halves their FMA-pipe
+// instruction count at unchanged precision.
+VV_DEVINL float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+VV_DEVINL float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+VV_DEVINL float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+VV_DEVINL float2 splat2(float v) { return make_float2(v, v); }
+// gelu / gelu' of two elements: the arithmetic of gelu_erf_both, paired (MUFU and the sign / abs bit operations stay scalar)
+VV_DEVINL void gelu_erf_both2(float2 x, float2* y, float2* dy) {
+  const float2 xs = mul2(x, splat2(-0.72134752044448170f));
+  const float2 ea = mul2(x, xs);                                      // -x^2 log2(e) / 2
+  const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = fma2(ax, splat2(0.3275911f * 0.70710678118654752f), splat2(1.0f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 poly = fma2(splat2(1.061405429f), t, splat2(-1.453152027f));
+  poly = fma2(poly, t, splat2(1.421413741f));
+  poly = fma2(poly, t, splat2(-0.284496736f));
+  poly = fma2(poly, t, splat2(0.254829592f));
+  const float2 q = mul2(poly, mul2(t, e));                            // erfc(|x| / sqrt2)
+  const float2 sh = make_float2(copysignf(0.5f, x.x), copysignf(0.5f, x.y));
+  const float2 nsh = make_float2(-sh.x, -sh.y);
+  const float2 cdf = fma2(nsh, q, add2(sh, splat2(0.5f)));            // Phi(x) = 1/2 + sign(x) (1/2 - q/2)
+  *y = mul2(x, cdf);
+  *dy = fma2(mul2(x, splat2(0.39894228040143268f)), e, cdf);
+}
+VV_DEVINL float2 gelu_erf2(float2 x) {
+  float2 y, dy;
+  gelu_erf_both2(x, &y, &dy);
+  return y;
+}
 VV_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -126,27 +126,39 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
   for (int g = 0; g < 4; ++g) {                                    // 4 groups of 8 columns
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      v[i] = LNX == LN_CONSUME ? fmaf(ln_a, __uint_as_float(r[g * 8 + i]), bv[g * 8 + i]) : __uint_as_float(r[g * 8 + i]) + bv[g * 8 + i];
+    for (int i = 0; i < 8; i += 2) {                                 // packed fp32: two columns per instruction
+      const float2 a2 = make_float2(__uint_as_float(r[g * 8 + i]), __uint_as_float(r[g * 8 + i + 1]));
+      const float2 b2 = make_float2(bv[g * 8 + i], bv[g * 8 + i + 1]);
+      const float2 o2 = LNX == LN_CONSUME ? fma2(splat2(ln_a), a2, b2) : add2(a2, b2);
+      v[i] = o2.x; v[i + 1] = o2.y;
+    }
     uint4 u16 = make_uint4(0, 0, 0, 0);
     if (EPI == EPI_GELU) {
       if (has_auxout) {                      // gelu and gelu' share their transcendental work; the backward pass needs only gelu'(u)
         float d[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gelu_erf_both(v[i], &v[i], &d[i]);
+        for (int i = 0; i < 8; i += 2) {
+          float2 y2, d2;
+          gelu_erf_both2(make_float2(v[i], v[i + 1]), &y2, &d2);
+          v[i] = y2.x; v[i + 1] = y2.y; d[i] = d2.x; d[i + 1] = d2.y;
+        }
         u16.x = pack16<F16>(d[0], d[1]); u16.y = pack16<F16>(d[2], d[3]);
         u16.z = pack16<F16>(d[4], d[5]); u16.w = pack16<F16>(d[6], d[7]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 8; i += 2) {
+          const float2 y2 = gelu_erf2(make_float2(v[i], v[i + 1]));
+          v[i] = y2.x; v[i + 1] = y2.y;
+        }
       }
     } else if (EPI == EPI_DGELU) {
       if (has_auxin) {                       // aux = gelu'(u) saved by the forward GEMM
         const uint4 w = *reinterpret_cast<const uint4*>(rowB + ((static_cast<uint32_t>(g) ^ sw64) << 4));
         const bool af = p.aux_f16 != 0;
         const float2 u0 = unpack16(w.x, af), u1 = unpack16(w.y, af), u2 = unpack16(w.z, af), u3 = unpack16(w.w, af);
-        v[0] *= u0.x; v[1] *= u0.y; v[2] *= u1.x; v[3] *= u1.y;
-        v[4] *= u2.x; v[5] *= u2.y; v[6] *= u3.x; v[7] *= u3.y;
+        const float2 m0 = mul2(make_float2(v[0], v[1]), u0), m1 = mul2(make_float2(v[2], v[3]), u1);
+        const float2 m2 = mul2(make_float2(v[4], v[5]), u2), m3 = mul2(make_float2(v[6], v[7]), u3);
+        v[0] = m0.x; v[1] = m0.y; v[2] = m1.x; v[3] = m1.y; v[4] = m2.x; v[5] = m2.y; v[6] = m3.x; v[7] = m3.y;
       }
     }
     const uint32_t cA0 = (static_cast<uint32_t>(2 * g) ^ sw128) << 4, cA1 = (static_cast<uint32_t>(2 * g + 1) ^ sw128) << 4;
@@ -469,8 +481,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (LNX == LN_CONSUME && colsum) {                                             // folded LayerNorm: c_n - rstd mean s_n
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            bv[4 * j] = fmaf(-ln_b, svv[j].x, bv[4 * j]); bv[4 * j + 1] = fmaf(-ln_b, svv[j].y, bv[4 * j + 1]);
-            bv[4 * j + 2] = fmaf(-ln_b, svv[j].z, bv[4 * j + 2]); bv[4 * j + 3] = fmaf(-ln_b, svv[j].w, bv[4 * j + 3]);
+            const float2 nb = splat2(-ln_b);
+            const float2 t0 = fma2(nb, make_float2(svv[j].x, svv[j].y), make_float2(bv[4 * j], bv[4 * j + 1]));
+            const float2 t1 = fma2(nb, make_float2(svv[j].z, svv[j].w), make_float2(bv[4 * j + 2], bv[4 * j + 3]));
+            bv[4 * j] = t0.x; bv[4 * j + 1] = t0.y; bv[4 * j + 2] = t1.x; bv[4 * j + 3] = t1.y;
           }
         }
         if (has_loads) {
