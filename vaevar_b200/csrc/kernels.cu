@@ -515,120 +515,137 @@ void launch_attn_bwd(const AttnArgs& a, cudaStream_t s) { launch_attn_d<true>(a,
 // =============================================================================================
 // Patch operators
 // =============================================================================================
-constexpr int P2T_TOK = 64;         // tokens per CTA: 64 consecutive tokens (the tile may span token rows)
+// The 2x2 / stride-2 patch operators are small GEMMs (K = 4 C_g <= 56 for P2T, K = D = 96 for T2P).  On the CUDA cores they were
+// bound by instruction issue (245 M FMA per launch at ~0.55 IPC per scheduler, ncu); they run on the tensor cores as
+// mma.sync.m16n8k8 TF32 tiles instead: fp32 operands rounded to TF32 (10-bit mantissa, like the fp16 operands of every other
+// Linear of the network), fp32 accumulation.
+VV_DEVINL uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+VV_DEVINL void mma_tf32_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
-// 128 threads = 16 channel groups x 8 token groups; a thread owns CPT = D/16 consecutive channels of 8 consecutive tokens:
-// per k two LDS.128 of the transposed patch tile and CPT weights (shared memory, loaded once per CTA) feed 8*CPT FMAs.
-template <int CPT>
+constexpr int P2T_TOK = 64;         // tokens per CTA (4 warps x one m16 tile); the tile may span token rows
+
+// tok_out[g][tok][c] = bias[g][c] + sum_k patch[tok][k] Wp[k][c] (+ APE): per warp 16 tokens x D channels, K padded to 8.
+// NT = D / 8 n-tiles.
+template <int NT>
 __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) float p2t_sm[];
+  constexpr int D = NT * 8;
+  constexpr int PS = P2T_TOK + 8;                      // patch row stride: (8 t + g) % 32 distinct -> conflict-free A fragments
+  constexpr int WS = D + 8;                            // weight row stride: (8 t + g) % 32 distinct -> conflict-free B fragments
   const int g = blockIdx.y;
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
   const int t0 = blockIdx.x * P2T_TOK;
-  const int D = a.D;
   pdl_launch_dependents();
   pdl_wait();
   const int cnt = a.kcnt[g];
-  const int K = cnt * 4;
+  const int K = cnt * 4, Kp = (K + 7) & ~7;
   const int cb = a.cbase[g];
-  float* patch = p2t_sm;                               // [K][64]: k = ci*4 + rowpar*2 + colpar
-  float* Ws = p2t_sm + K * P2T_TOK;                    // [K][D]
+  uint32_t* patch = reinterpret_cast<uint32_t*>(p2t_sm);          // [Kp][PS] tf32: k = ci*4 + rowpar*2 + colpar
+  uint32_t* Ws = patch + Kp * PS;                                 // [Kp][WS] tf32
   const long long HW = (long long)a.H * a.W;
   __shared__ int s_chan[32];
   if (threadIdx.x < cnt) s_chan[threadIdx.x] = a.chan[cb + threadIdx.x];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < cnt * 2 * 128; idx += blockDim.x) {
-    const int e = idx & 127, r = idx >> 7, ci = r >> 1, rp = r & 1;     // 128 pixels (64 tokens x 2 columns) of pixel-row parity rp
-    const int tok = t0 + (e >> 1), i = tok / W0, j = tok - i * W0;
-    const int ch = s_chan[ci];
-    patch[(ci * 4 + rp * 2 + (e & 1)) * P2T_TOK + (e >> 1)] = a.img_in[ch * HW + (long long)(2 * i + rp) * a.W + 2 * j + (e & 1)];
-  }
-  const float4* wsrc = reinterpret_cast<const float4*>(a.Wp + (long long)cb * 4 * D);
-  for (int idx = threadIdx.x; idx < K * D / 4; idx += blockDim.x) reinterpret_cast<float4*>(Ws)[idx] = __ldg(wsrc + idx);
-  __syncthreads();
-  const int cq = threadIdx.x & 15, tq = threadIdx.x >> 4;
-  const int c0 = cq * CPT, tk0 = tq * 8;
-  float acc[8][CPT];
-#pragma unroll
-  for (int q = 0; q < CPT; ++q) {
-    const float b0 = a.bias ? a.bias[g * D + c0 + q] : 0.f;
-#pragma unroll
-    for (int tt = 0; tt < 8; ++tt) acc[tt][q] = b0;
-  }
-#pragma unroll 2
-  for (int k = 0; k < K; ++k) {
-    const float4 pa = *reinterpret_cast<const float4*>(patch + k * P2T_TOK + tk0);
-    const float4 pb = *reinterpret_cast<const float4*>(patch + k * P2T_TOK + tk0 + 4);
-    const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-    float wv[CPT];
-#pragma unroll
-    for (int q = 0; q < CPT; q += 2) {
-      const float2 w2 = *reinterpret_cast<const float2*>(Ws + k * D + c0 + q);
-      wv[q] = w2.x; wv[q + 1] = w2.y;
+  for (int idx = threadIdx.x; idx < Kp * 32; idx += blockDim.x) {   // k-row x 32 token pairs
+    const int e2 = idx & 31, kk = idx >> 5;                         // kk = ci*4 + rp*2 + colpar, token pair (2 e2, 2 e2 + 1)
+    float v0 = 0.f, v1 = 0.f;
+    if (kk < K) {
+      const int ci = kk >> 2, rp = (kk >> 1) & 1, cp = kk & 1;
+      const float* img = a.img_in + s_chan[ci] * HW;
+      const int tk = t0 + 2 * e2, i0 = tk / W0, j0 = tk - i0 * W0;   // W0 is even: both tokens of the pair lie in one row
+      v0 = img[(long long)(2 * i0 + rp) * a.W + 2 * j0 + cp];
+      v1 = img[(long long)(2 * i0 + rp) * a.W + 2 * j0 + 2 + cp];
     }
+    *reinterpret_cast<uint2*>(patch + kk * PS + 2 * e2) = make_uint2(to_tf32(v0), to_tf32(v1));
+  }
+  const float* wsrc = a.Wp + (long long)cb * 4 * D;
+  for (int idx = threadIdx.x; idx < Kp * (D / 4); idx += blockDim.x) {
+    const int kk = idx / (D / 4), c4 = idx - kk * (D / 4);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk < K) w = __ldg(reinterpret_cast<const float4*>(wsrc + (long long)kk * D) + c4);
+    *reinterpret_cast<uint4*>(Ws + kk * WS + 4 * c4) = make_uint4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const int m0 = warp * 16;
+  float acc[NT][4];
 #pragma unroll
-    for (int tt = 0; tt < 8; ++tt)
+  for (int n = 0; n < NT; ++n) {
+    const float b0 = a.bias ? a.bias[g * D + n * 8 + 2 * tq] : 0.f, b1 = a.bias ? a.bias[g * D + n * 8 + 2 * tq + 1] : 0.f;
+    acc[n][0] = b0; acc[n][1] = b1; acc[n][2] = b0; acc[n][3] = b1;
+  }
+  for (int k0 = 0; k0 < Kp; k0 += 8) {
+    const uint32_t a0 = patch[(k0 + tq) * PS + m0 + gq], a1 = patch[(k0 + tq) * PS + m0 + gq + 8];
+    const uint32_t a2 = patch[(k0 + tq + 4) * PS + m0 + gq], a3 = patch[(k0 + tq + 4) * PS + m0 + gq + 8];
 #pragma unroll
-      for (int q = 0; q < CPT; ++q) acc[tt][q] = fmaf(pv[tt], wv[q], acc[tt][q]);
+    for (int n = 0; n < NT; ++n)
+      mma_tf32_1688(acc[n], a0, a1, a2, a3, Ws[(k0 + tq) * WS + n * 8 + gq], Ws[(k0 + tq + 4) * WS + n * 8 + gq]);
   }
 #pragma unroll
-  for (int tt = 0; tt < 8; ++tt) {
-    const long long o = ((long long)g * L0 + t0 + tk0 + tt) * D + c0;
+  for (int h = 0; h < 2; ++h) {
+    const long long o = ((long long)g * L0 + t0 + m0 + gq + 8 * h) * D + 2 * tq;
 #pragma unroll
-    for (int q = 0; q < CPT; q += 2) {
-      float2 v = make_float2(acc[tt][q], acc[tt][q + 1]);
-      if (a.ape) { const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.ape + o + q)); v.x += p2.x; v.y += p2.y; }
-      *reinterpret_cast<float2*>(a.tok_out + o + q) = v;
+    for (int n = 0; n < NT; ++n) {
+      float2 v = make_float2(acc[n][2 * h], acc[n][2 * h + 1]);
+      if (a.ape) { const float2 p2 = __ldg(reinterpret_cast<const float2*>(a.ape + o + n * 8)); v.x += p2.x; v.y += p2.y; }
+      *reinterpret_cast<float2*>(a.tok_out + o + n * 8) = v;
     }
   }
 }
 
-template <int CPT>
+template <int NT>
 static void launch_p2t_t(const PatchArgs& a, cudaStream_t s) {
   const int max_cnt = a.max_cnt > 0 ? a.max_cnt : 32;
-  const size_t smem = (size_t)max_cnt * 4 * (P2T_TOK + a.D) * sizeof(float);
+  const int Kp = (max_cnt * 4 + 7) & ~7;
+  const size_t smem = (size_t)Kp * ((P2T_TOK + 8) + (NT * 8 + 8)) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaFuncSetAttribute(p2t_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(p2t_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
   const int L0 = (a.H / 2) * (a.W / 2);
-  launch_kernel(p2t_kernel<CPT>, dim3(L0 / P2T_TOK, a.G), dim3(128), smem, s, a);
+  launch_kernel(p2t_kernel<NT>, dim3(L0 / P2T_TOK, a.G), dim3(128), smem, s, a);
 }
 bool p2t_supported(int D) { return D == 32 || D == 64 || D == 96 || D == 128; }
 void launch_p2t(const PatchArgs& a, cudaStream_t s) {
-  switch (a.D / 16) {
-    case 2: launch_p2t_t<2>(a, s); break;
+  switch (a.D / 8) {
     case 4: launch_p2t_t<4>(a, s); break;
-    case 6: launch_p2t_t<6>(a, s); break;
     case 8: launch_p2t_t<8>(a, s); break;
+    case 12: launch_p2t_t<12>(a, s); break;
+    case 16: launch_p2t_t<16>(a, s); break;
     default: break;
   }
 }
 
-constexpr int T2P_TOK = 128;        // tokens per CTA (consecutive tokens; the tile may span token rows)
-constexpr int T2P_SC = 7;           // output channels accumulated per pass
+constexpr int T2P_TOK = 128;        // tokens per CTA (8 warps x one m16 tile); the tile may span token rows
+constexpr int T2P_NT = 7;           // n-tiles of 8 (= 2 output channels x 4 pixel positions) per pass
 
-// Thread (p1, jj, p2) owns pixel (p1, p2) of tokens jj and jj + 64 for every output channel of the group: per 4 input channels
-// two x loads and T2P_SC weight loads (LDS.128, rows padded by 4 floats: conflict-free) feed 8*T2P_SC FMAs.  The group's
-// weights (zero-padded to a multiple of T2P_SC channels, so the inner loop is branch-free) and the 128-token tile live in
-// shared memory.
+// img_out[chan[slot]][2i+p1][2j+p2] = bias[slot] + sum_c X[tok][c] Wp[slot*4 + p1*2 + p2][c]: per warp 16 tokens x (4 cnt) outputs,
+// K = D.  The accumulator fragment (row = token, columns 2t, 2t+1) is a horizontally adjacent pixel pair: float2 stores.
 __global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
   extern __shared__ __align__(16) float t2p_sm[];
   const int g = blockIdx.y;
   const int W0 = a.W >> 1;
   const int L0 = (a.H >> 1) * W0;
   const int t0 = blockIdx.x * T2P_TOK;
-  const int D = a.D, RS = D + 4, D4 = D >> 2;
-  float* Xs = t2p_sm;                                  // [128][RS]
-  float* Ws = t2p_sm + T2P_TOK * RS;                   // [cnt_pad*4][RS]
+  const int D = a.D, RS = D + 4, D4 = D >> 2;         // (4 g + t) % 32 distinct -> conflict-free A and B fragments
+  uint32_t* Xs = reinterpret_cast<uint32_t*>(t2p_sm);             // [128][RS] tf32
+  uint32_t* Ws = Xs + T2P_TOK * RS;                               // [Np][RS] tf32, row n = slot*4 + p1*2 + p2
   pdl_launch_dependents();
   pdl_wait();
   const int cb = a.cbase[g], cnt = a.kcnt[g];
-  const int cnt_pad = (cnt + T2P_SC - 1) / T2P_SC * T2P_SC;
-  __shared__ int s_chan[32];                           // output channel and bias of every slot of the group: read once, not as a
-  __shared__ float s_bias[32];                         // dependent global round trip per slot inside the store loop
+  const int N = cnt * 4, Np = (N + 7) & ~7;
+  __shared__ int s_chan[32];
+  __shared__ float s_bias[32];
   if (threadIdx.x < cnt) {
     s_chan[threadIdx.x] = a.chan[cb + threadIdx.x];
     s_bias[threadIdx.x] = a.bias ? a.bias[cb + threadIdx.x] : 0.f;
@@ -636,47 +653,49 @@ __global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
   const float4* src = reinterpret_cast<const float4*>(a.tok_in + ((long long)g * L0 + t0) * D);
   for (int idx = threadIdx.x; idx < T2P_TOK * D4; idx += blockDim.x) {
     const int jj = idx / D4, c4 = idx - jj * D4;
-    *reinterpret_cast<float4*>(Xs + jj * RS + 4 * c4) = __ldg(src + idx);
+    const float4 v = __ldg(src + idx);
+    *reinterpret_cast<uint4*>(Xs + jj * RS + 4 * c4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
   }
   const float4* wsrc = reinterpret_cast<const float4*>(a.Wp + (long long)cb * 4 * D);
-  for (int idx = threadIdx.x; idx < cnt_pad * 4 * D4; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < Np * D4; idx += blockDim.x) {
     const int row = idx / D4, c4 = idx - row * D4;
-    *reinterpret_cast<float4*>(Ws + row * RS + 4 * c4) = row < cnt * 4 ? __ldg(wsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < N) w = __ldg(wsrc + idx);
+    *reinterpret_cast<uint4*>(Ws + row * RS + 4 * c4) = make_uint4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
   }
   __syncthreads();
-  const int p1 = threadIdx.x >> 7, xx = threadIdx.x & 127, jj = xx >> 1, p2 = xx & 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+  const int m0 = warp * 16;
   const long long HW = (long long)a.H * a.W;
-  const float* xr0 = Xs + jj * RS;
-  const float* xr1 = Xs + (jj + 64) * RS;
-  long long pix[2];
+  long long pix[2];                                    // pixel (2i + p1, 2j) of this thread's two tokens, p1 = (2 tq) >> 1 = tq >> 0 ...
+  const int p1 = (2 * tq) >> 1 & 1;                    // columns 2tq, 2tq+1 of an n-tile: pixel position pp = (2 tq) & 3 -> p1 = pp >> 1, p2 = 0 / 1
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int tok = t0 + jj + 64 * h, i = tok / W0, j = tok - i * W0;
-    pix[h] = (long long)(2 * i + p1) * a.W + 2 * j + p2;
+    const int tok = t0 + m0 + gq + 8 * h, i = tok / W0, j = tok - i * W0;
+    pix[h] = (long long)(2 * i + p1) * a.W + 2 * j;
   }
-  for (int s0 = 0; s0 < cnt; s0 += T2P_SC) {
-    float acc0[T2P_SC], acc1[T2P_SC];
+  for (int n0 = 0; n0 < Np; n0 += 8 * T2P_NT) {
+    float acc[T2P_NT][4];
 #pragma unroll
-    for (int q = 0; q < T2P_SC; ++q) acc0[q] = acc1[q] = 0.f;
-    const float* wr = Ws + ((s0 * 4) + p1 * 2 + p2) * RS;
-#pragma unroll 2
-    for (int c4 = 0; c4 < D4; ++c4) {
-      const float4 x0 = *reinterpret_cast<const float4*>(xr0 + 4 * c4);
-      const float4 x1 = *reinterpret_cast<const float4*>(xr1 + 4 * c4);
+    for (int n = 0; n < T2P_NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += 8) {
+      const uint32_t a0 = Xs[(m0 + gq) * RS + k0 + tq], a1 = Xs[(m0 + gq + 8) * RS + k0 + tq];
+      const uint32_t a2 = Xs[(m0 + gq) * RS + k0 + tq + 4], a3 = Xs[(m0 + gq + 8) * RS + k0 + tq + 4];
 #pragma unroll
-      for (int q = 0; q < T2P_SC; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(wr + q * 4 * RS + 4 * c4);
-        acc0[q] = fmaf(x0.x, w.x, fmaf(x0.y, w.y, fmaf(x0.z, w.z, fmaf(x0.w, w.w, acc0[q]))));
-        acc1[q] = fmaf(x1.x, w.x, fmaf(x1.y, w.y, fmaf(x1.z, w.z, fmaf(x1.w, w.w, acc1[q]))));
+      for (int n = 0; n < T2P_NT; ++n) {
+        if (n0 + 8 * n < Np)                           // block-uniform
+          mma_tf32_1688(acc[n], a0, a1, a2, a3, Ws[(n0 + 8 * n + gq) * RS + k0 + tq], Ws[(n0 + 8 * n + gq) * RS + k0 + tq + 4]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < T2P_SC; ++q) {
-      if (s0 + q < cnt) {
-        const float bb = s_bias[s0 + q];
-        float* dst = a.img_out + s_chan[s0 + q] * HW;
-        dst[pix[0]] = acc0[q] + bb;
-        dst[pix[1]] = acc1[q] + bb;
+    for (int n = 0; n < T2P_NT; ++n) {
+      const int col = n0 + 8 * n + 2 * tq;             // output column = slot*4 + pp
+      if (col < N) {
+        const int slot = col >> 2;
+        const float bb = s_bias[slot];
+        float* dst = a.img_out + s_chan[slot] * HW;
+        *reinterpret_cast<float2*>(dst + pix[0]) = make_float2(acc[n][0] + bb, acc[n][1] + bb);
+        *reinterpret_cast<float2*>(dst + pix[1]) = make_float2(acc[n][2] + bb, acc[n][3] + bb);
       }
     }
   }
@@ -684,8 +703,8 @@ __global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
 
 void launch_t2p(const PatchArgs& a, cudaStream_t s) {
   const int max_cnt = a.max_cnt > 0 ? a.max_cnt : 32;
-  const int cnt_pad = (max_cnt + T2P_SC - 1) / T2P_SC * T2P_SC;
-  const size_t smem = (size_t)(T2P_TOK + cnt_pad * 4) * (a.D + 4) * sizeof(float);
+  const int Np = (max_cnt * 4 + 7) & ~7;
+  const size_t smem = (size_t)(T2P_TOK + Np) * (a.D + 4) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
     cudaFuncSetAttribute(t2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
