@@ -214,3 +214,53 @@ def test_lbfgs_entry_evaluation_reuse_keeps_the_trajectory(chk):
     assert i1[-1]["skipped_evals"] == 2 and i0[-1]["skipped_evals"] == 0
     assert i0[-1]["func_evals"] - i1[-1]["func_evals"] == 2
     e.close()
+
+
+def _small_engine_and_nets(T):
+    from oracle import cost as oc
+    from oracle.lgunet import to_torch
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import Engine
+    from vaevar_b200.synth import make_case, make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    sd_d, sd_f = make_state_dict(ds, seed=0, gain=3.0, rich=True), make_state_dict(fs, seed=1, gain=3.0, rich=True)
+    e = Engine(ds, fs, T=T)
+    e.load_state_dict(0, sd_d); e.load_state_dict(1, sd_f); e.finalize()
+    case = make_case(T, *ds.img_size, obs_frac=0.1, seed=7)
+    nets = oc.OracleNets(to_torch(sd_d), ds, to_torch(sd_f), fs)
+    return e, case, nets, oc
+
+
+@pytest.mark.parametrize("kind", ["none", "all", "ragged"])
+def test_observation_mask_edge_cases(chk, kind):
+    """Masks the reference's free-column generator never produces but its loss accepts (da_4dvar.py:1207): no observation
+    at all, every grid point observed, and a ragged mask (independent per time, channel and point, with a per-point R)."""
+    T = 3
+    e, case, nets, oc = _small_engine_and_nets(T)
+    rng = np.random.Generator(np.random.PCG64(11))
+    H = case["H"]
+    if kind == "none":
+        H = np.zeros_like(H)
+    elif kind == "all":
+        H = np.ones_like(H)
+    else:
+        H = (rng.random(H.shape) < 0.07).astype(np.float32)
+        H[1] = 0.0                                                       # an empty time level in the middle of the window
+        case["R"] = (case["R"] * (0.5 + rng.random(H.shape))).astype(np.float32)
+    case["H"] = H
+    e.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+    assert e.n_obs == int(H.sum())
+    z = torch.from_numpy(case["z"]).cuda()
+    for _ in range(2):
+        J, grad = e.cost_grad(z)
+    torch.cuda.synchronize()
+    Jr, Jreg, Jobs, gr = oc.cost_and_grad(case["z"], oc.Case(case), nets)
+    assert abs(float(J[0]) / Jr - 1) < 1e-3
+    gn, grn = float(grad.double().norm()), float(np.linalg.norm(gr.astype(np.float64)))
+    assert abs(gn / grn - 1) < 1e-2
+    if kind == "none":
+        assert float(J[2]) == 0.0 and torch.equal(grad, z)               # J = |z|^2 / 2, grad = z exactly
+    else:
+        cos = float((grad.cpu().double().flatten() @ torch.from_numpy(gr).double().flatten()) / (gn * grn))
+        assert cos > 0.999
+    e.close()
