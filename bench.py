@@ -130,7 +130,28 @@ def run_reference(args):
             "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "J": J}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """ONE JSON line on stdout: everything any library prints to file descriptor 1 during the run (NCCL's version banner, ...)
+    is sent to stderr; emit() writes the result line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -145,6 +166,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -159,7 +181,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("VV_NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     T = args.T
@@ -349,7 +370,7 @@ def main():
         times, Jcpu, threads = cpu_oracle_eval(T, args.obs_frac, 0, repeats=1)
         line["cpu_baseline"] = {"value": 1e3 * times[0], "unit": "ms", "cores": threads, "kind": "port",
                                 "sample": f"1 full closure() (T={T}) of the CPU oracle (reference algorithm, fp32 torch, weight grads off), J={Jcpu:.8g}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
