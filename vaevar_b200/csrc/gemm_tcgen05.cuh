@@ -12,9 +12,16 @@
 //               (2 x BN columns), so the MMAs of tile i+1 run while tile i is drained
 //   warps 2..9  eight epilogue warps: warp w drains TMEM lane quarter (w & 3); the two warps of a quarter take alternate
 //               32-column chunks.  Per chunk: tcgen05.ld -> registers -> fused bias / GELU / GELU' / residual -> 128B- or
-//               64B-swizzled staging slab -> TMA store.  The residual and the saved pre-activation are TMA-LOADED into the
+//               64B-swizzled staging slab -> TMA store.  The residual and the saved gelu'(u) are TMA-LOADED into the
 //               slab the result then overwrites in place; slabs are double-buffered and the loads of chunk i+1 are issued
 //               while chunk i is processed, so no global access of the epilogue is issued by the LSU except the bias.
+//
+// Producer and MMA warps run warp-uniform loops with the TMA / tcgen05 instructions under elect.sync (a divergent lane-0
+// branch costs an ELECT + R2UR waterfall per instruction: 170 cycles per MMA).  The epilogue arithmetic is packed fp32
+// (FFMA2 / FMUL2 / FADD2).  Template parameters beyond the tile shape: F16 (operand format), LNX (plain / folds a LayerNorm
+// into the epilogue / emits LayerNorm statistics of its output), EPI (epilogue variant) -- one variant per instantiation keeps
+// each kernel inside the instruction cache.  The idle producer warp prefetches the NEXT GEMM's weights into L2.
+// Measurements behind these choices: DESIGN.md section 4; tools/gemm_trace.py, tools/gemm_boundary.py.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
