@@ -555,24 +555,48 @@ __global__ void __launch_bounds__(128) p2t_kernel(const PatchArgs a) {
   __shared__ int s_chan[32];
   if (threadIdx.x < cnt) s_chan[threadIdx.x] = a.chan[cb + threadIdx.x];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < Kp * 32; idx += blockDim.x) {   // k-row x 32 token pairs
-    const int e2 = idx & 31, kk = idx >> 5;                         // kk = ci*4 + rp*2 + colpar, token pair (2 e2, 2 e2 + 1)
-    float v0 = 0.f, v1 = 0.f;
-    if (kk < K) {
-      const int ci = kk >> 2, rp = (kk >> 1) & 1, cp = kk & 1;
-      const float* img = a.img_in + s_chan[ci] * HW;
-      const int tk = t0 + 2 * e2, i0 = tk / W0, j0 = tk - i0 * W0;   // W0 is even: both tokens of the pair lie in one row
-      v0 = img[(long long)(2 * i0 + rp) * a.W + 2 * j0 + cp];
-      v1 = img[(long long)(2 * i0 + rp) * a.W + 2 * j0 + 2 + cp];
+  // Both fills issue a batch of independent loads before the first store (a load -> convert -> store loop is one L2 round
+  // trip per iteration: 14 + 11 serialized round trips were two thirds of this kernel's time).
+  constexpr int GU = 7;
+  for (int base = threadIdx.x; base < Kp * 32; base += GU * 128) {   // k-row x 32 token pairs
+    float v0[GU], v1[GU];
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      const int idx = base + u * 128;
+      const int e2 = idx & 31, kk = idx >> 5;                       // kk = ci*4 + rp*2 + colpar, token pair (2 e2, 2 e2 + 1)
+      v0[u] = v1[u] = 0.f;
+      if (idx < Kp * 32 && kk < K) {
+        const int ci = kk >> 2, rp = (kk >> 1) & 1, cp = kk & 1;
+        const float* img = a.img_in + s_chan[ci] * HW;
+        const int tk = t0 + 2 * e2, i0 = tk / W0, j0 = tk - i0 * W0;   // W0 is even: both tokens of the pair lie in one row
+        v0[u] = img[(long long)(2 * i0 + rp) * a.W + 2 * j0 + cp];
+        v1[u] = img[(long long)(2 * i0 + rp) * a.W + 2 * j0 + 2 + cp];
+      }
     }
-    *reinterpret_cast<uint2*>(patch + kk * PS + 2 * e2) = make_uint2(to_tf32(v0), to_tf32(v1));
+#pragma unroll
+    for (int u = 0; u < GU; ++u) {
+      const int idx = base + u * 128;
+      if (idx < Kp * 32) *reinterpret_cast<uint2*>(patch + (idx >> 5) * PS + 2 * (idx & 31)) = make_uint2(to_tf32(v0[u]), to_tf32(v1[u]));
+    }
   }
   const float* wsrc = a.Wp + (long long)cb * 4 * D;
-  for (int idx = threadIdx.x; idx < Kp * (D / 4); idx += blockDim.x) {
-    const int kk = idx / (D / 4), c4 = idx - kk * (D / 4);
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kk < K) w = __ldg(reinterpret_cast<const float4*>(wsrc + (long long)kk * D) + c4);
-    *reinterpret_cast<uint4*>(Ws + kk * WS + 4 * c4) = make_uint4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  constexpr int WU = 6;
+  for (int base = threadIdx.x; base < Kp * (D / 4); base += WU * 128) {
+    float4 w[WU];
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int idx = base + u * 128;
+      const int kk = idx / (D / 4), c4 = idx - kk * (D / 4);
+      w[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < Kp * (D / 4) && kk < K) w[u] = __ldg(reinterpret_cast<const float4*>(wsrc + (long long)kk * D) + c4);
+    }
+#pragma unroll
+    for (int u = 0; u < WU; ++u) {
+      const int idx = base + u * 128;
+      const int kk = idx / (D / 4), c4 = idx - kk * (D / 4);
+      if (idx < Kp * (D / 4))
+        *reinterpret_cast<uint4*>(Ws + kk * WS + 4 * c4) = make_uint4(to_tf32(w[u].x), to_tf32(w[u].y), to_tf32(w[u].z), to_tf32(w[u].w));
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
@@ -651,17 +675,37 @@ __global__ void __launch_bounds__(256) t2p_kernel(const PatchArgs a) {
     s_bias[threadIdx.x] = a.bias ? a.bias[cb + threadIdx.x] : 0.f;
   }
   const float4* src = reinterpret_cast<const float4*>(a.tok_in + ((long long)g * L0 + t0) * D);
-  for (int idx = threadIdx.x; idx < T2P_TOK * D4; idx += blockDim.x) {
-    const int jj = idx / D4, c4 = idx - jj * D4;
-    const float4 v = __ldg(src + idx);
-    *reinterpret_cast<uint4*>(Xs + jj * RS + 4 * c4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  constexpr int FU = 6;                                // batches of independent loads, then the converts / stores
+  for (int base = threadIdx.x; base < T2P_TOK * D4; base += FU * 256) {
+    float4 v[FU];
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int idx = base + u * 256;
+      v[u] = idx < T2P_TOK * D4 ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int idx = base + u * 256;
+      const int jj = idx / D4, c4 = idx - jj * D4;
+      if (idx < T2P_TOK * D4)
+        *reinterpret_cast<uint4*>(Xs + jj * RS + 4 * c4) = make_uint4(to_tf32(v[u].x), to_tf32(v[u].y), to_tf32(v[u].z), to_tf32(v[u].w));
+    }
   }
   const float4* wsrc = reinterpret_cast<const float4*>(a.Wp + (long long)cb * 4 * D);
-  for (int idx = threadIdx.x; idx < Np * D4; idx += blockDim.x) {
-    const int row = idx / D4, c4 = idx - row * D4;
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < N) w = __ldg(wsrc + idx);
-    *reinterpret_cast<uint4*>(Ws + row * RS + 4 * c4) = make_uint4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+  for (int base = threadIdx.x; base < Np * D4; base += FU * 256) {
+    float4 w[FU];
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int idx = base + u * 256;
+      w[u] = (idx < Np * D4 && idx / D4 < N) ? __ldg(wsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < FU; ++u) {
+      const int idx = base + u * 256;
+      const int row = idx / D4, c4 = idx - row * D4;
+      if (idx < Np * D4)
+        *reinterpret_cast<uint4*>(Ws + row * RS + 4 * c4) = make_uint4(to_tf32(w[u].x), to_tf32(w[u].y), to_tf32(w[u].z), to_tf32(w[u].w));
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
