@@ -104,6 +104,25 @@ VV_API int vv_net_vjp(vv_engine* e, int net, const float* in_dev, const float* d
  * One fused pass on the device; out is a device array of 2*C doubles. */
 VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, double* out_dev, void* stream);
 
+/* ---- native-resolution seams; no engine handle, any field size ---------------------------------
+ * F.interpolate(x, (Ho, Wo)) with the default nearest rule (nf_model/vae.py:90 decoder_hr; da_4dvar.py:671, 679) on a (C,Hi,Wi)
+ * field, fused with the per-channel (de)normalisation the reference applies on the same side of the seam:
+ *   mode 0: out = in[src];  mode 1: out = (in[src] - mean[c]) / std[c]  (da_4dvar.py:667 then :671);
+ *   mode 2: out = in[src] * std[c] + mean[c]  (:679 then :681).   Bit-identical to the eager reference. */
+VV_API int vv_resample_nearest(const float* in_dev, float* out_dev, int C, int Hi, int Wi, int Ho, int Wo, int mode, const float* mean_dev,
+                               const float* std_dev, void* stream);
+/* Vector-Jacobian product of vv_resample_nearest (what autograd runs through integrate(..., True, False), da_4dvar.py:1191):
+ * din (C,Hi,Wi) from dout (C,Ho,Wo); deterministic ordered sums (ascending output row, then column), bit-identical to the
+ * reference's CPU backward.  mode 1: (sum) / std[c];  mode 2: sum of dout * std[c]. */
+VV_API int vv_resample_nearest_adjoint(const float* dout_dev, float* din_dev, int C, int Hi, int Wi, int Ho, int Wo, int mode,
+                                       const float* std_dev, void* stream);
+/* Observation term on a physical-unit field of n_grid elements (da_4dvar.py:1207 with a 0/1 H compacted by vv_compact_mask):
+ * J_out_dev[0] = obs_coeff * 1/2 * sum_k rinv[k] (x[idx[k]] - y[k])^2 in double; when grad_dev != NULL it is zero-filled and
+ * receives obs_coeff * rinv (x - y) at the observed points.  work_dev holds vv_obs_term_work_doubles() doubles. */
+VV_API int64_t vv_obs_term_work_doubles(void);
+VV_API int vv_obs_term(const float* x_dev, const int32_t* idx_dev, const float* y_dev, const float* rinv_dev, int64_t n_obs, float obs_coeff,
+                       double* J_out_dev, float* grad_dev, int64_t n_grid, double* work_dev, void* stream);
+
 /* torch.optim.LBFGS([z], history_size, max_iter, line_search_fn="strong_wolfe") + .step(closure)
  * (da_4dvar.py:1240, 1298-1299; torch/optim/lbfgs.py:333-537).  State persists across steps; the vectors never
  * leave the device, the controller reads back O(10) scalars per closure evaluation. */

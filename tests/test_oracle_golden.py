@@ -89,3 +89,36 @@ def test_state_dict_keys_match_reference_decoder():
     sd = make_state_dict(DECODER_FULL, seed=0)
     got = {f"{k}:{tuple(v.shape)}" for k, v in sd.items()}
     assert got == want
+
+
+# ---- native-resolution seams (oracle/seams.py against torch's own F.interpolate / autograd, tools/make_golden_seams.py) ----
+def test_seam_index_rule_matches_reference(gold):
+    from oracle import seams as oseams
+    g = gold("seams.npz")
+    assert np.array_equal(oseams.nearest_index(721, 128), g["up_rows"]) and np.array_equal(oseams.nearest_index(1440, 256), g["up_cols"])
+    assert np.array_equal(oseams.nearest_index(128, 721), g["down_rows"]) and np.array_equal(oseams.nearest_index(256, 1440), g["down_cols"])
+    # the up -> down round trip is NOT the identity at these sizes: pin that quirk too
+    rt = g["up_rows"][g["down_rows"]]
+    assert not np.array_equal(rt, np.arange(128)) and np.abs(rt - np.arange(128)).max() == 1
+
+
+def test_seam_forward_and_adjoint_bit_exact(gold):
+    from oracle import seams as oseams
+    g = gold("seams.npz")
+    lo, hi = tuple(g["lo"]), tuple(g["hi"])
+    assert np.array_equal(oseams.resample(g["xa"], lo, 1, g["mean"], g["std"]), g["down_norm"])
+    assert np.array_equal(oseams.resample_adjoint(g["g_lo"], hi, 1, g["std"]), g["down_norm_grad"])
+    assert np.array_equal(oseams.resample(g["zl"], hi, 2, g["mean"], g["std"]), g["up_denorm"])
+    assert np.array_equal(oseams.resample_adjoint(g["g_hi"], lo, 2, g["std"]), g["up_denorm_grad"])
+    for tag in ("plain", "double", "same"):
+        size = g[f"{tag}_out"].shape[1:]
+        assert np.array_equal(oseams.resample(g[f"{tag}_in"], size), g[f"{tag}_out"])
+        assert np.array_equal(oseams.resample_adjoint(g[f"{tag}_g"], lo), g[f"{tag}_grad"])
+
+
+def test_seam_obs_term_matches_reference(gold):
+    from oracle import seams as oseams
+    g = gold("seams.npz")
+    J, grad = oseams.obs_term(g["obs_x"], g["obs_H"], g["obs_yo"], g["obs_R"])
+    assert abs(J / float(g["obs_J64"]) - 1) < 1e-12 and abs(J / float(g["obs_J"]) - 1) < 1e-5
+    np.testing.assert_allclose(grad, g["obs_grad"], rtol=1e-5, atol=1e-7)

@@ -63,6 +63,10 @@ _SIGS = {
     "vv_test_winattn": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vv_test_obs": (C.c_int, [_P, _P, _P, _P, _P]),
     "vv_last_launch_count": (C.c_int, [_P]),
+    "vv_resample_nearest": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "vv_resample_nearest_adjoint": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "vv_obs_term_work_doubles": (C.c_int64, []),
+    "vv_obs_term": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, _P, _P, C.c_int64, _P, _P]),
 }
 EXPORTED = tuple(_SIGS)
 

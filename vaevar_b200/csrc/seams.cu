@@ -1,0 +1,250 @@
+// Native-resolution seams: the nearest-neighbour resampling between the network grid (128x256) and the
+// analysis grid (721x1440) that the reference applies with F.interpolate (nf_model/vae.py:87-90 decoder_hr; da_4dvar.py:670-671, 678-679
+// integrate(interpolation=True)), its adjoint, and the observation term evaluated directly on a physical-unit field of any size
+// (da_4dvar.py:1207).  All HBM-bound: one read and one write per element; one CTA per field row, float4 stores.
+//
+// Index rule (ATen nearest, legacy floor): src = dst when the sizes agree, dst >> 1 for an exact doubling, otherwise
+// min(int(floorf(dst * (float(in) / float(out)))), in - 1).  The (de)normalisation the reference applies on the same side of the seam is
+// fused with separate, correctly rounded operations (no FMA contraction), so results are bit-identical to the eager reference.
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/vaevar.h"
+#include "engine.h"
+
+namespace vv {
+namespace {
+
+struct AxisMap {
+  int in, out, kind;   // kind 0 identity, 1 halving, 2 scaled
+  float scale;
+  __device__ int src(int d) const {
+    if (kind == 0) return d;
+    if (kind == 1) return d >> 1;
+    const int s = (int)floorf(__fmul_rn((float)d, scale));
+    return s < in - 1 ? s : in - 1;
+  }
+  // smallest d in [0, out] with src(d) >= s.  src is non-decreasing, so a closed-form guess plus a fix-up walk is exact.
+  __device__ int lower(int s) const {
+    if (kind == 0) return s < out ? s : out;
+    if (kind == 1) return 2 * s < out ? 2 * s : out;
+    int d = (int)ceilf((float)s / scale);
+    d = d < 0 ? 0 : (d > out ? out : d);
+    while (d > 0 && src(d - 1) >= s) --d;
+    while (d < out && src(d) < s) ++d;
+    return d;
+  }
+};
+
+AxisMap make_axis(int in, int out) {
+  AxisMap a;
+  a.in = in; a.out = out;
+  a.kind = in == out ? 0 : (out == 2 * in ? 1 : 2);
+  a.scale = (float)in / (float)out;
+  return a;
+}
+
+__device__ __forceinline__ float seam_value(float v, int mode, float mu, float sd) {
+  if (mode == 1) return __fdiv_rn(__fsub_rn(v, mu), sd);
+  if (mode == 2) return __fadd_rn(__fmul_rn(v, sd), mu);
+  return v;
+}
+
+// One CTA per RPB consecutive output rows of one channel: the row decomposition costs one 32-bit division per CTA, the threads stride
+// over the columns, and a thread's column indices are computed once for its RPB rows (whose loads are independent).
+constexpr int RPB = 4;
+template <int VEC>
+__global__ void __launch_bounds__(128) resample_kernel(const float* __restrict__ in, float* __restrict__ out, AxisMap rows, AxisMap cols,
+                                                       int mode, const float* __restrict__ mean, const float* __restrict__ sd) {
+  const int groups = (rows.out + RPB - 1) / RPB;
+  const int c = blockIdx.x / groups, i0 = (blockIdx.x - c * groups) * RPB;
+  const float mu = mode ? mean[c] : 0.f, s = mode ? sd[c] : 1.f;
+  const float* src[RPB];
+#pragma unroll
+  for (int r = 0; r < RPB; ++r) src[r] = in + ((long long)c * rows.in + rows.src(i0 + r < rows.out ? i0 + r : rows.out - 1)) * cols.in;
+  float* dst = out + ((long long)c * rows.out + i0) * cols.out;
+  for (int jq = threadIdx.x; jq < cols.out / VEC; jq += blockDim.x) {
+    int sj[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) sj[u] = cols.src(jq * VEC + u);
+    float v[RPB][VEC];
+#pragma unroll
+    for (int r = 0; r < RPB; ++r)
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) v[r][u] = __ldg(src[r] + sj[u]);
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) {
+      if (i0 + r >= rows.out) break;
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) v[r][u] = seam_value(v[r][u], mode, mu, s);
+      float* d = dst + (long long)r * cols.out;
+      if constexpr (VEC == 4) *reinterpret_cast<float4*>(d + jq * 4) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+      else d[jq] = v[r][0];
+    }
+  }
+}
+
+// Adjoint when every source element is read by at most one output (down-sampling: the index map is strictly increasing): the
+// gradient field is zero-filled by the caller and one thread per OUTPUT element stores its cotangent (0 + g = g, so the result is the
+// ordered sum of the general kernel bit for bit).
+__global__ void __launch_bounds__(128) resample_adjoint_injective_kernel(const float* __restrict__ dout, float* __restrict__ din, AxisMap rows,
+                                                                         AxisMap cols, int mode, const float* __restrict__ sd) {
+  const int c = blockIdx.x / rows.out, i = blockIdx.x - c * rows.out;
+  const float s = mode ? sd[c] : 1.f;
+  const float* g = dout + (long long)blockIdx.x * cols.out;
+  float* d = din + ((long long)c * rows.in + rows.src(i)) * cols.in;
+  for (int j = threadIdx.x; j < cols.out; j += blockDim.x) {
+    const float v = __ldg(g + j);
+    d[cols.src(j)] = mode == 2 ? __fmul_rn(v, s) : (mode == 1 ? __fdiv_rn(v, s) : v);
+  }
+}
+
+// One CTA per source row (c, si), one thread per source element: ordered sum (ascending output row, then column - the order of the
+// reference's CPU backward) over the outputs that read it.  mode 1: (sum) / sd[c]  (adjoint of "normalise, then resample");
+// mode 2: sum of dout * sd[c]  (adjoint of "resample, then de-normalise").
+__global__ void __launch_bounds__(128) resample_adjoint_kernel(const float* __restrict__ dout, float* __restrict__ din, AxisMap rows,
+                                                               AxisMap cols, int mode, const float* __restrict__ sd) {
+  const int c = blockIdx.x / rows.in, si = blockIdx.x - c * rows.in;
+  const int i0 = rows.lower(si), i1 = rows.lower(si + 1);
+  const float s = mode ? sd[c] : 1.f;
+  for (int sj = threadIdx.x; sj < cols.in; sj += blockDim.x) {
+    const int j0 = cols.lower(sj), j1 = cols.lower(sj + 1);
+    float acc = 0.f;
+    for (int i = i0; i < i1; ++i) {
+      const float* g = dout + ((long long)c * rows.out + i) * cols.out;
+      for (int j = j0; j < j1; ++j) acc = __fadd_rn(acc, mode == 2 ? __fmul_rn(__ldg(g + j), s) : __ldg(g + j));
+    }
+    din[(long long)blockIdx.x * cols.in + sj] = mode == 1 ? __fdiv_rn(acc, s) : acc;
+  }
+}
+
+constexpr int OBS_BLOCKS = 148 * 4;
+
+// J partials (double) and, when grad != nullptr, the scatter of coeff * rinv * (x - y) into the zero-filled gradient field.
+__global__ void __launch_bounds__(256) obs_term_kernel(const float* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ y,
+                                                       const float* __restrict__ rinv, long long n, float coeff, float* __restrict__ grad,
+                                                       double* __restrict__ partials) {
+  double acc = 0.0;
+  const long long n4 = n >> 2;
+  for (long long q = blockIdx.x * 256LL + threadIdx.x; q < n4; q += gridDim.x * 256LL) {
+    const int4 id = __ldg(reinterpret_cast<const int4*>(idx) + q);
+    const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + q), ri = __ldg(reinterpret_cast<const float4*>(rinv) + q);
+    const float r0 = __ldg(x + id.x) - yy.x, r1 = __ldg(x + id.y) - yy.y, r2 = __ldg(x + id.z) - yy.z, r3 = __ldg(x + id.w) - yy.w;
+    acc += (double)(ri.x * r0 * r0) + (double)(ri.y * r1 * r1) + (double)(ri.z * r2 * r2) + (double)(ri.w * r3 * r3);
+    if (grad) {
+      grad[id.x] = coeff * ri.x * r0; grad[id.y] = coeff * ri.y * r1; grad[id.z] = coeff * ri.z * r2; grad[id.w] = coeff * ri.w * r3;
+    }
+  }
+  for (long long k = (n4 << 2) + blockIdx.x * 256LL + threadIdx.x; k < n; k += gridDim.x * 256LL) {
+    const int id = idx[k];
+    const float r = x[id] - y[k], w = rinv[k];
+    acc += (double)(w * r * r);
+    if (grad) grad[id] = coeff * w * r;
+  }
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void obs_term_final_kernel(const double* __restrict__ partials, int nparts, float coeff, double* __restrict__ J) {
+  __shared__ double red[256];
+  double t = 0.0;
+  for (int k = threadIdx.x; k < nparts; k += 256) t += partials[k];
+  red[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) J[0] = 0.5 * (double)coeff * red[0];
+}
+
+// host copy of AxisMap::src (one correctly rounded float product, like the device)
+int host_src(const AxisMap& a, int d) {
+  if (a.kind == 0) return d;
+  if (a.kind == 1) return d >> 1;
+  volatile float p = (float)d * a.scale;
+  const int s = (int)floorf(p);
+  return s < a.in - 1 ? s : a.in - 1;
+}
+bool strictly_increasing(const AxisMap& a) {
+  if (a.out > a.in) return false;
+  for (int d = 1; d < a.out; ++d)
+    if (host_src(a, d) <= host_src(a, d - 1)) return false;
+  return true;
+}
+
+int row_threads(int per_row) { return per_row >= 128 ? 128 : (per_row <= 32 ? 32 : (per_row + 31) / 32 * 32); }
+
+}  // namespace
+}  // namespace vv
+
+using namespace vv;
+
+#define SEAM_CHECK(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return -2; } } while (0)
+
+extern "C" {
+
+VV_API int vv_resample_nearest(const float* in_dev, float* out_dev, int C, int Hi, int Wi, int Ho, int Wo, int mode, const float* mean_dev,
+                               const float* std_dev, void* stream) {
+  SEAM_CHECK(in_dev && out_dev && C >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "vv_resample_nearest: bad argument");
+  SEAM_CHECK(mode >= 0 && mode <= 2 && (mode == 0 || (mean_dev && std_dev)), "vv_resample_nearest: mode %d needs mean and std", mode);
+  cudaStream_t s = (cudaStream_t)stream;
+  const AxisMap rows = make_axis(Hi, Ho), cols = make_axis(Wi, Wo);
+  const bool vec = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_dev) & 15) == 0);
+  SEAM_CHECK((long long)C * Ho < (1LL << 31) && (long long)C * Hi < (1LL << 31), "vv_resample_nearest: too many rows");
+  const int grid = C * ((Ho + RPB - 1) / RPB);
+  if (vec) resample_kernel<4><<<grid, row_threads(Wo / 4), 0, s>>>(in_dev, out_dev, rows, cols, mode, mean_dev, std_dev);
+  else resample_kernel<1><<<grid, row_threads(Wo), 0, s>>>(in_dev, out_dev, rows, cols, mode, mean_dev, std_dev);
+  const cudaError_t err = cudaGetLastError();
+  SEAM_CHECK(err == cudaSuccess, "vv_resample_nearest: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+VV_API int vv_resample_nearest_adjoint(const float* dout_dev, float* din_dev, int C, int Hi, int Wi, int Ho, int Wo, int mode,
+                                       const float* std_dev, void* stream) {
+  SEAM_CHECK(dout_dev && din_dev && C >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "vv_resample_nearest_adjoint: bad argument");
+  SEAM_CHECK(mode >= 0 && mode <= 2 && (mode == 0 || std_dev), "vv_resample_nearest_adjoint: mode %d needs std", mode);
+  cudaStream_t s = (cudaStream_t)stream;
+  SEAM_CHECK((long long)C * Ho < (1LL << 31) && (long long)C * Hi < (1LL << 31), "vv_resample_nearest_adjoint: too many rows");
+  const AxisMap rows = make_axis(Hi, Ho), cols = make_axis(Wi, Wo);
+  if ((Hi > Ho || Wi > Wo) && strictly_increasing(rows) && strictly_increasing(cols)) {
+    const cudaError_t e0 = cudaMemsetAsync(din_dev, 0, (size_t)C * Hi * Wi * sizeof(float), s);
+    SEAM_CHECK(e0 == cudaSuccess, "vv_resample_nearest_adjoint: %s", cudaGetErrorString(e0));
+    resample_adjoint_injective_kernel<<<C * Ho, row_threads(Wo), 0, s>>>(dout_dev, din_dev, rows, cols, mode, std_dev);
+  } else {
+    resample_adjoint_kernel<<<C * Hi, row_threads(Wi), 0, s>>>(dout_dev, din_dev, rows, cols, mode, std_dev);
+  }
+  const cudaError_t err = cudaGetLastError();
+  SEAM_CHECK(err == cudaSuccess, "vv_resample_nearest_adjoint: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+VV_API int64_t vv_obs_term_work_doubles(void) { return OBS_BLOCKS; }
+
+VV_API int vv_obs_term(const float* x_dev, const int32_t* idx_dev, const float* y_dev, const float* rinv_dev, int64_t n_obs, float coeff,
+                       double* J_out_dev, float* grad_dev, int64_t n_grid, double* work_dev, void* stream) {
+  SEAM_CHECK(x_dev && J_out_dev && work_dev && n_obs >= 0 && (n_obs == 0 || (idx_dev && y_dev && rinv_dev)), "vv_obs_term: bad argument");
+  SEAM_CHECK(!grad_dev || n_grid > 0, "vv_obs_term: the gradient field needs its size");
+  SEAM_CHECK(((reinterpret_cast<uintptr_t>(idx_dev) | reinterpret_cast<uintptr_t>(y_dev) | reinterpret_cast<uintptr_t>(rinv_dev)) & 15) == 0,
+             "vv_obs_term: idx / y / rinv must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (grad_dev) {
+    const cudaError_t e0 = cudaMemsetAsync(grad_dev, 0, (size_t)n_grid * sizeof(float), s);
+    SEAM_CHECK(e0 == cudaSuccess, "vv_obs_term: %s", cudaGetErrorString(e0));
+  }
+  obs_term_kernel<<<OBS_BLOCKS, 256, 0, s>>>(x_dev, idx_dev, y_dev, rinv_dev, n_obs, coeff, grad_dev, work_dev);
+  obs_term_final_kernel<<<1, 256, 0, s>>>(work_dev, OBS_BLOCKS, coeff, J_out_dev);
+  const cudaError_t err = cudaGetLastError();
+  SEAM_CHECK(err == cudaSuccess, "vv_obs_term: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+}  // extern "C"

@@ -6,8 +6,9 @@
     Metrics.WRMSE / Bias        utils/metrics.py:282-296, 65-82 (kept bit-for-bit incl. pi ~ 3.1416)
 
 The latent z, its gradient, the L-BFGS history and the trajectory never leave the GPU; per closure evaluation the
-controller reads back four doubles.  Resampling to 721x1440 (vae.py:90, da_4dvar.py:671,679) is the identity on the
-engine grid and is not performed.
+controller reads back four doubles.  The optimisation runs on the network grid, where the reference's resampling to 721x1440
+(vae.py:90, da_4dvar.py:671,679) is the identity; `integrate(..., interpolation=True)` (the forecast of a native-resolution
+analysis) goes through the seam kernels of seams.py.
 """
 from __future__ import annotations
 
@@ -68,8 +69,15 @@ class VaeVar4D:
         self._opt = None
 
     def integrate(self, xa: torch.Tensor, model=None, step: int = 1, interpolation: bool = False, detach: bool = True):
-        """(69,nlat,nlon) physical -> physical after `step` applications of the flow model (da_4dvar.py:666-681)."""
-        return self.engine.integrate(xa.to(self.device, torch.float32), step)
+        """(69,nlat,nlon) physical -> physical after `step` applications of the flow model (da_4dvar.py:666-681).  With
+        `interpolation` the field is brought to the network grid and back with the reference's nearest rule (:670-671, 678-679);
+        the per-channel (de)normalisation commutes with that index map, so it stays inside the engine call."""
+        xa = xa.to(self.device, torch.float32)
+        if not interpolation or tuple(xa.shape[-2:]) == (self.nlat, self.nlon):
+            return self.engine.integrate(xa, step)
+        from .seams import resample_nearest
+        x = self.engine.integrate(resample_nearest(xa, (self.nlat, self.nlon)), step)
+        return resample_nearest(x, tuple(xa.shape[-2:]))
 
     def _diagnostics(self, z, gt0):
         """WRMSE / Bias of the current analysis (da_4dvar.py:1256-1264) without leaving the device: the fused metric

@@ -15,7 +15,6 @@ from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .config import DECODER_FULL, ENCODER_FULL, NetConfig
 from .engine import Engine
@@ -138,7 +137,9 @@ class VAE_lr(nn.Module):
         return self.dec(z)
 
     def decoder_hr(self, z):
-        return F.interpolate(self.dec(z), (721, 1440))
+        """nf_model/vae.py:87-90; the nearest up-sampling and its adjoint are the seam kernels (seams.py), not torch ops."""
+        from .seams import interpolate_nearest
+        return interpolate_nearest(self.dec(z), (721, 1440))
 
     def forward(self, x):
         mu, log_var = self.encoder(x)
