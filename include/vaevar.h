@@ -84,6 +84,16 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
                 float obs_coeff, void* stream);
 VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs);
 
+/* The same closure on the reference's real geometry (da_4dvar.py:1185-1208 with decoder_hr, nf_model/vae.py:87-90, and
+ * integrate(x, flow, 1, True, False), da_4dvar.py:666-681): xb (C,Hh,Wh) and yo, H, R (T,C,Hh,Wh) live on an analysis grid finer than
+ * the network grid (721x1440 over 128x256).  Nearest resampling is an index map, so the engine keeps every field on the network grid
+ * and composes the maps into the observation indices and into one gather (and its adjoint) between flow steps; J and grad_z are those
+ * of the reference's loss.  vv_cost_grad / vv_cost / vv_lbfgs_* then work unchanged.  Synchronises. */
+VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
+                              float obs_coeff, void* stream);
+/* Analysis on the analysis grid after vv_set_case_native: (decoder_hr(z) stdTr) sigma + xb  (da_4dvar.py:1257-1259, 1301-1306). */
+VV_API int vv_decode_native(vv_engine* e, const float* z_dev, float* x_phys_out_dev, void* stream);
+
 /* closure() (da_4dvar.py:1242-1246): J_out_dev[3] = {J, J_reg, J_obs} (fp64), grad_dev = dJ/dz (same shape as z). */
 VV_API int vv_cost_grad(vv_engine* e, const float* z_dev, double* J_out_dev, float* grad_dev, void* stream);
 /* cal_loss() (da_4dvar.py:1210-1236): forward sweep only. */

@@ -7,7 +7,9 @@ torch_harmonics / xspharm):
     closure()          da_4dvar.py:1242-1246   (autograd supplies the gradient)
     integrate()        da_4dvar.py:666-681     (nlat,nlon parametrised; at the
                        128x256 benchmark grid the nearest resamples at :671,:679
-                       and vae.py:90 are identities and are dropped)
+                       and vae.py:90 are identities and are dropped; a Case built
+                       with `lr=(h,w)` keeps them: fields on the analysis grid,
+                       networks on the (h,w) grid, the reference's real geometry)
     outer L-BFGS loop  da_4dvar.py:1238-1240,1255-1306 with torch.optim.LBFGS as-is
     WRMSE / Bias       utils/metrics.py:282-296, 65-82, 473-474, 526-544
 The network applications are oracle.lgunet.lgunet_forward.
@@ -21,6 +23,7 @@ from typing import Dict, Optional
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from vaevar_b200.config import NetConfig, era5_stats
 from .lgunet import lgunet_forward
@@ -31,7 +34,8 @@ Tensor = torch.Tensor
 class Case:
     """Tensors captured by the reference closure (da_4dvar.py:1248-1251 and :640-647, :1181)."""
 
-    def __init__(self, case: Dict[str, np.ndarray], obs_coeff: float = 1.0):
+    def __init__(self, case: Dict[str, np.ndarray], obs_coeff: float = 1.0, lr=None):
+        self.lr = None if lr is None else tuple(lr)    # network grid when it differs from the analysis grid ((128, 256) in the reference)
         mean, std, stdtr = era5_stats()
         self.mean = torch.from_numpy(mean).float().reshape(-1, 1, 1)     # model_mean_gpu
         self.std = torch.from_numpy(std).float().reshape(-1, 1, 1)       # model_std_gpu
@@ -64,16 +68,26 @@ class OracleNets:
 def integrate(x: Tensor, c: Case, nets, steps: int = 1, detach: bool = True) -> Tensor:
     """da_4dvar.py:666-681.  x (69,nlat,nlon) physical -> physical."""
     z = ((x - c.mean) / c.std).unsqueeze(0)
+    if c.lr is not None:
+        z = F.interpolate(z, c.lr)                                       # :670-671
     for _ in range(steps):
         z = nets.flow(z)[:, :69]
         if detach:
             z = z.detach()
+    if c.lr is not None:
+        z = F.interpolate(z, tuple(x.shape[-2:]))                        # :678-679
     return z.reshape(x.shape) * c.std + c.mean
+
+
+def _decode(z: Tensor, c: Case, nets) -> Tensor:
+    """VAE_lr.decoder, or decoder_hr (nf_model/vae.py:87-90) when the analysis grid is finer than the network grid."""
+    d = nets.decode(z)
+    return d if c.lr is None else F.interpolate(d, tuple(c.xb.shape[-2:]))
 
 
 def trajectory(z: Tensor, c: Case, nets) -> Tensor:
     """x_pred (T,69,nlat,nlon): x_0 = xb + D(z) stdTr sigma, x_{t+1} = M(x_t); da_4dvar.py:1185-1195."""
-    x = (nets.decode(z) * c.stdTr) * c.std.reshape(1, -1, 1, 1) + c.xb
+    x = (_decode(z, c, nets) * c.stdTr) * c.std.reshape(1, -1, 1, 1) + c.xb
     x = x[0]
     xs = [x]
     for _ in range(c.T - 1):
@@ -122,7 +136,7 @@ def bias(pred: Tensor, gt: Tensor, data_std: Tensor) -> Tensor:
 def analysis(z: Tensor, c: Case, nets) -> Tensor:
     """xhat (69,nlat,nlon) physical; da_4dvar.py:1256-1259, 1301-1306."""
     with torch.no_grad():
-        out = nets.decode(z)
+        out = _decode(z, c, nets)
         return out[0] * c.stdTr[0] * c.std + c.xb
 
 
@@ -140,7 +154,7 @@ def one_step_da(c: Case, nets, nit: int = 1, max_iter: int = 10,
 
     Returns dict(xa, z, bg_wrmse, ana_wrmse, bg_bias, ana_bias, J_history, n_evals).
     """
-    nlat, nlon = c.xb.shape[-2:]
+    nlat, nlon = c.xb.shape[-2:] if c.lr is None else c.lr
     z = torch.zeros(1, latent, nlat, nlon) if z0 is None else torch.from_numpy(z0).clone()
     z.requires_grad_(True)
     opt = torch.optim.LBFGS([z], history_size=10, max_iter=max_iter, line_search_fn="strong_wolfe")

@@ -332,3 +332,64 @@ def test_seam_obs_term_against_oracle(chk, gold, n_grid, n_obs):
     assert abs(float(J) - Jo) <= 1e-6 * max(abs(Jo), 1e-30) + (0 if Jo else 1e-30)
     np.testing.assert_allclose(grad.cpu().numpy(), go, rtol=3e-6, atol=1e-9)
     assert np.array_equal(grad.cpu().numpy() != 0, (H != 0) & (go != 0))
+
+
+@pytest.mark.parametrize("tag,recompute,graph", [("rich", False, False), ("rich", True, True), ("plain", False, True)])
+def test_native_geometry_cost_grad_against_reference_golden(chk, gold, tag, recompute, graph):
+    """The reference's real geometry in miniature (analysis grid 181x360 over a 32x64 network grid, the ratios of 721x1440 over
+    128x256): decoder_hr and integrate(x, flow, 1, True, False) resample (vae.py:90, da_4dvar.py:670-679, 1185-1208).  The golden
+    numbers come from the reference's own modules; the engine composes the index maps instead of materialising 181x360 fields."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import LBFGS, Engine
+    from vaevar_b200.synth import make_case, make_state_dict
+    from vaevar_b200.da import wrmse
+    g = gold(f"cost_native_T3_{tag}.npz")
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    seed, gain, rich, T, hr = int(g["seed"]), float(g["gain"]), bool(g["rich"]), int(g["T"]), tuple(int(v) for v in g["hr"])
+    e = Engine(ds, fs, T=T, recompute=recompute, use_graph=graph)
+    e.load_state_dict(0, make_state_dict(ds, seed=seed, gain=gain, rich=rich))
+    e.load_state_dict(1, make_state_dict(fs, seed=seed + 1, gain=gain, rich=rich))
+    e.finalize()
+    case = make_case(T, *hr, obs_frac=float(g["obs_frac"]), seed=seed)
+    z = torch.from_numpy(make_case(1, *ds.img_size, obs_frac=0.1, seed=seed)["z"]).cuda()
+    e.set_case_native(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+    assert e.n_obs == int(g["n_obs"])
+    for _ in range(3):
+        J, grad = e.cost_grad(z)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["g_full"]).double().flatten()
+    gd = grad.double().cpu().flatten()
+    cos = float(gd @ ref / gd.norm() / ref.norm())
+    print(f"[parity native {tag} recompute={recompute}] J rel {abs(float(J[0]) / float(g['J']) - 1):.2e} (gate 1e-3), "
+          f"|grad| rel {abs(float(gd.norm()) / float(g['g_norm']) - 1):.2e} (gate 1e-2), grad cosine {cos:.6f} (gate 0.999)")
+    assert abs(float(J[0]) / float(g["J"]) - 1) < 1e-3
+    assert abs(float(J[1]) / float(g["J_reg"]) - 1) < 1e-6
+    assert abs(float(gd.norm()) / float(g["g_norm"]) - 1) < 1e-2
+    assert cos > 0.999
+    assert float(e.cost(z)[0]) == float(J[0])                                 # forward-only path agrees with the fused one
+    # background analysis (z = 0) on the analysis grid: (decoder_hr(0) stdTr) sigma + xb, every element
+    from vaevar_b200.config import era5_stats
+    mean, std, _ = era5_stats()
+    m, s = torch.from_numpy(mean).float().cuda().reshape(-1, 1, 1), torch.from_numpy(std).float().cuda().reshape(-1, 1, 1)
+    gt0 = torch.from_numpy(case["gt"][0]).cuda()
+    z0 = torch.zeros_like(z)
+    norm = lambda x: ((x - m) / s).unsqueeze(0)
+    w0 = wrmse(norm(e.decode_native(z0)), norm(gt0), torch.from_numpy(std).cuda()).cpu().numpy()
+    np.testing.assert_allclose(w0, g["bg_wrmse"], rtol=1e-3)
+    # LBFGS.step(max_iter=10) from z = 0 (da_4dvar.py:1238-1240, 1298-1299).  The forward pass runs on 16-bit operands, so an early
+    # line search can branch differently from the fp32 reference: the single-step number is reported, the 1 % gate is checked after
+    # the shipped script's Nit = 4 steps (as for the network-grid cases), on the plain weights (the x3-gain "rich" weights amplify the
+    # branching; their numbers are printed only).
+    if not recompute:
+        opt = LBFGS(e, history_size=10, max_iter=10)
+        stdc = torch.from_numpy(std).cuda()
+        for it in range(4):
+            opt.step(z0)
+            w = wrmse(norm(e.decode_native(z0)), norm(gt0), stdc).cpu().numpy()
+            ref_w = g["ana_wrmse"] if it == 0 else g["ana_wrmse_nit4"]
+            if it in (0, 3):
+                print(f"[parity native {tag}] after {it + 1} step(s): analysis WRMSE worst channel rel diff "
+                      f"{float(np.max(np.abs(w / ref_w - 1))):.2e}; J engine {opt.history()[-1]:.6g}, reference "
+                      f"{(g['J_history'] if it == 0 else g['J_history_nit4'])[-1]:.6g}")
+        assert float(np.max(np.abs(w / g["ana_wrmse_nit4"] - 1))) < (1e-2 if tag == "plain" else 5e-2)
+    e.close()

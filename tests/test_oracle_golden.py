@@ -52,6 +52,22 @@ def test_cost_and_grad_matches_reference(gold, tag):
     assert abs(np.linalg.norm(grad) / float(g["g_norm"]) - 1) < 1e-4
 
 
+def test_native_geometry_cost_and_grad_matches_reference(gold):
+    """Analysis grid 181x360 over a 32x64 network grid: decoder_hr and integrate(interpolation=True) resample (vae.py:90,
+    da_4dvar.py:670-679), generated with the reference's own modules."""
+    g = gold("cost_native_T3_rich.npz")
+    seed, gain, T, hr = int(g["seed"]), float(g["gain"]), int(g["T"]), tuple(int(v) for v in g["hr"])
+    nets = ocost.OracleNets(to_torch(make_state_dict(DS, seed=seed, gain=gain, rich=True)), DS,
+                            to_torch(make_state_dict(FS, seed=seed + 1, gain=gain, rich=True)), FS)
+    case = make_case(T, *hr, obs_frac=float(g["obs_frac"]), seed=seed)
+    z = make_case(1, *DS.img_size, obs_frac=0.1, seed=seed)["z"]
+    J, Jr, Jo, grad = ocost.cost_and_grad(z, ocost.Case(case, lr=DS.img_size), nets)
+    assert abs(J / float(g["J"]) - 1) < 2e-5 and abs(Jr / float(g["J_reg"]) - 1) < 1e-6
+    ref = g["g_full"]
+    assert float((grad.ravel() @ ref.ravel()) / np.linalg.norm(grad) / np.linalg.norm(ref)) > 1 - 1e-6
+    assert abs(np.linalg.norm(grad) / float(g["g_norm"]) - 1) < 1e-4
+
+
 def test_lbfgs_analysis_matches_reference(gold):
     g = gold("cost_small_T1.npz")
     nets = ocost.OracleNets(to_torch(make_state_dict(DS, seed=0)), DS)

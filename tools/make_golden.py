@@ -137,6 +137,29 @@ def golden_cost(tag, cfg_dec, cfg_flow, T, obs_frac, seed, gain, rich, lbfgs_ite
     print(f"cost_{tag}: J={J:.8g} J_reg={Jr:.6g} J_obs={Jo:.8g} |g|={out['g_norm']:.6g} ({dt:.1f}s)", flush=True)
 
 
+def golden_cost_native(tag, cfg_dec, cfg_flow, T, hr, obs_frac, seed, gain, rich, lbfgs_iters=10):
+    """The reference's real geometry in miniature: analysis grid `hr` finer than the network grid by the same non-integer ratios
+    as 721x1440 / 128x256, so decoder_hr (vae.py:90) and integrate(x, flow, 1, True, False) (da_4dvar.py:1191, 670-679) resample."""
+    from oracle.cost import Case, cost_and_grad, one_step_da
+    from vaevar_b200.synth import make_case, make_state_dict
+    dec = ref_net(cfg_dec, make_state_dict(cfg_dec, seed=seed, gain=gain, rich=rich))
+    flow = ref_net(cfg_flow, make_state_dict(cfg_flow, seed=seed + 1, gain=gain, rich=rich))
+    nets = RefNets(dec, flow)
+    case = make_case(T, *hr, obs_frac=obs_frac, seed=seed)
+    z = make_case(1, *cfg_dec.img_size, obs_frac=obs_frac, seed=seed)["z"]
+    c = Case(case, lr=cfg_dec.img_size)
+    J, Jr, Jo, g = cost_and_grad(z, c, nets)
+    r = one_step_da(c, nets, nit=1, max_iter=lbfgs_iters)
+    r4 = one_step_da(c, nets, nit=4, max_iter=lbfgs_iters)     # the shipped script's Nit=4 (da_4dvar_script.sh:14)
+    ia = sample_idx(r["xa"].size, 8192, seed=10)
+    np.savez_compressed(GOLD / f"cost_{tag}.npz", ana_wrmse_nit4=r4["ana_wrmse"], J_history_nit4=r4["J_history"], n_evals_nit4=r4["n_evals"],
+                        seed=seed, gain=gain, rich=rich, T=T, hr=np.array(hr), obs_frac=obs_frac, J=J, J_reg=Jr,
+                        J_obs=Jo, g_full=g, g_norm=np.float64(np.linalg.norm(g.astype(np.float64))), n_obs=np.int64(case["H"].sum()),
+                        bg_wrmse=r["bg_wrmse"], ana_wrmse=r["ana_wrmse"], bg_bias=r["bg_bias"], ana_bias=r["ana_bias"],
+                        J_history=r["J_history"], n_evals=r["n_evals"], xa_idx=ia, xa_val=r["xa"].ravel()[ia])
+    print(f"cost_{tag}: J={J:.8g} J_reg={Jr:.6g} J_obs={Jo:.8g} |g|={np.linalg.norm(g):.6g} evals={r['n_evals']}", flush=True)
+
+
 def golden_metrics():
     from utils.metrics import Metrics
     rng = np.random.Generator(np.random.PCG64(5))
@@ -178,6 +201,8 @@ if __name__ == "__main__":
         "net_small_flow_rich": lambda: golden_net("small_flow_rich", fs, 1, 3.0, True),
         "cost_small_T1": lambda: golden_cost("small_T1", ds, fs, 1, 0.10, 0, 1.0, False, lbfgs_iters=10, nit4=True),
         "cost_small_T3_rich": lambda: golden_cost("small_T3_rich", ds, fs, 3, 0.10, 2, 3.0, True, lbfgs_iters=10, nit4=True),
+        "cost_native_T3_rich": lambda: golden_cost_native("native_T3_rich", ds, fs, 3, (181, 360), 0.10, 4, 3.0, True),
+        "cost_native_T3_plain": lambda: golden_cost_native("native_T3_plain", ds, fs, 3, (181, 360), 0.10, 0, 1.0, False),
     }
     if a.full:
         jobs.update({

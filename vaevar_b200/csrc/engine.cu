@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "engine.h"
+#include "seams.cuh"
 
 namespace vv {
 
@@ -734,11 +735,28 @@ static int enqueue_forward(vv_engine* e, cudaStream_t s, bool with_obs) {
   const int T = e->cfg.T;
   const size_t CHW = (size_t)e->C * e->HW;
   launches += e->fwd[0].run(s);
-  // x_0 = xb + D(z) stdTr sigma  (da_4dvar.py:1187)  ->  normalised: (xb - mu)/sigma + D(z) stdTr
-  launch_chan_affine(e->XN, e->DOUT, e->stdTr, e->XB, e->inv_sigma, e->neg_mu_sig, e->C, e->HW, s); ++launches;
-  for (int t = 1; t < T; ++t) launches += e->fwd[t].run(s);                                  // x_t = M(x_{t-1})  (:1191-1193)
+  if (!e->native) {
+    // x_0 = xb + D(z) stdTr sigma  (da_4dvar.py:1187)  ->  normalised: (xb - mu)/sigma + D(z) stdTr
+    launch_chan_affine(e->XN, e->DOUT, e->stdTr, e->XB, e->inv_sigma, e->neg_mu_sig, e->C, e->HW, s); ++launches;
+    for (int t = 1; t < T; ++t) launches += e->fwd[t].run(s);                                // x_t = M(x_{t-1})  (:1191-1193)
+  } else {
+    // Analysis grid finer than the network grid (the reference's 721x1440 over 128x256).  Nearest resampling is an index map, so the
+    // fields on the analysis grid are never materialised: with F_0 = D(z) stdTr and F_t = M(N_{t-1}) on the network grid,
+    //   x_t on the analysis grid  = up(F_t) sigma + (xb for t = 0, mu otherwise)            (vae.py:90, da_4dvar.py:1187, 678-681)
+    //   N_t (input of the next M) = down((x_t - mu) / sigma) = S(F_t) (+ down((xb - mu) / sigma) for t = 0),  S = down o up  (:667-671)
+    // and the observation term reads up(F_t) through indices composed with the up-sampling map at vv_set_case_native.
+    const int H = e->net[0].H, W = e->net[0].W;
+    launch_chan_affine(e->XF, e->DOUT, e->stdTr, nullptr, nullptr, nullptr, e->C, e->HW, s);
+    launch_seam_gather(e->XN, e->XF, e->XBN, e->s_row, e->s_col, e->C, H, W, s);
+    launches += 2;
+    for (int t = 1; t < T; ++t) {
+      launches += e->fwd[t].run(s);
+      cudaMemcpyAsync(e->XF + (size_t)t * CHW, e->XN + (size_t)t * CHW, CHW * sizeof(float), cudaMemcpyDeviceToDevice, s);
+      if (t + 1 < T) { launch_seam_gather(e->XN + (size_t)t * CHW, e->XF + (size_t)t * CHW, nullptr, e->s_row, e->s_col, e->C, H, W, s); ++launches; }
+    }
+  }
   if (with_obs) {
-    launch_obs_misfit(e->XN, e->idx, e->yobs, e->rinv, e->sigma, e->mean, e->n_obs, e->HW, e->C, e->obs_coeff, e->resid, e->partials,
+    launch_obs_misfit(e->native ? e->XF : e->XN, e->idx, e->yobs, e->rinv, e->sigma, e->mean, e->n_obs, e->HW, e->C, e->obs_coeff, e->resid, e->partials,
                       reduce_blocks(), s);
     launch_reduce_partials(e->partials, reduce_blocks(), e->Jbuf + 3, s);
     DotPairs dp{}; dp.a[0] = e->Z; dp.b[0] = e->Z; dp.n_pairs = 1;
@@ -756,11 +774,21 @@ static int enqueue_backward(vv_engine* e, cudaStream_t s) {
   const size_t CHW = (size_t)e->C * e->HW;
   float* Gt = e->Gb[(T - 1) % 2];
   cudaMemsetAsync(Gt, 0, CHW * sizeof(float), s);
-  launch_obs_adjoint(Gt, e->idx, e->resid, e->obs_off[T - 1], e->obs_off[T], (long long)(T - 1) * CHW, s); ++launches;
+  // native geometry: several observations share a network-grid cell (sorted runs); otherwise the indices are unique
+  auto obs_adjoint = [&](float* G, int t) {
+    if (e->native) launch_obs_adjoint_runs(G, e->idx, e->resid, e->obs_off[t], e->obs_off[t + 1], (long long)t * CHW, s);
+    else launch_obs_adjoint(G, e->idx, e->resid, e->obs_off[t], e->obs_off[t + 1], (long long)t * CHW, s);
+  };
+  obs_adjoint(Gt, T - 1); ++launches;
   for (int t = T - 1; t >= 1; --t) {
     if (e->cfg.recompute && t != T - 1) launches += e->fwd[t].run(s);      // stash shared by the flow applications: rebuild step t
     launches += e->bwd[t].run(s);
-    launch_obs_adjoint(e->Gb[(t - 1) % 2], e->idx, e->resid, e->obs_off[t - 1], e->obs_off[t], (long long)(t - 1) * CHW, s); ++launches;
+    float* G = e->Gb[(t - 1) % 2];
+    if (e->native) {                                                       // dJ/dN_{t-1} -> dJ/dF_{t-1} through S^T
+      cudaMemcpyAsync(e->TMPF, G, CHW * sizeof(float), cudaMemcpyDeviceToDevice, s);
+      launch_seam_gather_adjoint(G, e->TMPF, e->s_row_lo, e->s_col_lo, e->C, e->net[0].H, e->net[0].W, s); ++launches;
+    }
+    obs_adjoint(G, t - 1); ++launches;
   }
   launch_chan_affine(e->GD, e->Gb[0], e->stdTr, nullptr, nullptr, nullptr, e->C, e->HW, s); ++launches;   // dJ/dD = G_0 stdTr
   launches += e->bwd[0].run(s);
@@ -953,12 +981,99 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
   if (e->graph_cg && (off != e->obs_off || total != e->n_obs || obs_coeff != e->obs_coeff)) {
     cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr;     // launch parameters baked into the graph changed
   }
+  if (e->native && e->graph_cg) { cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr; }
+  e->native = false;
   e->obs_off = off;
   e->n_obs = total;
   e->obs_coeff = obs_coeff;
   VV_CUDA(cudaMemcpyAsync(e->XB, xb_dev, CHW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   VV_CUDA(cudaStreamSynchronize(s));
   e->have_case = true;
+  return 0;
+}
+
+VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
+                              float obs_coeff, void* stream) {
+  VV_CHECK(e && xb_dev && yo_dev && H_dev && R_dev && Hh >= 1 && Wh >= 1, "bad argument");
+  VV_CHECK(e->have_consts, "vv_set_constants has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = build_plans(e);
+  if (rc) return rc;
+  const int T = e->cfg.T, C = e->C, H = e->net[0].H, W = e->net[0].W;
+  const long long CHW = (long long)C * e->HW, lvl = (long long)C * Hh * Wh;
+  VV_CHECK(CHW * T < (1LL << 31) && lvl < (1LL << 31), "observation space too large for int32 indices");
+  // ordered compaction per time level on the analysis grid (== torch.nonzero order within the level)
+  const long long nchunks = (lvl + 1023) / 1024;
+  int* counts = nullptr;
+  VV_CUDA(cudaMalloc(&counts, (size_t)T * (nchunks + 1) * sizeof(int)));
+  std::vector<long long> off(T + 1, 0);
+  std::vector<int> tot(T);
+  for (int t = 0; t < T; ++t) {
+    int* ct = counts + (size_t)t * (nchunks + 1);
+    launch_compact_count(H_dev + (size_t)t * lvl, lvl, ct, s);
+    launch_compact_scan(ct, nchunks, s);
+    cudaMemcpyAsync(&tot[t], ct + nchunks, sizeof(int), cudaMemcpyDeviceToHost, s);
+  }
+  cudaError_t er = cudaStreamSynchronize(s);
+  if (er != cudaSuccess) { cudaFree(counts); set_error("vv_set_case_native: %s", cudaGetErrorString(er)); return -1; }
+  for (int t = 0; t < T; ++t) off[t + 1] = off[t] + tot[t];
+  const long long total = off[T];
+  int* idx_hr = nullptr; float *y_hr = nullptr, *ri_hr = nullptr;
+  const size_t cap = (size_t)(total ? total : 1);
+  if (cudaMalloc(&idx_hr, cap * sizeof(int)) != cudaSuccess || cudaMalloc(&y_hr, cap * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&ri_hr, cap * sizeof(float)) != cudaSuccess) {
+    cudaFree(counts); cudaFree(idx_hr); cudaFree(y_hr); cudaFree(ri_hr);
+    set_error("vv_set_case_native: out of memory for %lld observations", total);
+    return -1;
+  }
+  for (int t = 0; t < T; ++t)
+    launch_compact_write(H_dev + (size_t)t * lvl, yo_dev + (size_t)t * lvl, R_dev + (size_t)t * lvl, lvl, counts + (size_t)t * (nchunks + 1),
+                         idx_hr + off[t], y_hr + off[t], ri_hr + off[t], s);
+  if (total > e->obs_cap) {
+    e->obs_cap = total + total / 8 + 1024;
+    e->idx = dalloc<int>(e, e->obs_cap); e->yobs = dalloc<float>(e, e->obs_cap);
+    e->rinv = dalloc<float>(e, e->obs_cap); e->resid = dalloc<float>(e, e->obs_cap);
+  }
+  if (!e->XF) {
+    e->XF = dalloc<float>(e, (size_t)CHW * T); e->XBN = dalloc<float>(e, CHW); e->TMPF = dalloc<float>(e, CHW);
+    e->s_row = dalloc<int>(e, H); e->s_col = dalloc<int>(e, W); e->s_row_lo = dalloc<int>(e, H + 1); e->s_col_lo = dalloc<int>(e, W + 1);
+  }
+  if (lvl > e->xbh_cap) { e->XBH = dalloc<float>(e, lvl); e->xbh_cap = lvl; }
+  rc = (e->idx && e->yobs && e->rinv && e->resid && e->XF && e->XBN && e->TMPF && e->s_col_lo && e->XBH) ? 0 : -1;
+  if (!rc) {
+    std::vector<int> row, col, row_lo, col_lo;
+    host_seam_tables(H, W, Hh, Wh, row, col, row_lo, col_lo);
+    cudaMemcpyAsync(e->s_row, row.data(), H * sizeof(int), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(e->s_col, col.data(), W * sizeof(int), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(e->s_row_lo, row_lo.data(), (H + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(e->s_col_lo, col_lo.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(e->XBH, xb_dev, lvl * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    launch_resample(xb_dev, e->XBN, C, Hh, Wh, H, W, 1, e->mean, e->sigma, s);               // down((xb - mu) / sigma), da_4dvar.py:667-671
+    cudaMemsetAsync(e->XB, 0, CHW * sizeof(float), s);
+    rc = native_compose_sort(idx_hr, y_hr, ri_hr, off.data(), T, xb_dev, e->mean, C, H, W, Hh, Wh, e->idx, e->yobs, e->rinv, s);
+    if (!rc && cudaStreamSynchronize(s) != cudaSuccess) { set_error("vv_set_case_native: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+  } else {
+    set_error("vv_set_case_native: out of memory");
+  }
+  cudaFree(counts); cudaFree(idx_hr); cudaFree(y_hr); cudaFree(ri_hr);
+  if (rc) return rc;
+  if (e->graph_cg) { cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr; }            // launch parameters baked into the graph changed
+  e->native = true; e->Hh = Hh; e->Wh = Wh;
+  e->obs_off = off;
+  e->n_obs = total;
+  e->obs_coeff = obs_coeff;
+  e->have_case = true;
+  return 0;
+}
+
+VV_API int vv_decode_native(vv_engine* e, const float* z_dev, float* x_phys_out_dev, void* stream) {
+  VV_CHECK(e && z_dev && x_phys_out_dev, "null argument");
+  VV_CHECK(e->have_consts && e->have_case && e->native, "vv_set_case_native has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  VV_CUDA(cudaMemcpyAsync(e->Z, z_dev, (size_t)e->Zc * e->HW * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  e->fwd[0].run(s);
+  launch_decode_hr(e->DOUT, e->stdTr, e->sigma, e->XBH, x_phys_out_dev, e->C, e->net[0].H, e->net[0].W, e->Hh, e->Wh, s);
+  VV_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -94,6 +94,12 @@ struct vv_engine {
   bool have_case = false;
   double *partials = nullptr, *dots = nullptr, *dot_scratch = nullptr, *Jbuf = nullptr;
   float* met_w = nullptr; double* met_part = nullptr;     // diagnostics scratch (latitude weights, block partials)
+  // native geometry (vv_set_case_native): analysis grid Hh x Wh finer than the network grid; see enqueue_forward
+  bool native = false;
+  int Hh = 0, Wh = 0;
+  float *XF = nullptr, *XBN = nullptr, *TMPF = nullptr, *XBH = nullptr;   // F_t stack, down((xb - mu) / sigma), scratch field, xb on the analysis grid
+  long long xbh_cap = 0;
+  int *s_row = nullptr, *s_col = nullptr, *s_row_lo = nullptr, *s_col_lo = nullptr;   // S = down o up tables and adjoint ranges
   // plans: index 0 = decoder application, 1..T-1 = flow applications
   std::vector<vv::Stash> stash;
   std::vector<vv::Plan> fwd, bwd;

@@ -10,39 +10,13 @@
 #include <cstdint>
 
 #include "../../include/vaevar.h"
+#include <cub/device/device_radix_sort.cuh>
+
 #include "engine.h"
+#include "seams.cuh"
 
 namespace vv {
 namespace {
-
-struct AxisMap {
-  int in, out, kind;   // kind 0 identity, 1 halving, 2 scaled
-  float scale;
-  __device__ int src(int d) const {
-    if (kind == 0) return d;
-    if (kind == 1) return d >> 1;
-    const int s = (int)floorf(__fmul_rn((float)d, scale));
-    return s < in - 1 ? s : in - 1;
-  }
-  // smallest d in [0, out] with src(d) >= s.  src is non-decreasing, so a closed-form guess plus a fix-up walk is exact.
-  __device__ int lower(int s) const {
-    if (kind == 0) return s < out ? s : out;
-    if (kind == 1) return 2 * s < out ? 2 * s : out;
-    int d = (int)ceilf((float)s / scale);
-    d = d < 0 ? 0 : (d > out ? out : d);
-    while (d > 0 && src(d - 1) >= s) --d;
-    while (d < out && src(d) < s) ++d;
-    return d;
-  }
-};
-
-AxisMap make_axis(int in, int out) {
-  AxisMap a;
-  a.in = in; a.out = out;
-  a.kind = in == out ? 0 : (out == 2 * in ? 1 : 2);
-  a.scale = (float)in / (float)out;
-  return a;
-}
 
 __device__ __forceinline__ float seam_value(float v, int mode, float mu, float sd) {
   if (mode == 1) return __fdiv_rn(__fsub_rn(v, mu), sd);
@@ -166,18 +140,10 @@ __global__ void obs_term_final_kernel(const double* __restrict__ partials, int n
   if (threadIdx.x == 0) J[0] = 0.5 * (double)coeff * red[0];
 }
 
-// host copy of AxisMap::src (one correctly rounded float product, like the device)
-int host_src(const AxisMap& a, int d) {
-  if (a.kind == 0) return d;
-  if (a.kind == 1) return d >> 1;
-  volatile float p = (float)d * a.scale;
-  const int s = (int)floorf(p);
-  return s < a.in - 1 ? s : a.in - 1;
-}
 bool strictly_increasing(const AxisMap& a) {
   if (a.out > a.in) return false;
   for (int d = 1; d < a.out; ++d)
-    if (host_src(a, d) <= host_src(a, d - 1)) return false;
+    if (host_axis_src(a, d) <= host_axis_src(a, d - 1)) return false;
   return true;
 }
 
@@ -186,9 +152,174 @@ int row_threads(int per_row) { return per_row >= 128 ? 128 : (per_row <= 32 ? 32
 }  // namespace
 }  // namespace vv
 
+// ---- pieces the engine composes into its cost graph when the analysis grid is finer than the network grid --------------------------
+namespace vv {
+namespace {
+
+__global__ void __launch_bounds__(256) seam_gather_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ add,
+                                                          const int* __restrict__ row, const int* __restrict__ col, int H, int W, long long n) {
+  const long long it = blockIdx.x * 256LL + threadIdx.x;
+  if (it >= n) return;
+  const int j = (int)(it % W);
+  const long long ci = it / W;
+  const int i = (int)(ci % H);
+  const long long c = ci / H;
+  const float v = __ldg(in + (c * H + row[i]) * W + col[j]);
+  out[it] = add ? v + add[it] : v;
+}
+
+__global__ void __launch_bounds__(256) seam_gather_adjoint_kernel(float* __restrict__ din, const float* __restrict__ dout,
+                                                                  const int* __restrict__ row_lo, const int* __restrict__ col_lo, int H, int W,
+                                                                  long long n) {
+  const long long it = blockIdx.x * 256LL + threadIdx.x;
+  if (it >= n) return;
+  const int q = (int)(it % W);
+  const long long ci = it / W;
+  const int r = (int)(ci % H);
+  const long long c = ci / H;
+  float acc = 0.f;
+  for (int i = row_lo[r]; i < row_lo[r + 1]; ++i)
+    for (int j = col_lo[q]; j < col_lo[q + 1]; ++j) acc += __ldg(dout + (c * H + i) * W + j);
+  din[it] = acc;
+}
+
+__global__ void __launch_bounds__(256) obs_adjoint_runs_kernel(float* __restrict__ G, const int* __restrict__ idx, const float* __restrict__ resid,
+                                                               long long k0, long long k1, long long base) {
+  for (long long k = k0 + blockIdx.x * 256LL + threadIdx.x; k < k1; k += gridDim.x * 256LL) {
+    const int id = idx[k];
+    if (k > k0 && idx[k - 1] == id) continue;          // not the head of its run
+    float a = resid[k];
+    for (long long m = k + 1; m < k1 && idx[m] == id; ++m) a += resid[m];
+    G[id - base] += a;
+  }
+}
+
+__global__ void __launch_bounds__(256) compose_obs_kernel(const int* __restrict__ idx_hr, const float* __restrict__ y, const float* __restrict__ xb_hr,
+                                                          const float* __restrict__ mean, AxisMap rows, AxisMap cols, int HhWh, int Wh, int HW,
+                                                          int W, int base, long long n, long long k_off, int* __restrict__ key,
+                                                          float* __restrict__ y2, int* __restrict__ iota) {
+  const long long k = blockIdx.x * 256LL + threadIdx.x;
+  if (k >= n) return;
+  const int p = idx_hr[k];
+  const int c = p / HhWh, rem = p - c * HhWh;
+  const int pi = rem / Wh, pj = rem - pi * Wh;
+  key[k] = base + c * HW + rows.src(pi) * W + cols.src(pj);
+  y2[k] = xb_hr ? (y[k] - xb_hr[p]) + mean[c] : y[k];
+  iota[k] = (int)(k_off + k);
+}
+
+__global__ void __launch_bounds__(256) permute_obs_kernel(const int* __restrict__ perm, const float* __restrict__ y2, const float* __restrict__ rinv,
+                                                          long long n, float* __restrict__ y_out, float* __restrict__ rinv_out) {
+  const long long k = blockIdx.x * 256LL + threadIdx.x;
+  if (k >= n) return;
+  const int p = perm[k];
+  y_out[k] = y2[p];
+  rinv_out[k] = rinv[p];
+}
+
+__global__ void __launch_bounds__(128) decode_hr_kernel(const float* __restrict__ D, const float* __restrict__ stdTr, const float* __restrict__ sigma,
+                                                        const float* __restrict__ xb_hr, float* __restrict__ out, AxisMap rows, AxisMap cols) {
+  const int c = blockIdx.x / rows.out, i = blockIdx.x - c * rows.out;
+  const float a = stdTr[c], b = sigma[c];
+  const float* src = D + ((long long)c * rows.in + rows.src(i)) * cols.in;
+  const long long o = (long long)blockIdx.x * cols.out;
+  for (int j = threadIdx.x; j < cols.out; j += blockDim.x)
+    out[o + j] = __fadd_rn(__fmul_rn(__fmul_rn(__ldg(src + cols.src(j)), a), b), xb_hr[o + j]);
+}
+
+unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
+
+}  // namespace
+
+int host_axis_src(const AxisMap& a, int d) {
+  if (a.kind == 0) return d;
+  if (a.kind == 1) return d >> 1;
+  volatile float p = (float)d * a.scale;
+  const int s = (int)floorf(p);
+  return s < a.in - 1 ? s : a.in - 1;
+}
+
+void host_seam_tables(int H, int W, int Hh, int Wh, std::vector<int>& row, std::vector<int>& col, std::vector<int>& row_lo,
+                      std::vector<int>& col_lo) {
+  auto one = [](int n, int nh, std::vector<int>& map, std::vector<int>& lo) {
+    const AxisMap up = make_axis(n, nh), down = make_axis(nh, n);      // analysis row -> network row; network row -> analysis row
+    map.resize(n);
+    for (int i = 0; i < n; ++i) map[i] = host_axis_src(up, host_axis_src(down, i));
+    lo.assign(n + 1, n);
+    int i = 0;
+    for (int r = 0; r <= n; ++r) {                                     // map is non-decreasing
+      while (i < n && map[i] < r) ++i;
+      lo[r] = i;
+    }
+  };
+  one(H, Hh, row, row_lo);
+  one(W, Wh, col, col_lo);
+}
+
+void launch_seam_gather(float* out, const float* in, const float* add, const int* row, const int* col, int C, int H, int W, cudaStream_t s) {
+  const long long n = (long long)C * H * W;
+  seam_gather_kernel<<<blocks_for(n), 256, 0, s>>>(out, in, add, row, col, H, W, n);
+}
+void launch_seam_gather_adjoint(float* din, const float* dout, const int* row_lo, const int* col_lo, int C, int H, int W, cudaStream_t s) {
+  const long long n = (long long)C * H * W;
+  seam_gather_adjoint_kernel<<<blocks_for(n), 256, 0, s>>>(din, dout, row_lo, col_lo, H, W, n);
+}
+void launch_obs_adjoint_runs(float* G, const int* idx, const float* resid, long long k0, long long k1, long long base, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const long long want = (k1 - k0 + 255) / 256;
+  obs_adjoint_runs_kernel<<<(unsigned)(want < 1184 ? want : 1184), 256, 0, s>>>(G, idx, resid, k0, k1, base);
+}
+void launch_decode_hr(const float* D, const float* stdTr, const float* sigma, const float* xb_hr, float* out, int C, int H, int W, int Hh,
+                      int Wh, cudaStream_t s) {
+  decode_hr_kernel<<<C * Hh, 128, 0, s>>>(D, stdTr, sigma, xb_hr, out, make_axis(H, Hh), make_axis(W, Wh));
+}
+
+int native_compose_sort(const int* idx_hr, const float* y, const float* rinv, const long long* off, int T, const float* xb_hr, const float* mean,
+                        int C, int H, int W, int Hh, int Wh, int* idx_out, float* y_out, float* rinv_out, cudaStream_t s) {
+  const long long total = off[T];
+  if (total == 0) return 0;
+  int *key = nullptr, *iota = nullptr, *perm = nullptr;
+  float* y2 = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, idx_out, iota, perm, (int)total, 0, 31, s);
+  bool ok = cudaMalloc(&key, total * sizeof(int)) == cudaSuccess && cudaMalloc(&iota, total * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&perm, total * sizeof(int)) == cudaSuccess && cudaMalloc(&y2, total * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1) == cudaSuccess;
+  if (ok) {
+    const AxisMap rows = make_axis(H, Hh), cols = make_axis(W, Wh);
+    for (int t = 0; t < T; ++t) {
+      const long long n = off[t + 1] - off[t];
+      if (n <= 0) continue;
+      compose_obs_kernel<<<blocks_for(n), 256, 0, s>>>(idx_hr + off[t], y + off[t], t == 0 ? xb_hr : nullptr, mean, rows, cols, Hh * Wh, Wh,
+                                                      H * W, W, (int)((long long)t * C * H * W), n, off[t], key + off[t], y2 + off[t],
+                                                      iota + off[t]);
+    }
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, idx_out, iota, perm, (int)total, 0, 31, s);
+    permute_obs_kernel<<<blocks_for(total), 256, 0, s>>>(perm, y2, rinv, total, y_out, rinv_out);
+    ok = cudaStreamSynchronize(s) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+  }
+  cudaFree(key); cudaFree(iota); cudaFree(perm); cudaFree(y2); cudaFree(tmp);
+  if (!ok) { set_error("native_compose_sort: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+  return 0;
+}
+
+}  // namespace vv
+
 using namespace vv;
 
 #define SEAM_CHECK(cond, ...) do { if (!(cond)) { set_error(__VA_ARGS__); return -2; } } while (0)
+
+namespace vv {
+void launch_resample(const float* in, float* out, int C, int Hi, int Wi, int Ho, int Wo, int mode, const float* mean, const float* sd,
+                     cudaStream_t s) {
+  const AxisMap rows = make_axis(Hi, Ho), cols = make_axis(Wi, Wo);
+  const bool vec = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const int grid = C * ((Ho + RPB - 1) / RPB);
+  if (vec) resample_kernel<4><<<grid, row_threads(Wo / 4), 0, s>>>(in, out, rows, cols, mode, mean, sd);
+  else resample_kernel<1><<<grid, row_threads(Wo), 0, s>>>(in, out, rows, cols, mode, mean, sd);
+}
+}  // namespace vv
 
 extern "C" {
 
@@ -196,13 +327,8 @@ VV_API int vv_resample_nearest(const float* in_dev, float* out_dev, int C, int H
                                const float* std_dev, void* stream) {
   SEAM_CHECK(in_dev && out_dev && C >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1, "vv_resample_nearest: bad argument");
   SEAM_CHECK(mode >= 0 && mode <= 2 && (mode == 0 || (mean_dev && std_dev)), "vv_resample_nearest: mode %d needs mean and std", mode);
-  cudaStream_t s = (cudaStream_t)stream;
-  const AxisMap rows = make_axis(Hi, Ho), cols = make_axis(Wi, Wo);
-  const bool vec = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_dev) & 15) == 0);
   SEAM_CHECK((long long)C * Ho < (1LL << 31) && (long long)C * Hi < (1LL << 31), "vv_resample_nearest: too many rows");
-  const int grid = C * ((Ho + RPB - 1) / RPB);
-  if (vec) resample_kernel<4><<<grid, row_threads(Wo / 4), 0, s>>>(in_dev, out_dev, rows, cols, mode, mean_dev, std_dev);
-  else resample_kernel<1><<<grid, row_threads(Wo), 0, s>>>(in_dev, out_dev, rows, cols, mode, mean_dev, std_dev);
+  launch_resample(in_dev, out_dev, C, Hi, Wi, Ho, Wo, mode, mean_dev, std_dev, (cudaStream_t)stream);
   const cudaError_t err = cudaGetLastError();
   SEAM_CHECK(err == cudaSuccess, "vv_resample_nearest: %s", cudaGetErrorString(err));
   return 0;

@@ -98,6 +98,20 @@ class Engine:
         xb, yo, H, R = (_dev32(x, self.device) for x in (xb, yo, H, R))
         _lib.check(self.lib.vv_set_case(self._h, _ptr(xb), _ptr(yo), _ptr(H), _ptr(R), float(obs_coeff), _stream()))
 
+    def set_case_native(self, xb, yo, H, R, obs_coeff: float = 1.0):
+        """The closure on the reference's real geometry: xb (C,Hh,Wh), yo / H / R (T,C,Hh,Wh) on an analysis grid finer than the
+        network grid (decoder_hr, integrate(..., interpolation=True); nf_model/vae.py:87-90, da_4dvar.py:666-681, 1185-1208)."""
+        xb, yo, H, R = (_dev32(x, self.device) for x in (xb, yo, H, R))
+        self.native_grid = tuple(int(v) for v in xb.shape[-2:])
+        _lib.check(self.lib.vv_set_case_native(self._h, _ptr(xb), _ptr(yo), _ptr(H), _ptr(R), self.native_grid[0], self.native_grid[1],
+                                               float(obs_coeff), _stream()))
+
+    def decode_native(self, z: torch.Tensor) -> torch.Tensor:
+        """(decoder_hr(z) stdTr) sigma + xb on the analysis grid (da_4dvar.py:1257-1259, 1301-1306)."""
+        out = torch.empty(self.n_state, *self.native_grid, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.vv_decode_native(self._h, _ptr(z.contiguous()), _ptr(out), _stream()))
+        return out
+
     @property
     def n_obs(self) -> int:
         n = C.c_int64()
