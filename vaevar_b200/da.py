@@ -67,14 +67,19 @@ class VaeVar4D:
         self.metrics_list = {k: [] for k in ("bg_wrmse", "bg_bias", "ana_wrmse", "ana_bias")}
         self.history = []
         self._opt = None
+        self._native = False
 
     def integrate(self, xa: torch.Tensor, model=None, step: int = 1, interpolation: bool = False, detach: bool = True):
         """(69,nlat,nlon) physical -> physical after `step` applications of the flow model (da_4dvar.py:666-681).  With
         `interpolation` the field is brought to the network grid and back with the reference's nearest rule (:670-671, 678-679);
         the per-channel (de)normalisation commutes with that index map, so it stays inside the engine call."""
         xa = xa.to(self.device, torch.float32)
-        if not interpolation or tuple(xa.shape[-2:]) == (self.nlat, self.nlon):
+        if tuple(xa.shape[-2:]) == (self.nlat, self.nlon):
             return self.engine.integrate(xa, step)
+        if not interpolation and self.verbose:
+            # run_assimilation forecasts with a native-resolution model (LGUnet_all_1, da_4dvar.py:1329); until that network lands
+            # the forecast of a native-resolution analysis is the flow model behind the two seams
+            print("integrate: field is on the analysis grid, resampling to the network grid and back", flush=True)
         from .seams import resample_nearest
         x = self.engine.integrate(resample_nearest(xa, (self.nlat, self.nlon)), step)
         return resample_nearest(x, tuple(xa.shape[-2:]))
@@ -82,14 +87,21 @@ class VaeVar4D:
     def _diagnostics(self, z, gt0):
         """WRMSE / Bias of the current analysis (da_4dvar.py:1256-1264) without leaving the device: the fused metric
         kernel normalises both fields and applies utils/metrics.py's latitude weighting in one pass."""
-        return self.engine.metrics(self.engine.decode(z), gt0)
+        if not self._native:
+            return self.engine.metrics(self.engine.decode(z), gt0)
+        m, s = self.model_mean_gpu.reshape(-1, 1, 1), self.model_std_gpu.reshape(-1, 1, 1)
+        xn, gn = ((self.engine.decode_native(z) - m) / s).unsqueeze(0), ((gt0 - m) / s).unsqueeze(0)
+        std64 = torch.from_numpy(self.model_std).to(self.device)
+        return wrmse(xn, gn, std64), bias(xn, gn, std64)
 
     def one_step_DA(self, gt, xb, yo, H, R, mode: str = "vae4dvar"):
         if mode != "vae4dvar":
             raise NotImplementedError("not implemented da mode")            # da_4dvar.py:1308-1309
         dev = self.device
         gt0 = torch.as_tensor(gt[0]).to(dev, torch.float32)
-        self.engine.set_case(xb, yo, H, R, self.obs_coeff)
+        # fields on a finer grid than the networks' (the reference's 721x1440 over 128x256): decoder_hr / integrate(..., True, False)
+        self._native = tuple(torch.as_tensor(xb).shape[-2:]) != (self.nlat, self.nlon)
+        (self.engine.set_case_native if self._native else self.engine.set_case)(xb, yo, H, R, self.obs_coeff)
         z = torch.zeros(1, self.latent, self.nlat, self.nlon, device=dev)   # da_4dvar.py:1238
         if self._opt is None:                                               # da_4dvar.py:1240: a new optimiser per cycle --
             self._opt = LBFGS(self.engine, history_size=10, max_iter=10)    # here one object, reset (its 30 device vectors are kept)
@@ -112,7 +124,7 @@ class VaeVar4D:
                 self.metrics_list["ana_bias"].append(b.cpu())
             if kk < self.Nit:
                 self.history.append(opt.step(z))                            # lbfgs.step(closure), da_4dvar.py:1298-1299
-        xa = self.engine.decode(z)
+        xa = self.engine.decode_native(z) if self._native else self.engine.decode(z)
         torch.cuda.synchronize()
         if self.verbose:
             print("DA finished. Time consumed: %.3f (s)" % (time.time() - t0), flush=True)
