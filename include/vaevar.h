@@ -91,6 +91,14 @@ VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs);
  * of the reference's loss.  vv_cost_grad / vv_cost / vv_lbfgs_* then work unchanged.  Synchronises. */
 VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
                               float obs_coeff, void* stream);
+/* The real-observation branch of the loss (da_4dvar.py:1196-1206): yo, H, R (T,A,Hh,Wh) live in an AUGMENTED channel space in which
+ * observed channel a = sum_j tap_w[a*taps+j] * x[tap_chan[a*taps+j]] at the same grid point (the reference: A = 204 = 4 surface
+ * channels + 5 variables x 40 pressure levels, rows of obs_interpolater.interp, da_4dvar.py:62-82, two taps each).  tap_chan / tap_w
+ * are HOST arrays of A*taps entries (weight 0 for an unused tap).  The grid may be the network grid or a finer analysis grid; the
+ * index maps are composed as for vv_set_case_native.  Synchronises. */
+VV_API int vv_set_case_obsop(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
+                             int n_obs_channels, int taps, const int32_t* tap_chan_host, const float* tap_w_host, float obs_coeff,
+                             void* stream);
 /* Analysis on the analysis grid after vv_set_case_native: (decoder_hr(z) stdTr) sigma + xb  (da_4dvar.py:1257-1259, 1301-1306). */
 VV_API int vv_decode_native(vv_engine* e, const float* z_dev, float* x_phys_out_dev, void* stream);
 

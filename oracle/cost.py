@@ -3,7 +3,8 @@
 CPU fp32 restatement of the VAE-Var inner loop of the reference driver, which
 itself cannot be imported (da_4dvar.py:18,23-25 pull in petrel_client /
 torch_harmonics / xspharm):
-    loss(z)            da_4dvar.py:1183-1208
+    loss(z)            da_4dvar.py:1183-1208   (incl. the real-observation branch :1196-1206 when the
+                       Case carries the 40 x 13 level-interpolation matrix of obs_interpolater, :62-82)
     closure()          da_4dvar.py:1242-1246   (autograd supplies the gradient)
     integrate()        da_4dvar.py:666-681     (nlat,nlon parametrised; at the
                        128x256 benchmark grid the nearest resamples at :671,:679
@@ -34,7 +35,8 @@ Tensor = torch.Tensor
 class Case:
     """Tensors captured by the reference closure (da_4dvar.py:1248-1251 and :640-647, :1181)."""
 
-    def __init__(self, case: Dict[str, np.ndarray], obs_coeff: float = 1.0, lr=None):
+    def __init__(self, case: Dict[str, np.ndarray], obs_coeff: float = 1.0, lr=None, interp=None):
+        self.interp = None if interp is None else torch.as_tensor(interp, dtype=torch.float32)    # obs_interp.interp (dim_out, 13)
         self.lr = None if lr is None else tuple(lr)    # network grid when it differs from the analysis grid ((128, 256) in the reference)
         mean, std, stdtr = era5_stats()
         self.mean = torch.from_numpy(mean).float().reshape(-1, 1, 1)     # model_mean_gpu
@@ -96,10 +98,39 @@ def trajectory(z: Tensor, c: Case, nets) -> Tensor:
     return torch.stack(xs, 0)
 
 
+def obs_interp_matrix(dim_in: int = 13, dim_out: int = 40) -> np.ndarray:
+    """obs_interpolater.get_interp (da_4dvar.py:62-82): rows = `dim_out` pressure levels equally spaced in log p between 50 and
+    1000 hPa (rounded), columns = the 13 model levels; linear interpolation in log p, float64 weights stored as float32."""
+    level = [50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000]
+    new = np.round(np.exp(np.linspace(3.91202301, 6.90775528, dim_out)))
+    w = torch.zeros(dim_out, dim_in)
+    for i in range(len(new)):
+        for j in range(len(level)):
+            if new[i] == level[j]:
+                w[i, j] = 1
+            elif j + 1 < len(level) and level[j] < new[i] < level[j + 1]:
+                d = np.log(level[j + 1]) - np.log(level[j])
+                w[i, j] = (np.log(level[j + 1]) - np.log(new[i])) / d
+                w[i, j + 1] = (np.log(new[i]) - np.log(level[j])) / d
+    return w.numpy()
+
+
+def augment_levels(x_pred: Tensor, interp: Tensor, nlev: int = 13) -> Tensor:
+    """(T,69,H,W) -> (T,4+5*dim_out,H,W): the four surface channels, then each of the five upper-air variables interpolated from its
+    13 model levels to the observation levels (da_4dvar.py:1196-1206)."""
+    parts = [x_pred[:, :4]]
+    for i in range(5):
+        mat = x_pred[:, 4 + i * nlev:4 + (i + 1) * nlev]
+        parts.append(F.linear(mat.transpose(1, 3), interp).transpose(1, 3))
+    return torch.cat(parts, 1)
+
+
 def loss_terms(z, c, nets):
     """(J_reg, J_obs) with J = J_reg + obs_coeff J_obs; da_4dvar.py:1184,1207-1208."""
     j_reg = torch.sum(z ** 2) / 2
     x_pred = trajectory(z, c, nets)
+    if c.interp is not None:
+        x_pred = augment_levels(x_pred, c.interp)
     j_obs = torch.sum(c.H * (x_pred - c.yo) ** 2 / c.R) / 2
     return j_reg, j_obs
 

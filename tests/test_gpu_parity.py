@@ -418,3 +418,60 @@ def test_one_step_DA_on_native_geometry(chk, gold):
     from vaevar_b200.seams import resample_nearest
     ref = resample_nearest(agent.engine.integrate(resample_nearest(xa, ds.img_size), 1), hr)
     assert torch.equal(xf, ref)
+
+
+@pytest.mark.parametrize("tag,recompute,graph", [("realobs_T2", False, False), ("realobs_native_T2", False, True), ("realobs_native_T2", True, True)])
+def test_real_observation_operator_against_reference_golden(chk, gold, tag, recompute, graph):
+    """The real-observation branch of the loss (da_4dvar.py:1196-1206): 204-channel yo / H / R, 13 -> 40 level interpolation in
+    log-pressure with the matrix of the reference's own obs_interpolater (:62-82), on the network grid and on a finer analysis grid.
+    The golden J and gradient come from the reference's modules (tools/make_golden.py::golden_real_obs)."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.engine import Engine
+    from vaevar_b200.synth import make_case, make_real_obs, make_state_dict
+    g = gold(f"cost_{tag}.npz")
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    seed, T, hr = int(g["seed"]), int(g["T"]), tuple(int(v) for v in g["hr"])
+    e = Engine(ds, fs, T=T, recompute=recompute, use_graph=graph)
+    e.load_state_dict(0, make_state_dict(ds, seed=seed)); e.load_state_dict(1, make_state_dict(fs, seed=seed + 1)); e.finalize()
+    case = make_case(T, *hr, obs_frac=0.10, seed=seed)
+    case.update(make_real_obs(case["gt"], g["interp"], seed=seed))
+    z = torch.from_numpy(make_case(1, *ds.img_size, obs_frac=0.1, seed=seed)["z"]).cuda()
+    e.set_case_real_obs(case["xb"], case["yo"], case["H"], case["R"], g["interp"], 1.0)
+    assert e.n_obs == int(g["n_obs"])
+    for _ in range(3):
+        J, grad = e.cost_grad(z)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["g_full"]).double().flatten()
+    gd = grad.double().cpu().flatten()
+    cos = float(gd @ ref / gd.norm() / ref.norm())
+    print(f"[parity {tag} recompute={recompute}] J rel {abs(float(J[0]) / float(g['J']) - 1):.2e} (gate 1e-3), "
+          f"|grad| rel {abs(float(gd.norm()) / float(g['g_norm']) - 1):.2e} (gate 1e-2), grad cosine {cos:.6f} (gate 0.999)")
+    assert abs(float(J[0]) / float(g["J"]) - 1) < 1e-3
+    assert abs(float(gd.norm()) / float(g["g_norm"]) - 1) < 1e-2
+    assert cos > 0.999
+    # switching the same engine back to the plain network-grid closure still works (launch graph rebuilt)
+    lr_case = make_case(T, *ds.img_size, obs_frac=0.10, seed=seed)
+    e.set_case(lr_case["xb"], lr_case["yo"], lr_case["H"], lr_case["R"], 1.0)
+    J2, g2 = e.cost_grad(z)
+    assert bool(torch.isfinite(g2).all()) and float(J2[0]) > 0 and e.n_obs == int(lr_case["H"].sum())
+    e.close()
+
+
+def test_one_step_DA_with_real_observations(chk, gold):
+    """The host mirror with obs_type "real_simu" (da_4dvar.py:476, 493, 1196-1206): observations in the 204-channel space built with
+    its own obs_interpolater; every L-BFGS step must lower the cost, the analysis comes back on the observation grid."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.da import VaeVar4D
+    from vaevar_b200.synth import make_case, make_real_obs, make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    agent = VaeVar4D(ds, fs, make_state_dict(ds, seed=0), make_state_dict(fs, seed=1), da_win=2, Nit=2, verbose=False, obs_type="real_simu")
+    case = make_case(2, 91, 180, obs_frac=0.10, seed=3)
+    case.update(make_real_obs(case["gt"], agent.obs_interp.interp.numpy(), frac=0.05, seed=3))
+    xa = agent.one_step_DA(case["gt"], case["xb"], case["yo"], case["H"], case["R"], "vae4dvar")
+    assert tuple(xa.shape) == (69, 91, 180) and bool(torch.isfinite(xa).all())
+    bg, ana = agent.metrics_list["bg_wrmse"][-1].numpy(), agent.metrics_list["ana_wrmse"][-1].numpy()
+    h = agent.history
+    print(f"[real obs one_step_DA] mean WRMSE/background {float(np.mean(ana / bg)):.4f}; n_obs {agent.engine.n_obs}; "
+          f"J {h[0]['loss0']:.6g} -> {h[0]['loss']:.6g} -> {h[1]['loss']:.6g}")
+    assert h[0]["loss"] < h[0]["loss0"] and h[1]["loss"] <= h[0]["loss"]      # every L-BFGS step lowers the cost
+    assert agent.engine.n_obs == int(case["H"].sum())

@@ -124,3 +124,25 @@ def test_cycled_da_resumes_from_its_checkpoint(tmp_path):
     assert (tmp_path / "cut" / "current_time.txt").read_text() == "4"
     import numpy as np
     assert np.load(tmp_path / "cut" / "ana_wrmse.npy").shape == (4, 3)
+
+
+def test_obs_interpolater_matches_reference_class(gold):
+    """vaevar_b200.da.obs_interpolater against the matrices produced by the reference's own class (da_4dvar.py:62-94; cut out of
+    its source and executed by tools/make_golden.py::reference_obs_interp), bit for bit; and the tap table built from it."""
+    from vaevar_b200.da import obs_interpolater
+    from vaevar_b200.engine import obs_taps
+    g = gold("obs_interp.npz")
+    o = obs_interpolater(13, 40)
+    assert np.array_equal(o.interp.numpy(), g["interp"]) and np.array_equal(o.interp_inv.numpy(), g["interp_inv"])
+    assert np.array_equal(o.height_level_new, g["height_level_new"])
+    chan, w = obs_taps(g["interp"])
+    assert chan.shape == (204, 2) and w.shape == (204, 2)
+    dense = np.zeros((204, 69), np.float32)                       # the augmentation of da_4dvar.py:1196-1206 as one matrix
+    dense[:4, :4] = np.eye(4)
+    for v in range(5):
+        dense[4 + 40 * v:4 + 40 * (v + 1), 4 + 13 * v:4 + 13 * (v + 1)] = g["interp"]
+    mine = np.zeros_like(dense)
+    for a in range(204):
+        for j in range(2):
+            mine[a, chan[a, j]] += w[a, j]
+    assert np.array_equal(mine, dense)

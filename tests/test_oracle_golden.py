@@ -68,6 +68,28 @@ def test_native_geometry_cost_and_grad_matches_reference(gold):
     assert abs(np.linalg.norm(grad) / float(g["g_norm"]) - 1) < 1e-4
 
 
+@pytest.mark.parametrize("tag", ["realobs_T2", "realobs_native_T2"])
+def test_real_observation_branch_matches_reference(gold, tag):
+    """da_4dvar.py:1196-1206 with the level-interpolation matrix produced by the reference's own obs_interpolater (:62-82)."""
+    from vaevar_b200.synth import make_real_obs
+    g = gold(f"cost_{tag}.npz")
+    seed, T, hr = int(g["seed"]), int(g["T"]), tuple(int(v) for v in g["hr"])
+    assert np.array_equal(ocost.obs_interp_matrix(13, 40), g["interp"])
+    assert g["interp"].shape == (40, 13) and (np.count_nonzero(g["interp"], axis=1) <= 2).all()
+    np.testing.assert_allclose(g["interp"].sum(1), 1.0, rtol=1e-6)
+    nets = ocost.OracleNets(to_torch(make_state_dict(DS, seed=seed)), DS, to_torch(make_state_dict(FS, seed=seed + 1)), FS)
+    case = make_case(T, *hr, obs_frac=0.10, seed=seed)
+    case.update(make_real_obs(case["gt"], g["interp"], seed=seed))
+    assert int(case["H"].sum()) == int(g["n_obs"]) and case["H"].shape[1] == 204
+    z = make_case(1, *DS.img_size, obs_frac=0.1, seed=seed)["z"]
+    c = ocost.Case(case, lr=None if hr == tuple(DS.img_size) else DS.img_size, interp=g["interp"])
+    J, Jr, Jo, grad = ocost.cost_and_grad(z, c, nets)
+    assert abs(J / float(g["J"]) - 1) < 2e-5
+    ref = g["g_full"]
+    assert float((grad.ravel() @ ref.ravel()) / np.linalg.norm(grad) / np.linalg.norm(ref)) > 1 - 1e-6
+    assert abs(np.linalg.norm(grad) / float(g["g_norm"]) - 1) < 1e-4
+
+
 def test_lbfgs_analysis_matches_reference(gold):
     g = gold("cost_small_T1.npz")
     nets = ocost.OracleNets(to_torch(make_state_dict(DS, seed=0)), DS)

@@ -160,6 +160,46 @@ def golden_cost_native(tag, cfg_dec, cfg_flow, T, hr, obs_frac, seed, gain, rich
     print(f"cost_{tag}: J={J:.8g} J_reg={Jr:.6g} J_obs={Jo:.8g} |g|={np.linalg.norm(g):.6g} evals={r['n_evals']}", flush=True)
 
 
+def reference_obs_interp():
+    """The reference's own obs_interpolater (da_4dvar.py:62-94) - the file cannot be imported (petrel_client, torch_harmonics at
+    :18-25), so the class is cut out of its source with ast and executed with `.cuda()` removed (no GPU in the build container)."""
+    import ast
+    src = open(f"{REF}/da_4dvar.py").read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "obs_interpolater")
+    code = ast.get_source_segment(src, node).replace(".cuda()", "")
+    ns = {"np": np, "torch": torch}
+    exec(code, ns)
+    return ns["obs_interpolater"](13, 40)
+
+
+def golden_obs_interp():
+    oi = reference_obs_interp()
+    np.savez_compressed(GOLD / "obs_interp.npz", interp=oi.interp.numpy(), interp_inv=oi.interp_inv.numpy(),
+                        height_level=np.asarray(oi.height_level), height_level_new=np.asarray(oi.height_level_new))
+    print("obs_interp", oi.interp.shape, oi.interp_inv.shape)
+
+
+def golden_real_obs(tag, cfg_dec, cfg_flow, T, hr, seed):
+    """The real-observation branch of the loss (da_4dvar.py:1196-1206): 204-channel yo / H / R on the analysis grid, the level
+    interpolation from the reference's own obs_interpolater, network modules from the reference."""
+    from oracle.cost import Case, cost_and_grad, obs_interp_matrix
+    from vaevar_b200.synth import make_case, make_real_obs, make_state_dict
+    oi = reference_obs_interp()
+    interp = oi.interp.numpy()
+    assert np.array_equal(interp, obs_interp_matrix(13, 40)), "oracle restatement of get_interp differs from the reference"
+    dec = ref_net(cfg_dec, make_state_dict(cfg_dec, seed=seed))
+    flow = ref_net(cfg_flow, make_state_dict(cfg_flow, seed=seed + 1))
+    case = make_case(T, *hr, obs_frac=0.10, seed=seed)
+    case.update(make_real_obs(case["gt"], interp, seed=seed))
+    z = make_case(1, *cfg_dec.img_size, obs_frac=0.1, seed=seed)["z"]
+    c = Case(case, lr=None if tuple(hr) == tuple(cfg_dec.img_size) else cfg_dec.img_size, interp=interp)
+    J, Jr, Jo, g = cost_and_grad(z, c, RefNets(dec, flow))
+    np.savez_compressed(GOLD / f"cost_{tag}.npz", seed=seed, T=T, hr=np.array(hr), interp=interp, J=J, J_reg=Jr, J_obs=Jo, g_full=g,
+                        g_norm=np.float64(np.linalg.norm(g.astype(np.float64))), n_obs=np.int64(case["H"].sum()),
+                        height_level_new=np.asarray(oi.height_level_new))
+    print(f"cost_{tag}: J={J:.8g} J_obs={Jo:.8g} |g|={np.linalg.norm(g):.6g} n_obs={int(case['H'].sum())}", flush=True)
+
+
 def golden_metrics():
     from utils.metrics import Metrics
     rng = np.random.Generator(np.random.PCG64(5))
@@ -202,6 +242,9 @@ if __name__ == "__main__":
         "cost_small_T1": lambda: golden_cost("small_T1", ds, fs, 1, 0.10, 0, 1.0, False, lbfgs_iters=10, nit4=True),
         "cost_small_T3_rich": lambda: golden_cost("small_T3_rich", ds, fs, 3, 0.10, 2, 3.0, True, lbfgs_iters=10, nit4=True),
         "cost_native_T3_rich": lambda: golden_cost_native("native_T3_rich", ds, fs, 3, (181, 360), 0.10, 4, 3.0, True),
+        "obs_interp": golden_obs_interp,
+        "cost_realobs_T2": lambda: golden_real_obs("realobs_T2", ds, fs, 2, ds.img_size, 5),
+        "cost_realobs_native_T2": lambda: golden_real_obs("realobs_native_T2", ds, fs, 2, (181, 360), 6),
         "cost_native_T3_plain": lambda: golden_cost_native("native_T3_plain", ds, fs, 3, (181, 360), 0.10, 0, 1.0, False),
     }
     if a.full:

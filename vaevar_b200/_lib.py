@@ -37,6 +37,7 @@ _SIGS = {
     "vv_set_case": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P]),
     "vv_set_case_native": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
     "vv_decode_native": (C.c_int, [_P, _P, _P, _P]),
+    "vv_set_case_obsop": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P]),
     "vv_metrics": (C.c_int, [_P, _P, _P, _P, _P]),
     "vv_num_obs": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "vv_cost_grad": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -756,8 +756,12 @@ static int enqueue_forward(vv_engine* e, cudaStream_t s, bool with_obs) {
     }
   }
   if (with_obs) {
-    launch_obs_misfit(e->native ? e->XF : e->XN, e->idx, e->yobs, e->rinv, e->sigma, e->mean, e->n_obs, e->HW, e->C, e->obs_coeff, e->resid, e->partials,
-                      reduce_blocks(), s);
+    if (e->taps)
+      launch_obs_taps_misfit(e->XF, e->tap_ia, e->tap_coef, e->taps, e->yobs, e->rinv, e->n_obs, e->obs_coeff, e->resid, e->partials,
+                             reduce_blocks(), s);
+    else
+      launch_obs_misfit(e->native ? e->XF : e->XN, e->idx, e->yobs, e->rinv, e->sigma, e->mean, e->n_obs, e->HW, e->C, e->obs_coeff, e->resid,
+                        e->partials, reduce_blocks(), s);
     launch_reduce_partials(e->partials, reduce_blocks(), e->Jbuf + 3, s);
     DotPairs dp{}; dp.a[0] = e->Z; dp.b[0] = e->Z; dp.n_pairs = 1;
     launch_multi_dot(dp, (long long)e->Zc * e->HW, e->dots, e->dot_scratch, s);
@@ -776,7 +780,10 @@ static int enqueue_backward(vv_engine* e, cudaStream_t s) {
   cudaMemsetAsync(Gt, 0, CHW * sizeof(float), s);
   // native geometry: several observations share a network-grid cell (sorted runs); otherwise the indices are unique
   auto obs_adjoint = [&](float* G, int t) {
-    if (e->native) launch_obs_adjoint_runs(G, e->idx, e->resid, e->obs_off[t], e->obs_off[t + 1], (long long)t * CHW, s);
+    if (e->taps)
+      launch_obs_taps_adjoint(G, e->pair_cell, e->pair_src, e->pair_coef, e->resid, e->obs_off[t] * e->taps, e->obs_off[t + 1] * e->taps,
+                              (long long)t * CHW, s);
+    else if (e->native) launch_obs_adjoint_runs(G, e->idx, e->resid, e->obs_off[t], e->obs_off[t + 1], (long long)t * CHW, s);
     else launch_obs_adjoint(G, e->idx, e->resid, e->obs_off[t], e->obs_off[t + 1], (long long)t * CHW, s);
   };
   obs_adjoint(Gt, T - 1); ++launches;
@@ -983,6 +990,7 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
   }
   if (e->native && e->graph_cg) { cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr; }
   e->native = false;
+  e->taps = 0;
   e->obs_off = off;
   e->n_obs = total;
   e->obs_coeff = obs_coeff;
@@ -992,16 +1000,17 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
   return 0;
 }
 
-VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
-                              float obs_coeff, void* stream) {
+// A observed channels with K taps each (K = 0: the C state channels observed directly).
+static int set_case_native_impl(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
+                                int A, int K, const int* tap_chan_host, const float* tap_w_host, float obs_coeff, void* stream) {
   VV_CHECK(e && xb_dev && yo_dev && H_dev && R_dev && Hh >= 1 && Wh >= 1, "bad argument");
   VV_CHECK(e->have_consts, "vv_set_constants has not been called");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = build_plans(e);
   if (rc) return rc;
   const int T = e->cfg.T, C = e->C, H = e->net[0].H, W = e->net[0].W;
-  const long long CHW = (long long)C * e->HW, lvl = (long long)C * Hh * Wh;
-  VV_CHECK(CHW * T < (1LL << 31) && lvl < (1LL << 31), "observation space too large for int32 indices");
+  const long long CHW = (long long)C * e->HW, lvl = (long long)A * Hh * Wh, lvl_x = (long long)C * Hh * Wh;
+  VV_CHECK(CHW * T < (1LL << 31) && lvl < (1LL << 31) && lvl_x < (1LL << 31), "observation space too large for int32 indices");
   // ordered compaction per time level on the analysis grid (== torch.nonzero order within the level)
   const long long nchunks = (lvl + 1023) / 1024;
   int* counts = nullptr;
@@ -1038,8 +1047,23 @@ VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo
     e->XF = dalloc<float>(e, (size_t)CHW * T); e->XBN = dalloc<float>(e, CHW); e->TMPF = dalloc<float>(e, CHW);
     e->s_row = dalloc<int>(e, H); e->s_col = dalloc<int>(e, W); e->s_row_lo = dalloc<int>(e, H + 1); e->s_col_lo = dalloc<int>(e, W + 1);
   }
-  if (lvl > e->xbh_cap) { e->XBH = dalloc<float>(e, lvl); e->xbh_cap = lvl; }
+  if (lvl_x > e->xbh_cap) { e->XBH = dalloc<float>(e, lvl_x); e->xbh_cap = lvl_x; }
   rc = (e->idx && e->yobs && e->rinv && e->resid && e->XF && e->XBN && e->TMPF && e->s_col_lo && e->XBH) ? 0 : -1;
+  int* tap_chan = nullptr; float* tap_w = nullptr;
+  if (!rc && K > 0) {
+    if (total * K >= (1LL << 31)) { set_error("too many observation taps for int32 indices"); rc = -2; }
+    if (!rc && total * K > e->pair_cap) {
+      e->pair_cap = total * K + total * K / 8 + 1024;
+      e->tap_ia = dalloc<int>(e, e->pair_cap); e->pair_cell = dalloc<int>(e, e->pair_cap); e->pair_src = dalloc<int>(e, e->pair_cap);
+      e->tap_coef = dalloc<float>(e, e->pair_cap); e->pair_coef = dalloc<float>(e, e->pair_cap);
+      if (!e->pair_coef || !e->tap_ia || !e->pair_cell || !e->pair_src || !e->tap_coef) rc = -1;
+    }
+    if (!rc && (cudaMalloc(&tap_chan, (size_t)A * K * sizeof(int)) != cudaSuccess || cudaMalloc(&tap_w, (size_t)A * K * sizeof(float)) != cudaSuccess)) rc = -1;
+    if (!rc) {
+      cudaMemcpyAsync(tap_chan, tap_chan_host, (size_t)A * K * sizeof(int), cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(tap_w, tap_w_host, (size_t)A * K * sizeof(float), cudaMemcpyHostToDevice, s);
+    }
+  }
   if (!rc) {
     std::vector<int> row, col, row_lo, col_lo;
     host_seam_tables(H, W, Hh, Wh, row, col, row_lo, col_lo);
@@ -1047,23 +1071,42 @@ VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo
     cudaMemcpyAsync(e->s_col, col.data(), W * sizeof(int), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(e->s_row_lo, row_lo.data(), (H + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(e->s_col_lo, col_lo.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, s);
-    cudaMemcpyAsync(e->XBH, xb_dev, lvl * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(e->XBH, xb_dev, lvl_x * sizeof(float), cudaMemcpyDeviceToDevice, s);
     launch_resample(xb_dev, e->XBN, C, Hh, Wh, H, W, 1, e->mean, e->sigma, s);               // down((xb - mu) / sigma), da_4dvar.py:667-671
     cudaMemsetAsync(e->XB, 0, CHW * sizeof(float), s);
-    rc = native_compose_sort(idx_hr, y_hr, ri_hr, off.data(), T, xb_dev, e->mean, C, H, W, Hh, Wh, e->idx, e->yobs, e->rinv, s);
+    if (K > 0)
+      rc = native_compose_taps(idx_hr, y_hr, ri_hr, off.data(), T, xb_dev, e->mean, e->sigma, tap_chan, tap_w, K, C, H, W, Hh, Wh, e->tap_ia,
+                               e->tap_coef, e->yobs, e->rinv, e->pair_cell, e->pair_src, e->pair_coef, s);
+    else
+      rc = native_compose_sort(idx_hr, y_hr, ri_hr, off.data(), T, xb_dev, e->mean, C, H, W, Hh, Wh, e->idx, e->yobs, e->rinv, s);
     if (!rc && cudaStreamSynchronize(s) != cudaSuccess) { set_error("vv_set_case_native: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-  } else {
+  } else if (rc == -1) {
     set_error("vv_set_case_native: out of memory");
   }
-  cudaFree(counts); cudaFree(idx_hr); cudaFree(y_hr); cudaFree(ri_hr);
+  cudaFree(counts); cudaFree(idx_hr); cudaFree(y_hr); cudaFree(ri_hr); cudaFree(tap_chan); cudaFree(tap_w);
   if (rc) return rc;
   if (e->graph_cg) { cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr; }            // launch parameters baked into the graph changed
   e->native = true; e->Hh = Hh; e->Wh = Wh;
+  e->taps = K;
   e->obs_off = off;
   e->n_obs = total;
   e->obs_coeff = obs_coeff;
   e->have_case = true;
   return 0;
+}
+
+VV_API int vv_set_case_native(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
+                              float obs_coeff, void* stream) {
+  return set_case_native_impl(e, xb_dev, yo_dev, H_dev, R_dev, Hh, Wh, e ? e->C : 0, 0, nullptr, nullptr, obs_coeff, stream);
+}
+
+VV_API int vv_set_case_obsop(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, int Hh, int Wh,
+                             int n_obs_channels, int taps, const int32_t* tap_chan_host, const float* tap_w_host, float obs_coeff,
+                             void* stream) {
+  VV_CHECK(e && n_obs_channels >= 1 && taps >= 1 && taps <= 64 && tap_chan_host && tap_w_host, "bad observation operator");
+  for (int i = 0; i < n_obs_channels * taps; ++i)
+    VV_CHECK(tap_chan_host[i] >= 0 && tap_chan_host[i] < e->C, "tap %d reads state channel %d (of %d)", i, tap_chan_host[i], e->C);
+  return set_case_native_impl(e, xb_dev, yo_dev, H_dev, R_dev, Hh, Wh, n_obs_channels, taps, tap_chan_host, tap_w_host, obs_coeff, stream);
 }
 
 VV_API int vv_decode_native(vv_engine* e, const float* z_dev, float* x_phys_out_dev, void* stream) {

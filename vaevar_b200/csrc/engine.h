@@ -100,6 +100,11 @@ struct vv_engine {
   float *XF = nullptr, *XBN = nullptr, *TMPF = nullptr, *XBH = nullptr;   // F_t stack, down((xb - mu) / sigma), scratch field, xb on the analysis grid
   long long xbh_cap = 0;
   int *s_row = nullptr, *s_col = nullptr, *s_row_lo = nullptr, *s_col_lo = nullptr;   // S = down o up tables and adjoint ranges
+  // channel-mixing observation operator (vv_set_case_obsop): K taps per observation, and the same taps sorted by cell for the adjoint
+  int taps = 0;
+  long long pair_cap = 0;
+  int *tap_ia = nullptr, *pair_cell = nullptr, *pair_src = nullptr;
+  float *tap_coef = nullptr, *pair_coef = nullptr;
   // plans: index 0 = decoder application, 1..T-1 = flow applications
   std::vector<vv::Stash> stash;
   std::vector<vv::Plan> fwd, bwd;

@@ -227,6 +227,75 @@ __global__ void __launch_bounds__(128) decode_hr_kernel(const float* __restrict_
     out[o + j] = __fadd_rn(__fmul_rn(__fmul_rn(__ldg(src + cols.src(j)), a), b), xb_hr[o + j]);
 }
 
+__global__ void __launch_bounds__(256) compose_taps_kernel(const int* __restrict__ idx_hr, const float* __restrict__ y, const float* __restrict__ xb_hr,
+                                                           const float* __restrict__ mean, const float* __restrict__ sigma,
+                                                           const int* __restrict__ tap_chan, const float* __restrict__ tap_w, int K,
+                                                           AxisMap rows, AxisMap cols, int HhWh, int Wh, int HW, int W, int base, long long n,
+                                                           long long k_off, int* __restrict__ ia, float* __restrict__ coef,
+                                                           float* __restrict__ y2, int* __restrict__ iota) {
+  const long long k = blockIdx.x * 256LL + threadIdx.x;
+  if (k >= n) return;
+  const int p = idx_hr[k];
+  const int a = p / HhWh, rem = p - a * HhWh;
+  const int pi = rem / Wh, pj = rem - pi * Wh;
+  const int cell = rows.src(pi) * W + cols.src(pj);
+  float yy = y[k];
+  for (int j = 0; j < K; ++j) {
+    const int c = tap_chan[a * K + j];
+    const float w = tap_w[a * K + j];
+    const long long q = (k_off + k) * K + j;
+    ia[q - k_off * K] = base + c * HW + cell;
+    coef[q - k_off * K] = w * sigma[c];
+    iota[q - k_off * K] = (int)q;
+    if (w != 0.f) yy -= w * (xb_hr ? xb_hr[(long long)c * HhWh + rem] : mean[c]);
+  }
+  y2[k] = yy;
+}
+
+__global__ void __launch_bounds__(256) permute_pairs_kernel(const int* __restrict__ perm, const float* __restrict__ coef, int K, long long n,
+                                                            int* __restrict__ src, float* __restrict__ coef_out) {
+  const long long q = blockIdx.x * 256LL + threadIdx.x;
+  if (q >= n) return;
+  const int p = perm[q];
+  src[q] = p / K;
+  coef_out[q] = coef[p];
+}
+
+__global__ void __launch_bounds__(256) obs_taps_misfit_kernel(const float* __restrict__ F, const int* __restrict__ ia, const float* __restrict__ coef,
+                                                              int K, const float* __restrict__ y, const float* __restrict__ rinv, long long n,
+                                                              float coeff, float* __restrict__ resid, double* __restrict__ partials) {
+  double acc = 0.0;
+  for (long long k = blockIdx.x * 256LL + threadIdx.x; k < n; k += gridDim.x * 256LL) {
+    float r = -y[k];
+    for (int j = 0; j < K; ++j) r = fmaf(coef[k * K + j], __ldg(F + ia[k * K + j]), r);
+    const float w = rinv[k];
+    resid[k] = coeff * w * r;
+    acc += 0.5 * (double)(w * r * r);
+  }
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) obs_taps_adjoint_kernel(float* __restrict__ G, const int* __restrict__ cell, const int* __restrict__ src,
+                                                               const float* __restrict__ coef, const float* __restrict__ resid, long long q0,
+                                                               long long q1, long long base) {
+  for (long long q = q0 + blockIdx.x * 256LL + threadIdx.x; q < q1; q += gridDim.x * 256LL) {
+    const int id = cell[q];
+    if (q > q0 && cell[q - 1] == id) continue;
+    float a = coef[q] * resid[src[q]];
+    for (long long m = q + 1; m < q1 && cell[m] == id; ++m) a = fmaf(coef[m], resid[src[m]], a);
+    G[id - base] += a;
+  }
+}
+
 unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 
 }  // namespace
@@ -272,6 +341,47 @@ void launch_obs_adjoint_runs(float* G, const int* idx, const float* resid, long 
 void launch_decode_hr(const float* D, const float* stdTr, const float* sigma, const float* xb_hr, float* out, int C, int H, int W, int Hh,
                       int Wh, cudaStream_t s) {
   decode_hr_kernel<<<C * Hh, 128, 0, s>>>(D, stdTr, sigma, xb_hr, out, make_axis(H, Hh), make_axis(W, Wh));
+}
+
+void launch_obs_taps_misfit(const float* F, const int* ia, const float* coef, int K, const float* y, const float* rinv, long long n,
+                            float coeff, float* resid, double* partials, int nblocks, cudaStream_t s) {
+  obs_taps_misfit_kernel<<<nblocks, 256, 0, s>>>(F, ia, coef, K, y, rinv, n, coeff, resid, partials);
+}
+void launch_obs_taps_adjoint(float* G, const int* pair_cell, const int* pair_src, const float* pair_coef, const float* resid, long long q0,
+                             long long q1, long long base, cudaStream_t s) {
+  if (q1 <= q0) return;
+  const long long want = (q1 - q0 + 255) / 256;
+  obs_taps_adjoint_kernel<<<(unsigned)(want < 1184 ? want : 1184), 256, 0, s>>>(G, pair_cell, pair_src, pair_coef, resid, q0, q1, base);
+}
+
+int native_compose_taps(const int* idx_hr, const float* y, const float* rinv, const long long* off, int T, const float* xb_hr, const float* mean,
+                        const float* sigma, const int* tap_chan, const float* tap_w, int K, int C, int H, int W, int Hh, int Wh, int* tap_ia,
+                        float* tap_coef, float* y_out, float* rinv_out, int* pair_cell, int* pair_src, float* pair_coef, cudaStream_t s) {
+  const long long total = off[T], pairs = total * K;
+  if (total == 0) return 0;
+  int *iota = nullptr, *perm = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, tap_ia, pair_cell, iota, perm, (int)pairs, 0, 31, s);
+  bool ok = cudaMalloc(&iota, pairs * sizeof(int)) == cudaSuccess && cudaMalloc(&perm, pairs * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1) == cudaSuccess;
+  if (ok) {
+    const AxisMap rows = make_axis(H, Hh), cols = make_axis(W, Wh);
+    for (int t = 0; t < T; ++t) {
+      const long long n = off[t + 1] - off[t];
+      if (n <= 0) continue;
+      compose_taps_kernel<<<blocks_for(n), 256, 0, s>>>(idx_hr + off[t], y + off[t], t == 0 ? xb_hr : nullptr, mean, sigma, tap_chan, tap_w, K, rows,
+                                                       cols, Hh * Wh, Wh, H * W, W, (int)((long long)t * C * H * W), n, off[t], tap_ia + off[t] * K,
+                                                       tap_coef + off[t] * K, y_out + off[t], iota + off[t] * K);
+    }
+    cudaMemcpyAsync(rinv_out, rinv, total * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, tap_ia, pair_cell, iota, perm, (int)pairs, 0, 31, s);
+    permute_pairs_kernel<<<blocks_for(pairs), 256, 0, s>>>(perm, tap_coef, K, pairs, pair_src, pair_coef);
+    ok = cudaStreamSynchronize(s) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+  }
+  cudaFree(iota); cudaFree(perm); cudaFree(tmp);
+  if (!ok) { set_error("native_compose_taps: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+  return 0;
 }
 
 int native_compose_sort(const int* idx_hr, const float* y, const float* rinv, const long long* off, int T, const float* xb_hr, const float* mean,

@@ -55,6 +55,21 @@ void launch_obs_adjoint_runs(float* G, const int* idx, const float* resid, long 
 // y0 = (y - xb_hr[p]) + mean[c], so that field * sigma + mean - y0 = field * sigma + xb_hr[p] - y.
 int native_compose_sort(const int* idx_hr, const float* y, const float* rinv, const long long* off_host, int T, const float* xb_hr,
                         const float* mean, int C, int H, int W, int Hh, int Wh, int* idx_out, float* y_out, float* rinv_out, cudaStream_t s);
+// Channel-mixing sparse observation operator (the reference's real-observation branch, da_4dvar.py:1196-1206: observed channel a =
+// sum_j tap_w[a][j] * x[tap_chan[a][j]] at the same grid point, K taps per observed channel).  Observations compacted per time level
+// in the (A, Hh, Wh) observed space; outputs: per observation K (field index, coefficient = w * sigma) taps into the (T,C,H,W) stack
+// and y' = y - sum_j w_j * (xb_hr | mean), so that r = sum_j coef_j F[ia_j] - y'; and the same taps as (cell, observation, coefficient)
+// triples stably sorted by cell for the adjoint.
+int native_compose_taps(const int* idx_hr, const float* y, const float* rinv, const long long* off_host, int T, const float* xb_hr,
+                        const float* mean, const float* sigma, const int* tap_chan, const float* tap_w, int K, int C, int H, int W, int Hh,
+                        int Wh, int* tap_ia, float* tap_coef, float* y_out, float* rinv_out, int* pair_cell, int* pair_src, float* pair_coef,
+                        cudaStream_t s);
+// resid[k] = coeff * rinv[k] * r_k,  partials = per-block sums of rinv r^2 / 2 (double)
+void launch_obs_taps_misfit(const float* F, const int* ia, const float* coef, int K, const float* y, const float* rinv, long long n,
+                            float coeff, float* resid, double* partials, int nblocks, cudaStream_t s);
+// G[cell - base] += sum over each run of equal cells in [q0, q1) of pair_coef * resid[pair_src]
+void launch_obs_taps_adjoint(float* G, const int* pair_cell, const int* pair_src, const float* pair_coef, const float* resid, long long q0,
+                             long long q1, long long base, cudaStream_t s);
 // x_hr = (D[src] * stdTr[c]) * sigma[c] + xb_hr   (da_4dvar.py:1257-1259, 1301-1306 with decoder_hr)
 void launch_decode_hr(const float* D, const float* stdTr, const float* sigma, const float* xb_hr, float* out, int C, int H, int W, int Hh,
                       int Wh, cudaStream_t s);

@@ -40,12 +40,44 @@ def bias(pred, gt, data_std):
     return torch.mean(torch.mean(w * (pred - gt), dim=(-1, -2)), dim=0) * data_std
 
 
+class obs_interpolater:
+    """da_4dvar.py:62-94: linear interpolation in log-pressure between the 13 model levels and `dim_out` observation levels
+    (`interp`, (dim_out, dim_in)) and back (`interp_inv`, (dim_in, dim_out)); float32 tensors like the reference's."""
+
+    def __init__(self, dim_in: int = 13, dim_out: int = 40, device="cpu"):
+        self.dim_in, self.dim_out, self.device = dim_in, dim_out, device
+        self.height_level = [50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000]
+        self.height_level_new = np.round(np.exp(np.linspace(3.91202301, 6.90775528, dim_out)))
+        self.interp = self._between(self.height_level_new, np.asarray(self.height_level, np.float64)).to(device)
+        self.interp_inv = self._between(np.asarray(self.height_level, np.float64), self.height_level_new).to(device)
+
+    @staticmethod
+    def _between(targets, nodes) -> torch.Tensor:
+        """Row i: weights of `nodes` that reproduce targets[i]: 1 on an exact hit, otherwise the two log-linear weights of the
+        bracketing pair (strictly inside it); rows outside every bracket stay zero, as in the reference's double loop."""
+        w = torch.zeros(len(targets), len(nodes))
+        ln = np.log(nodes)
+        for i, tv in enumerate(targets):
+            hit = np.flatnonzero(nodes == tv)
+            for j in hit:
+                w[i, j] = 1
+            j = int(np.searchsorted(nodes, tv)) - 1
+            if len(hit) == 0 and 0 <= j < len(nodes) - 1 and nodes[j] < tv < nodes[j + 1]:
+                d = ln[j + 1] - ln[j]
+                w[i, j] = (ln[j + 1] - np.log(tv)) / d
+                w[i, j + 1] = (np.log(tv) - ln[j]) / d
+        return w
+
+
 class VaeVar4D:
     """Engine-backed stand-in for `cyclic_4dvar` restricted to da_mode == "vae4dvar"."""
 
     def __init__(self, dec_cfg: NetConfig, flow_cfg: Optional[NetConfig], dec_sd: Dict, flow_sd: Optional[Dict],
                  da_win: int = 1, Nit: int = 4, obs_coeff: float = 1.0, device: str = "cuda:0",
-                 recompute: bool = False, use_graph: bool = True, verbose: bool = True, engine: Optional[Engine] = None):
+                 recompute: bool = False, use_graph: bool = True, verbose: bool = True, engine: Optional[Engine] = None,
+                 obs_type: str = "free", interp_dim: int = 40):
+        self.obs_type = obs_type                                             # da_4dvar.py:476; "real..." selects the augmented obs space
+        self.obs_interp = obs_interpolater(13, interp_dim)                   # da_4dvar.py:493
         self.da_win, self.Nit, self.obs_coeff, self.verbose = da_win, Nit, obs_coeff, verbose
         self.device = torch.device(device)
         if engine is not None:                       # an already loaded engine (same networks, same window length)
@@ -101,7 +133,11 @@ class VaeVar4D:
         gt0 = torch.as_tensor(gt[0]).to(dev, torch.float32)
         # fields on a finer grid than the networks' (the reference's 721x1440 over 128x256): decoder_hr / integrate(..., True, False)
         self._native = tuple(torch.as_tensor(xb).shape[-2:]) != (self.nlat, self.nlon)
-        (self.engine.set_case_native if self._native else self.engine.set_case)(xb, yo, H, R, self.obs_coeff)
+        if self.obs_type[:4] == "real":                                      # yo / H / R in the 204-channel space, da_4dvar.py:1196-1206
+            self._native = True
+            self.engine.set_case_real_obs(xb, yo, H, R, self.obs_interp.interp, self.obs_coeff)
+        else:
+            (self.engine.set_case_native if self._native else self.engine.set_case)(xb, yo, H, R, self.obs_coeff)
         z = torch.zeros(1, self.latent, self.nlat, self.nlon, device=dev)   # da_4dvar.py:1238
         if self._opt is None:                                               # da_4dvar.py:1240: a new optimiser per cycle --
             self._opt = LBFGS(self.engine, history_size=10, max_iter=10)    # here one object, reset (its 30 device vectors are kept)

@@ -106,6 +106,19 @@ class Engine:
         _lib.check(self.lib.vv_set_case_native(self._h, _ptr(xb), _ptr(yo), _ptr(H), _ptr(R), self.native_grid[0], self.native_grid[1],
                                                float(obs_coeff), _stream()))
 
+    def set_case_real_obs(self, xb, yo, H, R, interp, obs_coeff: float = 1.0, n_surface: int = 4, n_vars: int = 5):
+        """The real-observation branch (da_4dvar.py:1196-1206): yo / H / R (T, n_surface + n_vars * dim_out, Hh, Wh) in the augmented
+        space, `interp` = obs_interpolater.interp (dim_out, nlev) (da_4dvar.py:62-82).  The grid may be the network grid or finer."""
+        interp = np.asarray(interp.detach().cpu() if isinstance(interp, torch.Tensor) else interp, np.float32)
+        tap_chan, tap_w = obs_taps(interp, n_surface, n_vars)
+        xb, yo, H, R = (_dev32(x, self.device) for x in (xb, yo, H, R))
+        if yo.shape[1] != tap_chan.shape[0]:
+            raise ValueError(f"yo has {yo.shape[1]} channels, the operator produces {tap_chan.shape[0]}")
+        self.native_grid = tuple(int(v) for v in xb.shape[-2:])
+        _lib.check(self.lib.vv_set_case_obsop(self._h, _ptr(xb), _ptr(yo), _ptr(H), _ptr(R), self.native_grid[0], self.native_grid[1],
+                                              tap_chan.shape[0], tap_chan.shape[1], tap_chan.ctypes.data_as(C.c_void_p),
+                                              tap_w.ctypes.data_as(C.c_void_p), float(obs_coeff), _stream()))
+
     def decode_native(self, z: torch.Tensor) -> torch.Tensor:
         """(decoder_hr(z) stdTr) sigma + xb on the analysis grid (da_4dvar.py:1257-1259, 1301-1306)."""
         out = torch.empty(self.n_state, *self.native_grid, dtype=torch.float32, device=self.device)
@@ -251,6 +264,25 @@ class LBFGS:
             self.close()
         except Exception:
             pass
+
+
+def obs_taps(interp: np.ndarray, n_surface: int = 4, n_vars: int = 5):
+    """(tap_chan int32 [A, K], tap_w float32 [A, K]) of the augmentation at da_4dvar.py:1196-1206: the surface channels pass through,
+    each upper-air variable's nlev model levels go through `interp` (dim_out, nlev); K = most non-zeros in a row of interp."""
+    dim_out, nlev = interp.shape
+    K = max(1, int(np.count_nonzero(interp, axis=1).max()))
+    A = n_surface + n_vars * dim_out
+    chan, w = np.zeros((A, K), np.int32), np.zeros((A, K), np.float32)
+    for a in range(n_surface):
+        chan[a, :], w[a, 0] = a, 1.0
+    for v in range(n_vars):
+        for o in range(dim_out):
+            nz = np.flatnonzero(interp[o])
+            a = n_surface + v * dim_out + o
+            chan[a, :] = n_surface + v * nlev + (nz[0] if len(nz) else 0)
+            for j, l in enumerate(nz):
+                chan[a, j], w[a, j] = n_surface + v * nlev + l, interp[o, l]
+    return np.ascontiguousarray(chan), np.ascontiguousarray(w)
 
 
 def compact_mask(H: torch.Tensor, yo: torch.Tensor, R: torch.Tensor):

@@ -149,3 +149,24 @@ def make_case(T: int, nlat: int = 128, nlon: int = 256, obs_frac: float = 0.10, 
     R = np.broadcast_to(var.reshape(1, 69, 1, 1), (T, 69, nlat, nlon)).copy()
     z = (z_std * rng.standard_normal((1, latent, nlat, nlon), dtype=np.float32)).astype(np.float32)
     return dict(gt=gt, xb=xb, yo=gt.copy(), H=H, R=R, z=z)
+
+
+def make_real_obs(gt: np.ndarray, interp: np.ndarray, frac: float = 0.02, seed: int = 0, obs_std: float = 0.005, nlev: int = 13):
+    """Synthetic stand-in for data_reader.get_real_obs + get_R_matrix_from_gt (da_4dvar.py:745-756, 766-800, obs_type "real_simu"):
+    observations live in the AUGMENTED space (4 surface channels + 5 variables x interp.shape[0] pressure levels), each augmented
+    channel has its own sparse random mask (a different one per time level), yo = H * aug(gt), R = aug(obs variance).
+    Returns dict(yo, H, R) of shape (T, 4 + 5 * dim_out, nlat, nlon), float32."""
+    T, _, nlat, nlon = gt.shape
+    rng = np.random.Generator(np.random.PCG64(2000 + seed))
+
+    def aug(x):
+        parts = [x[:, :4]]
+        for i in range(5):
+            parts.append(np.einsum("ol,tlhw->tohw", interp.astype(np.float32), x[:, 4 + i * nlev:4 + (i + 1) * nlev]).astype(np.float32))
+        return np.concatenate(parts, 1)
+
+    gt_aug = aug(gt)
+    H = (rng.random(gt_aug.shape, dtype=np.float32) < frac).astype(np.float32)
+    var = obs_variance(obs_std, 2).astype(np.float32).reshape(1, 69, 1, 1)
+    R = np.broadcast_to(aug(np.broadcast_to(var, (T, 69, 1, 1))), gt_aug.shape).copy()
+    return dict(yo=(gt_aug * H).astype(np.float32), H=H, R=R)
