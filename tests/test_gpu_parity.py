@@ -475,3 +475,41 @@ def test_one_step_DA_with_real_observations(chk, gold):
           f"J {h[0]['loss0']:.6g} -> {h[0]['loss']:.6g} -> {h[1]['loss']:.6g}")
     assert h[0]["loss"] < h[0]["loss0"] and h[1]["loss"] <= h[0]["loss"]      # every L-BFGS step lowers the cost
     assert agent.engine.n_obs == int(case["H"].sum())
+
+
+def test_vae_lr_surface_encoder_decoder_forward(chk, gold, tmp_path, monkeypatch):
+    """VAE_lr's call surface (nf_model/vae.py:53-102) on the engine: encoder -> (mu, log_var) via chunk(2, 1), decoder, decoder_hr,
+    forward -> (recon, mu, log_var); the encoder output against the golden produced by the reference's LGUnet_all with the same weights,
+    and gradients flowing back to the input through both networks."""
+    import yaml
+    from vaevar_b200.config import DECODER_FULL, ENCODER_FULL, small
+    from vaevar_b200.modules import VAE_lr
+    from vaevar_b200.synth import make_state_dict
+    es, ds = small(ENCODER_FULL), small(DECODER_FULL)
+    (tmp_path / "nf_model").mkdir()
+    (tmp_path / "nf_model" / "small.yaml").write_text(yaml.safe_dump({"encoder": es.to_reference_kwargs(), "decoder": ds.to_reference_kwargs()}))
+    monkeypatch.chdir(tmp_path)                                   # vae.py:57 opens nf_model/<param_path>.yaml relative to the cwd
+    vae = VAE_lr("small").eval().to("cuda")
+    g = gold("net_small_enc.npz")
+    sd = make_state_dict(es, seed=int(g["seed"]), gain=float(g["gain"]), rich=bool(g["rich"]))
+    vae.enc.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    rng = np.random.Generator(np.random.PCG64(int(g["seed"]) + 77))
+    x = torch.from_numpy(rng.standard_normal((1, es.in_chans, *es.img_size), dtype=np.float32)).cuda().requires_grad_(True)
+    mu, log_var = vae.encoder(x)
+    assert mu.shape == log_var.shape == (1, 32, *es.img_size)
+    y = torch.cat([mu, log_var], 1).detach().cpu().numpy().ravel()
+    ref = g["y_val"]
+    err = np.abs(y[g["y_idx"]] - ref).max() / np.abs(ref).max()
+    print(f"[parity VAE_lr.encoder] max abs err / max |y| = {err:.2e} (gate 2e-2, 16-bit operands); |y|_1 rel "
+          f"{abs(np.abs(y.astype(np.float64)).sum() / float(g['y_abs']) - 1):.2e}")
+    assert err < 2e-2 and abs(np.abs(y.astype(np.float64)).sum() / float(g["y_abs"]) - 1) < 1e-2
+    recon, mu2, lv2 = vae(x)
+    assert recon.shape == (1, 69, *ds.img_size) and torch.equal(mu2, mu) and torch.equal(lv2, log_var)
+    (recon.square().mean() + mu2.square().mean()).backward()
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all()) and float(x.grad.abs().sum()) > 0
+    z = torch.randn(1, 32, *ds.img_size, device="cuda")
+    hr = vae.decoder_hr(z)
+    assert hr.shape == (1, 69, 721, 1440)
+    lo = vae.decoder(z)
+    from oracle import seams as oseams
+    assert np.array_equal(hr[0].cpu().numpy(), oseams.resample(lo[0].detach().cpu().numpy(), (721, 1440)))

@@ -30,6 +30,11 @@ def test_net_small_decoder_matches_reference(gold):
     _net_check(gold("net_small_dec.npz"), DS)
 
 
+def test_net_small_encoder_matches_reference(gold):
+    from vaevar_b200.config import ENCODER_FULL
+    _net_check(gold("net_small_enc.npz"), small(ENCODER_FULL))
+
+
 def test_net_small_flow_rich_matches_reference(gold):
     _net_check(gold("net_small_flow_rich.npz"), FS)
 

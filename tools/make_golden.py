@@ -232,13 +232,14 @@ if __name__ == "__main__":
     install_shim()
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.config import DECODER_FULL, ENCODER_FULL, FLOW_FULL, small
     ds, fs = small(DECODER_FULL), small(FLOW_FULL)
     jobs = {
         "metrics": golden_metrics,
         "vae": golden_vae_surface,
         "net_small_dec": lambda: golden_net("small_dec", ds, 0, 1.0, False),
         "net_small_flow_rich": lambda: golden_net("small_flow_rich", fs, 1, 3.0, True),
+        "net_small_enc": lambda: golden_net("small_enc", small(ENCODER_FULL), 5, 2.0, True),      # VAE_lr.enc (nf_model/vae.py:64, 72-76)
         "cost_small_T1": lambda: golden_cost("small_T1", ds, fs, 1, 0.10, 0, 1.0, False, lbfgs_iters=10, nit4=True),
         "cost_small_T3_rich": lambda: golden_cost("small_T3_rich", ds, fs, 3, 0.10, 2, 3.0, True, lbfgs_iters=10, nit4=True),
         "cost_native_T3_rich": lambda: golden_cost_native("native_T3_rich", ds, fs, 3, (181, 360), 0.10, 4, 3.0, True),
