@@ -513,3 +513,25 @@ def test_vae_lr_surface_encoder_decoder_forward(chk, gold, tmp_path, monkeypatch
     lo = vae.decoder(z)
     from oracle import seams as oseams
     assert np.array_equal(hr[0].cpu().numpy(), oseams.resample(lo[0].detach().cpu().numpy(), (721, 1440)))
+
+
+def test_cycled_da_real_simu_observations_on_an_analysis_grid(chk, tmp_path):
+    """Two cycles of run_assimilation (da_4dvar.py:1314-1342) with obs_type "real_simu": 204-channel observations of an
+    identical-twin truth that lives on a 91x180 analysis grid over the 32x64 network grid; forecast through the seams; resume files."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, era5_stats, small
+    from vaevar_b200.cycle import CycledDA, RealSimuObs
+    from vaevar_b200.da import VaeVar4D
+    from vaevar_b200.synth import make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    agent = VaeVar4D(ds, fs, make_state_dict(ds, seed=0), make_state_dict(fs, seed=1), da_win=2, Nit=1, verbose=False, obs_type="real_simu")
+    mean, std, _ = era5_stats()
+    gen = torch.Generator().manual_seed(0)
+    m = torch.from_numpy(mean).float().reshape(-1, 1, 1); s = torch.from_numpy(std).float().reshape(-1, 1, 1)
+    truth0 = m + s * torch.randn(69, 91, 180, generator=gen)
+    xb0 = truth0 + 0.1 * s * torch.randn(69, 91, 180, generator=gen)
+    run = CycledDA(agent, RealSimuObs(agent, truth0, obs_frac=0.05), xb0, name="r", root=str(tmp_path), n_cycles=2, resume=False)
+    r = run.run_assimilation()
+    assert r["cycles"] == 2 and tuple(run.xb.shape) == (69, 91, 180) and bool(torch.isfinite(run.xb).all())
+    assert all(h["loss"] < h["loss0"] for h in agent.history)
+    assert np.load(tmp_path / "r" / "xb.npy").shape == (69, 91, 180) and (tmp_path / "r" / "current_time.txt").read_text() == "2"
+    assert np.load(tmp_path / "r" / "ana_wrmse.npy").shape == (2, 69)

@@ -146,3 +146,42 @@ def test_obs_interpolater_matches_reference_class(gold):
         for j in range(2):
             mine[a, chan[a, j]] += w[a, j]
     assert np.array_equal(mine, dense)
+
+
+def test_real_simu_observation_source(gold):
+    """RealSimuObs against the reference's formulas (da_4dvar.py:745-756, 766-800): augmented truth with the reference's own
+    interpolation matrix, yo = aug(gt) * H, R = aug(R_static), quality-control filter."""
+    from vaevar_b200.cycle import RealSimuObs, augment_levels
+    from vaevar_b200.da import obs_interpolater
+    from vaevar_b200.synth import obs_variance
+    g = gold("obs_interp.npz")
+
+    class Agent(_FakeAgent):
+        def __init__(self):
+            super().__init__()
+            self.nchannel, self.da_win = 69, 2
+            self.obs_interp = obs_interpolater(13, 40)
+
+    a = Agent()
+    truth0 = torch.randn(69, 4, 8)
+    src = RealSimuObs(a, truth0, obs_frac=0.3, seed=1)
+    yo, H, R, gt = src.window(0)
+    assert yo.shape == H.shape == R.shape == (2, 204, 4, 8) and gt.shape == (2, 69, 4, 8)
+    interp = torch.from_numpy(g["interp"])
+    ref = [gt[:, :4]] + [torch.nn.functional.linear(gt[:, 4 + 13 * i:4 + 13 * (i + 1)].transpose(1, 3), interp).transpose(1, 3) for i in range(5)]
+    ref = torch.cat(ref, 1)                                                     # the reference's expression, da_4dvar.py:770-776
+    torch.testing.assert_close(augment_levels(gt, interp), ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(yo, ref * H, rtol=1e-6, atol=1e-6)
+    assert set(np.unique(H.numpy())) <= {0.0, 1.0} and 0.2 < float(H.mean()) < 0.4
+    var = torch.from_numpy(obs_variance(0.005, 2).astype(np.float32)).reshape(1, 69, 1, 1).expand(2, 69, 4, 8)
+    Rref = torch.cat([var[:, :4]] + [torch.nn.functional.linear(var[:, 4 + 13 * i:4 + 13 * (i + 1)].transpose(1, 3), interp).transpose(1, 3)
+                                      for i in range(5)], 1)                     # get_R_matrix_from_gt, :745-756
+    torch.testing.assert_close(R, Rref, rtol=1e-6, atol=0)
+    yo2, H2, _, _ = src.window(0)
+    assert torch.equal(H, H2) and torch.equal(yo, yo2)                           # reproducible per cycle
+    # quality control (:780-787): a "real" observation 10 sigma off the truth is filtered out, the rest stays
+    bad = torch.zeros(2, 204, 4, 8); bad[:, 7] = 10.0
+    src_qc = RealSimuObs(a, truth0, obs_frac=0.3, seed=1, filter_coeff=3.0, std_layer_aug=np.ones(204, np.float32),
+                         yo_real=lambda cycle: ref + bad)
+    _, Hq, _, _ = src_qc.window(0)
+    assert float(Hq[:, 7].sum()) == 0.0 and torch.equal(Hq[:, :7], H[:, :7]) and torch.equal(Hq[:, 8:], H[:, 8:])

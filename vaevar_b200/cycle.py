@@ -47,15 +47,56 @@ class TwinObs:
         var = obs_variance(obs_std, modify_tp).reshape(1, C, 1, 1)
         self.R = torch.from_numpy(np.broadcast_to(var, (T, C, nlat, nlon)).copy()).to(agent.device)
 
-    def window(self, cycle: int):
+    def truth_window(self, cycle: int) -> torch.Tensor:
         while self._cycle < cycle:                         # advance the truth run to the start of this window
             self.truth = self.agent.integrate(self.truth, None, self.steps)
             self._cycle += 1
         gt = [self.truth]
         for _ in range(self.agent.da_win - 1):
             gt.append(self.agent.integrate(gt[-1], None, 1))
-        gt = torch.stack(gt)
+        return torch.stack(gt)
+
+    def window(self, cycle: int):
+        gt = self.truth_window(cycle)
         return gt.clone(), self.H, self.R, gt
+
+
+def augment_levels(x: torch.Tensor, interp: torch.Tensor, nlev: int = 13) -> torch.Tensor:
+    """(T,69,H,W) -> (T,4+5*dim_out,H,W): surface channels, then every upper-air variable interpolated from its model levels to the
+    observation levels (da_4dvar.py:770-776, 747-754, 1196-1206).  Data preparation, not the hot path: plain torch on x's device."""
+    parts = [x[:, :4]]
+    for i in range(5):
+        parts.append(torch.einsum("ol,tlhw->tohw", interp.to(x), x[:, 4 + i * nlev:4 + (i + 1) * nlev]))
+    return torch.cat(parts, 1)
+
+
+class RealSimuObs(TwinObs):
+    """The "real_simu" observation branch of get_obs_info (da_4dvar.py:766-800) over the identical-twin truth: observations live in
+    the augmented space of `agent.obs_interp` (4 + 5 x 40 channels), each augmented channel and time level has its own sparse
+    mask (the offline stand-in for data_reader.get_real_obs' station / sounding locations), an optional quality-control filter keeps
+    |yo_real - aug(gt)| < filter_coeff * std_layer_aug (:780-787), yo = aug(gt) * H (:796-797) and R = aug(R_static)
+    (get_R_matrix_from_gt, :745-756).  Use with VaeVar4D(obs_type="real_simu")."""
+
+    def __init__(self, agent: VaeVar4D, truth0: torch.Tensor, obs_frac: float = 0.02, seed: int = 0, obs_std: float = 0.005,
+                 modify_tp: int = 2, steps_per_cycle: int = 1, filter_coeff: Optional[float] = None, std_layer_aug=None, yo_real=None):
+        self.agent, self.steps = agent, steps_per_cycle
+        self.truth = truth0.to(agent.device, torch.float32)
+        self._cycle = 0
+        self.obs_frac, self.seed = obs_frac, seed
+        self.filter_coeff, self.std_layer_aug, self.yo_real = filter_coeff, std_layer_aug, yo_real
+        var = torch.from_numpy(obs_variance(obs_std, modify_tp).astype(np.float32)).reshape(1, agent.nchannel, 1, 1).to(agent.device)
+        self.R_aug = augment_levels(var.expand(agent.da_win, -1, -1, -1), agent.obs_interp.interp)       # (T, A, 1, 1)
+
+    def window(self, cycle: int):
+        gt = self.truth_window(cycle)
+        gt_aug = augment_levels(gt, self.agent.obs_interp.interp)
+        gen = torch.Generator(device=gt.device).manual_seed(3000 + 977 * self.seed + cycle)
+        H = (torch.rand(gt_aug.shape, device=gt.device, generator=gen) < self.obs_frac).float()
+        if self.filter_coeff is not None and self.yo_real is not None:
+            lim = self.filter_coeff * torch.as_tensor(self.std_layer_aug, dtype=torch.float32, device=gt.device).reshape(1, -1, 1, 1)
+            d = self.yo_real(cycle).to(gt_aug) - gt_aug
+            H = H * ((d < lim) & (d > -lim)).float()
+        return gt_aug * H, H, self.R_aug.expand_as(gt_aug).contiguous(), gt
 
 
 class CycledDA:
