@@ -121,6 +121,8 @@ VV_API int vv_net_vjp(vv_engine* e, int net, const float* in_dev, const float* d
  * fields x and gt (C,H,W), which are normalised with the constants of vv_set_constants first, as the reference does.
  * One fused pass on the device; out is a device array of 2*C doubles. */
 VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, double* out_dev, void* stream);
+/* The same diagnostics for (C,H,W) fields on any grid (the analysis grid of vv_set_case_native). */
+VV_API int vv_metrics_grid(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, int H, int W, double* out_dev, void* stream);
 
 /* ---- native-resolution seams; no engine handle, any field size ---------------------------------
  * F.interpolate(x, (Ho, Wo)) with the default nearest rule (nf_model/vae.py:90 decoder_hr; da_4dvar.py:671, 679) on a (C,Hi,Wi)

@@ -161,6 +161,14 @@ def test_fused_metrics_kernel_against_reference_golden(chk, gold):
     # the physical round trip (x sigma + mu, then back) costs ~1e-6 relative of the normalised values
     np.testing.assert_allclose(w.cpu().numpy(), g["wrmse"], rtol=2e-5)
     np.testing.assert_allclose(b.cpu().numpy(), g["bias"], rtol=2e-3, atol=2e-6 * float(std.max()))
+    # any grid (the analysis grid of the native geometry), against the oracle restatement of utils/metrics.py
+    from oracle import cost as oc
+    rng = np.random.default_rng(11)
+    p2, g2 = (torch.from_numpy(rng.standard_normal((69, 45, 90), dtype=np.float32)) for _ in range(2))
+    w2, b2 = e.metrics(p2.cuda() * s + m, g2.cuda() * s + m)
+    std64 = torch.from_numpy(std)
+    np.testing.assert_allclose(w2.cpu().numpy(), oc.wrmse(p2[None], g2[None], std64).numpy(), rtol=2e-5)
+    np.testing.assert_allclose(b2.cpu().numpy(), oc.bias(p2[None], g2[None], std64).numpy(), rtol=2e-3, atol=2e-6 * float(std.max()))
     e.close()
 
 

@@ -39,6 +39,7 @@ _SIGS = {
     "vv_decode_native": (C.c_int, [_P, _P, _P, _P]),
     "vv_set_case_obsop": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_float, _P]),
     "vv_metrics": (C.c_int, [_P, _P, _P, _P, _P]),
+    "vv_metrics_grid": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "vv_num_obs": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "vv_cost_grad": (C.c_int, [_P, _P, _P, _P, _P]),
     "vv_cost": (C.c_int, [_P, _P, _P, _P]),

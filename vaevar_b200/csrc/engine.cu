@@ -1120,18 +1120,26 @@ VV_API int vv_decode_native(vv_engine* e, const float* z_dev, float* x_phys_out_
   return 0;
 }
 
-VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, double* out_dev, void* stream) {
-  VV_CHECK(e && x_phys_dev && gt_phys_dev && out_dev, "null argument");
+VV_API int vv_metrics_grid(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, int H, int W, double* out_dev, void* stream) {
+  VV_CHECK(e && x_phys_dev && gt_phys_dev && out_dev && H >= 2 && W >= 1, "bad argument");
   VV_CHECK(e->have_consts, "vv_set_constants has not been called");
-  if (!e->met_w) {
-    e->met_w = dalloc<float>(e, (size_t)e->net[0].H);
+  if (!e->met_part) {
     e->met_part = dalloc<double>(e, (size_t)metrics_scratch_doubles(e->C));
-    VV_CHECK(e->met_w && e->met_part, "out of memory for the metric scratch");
+    VV_CHECK(e->met_part, "out of memory for the metric scratch");
   }
-  launch_metrics(x_phys_dev, gt_phys_dev, e->mean, e->sigma, e->C, e->net[0].H, e->net[0].W, e->met_w, e->met_part, out_dev,
-                 (cudaStream_t)stream);
+  if (H > e->met_w_cap) {
+    e->met_w = dalloc<float>(e, (size_t)H);
+    VV_CHECK(e->met_w, "out of memory for the metric scratch");
+    e->met_w_cap = H;
+  }
+  launch_metrics(x_phys_dev, gt_phys_dev, e->mean, e->sigma, e->C, H, W, e->met_w, e->met_part, out_dev, (cudaStream_t)stream);
   VV_CUDA(cudaGetLastError());
   return 0;
+}
+
+VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phys_dev, double* out_dev, void* stream) {
+  VV_CHECK(e, "null argument");
+  return vv_metrics_grid(e, x_phys_dev, gt_phys_dev, e->net[0].H, e->net[0].W, out_dev, stream);
 }
 
 VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs) {

@@ -94,6 +94,7 @@ struct vv_engine {
   bool have_case = false;
   double *partials = nullptr, *dots = nullptr, *dot_scratch = nullptr, *Jbuf = nullptr;
   float* met_w = nullptr; double* met_part = nullptr;     // diagnostics scratch (latitude weights, block partials)
+  int met_w_cap = 0;
   // native geometry (vv_set_case_native): analysis grid Hh x Wh finer than the network grid; see enqueue_forward
   bool native = false;
   int Hh = 0, Wh = 0;

@@ -119,12 +119,7 @@ class VaeVar4D:
     def _diagnostics(self, z, gt0):
         """WRMSE / Bias of the current analysis (da_4dvar.py:1256-1264) without leaving the device: the fused metric
         kernel normalises both fields and applies utils/metrics.py's latitude weighting in one pass."""
-        if not self._native:
-            return self.engine.metrics(self.engine.decode(z), gt0)
-        m, s = self.model_mean_gpu.reshape(-1, 1, 1), self.model_std_gpu.reshape(-1, 1, 1)
-        xn, gn = ((self.engine.decode_native(z) - m) / s).unsqueeze(0), ((gt0 - m) / s).unsqueeze(0)
-        std64 = torch.from_numpy(self.model_std).to(self.device)
-        return wrmse(xn, gn, std64), bias(xn, gn, std64)
+        return self.engine.metrics(self.engine.decode_native(z) if self._native else self.engine.decode(z), gt0)
 
     def one_step_DA(self, gt, xb, yo, H, R, mode: str = "vae4dvar"):
         if mode != "vae4dvar":

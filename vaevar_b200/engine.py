@@ -154,7 +154,10 @@ class Engine:
         """(Metrics.WRMSE, Metrics.Bias) per channel of two PHYSICAL (C,H,W) fields, as da_4dvar.py:1260-1264 computes them
         (utils/metrics.py:526-544, 473-474): one fused device pass, float64 device tensors of length C."""
         out = torch.empty(2 * self.n_state, dtype=torch.float64, device=self.device)
-        _lib.check(self.lib.vv_metrics(self._h, _ptr(x_phys.contiguous()), _ptr(gt_phys.contiguous()), _ptr(out), _stream()))
+        if x_phys.shape != gt_phys.shape or x_phys.shape[0] != self.n_state:
+            raise ValueError("metrics takes two (C,H,W) fields of the same grid")
+        _lib.check(self.lib.vv_metrics_grid(self._h, _ptr(x_phys.contiguous()), _ptr(gt_phys.contiguous()), int(x_phys.shape[-2]),
+                                            int(x_phys.shape[-1]), _ptr(out), _stream()))
         return out[: self.n_state], out[self.n_state:]
 
     def integrate(self, x: torch.Tensor, steps: int = 1) -> torch.Tensor:
