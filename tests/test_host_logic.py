@@ -65,6 +65,44 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _cases_worker(rank, world, port, q):
+    from vaevar_b200.dist import run_cases
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Agent(_FakeAgent):
+        def one_step_DA(self, gt, xb, yo, H, R, mode="vae4dvar"):
+            seed = float(xb.flatten()[0])
+            self.metrics_list["ana_wrmse"].append(torch.full((self.nchannel,), seed))
+            self.metrics_list["ana_bias"].append(torch.full((self.nchannel,), -seed))
+            self.history.append({"loss": 10.0 + seed, "gmax": 0.5 * seed})
+            return xb
+
+    a = Agent()
+    a.history = []
+    mk = lambda i: {k: torch.full((1, 3, 4, 8), float(i)) for k in ("gt", "yo", "H", "R")} | {"xb": torch.full((3, 4, 8), float(i))}
+    r = run_cases(a, 5, mk, rank, world, "cpu")
+    q.put((rank, {k: r[k] for k in ("n_cases", "mean_J", "mean_gmax", "rms_wrmse", "mean_bias", "cases_on_this_rank", "world")}))
+    dist.destroy_process_group()
+
+
+def test_run_cases_world2_gloo():
+    """SURVEY 8(d) config 4 host logic: 5 cases over 2 ranks, results identical on both ranks and equal to the serial sums."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cases_worker, args=(r, 2, 29537, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert got[0]["cases_on_this_rank"] == 3 and got[1]["cases_on_this_rank"] == 2
+    for r in range(2):
+        g = got[r]
+        assert g["n_cases"] == 5 and g["world"] == 2
+        assert abs(g["mean_J"] - (10.0 + 2.0)) < 1e-12 and abs(g["mean_gmax"] - 1.0) < 1e-12
+        assert np.allclose(g["rms_wrmse"], np.sqrt((0 + 1 + 4 + 9 + 16) / 5.0)) and np.allclose(g["mean_bias"], -2.0)
+    assert got[0]["rms_wrmse"] == got[1]["rms_wrmse"]
+
+
 def test_metric_reduction_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

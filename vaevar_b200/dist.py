@@ -4,7 +4,8 @@ float64 metric accumulator (count, sum J, sum |grad J|, per-channel sum WRMSE^2 
 utils/misc.py:33-45 in the reference's training code."""
 from __future__ import annotations
 
-from typing import List
+import time
+from typing import Callable, Dict, List
 
 import torch
 import torch.distributed as dist
@@ -39,3 +40,31 @@ class MetricAccumulator:
         n = max(float(self.buf[0]), 1.0)
         return {"n_cases": int(self.buf[0]), "mean_J": float(self.buf[1]) / n, "mean_gmax": float(self.buf[2]) / n,
                 "rms_wrmse": (self.buf[3:3 + self.C] / n).sqrt().tolist(), "mean_bias": (self.buf[3 + self.C:] / n).tolist()}
+
+
+def run_cases(agent, n_cases: int, make_case_fn: Callable[[int], Dict], rank: int = 0, world: int = 1, device="cpu") -> Dict:
+    """`n_cases` independent assimilation cases (seeds 0..n-1), case i on rank i mod world, each one
+    `agent.one_step_DA(gt, xb, yo, H, R)`; per-case results go into a MetricAccumulator that is summed over ranks once at the end;
+    the elapsed time is the maximum over ranks.  Returns the summary with `cases_per_hour` (identical on every rank)."""
+    acc = MetricAccumulator(agent.nchannel, device)
+    cuda = torch.device(device).type == "cuda"
+    if dist.is_available() and dist.is_initialized() and world > 1:
+        dist.barrier()
+    if cuda:
+        torch.cuda.synchronize()
+    t0 = time.time()
+    mine = shard_cases(n_cases, rank, world)
+    for i in mine:
+        c = make_case_fn(i)
+        agent.one_step_DA(c["gt"], c["xb"], c["yo"], c["H"], c["R"], "vae4dvar")
+        info = agent.history[-1]
+        acc.add(float(info["loss"]), float(info["gmax"]), agent.metrics_list["ana_wrmse"][-1], agent.metrics_list["ana_bias"][-1])
+    if cuda:
+        torch.cuda.synchronize()
+    el = torch.tensor([time.time() - t0], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    acc.reduce()
+    out = acc.summary()
+    out.update(seconds=float(el), cases_per_hour=3600.0 * out["n_cases"] / max(float(el), 1e-9), world=world, cases_on_this_rank=len(mine))
+    return out
