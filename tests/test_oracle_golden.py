@@ -165,3 +165,21 @@ def test_seam_obs_term_matches_reference(gold):
     J, grad = oseams.obs_term(g["obs_x"], g["obs_H"], g["obs_yo"], g["obs_R"])
     assert abs(J / float(g["obs_J64"]) - 1) < 1e-12 and abs(J / float(g["obs_J"]) - 1) < 1e-5
     np.testing.assert_allclose(grad, g["obs_grad"], rtol=1e-5, atol=1e-7)
+
+
+# ---- the forecast network LGUnet_all_1: oracle restatement pinned to the reference module ----
+def test_lgunet_all_1_oracle_matches_reference(gold):
+    from oracle.lgunet1 import NET1_SMALL, lgunet1_forward, shift_mask, synth_state_dict
+    g = gold("net1_small.npz")
+    shapes = {str(n): eval(str(s)) for n, s in zip(g["names"], g["shapes"])}
+    sd = synth_state_dict(shapes, seed=int(g["seed"]))
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(int(g["x_seed"]))).standard_normal((1, 69, *NET1_SMALL.img_size), dtype=np.float32))
+    with torch.no_grad():
+        y = lgunet1_forward(x, sd, NET1_SMALL).numpy()
+    assert tuple(y.shape) == tuple(g["y_shape"]) == (1, 138, 49, 96)
+    np.testing.assert_allclose(y.ravel()[g["y_idx"]], g["y_val"], rtol=2e-4, atol=2e-5)
+    assert abs(np.abs(y.astype(np.float64)).sum() / float(g["y_abs"]) - 1) < 1e-5
+    # the shift mask is latitude-only (the third longitude slice of create_mask overwrites the first two) and 0 / -inf
+    m = shift_mask(24, 48, (6, 12), (3, 6))
+    assert m.shape == (16, 72, 72) and float(m[:12].abs().sum()) == 0.0
+    assert all(torch.equal(m[12], m[k]) for k in range(13, 16)) and set(np.unique(m[12].numpy())) == {-np.inf, 0.0}

@@ -200,6 +200,27 @@ def golden_real_obs(tag, cfg_dec, cfg_flow, T, hr, seed):
     print(f"cost_{tag}: J={J:.8g} J_obs={Jo:.8g} |g|={np.linalg.norm(g):.6g} n_obs={int(case['H'].sum())}", flush=True)
 
 
+def golden_lgunet1():
+    """The forecast network LGUnet_all_1 (networks/LGUnet_all.py:743-777) at a small configuration with the real patch (3, 2) /
+    stride 2 / window (6, 12) geometry, run by the reference module itself; weights are synthesised by name (oracle.lgunet1)."""
+    from networks.LGUnet_all import LGUnet_all_1
+    from oracle.lgunet1 import NET1_SMALL, synth_state_dict
+    cfg = NET1_SMALL
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = LGUnet_all_1(**cfg.to_reference_kwargs()).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    net.load_state_dict(synth_state_dict(shapes, seed=3), strict=True)
+    rng = np.random.Generator(np.random.PCG64(123))
+    x = rng.standard_normal((1, 69, *cfg.img_size), dtype=np.float32)
+    with torch.no_grad():
+        y = net(torch.from_numpy(x)).numpy()
+    iy = sample_idx(y.size, 8192, seed=12)
+    np.savez_compressed(GOLD / "net1_small.npz", names=np.array(list(shapes)), shapes=np.array([str(list(s)) for s in shapes.values()]),
+                        seed=3, x_seed=123, y_idx=iy, y_val=y.ravel()[iy], y_abs=np.float64(np.abs(y.astype(np.float64)).sum()),
+                        y_shape=np.array(y.shape))
+    print(f"net1_small: {len(shapes)} tensors, {sum(int(np.prod(s)) for s in shapes.values())} params, |y|_1={np.abs(y).sum():.6g}")
+
+
 def golden_metrics():
     from utils.metrics import Metrics
     rng = np.random.Generator(np.random.PCG64(5))
@@ -244,6 +265,7 @@ if __name__ == "__main__":
         "cost_small_T3_rich": lambda: golden_cost("small_T3_rich", ds, fs, 3, 0.10, 2, 3.0, True, lbfgs_iters=10, nit4=True),
         "cost_native_T3_rich": lambda: golden_cost_native("native_T3_rich", ds, fs, 3, (181, 360), 0.10, 4, 3.0, True),
         "obs_interp": golden_obs_interp,
+        "net1_small": golden_lgunet1,
         "cost_realobs_T2": lambda: golden_real_obs("realobs_T2", ds, fs, 2, ds.img_size, 5),
         "cost_realobs_native_T2": lambda: golden_real_obs("realobs_native_T2", ds, fs, 2, (181, 360), 6),
         "cost_native_T3_plain": lambda: golden_cost_native("native_T3_plain", ds, fs, 3, (181, 360), 0.10, 0, 1.0, False),
