@@ -140,6 +140,11 @@ VV_API int vv_resample_nearest_adjoint(const float* dout_dev, float* din_dev, in
  * J_out_dev[0] = obs_coeff * 1/2 * sum_k rinv[k] (x[idx[k]] - y[k])^2 in double; when grad_dev != NULL it is zero-filled and
  * receives obs_coeff * rinv (x - y) at the observed points.  work_dev holds vv_obs_term_work_doubles() doubles. */
 VV_API int64_t vv_obs_term_work_doubles(void);
+/* Host-only (no device call): the index tables the seams use between a network grid (H,W) and an analysis grid (Hh,Wh) - source row /
+ * column of every up-sampled (Hh / Wh entries) and down-sampled (H / W entries) element, the round trip S = down o up (H / W entries)
+ * and, per source row / column of S, the first output that reads it (H + 1 / W + 1 entries).  For tests of the index rule. */
+VV_API int vv_debug_seam_tables(int H, int W, int Hh, int Wh, int32_t* up_rows, int32_t* up_cols, int32_t* down_rows, int32_t* down_cols,
+                                int32_t* s_row, int32_t* s_col, int32_t* s_row_lo, int32_t* s_col_lo);
 VV_API int vv_obs_term(const float* x_dev, const int32_t* idx_dev, const float* y_dev, const float* rinv_dev, int64_t n_obs, float obs_coeff,
                        double* J_out_dev, float* grad_dev, int64_t n_grid, double* work_dev, void* stream);
 

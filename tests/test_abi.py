@@ -51,3 +51,28 @@ def test_product_does_not_import_oracle():
     for p in (ROOT / "vaevar_b200").glob("*.py"):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
+
+
+@pytest.mark.parametrize("lr,hr", [((128, 256), (721, 1440)), ((32, 64), (181, 360)), ((8, 16), (16, 32)), ((7, 9), (7, 9)), ((5, 6), (3, 4))])
+def test_seam_index_tables_follow_the_reference_rule(lib, gold, lr, hr):
+    """Host-only entry point (no device call): the library's nearest-resampling tables against the oracle's restatement of ATen's
+    rule and, at the reference's sizes, against the tables read off torch's own F.interpolate (tests/golden/seams.npz)."""
+    import numpy as np
+    from oracle.seams import nearest_index
+    (H, W), (Hh, Wh) = lr, hr
+    arr = lambda n: np.zeros(n, np.int32)
+    ur, uc, dr, dc, sr, sc, srl, scl = arr(Hh), arr(Wh), arr(H), arr(W), arr(H), arr(W), arr(H + 1), arr(W + 1)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.vv_debug_seam_tables(H, W, Hh, Wh, P(ur), P(uc), P(dr), P(dc), P(sr), P(sc), P(srl), P(scl)) == 0
+    assert np.array_equal(ur, nearest_index(Hh, H)) and np.array_equal(uc, nearest_index(Wh, W))
+    assert np.array_equal(dr, nearest_index(H, Hh)) and np.array_equal(dc, nearest_index(W, Wh))
+    if (lr, hr) == ((128, 256), (721, 1440)):
+        g = gold("seams.npz")
+        assert np.array_equal(ur, g["up_rows"]) and np.array_equal(uc, g["up_cols"])
+        assert np.array_equal(dr, g["down_rows"]) and np.array_equal(dc, g["down_cols"])
+        assert not np.array_equal(sr, np.arange(H))                 # the round trip is not the identity at the reference's sizes
+    assert np.array_equal(sr, ur[dr]) and np.array_equal(sc, uc[dc])  # S = down o up
+    for tab, lo, n in ((sr, srl, H), (sc, scl, W)):
+        assert lo[0] == 0 and lo[n] == n and (np.diff(lo) >= 0).all()
+        for r in range(n):
+            assert (tab[lo[r]:lo[r + 1]] == r).all() and (tab[:lo[r]] < r).all() and (tab[lo[r + 1]:] > r).all()

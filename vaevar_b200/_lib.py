@@ -70,6 +70,7 @@ _SIGS = {
     "vv_resample_nearest": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "vv_resample_nearest_adjoint": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "vv_obs_term_work_doubles": (C.c_int64, []),
+    "vv_debug_seam_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vv_obs_term": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, _P, _P, C.c_int64, _P, _P]),
 }
 EXPORTED = tuple(_SIGS)

@@ -463,6 +463,24 @@ VV_API int vv_resample_nearest_adjoint(const float* dout_dev, float* din_dev, in
   return 0;
 }
 
+VV_API int vv_debug_seam_tables(int H, int W, int Hh, int Wh, int32_t* up_rows, int32_t* up_cols, int32_t* down_rows, int32_t* down_cols,
+                                int32_t* s_row, int32_t* s_col, int32_t* s_row_lo, int32_t* s_col_lo) {
+  SEAM_CHECK(H >= 1 && W >= 1 && Hh >= 1 && Wh >= 1 && up_rows && up_cols && down_rows && down_cols && s_row && s_col && s_row_lo && s_col_lo,
+             "vv_debug_seam_tables: bad argument");
+  const AxisMap ur = make_axis(H, Hh), uc = make_axis(W, Wh), dr = make_axis(Hh, H), dc = make_axis(Wh, W);
+  for (int i = 0; i < Hh; ++i) up_rows[i] = host_axis_src(ur, i);
+  for (int j = 0; j < Wh; ++j) up_cols[j] = host_axis_src(uc, j);
+  for (int i = 0; i < H; ++i) down_rows[i] = host_axis_src(dr, i);
+  for (int j = 0; j < W; ++j) down_cols[j] = host_axis_src(dc, j);
+  std::vector<int> row, col, row_lo, col_lo;
+  host_seam_tables(H, W, Hh, Wh, row, col, row_lo, col_lo);
+  for (int i = 0; i < H; ++i) s_row[i] = row[i];
+  for (int j = 0; j < W; ++j) s_col[j] = col[j];
+  for (int i = 0; i <= H; ++i) s_row_lo[i] = row_lo[i];
+  for (int j = 0; j <= W; ++j) s_col_lo[j] = col_lo[j];
+  return 0;
+}
+
 VV_API int64_t vv_obs_term_work_doubles(void) { return OBS_BLOCKS; }
 
 VV_API int vv_obs_term(const float* x_dev, const int32_t* idx_dev, const float* y_dev, const float* rinv_dev, int64_t n_obs, float coeff,
