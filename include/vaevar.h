@@ -51,6 +51,10 @@ typedef struct {
   int use_graph; /* 1 = capture cost+grad into a CUDA graph on first use */
   int forward_fp16; /* 1 = forward activations and weights in IEEE fp16 (11-bit significand: 8x less rounding noise in
                        J(z) than bf16, which the strong-Wolfe line search needs), gradients in bf16; 0 = bf16 throughout */
+  int no_ln_fold; /* 0 = norm1 / norm2 of every Swin block (swinblock.py:226,232) are folded into the qkv / fc1 GEMMs (the GEMM runs
+                     on a row-centred 16-bit copy of the residual stream, see vv_ln_fold_health); 1 = they run as LayerNorm kernels
+                     with two-pass fp32 statistics in front of plain GEMMs (slower by ~35 launches per application, and safe for
+                     any residual stream) */
 } vv_config;
 
 typedef struct vv_engine vv_engine;
@@ -101,6 +105,12 @@ VV_API int vv_set_case_obsop(vv_engine* e, const float* xb_dev, const float* yo_
                              void* stream);
 /* Analysis on the analysis grid after vv_set_case_native: (decoder_hr(z) stdTr) sigma + xb  (da_4dvar.py:1257-1259, 1301-1306). */
 VV_API int vv_decode_native(vv_engine* e, const float* z_dev, float* x_phys_out_dev, void* stream);
+
+/* Health of the folded LayerNorms since the last call (or engine creation): counts[0] = (row, LayerNorm) pairs whose mean is
+ * further than 32 standard deviations from the row's stage-input mean (the centred 16-bit operand then carries > 1.5 % rounding
+ * error), counts[1] = rows whose centred values approach the fp16 range.  Non-zero counts mean: recreate the engine with
+ * no_ln_fold = 1.  Synchronises the engine's stream; resets the counters. */
+VV_API int vv_ln_fold_health(vv_engine* e, uint32_t counts_host[2]);
 
 /* closure() (da_4dvar.py:1242-1246): J_out_dev[3] = {J, J_reg, J_obs} (fp64), grad_dev = dJ/dz (same shape as z). */
 VV_API int vv_cost_grad(vv_engine* e, const float* z_dev, double* J_out_dev, float* grad_dev, void* stream);
@@ -187,13 +197,19 @@ VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, v
 VV_API int vv_test_gemm(const void* A_16_dev, const void* B_16_dev, const float* bias_dev, const float* res_dev, float* out_f32_dev,
                  void* out_16_dev, void* aux_16_dev, int M, int N, int K, int batch, int epi, void* stream);
 /* GEMM with a LayerNorm folded into it (the forward pass's norm1 -> qkv and norm2 -> fc1, swinblock.py:268,305):
- * out = epi(LN(x) W^T + b) evaluated as rstd (x W'^T - mean s) + c, with A = the raw 16-bit rows of x, B = W' = W o gamma,
- * cbias = c = b + W beta, colsum = s = W' 1, stats = per-row (sum, sumsq) partials [batch][parts][M] float2, C = row length.
- * If stats_out is given the GEMM also emits the partials of the rows of its fp32 output ([batch][*parts_out][M] float2), as
- * the proj / fc2 GEMMs do for the LayerNorm that follows them. */
+ * out = epi(LN(x) W^T + b) evaluated as rstd ((x - shift) W'^T - (mean - shift) s) + c, with A = the 16-bit rows of x - shift (shift =
+ * a per-row offset, null = 0), B = W' = W o gamma, cbias = c = b + W beta, colsum = s = W' 1, stats = per-row (mean, M2) partials
+ * [batch][parts][M] float2 left by a producer of tile width prod_bn (0 = a single partial over the row), C = row length; rows whose
+ * remaining offset endangers the 16-bit operand are counted in health_dev[2] (null = off).
+ * If stats_out is given the GEMM is the PRODUCER instead: it emits the partials of the rows of its fp32 output
+ * ([batch][parts_out[0]][M] float2, tile width parts_out[1]) and the 16-bit copy out_16 = out - shift, as the proj / fc2 GEMMs do for
+ * the LayerNorm that follows them.  res_f32 (optional): fp32 residual [batch][M][N] added before everything else. */
 VV_API int vv_test_gemm_ln(const void* A_16_dev, const void* B_16_dev, const float* cbias_dev, const float* colsum_dev, const float* stats_dev,
                     int parts, int C, float eps, void* out_16_dev, void* aux_16_dev, float* out_f32_dev, float* stats_out_dev,
-                    int* parts_out_host, int M, int N, int K, int batch, int epi, void* stream);
+                    int* parts_out_host, int M, int N, int K, int batch, int epi, const float* shift_dev, int prod_bn,
+                    uint32_t* health_dev, const float* res_f32_dev, void* stream);
+/* Statistics pass at a stage input: x (rows, C) fp32 -> out_16 = x - mean (16-bit), stats (rows) float2 = (mean, M2), shift = mean. */
+VV_API int vv_test_ln_stats(const float* x_dev, void* out_16_dev, float* stats_dev, float* shift_dev, int rows, int C, int f16, void* stream);
 /* Debug: GEMM launches built after this call stamp per-CTA clock64 values into trace_dev (64 x uint64 per CTA; layout in
  * tools/gemm_trace.py); null switches tracing off. */
 VV_API int vv_debug_gemm_trace(void* trace_dev);
@@ -210,7 +226,8 @@ VV_API int vv_test_obs(vv_engine* e, const float* xn_dev, double* J_obs_dev, flo
 /* Steady-state time of every launch of one application plan (app 0 = decoder, >= 1 = flow; bwd = 0/1): each op is run
  * `reps` times between CUDA events. ms_out / kind_out / flop_out hold `cap` entries; returns the number of ops.
  * kind: 0 GEMM, 1 LN fwd, 2 LN bwd, 3 attention fwd, 4 attention bwd, 5 P2T, 6 T2P. */
-VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap);
+VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap,
+                          int flush_l2 /* 1: every timed launch starts on a cold L2 (256 MiB overwritten outside the timed events) */);
 /* Number of kernel launches the last vv_cost_grad enqueued (for bench.py's gpu_launches). */
 VV_API int vv_last_launch_count(vv_engine* e);
 

@@ -36,7 +36,7 @@ def test_config_struct_layout_matches_header():
     from vaevar_b200 import _lib
     # 3 + 8 + 8 + 3 + 2 + 2 + 1 + 8 + 8 + 1 ints
     assert ctypes.sizeof(_lib.NetConfigC) == 4 * 44
-    assert ctypes.sizeof(_lib.ConfigC) == 2 * 4 * 44 + 5 * 4     # has_flow, T, recompute, use_graph, forward_fp16
+    assert ctypes.sizeof(_lib.ConfigC) == 2 * 4 * 44 + 6 * 4     # has_flow, T, recompute, use_graph, forward_fp16, no_ln_fold
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -105,7 +105,7 @@ def golden_net(tag, cfg, seed, gain, rich):
     return sd, net
 
 
-def golden_cost(tag, cfg_dec, cfg_flow, T, obs_frac, seed, gain, rich, lbfgs_iters=0, nit4=False):
+def golden_cost(tag, cfg_dec, cfg_flow, T, obs_frac, seed, gain, rich, lbfgs_iters=0, nit4=False, nit_track=0):
     from oracle.cost import Case, cost_and_grad, one_step_da
     from vaevar_b200.synth import make_case, make_state_dict
     sd_d = make_state_dict(cfg_dec, seed=seed, gain=gain, rich=rich)
@@ -133,6 +133,11 @@ def golden_cost(tag, cfg_dec, cfg_flow, T, obs_frac, seed, gain, rich, lbfgs_ite
     if nit4:   # the shipped script's Nit=4 outer steps (da_4dvar_script.sh:14): a converged analysis
         r = one_step_da(c, nets, nit=4, max_iter=lbfgs_iters)
         out.update(ana_wrmse_nit4=r["ana_wrmse"], ana_bias_nit4=r["ana_bias"], J_history_nit4=r["J_history"], n_evals_nit4=r["n_evals"])
+    if nit_track:  # one Nit-step run (da_4dvar_script.sh:14) recording the analysis WRMSE / Bias after every outer step
+        tr_w, tr_b = [], []
+        r = one_step_da(c, nets, nit=nit_track, max_iter=10, log=lambda kk, w, b: (tr_w.append(w.numpy().copy()), tr_b.append(b.numpy().copy())))
+        out.update(wrmse_per_outer=np.stack(tr_w), bias_per_outer=np.stack(tr_b), J_history_nit4=r["J_history"], n_evals_nit4=r["n_evals"],
+                   ana_wrmse_nit4=r["ana_wrmse"], bg_wrmse=r["bg_wrmse"])
     np.savez_compressed(GOLD / f"cost_{tag}.npz", **out)
     print(f"cost_{tag}: J={J:.8g} J_reg={Jr:.6g} J_obs={Jo:.8g} |g|={out['g_norm']:.6g} ({dt:.1f}s)", flush=True)
 
@@ -277,6 +282,10 @@ if __name__ == "__main__":
             "cost_full_T1": lambda: golden_cost("full_T1", DECODER_FULL, FLOW_FULL, 1, 0.10, 0, 1.0, False, lbfgs_iters=10, nit4=True),
             "cost_full_T6": lambda: golden_cost("full_T6", DECODER_FULL, FLOW_FULL, 6, 0.10, 0, 1.0, False),
             "cost_full_T2_rich": lambda: golden_cost("full_T2_rich", DECODER_FULL, FLOW_FULL, 2, 0.10, 3, 3.0, True),
+            # BASELINE.json configs[2]: 12-step window, 5 % observations (one closure; the engine runs it with adjoint recompute)
+            "cost_full_T12_obs05": lambda: golden_cost("full_T12_obs05", DECODER_FULL, FLOW_FULL, 12, 0.05, 7, 1.0, False),
+            # the headline config with the shipped script's optimisation: Nit=4 x LBFGS.step(max_iter=10), WRMSE after every outer step
+            "cost_full_T6_nit4": lambda: golden_cost("full_T6_nit4", DECODER_FULL, FLOW_FULL, 6, 0.10, 0, 1.0, False, nit_track=4),
         })
     for name, fn in jobs.items():
         if a.only and a.only not in name:

@@ -21,7 +21,7 @@ class NetConfigC(C.Structure):
 
 class ConfigC(C.Structure):
     _fields_ = [("dec", NetConfigC), ("flow", NetConfigC), ("has_flow", C.c_int), ("T", C.c_int),
-                ("recompute", C.c_int), ("use_graph", C.c_int), ("forward_fp16", C.c_int)]
+                ("recompute", C.c_int), ("use_graph", C.c_int), ("forward_fp16", C.c_int), ("no_ln_fold", C.c_int)]
 
 
 _P = C.c_void_p
@@ -41,6 +41,7 @@ _SIGS = {
     "vv_metrics": (C.c_int, [_P, _P, _P, _P, _P]),
     "vv_metrics_grid": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "vv_num_obs": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "vv_ln_fold_health": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vv_cost_grad": (C.c_int, [_P, _P, _P, _P, _P]),
     "vv_cost": (C.c_int, [_P, _P, _P, _P]),
     "vv_decode": (C.c_int, [_P, _P, _P, _P]),
@@ -57,10 +58,11 @@ _SIGS = {
     "vv_lbfgs_set_noise": (C.c_int, [_P, C.c_double]),
     "vv_lbfgs_steps": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "vv_lbfgs_create_testfn": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(_P)]),
-    "vv_profile_ops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int]),
+    "vv_profile_ops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "vv_test_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vv_test_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.POINTER(C.c_int), C.c_int, C.c_int,
-                                  C.c_int, C.c_int, C.c_int, _P]),
+                                  C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "vv_test_ln_stats": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vv_debug_gemm_trace": (C.c_int, [_P]),
     "vv_debug_gemm_mode": (C.c_int, [C.c_int]),
     "vv_test_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),

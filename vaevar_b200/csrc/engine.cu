@@ -118,6 +118,15 @@ static T* dalloc(vv_engine* e, size_t n) {
   e->allocs.push_back(p);
   return static_cast<T*>(p);
 }
+// Release a buffer obtained from dalloc (re-allocation of per-case buffers that outgrew their capacity).
+template <typename T>
+static void dfree(vv_engine* e, T*& p) {
+  if (!p) return;
+  auto it = std::find(e->allocs.begin(), e->allocs.end(), static_cast<void*>(p));
+  if (it != e->allocs.end()) e->allocs.erase(it);
+  cudaFree(p);
+  p = nullptr;
+}
 template <typename T>
 static T* dupload(vv_engine* e, const std::vector<T>& h) {
   T* d = dalloc<T>(e, h.size());
@@ -226,7 +235,7 @@ static int build_blocks(vv_engine* e, WeightReader& R, std::vector<BlockW>& out,
     w.sqkv = dalloc<float>(e, (size_t)G * 3 * d); w.cqkv = dalloc<float>(e, (size_t)G * 3 * d);
     w.s1 = dalloc<float>(e, (size_t)G * 4 * d); w.c1 = dalloc<float>(e, (size_t)G * 4 * d);
     if (!w.sqkv || !w.cqkv || !w.s1 || !w.c1) return -1;
-    for (int g = 0; g < G; ++g) {
+    for (int g = 0; g < G && !e->cfg.no_ln_fold; ++g) {
       const std::string p = stage_prefix[g] + ".blocks." + std::to_string(b);
       const float* wq = R.dev(p + ".attn.qkv.weight", 3 * dd);
       const float* w1 = R.dev(p + ".mlp.fc1.weight", 4 * dd);
@@ -378,6 +387,7 @@ struct Temps {
   bf16 *h, *ao, *a, *du, *dao, *dqkv, *dx1b, *dhb;
   float *dh, *dx1;
   float* lnst; size_t lnst_cap;      // LayerNorm statistics partials: float2 [batch][parts][rows]; capacity in float2
+  float* lnshift;                    // per-row shift of the centred 16-bit copy: [batch][rows]
   // seams (forward)
   bf16 *MB, *EPIN, *TB, *CAT0, *CAT1, *U1B;
   float* NU;
@@ -389,6 +399,7 @@ struct Temps {
 struct Builder {
   vv_engine* e; Net* n; Temps t; const char* err = nullptr;
   int f16 = 0;        // forward activations / weights in fp16 (gradients always bf16)
+  bool fold = true;   // norm1 / norm2 folded into the qkv / fc1 GEMMs (vv_config::no_ln_fold)
 
   void gemm(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g) {
     Op o{}; o.kind = Op::GEMM;
@@ -406,14 +417,14 @@ struct Builder {
   void ln_f(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
             const float* gamma, const float* beta, bf16* ob, long long ld_ob, long long ob_bs, float* of, long long ld_of, long long of_bs) {
     Op o{}; o.kind = Op::LN_F;
-    o.lnf = LnArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, beta, (long long)C, ob, ld_ob, ob_bs, of, ld_of, of_bs, f16, nullptr};
+    o.lnf = LnArgs{rows, C, batch, map, gh, gw, eps, x, ld_x, x_bs, gamma, beta, (long long)C, ob, ld_ob, ob_bs, of, ld_of, of_bs, f16, nullptr, nullptr};
     P.ops.push_back(o);
   }
   // statistics-only LayerNorm pass (raw 16-bit copy of x into t.h + (sum, sumsq) per row) for a stage input no GEMM produced
   void ln_stats(Plan& P, int rows, int C, int batch, const float* x) {
     const long long rd = (long long)rows * C;
     Op o{}; o.kind = Op::LN_F;
-    o.lnf = LnArgs{rows, C, batch, MAP_PLAIN, 0, 0, 0.f, x, (long long)C, rd, nullptr, nullptr, 0, t.h, (long long)C, rd, nullptr, 0, 0, f16, t.lnst};
+    o.lnf = LnArgs{rows, C, batch, MAP_PLAIN, 0, 0, 0.f, x, (long long)C, rd, nullptr, nullptr, 0, t.h, (long long)C, rd, nullptr, 0, 0, f16, t.lnst, t.lnshift};
     P.ops.push_back(o);
   }
   void ln_b(Plan& P, int rows, int C, int batch, int map, int gh, int gw, float eps, const float* x, long long ld_x, long long x_bs,
@@ -425,52 +436,73 @@ struct Builder {
     P.ops.push_back(o);
   }
   // GEMM whose fp32 output is the input of a LayerNorm folded into the NEXT GEMM: it also writes the raw 16-bit copy of its
-  // output rows (width C) into t.h and their (sum, sumsq) partials into t.lnst.  Returns the number of partials per row.
-  int gemm_with_stats(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g, int C) {
+  // output rows (width C), centred on the row's stage-input mean (t.lnshift), into t.h and their (mean, M2) partials into t.lnst.
+  // Returns the number of partials per row; prod_bn receives the producer's tile width (the consumer needs it to weigh them).
+  int gemm_with_stats(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g, int C,
+                      int& prod_bn) {
     g.out_bf16 = t.h; g.ld_bf16 = C; g.bf16_bs = (long long)g.M * C;
     g.stats_out = t.lnst;
+    g.ln_shift = t.lnshift;
     gemm(P, A, lda, a_bs, B, ldb, b_bs, g);
     GemmDesc& d = P.ops.back().gemm;
     const int parts = 2 * ((g.N + d.bn - 1) / d.bn);
     d.a.stats_out_bs = (long long)parts * g.M * 2;
     if ((size_t)parts * g.M * g.batch > t.lnst_cap && !err) err = "LayerNorm statistics buffer too small";
+    prod_bn = d.bn;
     return parts;
   }
-  void fold_ln(GemmArgs& g, int parts, const float* colsum, int C, float eps) const {
+  void fold_ln(GemmArgs& g, int parts, int prod_bn, const float* colsum, int C, float eps) const {
     g.ln_stats = t.lnst; g.ln_parts = parts; g.ln_stats_bs = (long long)parts * g.M * 2; g.ln_colsum = colsum;
+    g.ln_prod_bn = prod_bn; g.ln_c = C; g.ln_shift = t.lnshift; g.ln_health = e->ln_health;
     g.ln_inv_c = 1.0f / (float)C; g.ln_eps = eps;
   }
 
   // SwinTransformerBlock.forward, swinblock.py:265-309
   // norm1 / norm2 are folded into the qkv / fc1 GEMMs (GemmArgs::ln_stats): no LayerNorm launches inside a stage.
-  // parts: in = number of statistics partials already in t.lnst for `x` (0: none -- a statistics pass is issued);
-  //        out = partials for x_out if emit_next (the next block's norm1), else 0.
+  // parts: in = number of statistics partials already in t.lnst for `x` (0: none -- a statistics pass is issued, which also fixes
+  //        the rows' shifts for the whole stage); out = partials for x_out if emit_next (the next block's norm1), else 0.
+  // prod_bn: tile width of the GEMM that produced those partials (0: the statistics kernel).
+  // fold == false: plain LayerNorm kernels (two-pass fp32 statistics) in front of plain GEMMs.
   void block_fwd(Plan& P, const BlockW& w, int gh, int gw, int shift, const float* x, float* x_out, BlkStash& st,
-                 bf16* copy_b, long long ld_c, long long bs_c, int& parts, bool emit_next) {
+                 bf16* copy_b, long long ld_c, long long bs_c, int& parts, int& prod_bn, bool emit_next) {
     const int G = w.G, d = w.d, rows = gh * gw;
     const long long rd = (long long)rows * d;
-    if (parts == 0) { ln_stats(P, rows, d, G, x); parts = 1; }
     GemmArgs g = ga(rows, 3 * d, d, G);
-    g.bias = w.cqkv; g.bias_bs = 3 * d; g.out_bf16 = st.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd;
-    fold_ln(g, parts, w.sqkv, d, 1e-5f);
+    g.out_bf16 = st.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd; g.bias_bs = 3 * d;
+    if (fold) {
+      if (parts == 0) { ln_stats(P, rows, d, G, x); parts = 1; prod_bn = 0; }
+      g.bias = w.cqkv;
+      fold_ln(g, parts, prod_bn, w.sqkv, d, 1e-5f);
+    } else {
+      ln_f(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, w.be1, t.h, d, rd, nullptr, 0, 0);
+      g.bias = w.bqkv;
+    }
     gemm(P, t.h, d, rd, w.Wqkv, d, 3LL * d * d, g);
     Op o{}; o.kind = Op::ATT_F;
     o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, t.ao, d, rd, nullptr, nullptr, f16};
     P.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = st.x1; g.ld_f32 = d; g.f32_bs = rd;
-    const int parts2 = gemm_with_stats(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g, d);
+    int parts2 = 0, bn2 = 0;
+    if (fold) parts2 = gemm_with_stats(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g, d, bn2);
+    else gemm(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g);
     g = ga(rows, 4 * d, d, G);
-    g.epi = EPI_GELU; g.bias = w.c1; g.bias_bs = 4 * d; g.aux_out = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd;
+    g.epi = EPI_GELU; g.bias_bs = 4 * d; g.aux_out = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd;
     g.out_bf16 = t.a; g.ld_bf16 = 4 * d; g.bf16_bs = 4 * rd;
-    fold_ln(g, parts2, w.s1, d, 1e-5f);
+    if (fold) {
+      g.bias = w.c1;
+      fold_ln(g, parts2, bn2, w.s1, d, 1e-5f);
+    } else {
+      ln_f(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, w.be2, t.h, d, rd, nullptr, 0, 0);
+      g.bias = w.b1;
+    }
     gemm(P, t.h, d, rd, w.W1, d, 4LL * d * d, g);
     g = ga(rows, d, 4 * d, G);
     g.bias = w.b2; g.bias_bs = d; g.res = st.x1; g.ld_res = d; g.res_bs = rd; g.out_f32 = x_out; g.ld_f32 = d; g.f32_bs = rd;
-    if (emit_next) {
-      parts = gemm_with_stats(P, t.a, 4 * d, 4 * rd, w.W2, 4 * d, 4LL * d * d, g, d);
+    if (emit_next && fold) {
+      parts = gemm_with_stats(P, t.a, 4 * d, 4 * rd, w.W2, 4 * d, 4LL * d * d, g, d, prod_bn);
     } else {
-      if (copy_b) { g.out_bf16 = copy_b; g.ld_bf16 = ld_c; g.bf16_bs = bs_c; }
+      if (copy_b && !emit_next) { g.out_bf16 = copy_b; g.ld_bf16 = ld_c; g.bf16_bs = bs_c; }
       gemm(P, t.a, 4 * d, 4 * rd, w.W2, 4 * d, 4LL * d * d, g);
       parts = 0;
     }
@@ -498,10 +530,10 @@ struct Builder {
     ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, nullptr, d, rd, t.dx1, d, rd, g32, d, rd, g16, d, rd, t.dhb);
   }
   void stage_fwd(Plan& P, const std::vector<BlockW>& ws, int gh, int gw, StageStash& st, bf16* copy_b, long long ld_c, long long bs_c) {
-    int parts = 0;
+    int parts = 0, prod_bn = 0;
     for (size_t b = 0; b < ws.size(); ++b) {
       const bool last = b + 1 == ws.size();
-      block_fwd(P, ws[b], gh, gw, (b % 2) ? 2 : 0, st.x[b], st.x[b + 1], st.b[b], last ? copy_b : nullptr, ld_c, bs_c, parts, !last);
+      block_fwd(P, ws[b], gh, gw, (b % 2) ? 2 : 0, st.x[b], st.x[b + 1], st.b[b], last ? copy_b : nullptr, ld_c, bs_c, parts, prod_bn, !last);
     }
   }
   void stage_bwd(Plan& P, const std::vector<BlockW>& ws, int gh, int gw, StageStash& st, float* g32, bf16* g16) {
@@ -550,10 +582,10 @@ struct Builder {
   }
   void stage_fwd_trunk(Plan& P, Stash& S) {
     Net& N = *n;
-    int parts = 0;
+    int parts = 0, prod_bn = 0;
     for (size_t b = 0; b < N.lg.size(); ++b) {
       const bool last = b + 1 == N.lg.size();
-      block_fwd(P, N.lg[b], N.h1, N.w1, shift_of_trunk(b), S.lg.x[b], S.lg.x[b + 1], S.lg.b[b], last ? t.TB : nullptr, N.E, 0, parts, !last);
+      block_fwd(P, N.lg[b], N.h1, N.w1, shift_of_trunk(b), S.lg.x[b], S.lg.x[b + 1], S.lg.b[b], last ? t.TB : nullptr, N.E, 0, parts, prod_bn, !last);
     }
   }
   int shift_of_trunk(size_t b) const {          // block index inside its Layer decides the shift (transformer.py:502)
@@ -662,7 +694,8 @@ static int alloc_temps(vv_engine* e, Temps& t) {
       if (e->net[k].finalized) { tower_rows = std::max(tower_rows, (size_t)e->net[k].G * e->net[k].L0); trunk_rows = std::max(trunk_rows, (size_t)e->net[k].L1); }
     t.lnst_cap = std::max(8 * tower_rows, 40 * trunk_rows);
     t.lnst = dalloc<float>(e, 2 * t.lnst_cap);
-    if (!t.lnst) return -1;
+    t.lnshift = dalloc<float>(e, std::max(tower_rows, trunk_rows));
+    if (!t.lnst || !t.lnshift) return -1;
   }
   t.gU1 = dalloc<float>(e, m_l0d); t.gU1b = dalloc<bf16>(e, m_l0d);
   t.gU0 = dalloc<float>(e, 2 * m_l1d); t.gU0b = dalloc<bf16>(e, 2 * m_l1d);
@@ -685,6 +718,9 @@ static int build_plans(vv_engine* e) {
   const int napp = flow ? std::max(T, 2) : 1;
   Temps t{};
   if (alloc_temps(e, t)) return -1;
+  e->ln_health = dalloc<unsigned int>(e, 2);
+  if (!e->ln_health) return -1;
+  cudaMemset(e->ln_health, 0, 2 * sizeof(unsigned int));
   const size_t CHW = (size_t)e->C * e->HW;
   e->Z = dalloc<float>(e, (size_t)e->Zc * e->HW); e->GZ = dalloc<float>(e, (size_t)e->Zc * e->HW);
   e->DOUT = dalloc<float>(e, CHW); e->GD = dalloc<float>(e, CHW); e->XB = dalloc<float>(e, CHW);
@@ -700,6 +736,7 @@ static int build_plans(vv_engine* e) {
     else if (alloc_stash(e, n, e->stash[a])) return -1;
     Builder B{e, &n, t};
     B.f16 = e->cfg.forward_fp16 ? 1 : 0;
+    B.fold = e->cfg.no_ln_fold == 0;
     if (a == 0) {
       B.net_fwd(e->fwd[a], e->stash[a], e->Z, e->DOUT);
       B.net_bwd(e->bwd[a], e->stash[a], e->GD, e->GZ);
@@ -935,8 +972,18 @@ VV_API int vv_set_constants(vv_engine* e, const float* mean, const float* std, c
   const int C = e->C;
   std::vector<float> m(mean, mean + C), s(std, std + C), t(stdTr, stdTr + C), is(C), nm(C);
   for (int c = 0; c < C; ++c) { is[c] = 1.0f / s[c]; nm[c] = -m[c] / s[c]; }
-  e->mean = dupload(e, m); e->sigma = dupload(e, s); e->stdTr = dupload(e, t); e->inv_sigma = dupload(e, is); e->neg_mu_sig = dupload(e, nm);
+  if (e->have_consts) {            // a second call updates the constants in place: the launch graph keeps the same pointers
+    const size_t nb = (size_t)C * sizeof(float);
+    VV_CUDA(cudaDeviceSynchronize());
+    VV_CUDA(cudaMemcpy(e->mean, m.data(), nb, cudaMemcpyHostToDevice)); VV_CUDA(cudaMemcpy(e->sigma, s.data(), nb, cudaMemcpyHostToDevice));
+    VV_CUDA(cudaMemcpy(e->stdTr, t.data(), nb, cudaMemcpyHostToDevice)); VV_CUDA(cudaMemcpy(e->inv_sigma, is.data(), nb, cudaMemcpyHostToDevice));
+    VV_CUDA(cudaMemcpy(e->neg_mu_sig, nm.data(), nb, cudaMemcpyHostToDevice));
+  } else {
+    e->mean = dupload(e, m); e->sigma = dupload(e, s); e->stdTr = dupload(e, t); e->inv_sigma = dupload(e, is); e->neg_mu_sig = dupload(e, nm);
+    VV_CHECK(e->mean && e->sigma && e->stdTr && e->inv_sigma && e->neg_mu_sig, "out of memory for the constants");
+  }
   e->have_consts = true;
+  e->generation++;
   return 0;
 }
 
@@ -958,6 +1005,21 @@ VV_API int vv_compact_mask(const float* H_dev, const float* yo_dev, const float*
   return 0;
 }
 
+// (Re-)allocate the per-observation buffers for `total` observations.  The old buffers are freed first and the capacity is only
+// raised once every allocation has succeeded; a launch graph that baked the old pointers in is dropped.
+static int reserve_obs(vv_engine* e, long long total) {
+  if (total <= e->obs_cap) return 0;
+  const long long cap = total + total / 8 + 1024;
+  if (e->graph_cg) { cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr; }
+  cudaDeviceSynchronize();
+  dfree(e, e->idx); dfree(e, e->yobs); dfree(e, e->rinv); dfree(e, e->resid);
+  e->obs_cap = 0;
+  e->idx = dalloc<int>(e, cap); e->yobs = dalloc<float>(e, cap); e->rinv = dalloc<float>(e, cap); e->resid = dalloc<float>(e, cap);
+  VV_CHECK(e->idx && e->yobs && e->rinv && e->resid, "out of memory for %lld observations", total);
+  e->obs_cap = cap;
+  return 0;
+}
+
 VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, const float* H_dev, const float* R_dev, float obs_coeff, void* stream) {
   VV_CHECK(e && xb_dev && yo_dev && H_dev && R_dev, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
@@ -975,13 +1037,7 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
   VV_CUDA(cudaMemcpyAsync(offs.data(), e->chunk_counts, (nchunks + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
   VV_CUDA(cudaStreamSynchronize(s));
   const long long total = offs[nchunks];
-  if (total > e->obs_cap) {
-    e->obs_cap = total + total / 8 + 1024;
-    e->idx = dalloc<int>(e, e->obs_cap); e->yobs = dalloc<float>(e, e->obs_cap);
-    e->rinv = dalloc<float>(e, e->obs_cap); e->resid = dalloc<float>(e, e->obs_cap);
-    VV_CHECK(e->idx && e->yobs && e->rinv && e->resid, "out of memory for observations");
-    if (e->graph_cg) { cudaGraphExecDestroy(e->graph_cg); e->graph_cg = nullptr; }
-  }
+  if ((rc = reserve_obs(e, total))) return rc;
   launch_compact_write(H_dev, yo_dev, R_dev, n, e->chunk_counts, e->idx, e->yobs, e->rinv, s);
   std::vector<long long> off(T + 1);
   for (int t = 0; t <= T; ++t) off[t] = offs[(size_t)(t * (CHW / 1024))];
@@ -997,6 +1053,7 @@ VV_API int vv_set_case(vv_engine* e, const float* xb_dev, const float* yo_dev, c
   VV_CUDA(cudaMemcpyAsync(e->XB, xb_dev, CHW * sizeof(float), cudaMemcpyDeviceToDevice, s));
   VV_CUDA(cudaStreamSynchronize(s));
   e->have_case = true;
+  e->generation++;
   return 0;
 }
 
@@ -1038,25 +1095,31 @@ static int set_case_native_impl(vv_engine* e, const float* xb_dev, const float* 
   for (int t = 0; t < T; ++t)
     launch_compact_write(H_dev + (size_t)t * lvl, yo_dev + (size_t)t * lvl, R_dev + (size_t)t * lvl, lvl, counts + (size_t)t * (nchunks + 1),
                          idx_hr + off[t], y_hr + off[t], ri_hr + off[t], s);
-  if (total > e->obs_cap) {
-    e->obs_cap = total + total / 8 + 1024;
-    e->idx = dalloc<int>(e, e->obs_cap); e->yobs = dalloc<float>(e, e->obs_cap);
-    e->rinv = dalloc<float>(e, e->obs_cap); e->resid = dalloc<float>(e, e->obs_cap);
-  }
+  rc = reserve_obs(e, total);
+  if (rc) { cudaFree(counts); cudaFree(idx_hr); cudaFree(y_hr); cudaFree(ri_hr); return rc; }
   if (!e->XF) {
     e->XF = dalloc<float>(e, (size_t)CHW * T); e->XBN = dalloc<float>(e, CHW); e->TMPF = dalloc<float>(e, CHW);
     e->s_row = dalloc<int>(e, H); e->s_col = dalloc<int>(e, W); e->s_row_lo = dalloc<int>(e, H + 1); e->s_col_lo = dalloc<int>(e, W + 1);
   }
-  if (lvl_x > e->xbh_cap) { e->XBH = dalloc<float>(e, lvl_x); e->xbh_cap = lvl_x; }
+  if (lvl_x > e->xbh_cap) {
+    cudaDeviceSynchronize();
+    dfree(e, e->XBH); e->xbh_cap = 0;
+    e->XBH = dalloc<float>(e, lvl_x);
+    if (e->XBH) e->xbh_cap = lvl_x;
+  }
   rc = (e->idx && e->yobs && e->rinv && e->resid && e->XF && e->XBN && e->TMPF && e->s_col_lo && e->XBH) ? 0 : -1;
   int* tap_chan = nullptr; float* tap_w = nullptr;
   if (!rc && K > 0) {
     if (total * K >= (1LL << 31)) { set_error("too many observation taps for int32 indices"); rc = -2; }
     if (!rc && total * K > e->pair_cap) {
-      e->pair_cap = total * K + total * K / 8 + 1024;
-      e->tap_ia = dalloc<int>(e, e->pair_cap); e->pair_cell = dalloc<int>(e, e->pair_cap); e->pair_src = dalloc<int>(e, e->pair_cap);
-      e->tap_coef = dalloc<float>(e, e->pair_cap); e->pair_coef = dalloc<float>(e, e->pair_cap);
+      const long long cap = total * K + total * K / 8 + 1024;
+      cudaDeviceSynchronize();
+      dfree(e, e->tap_ia); dfree(e, e->pair_cell); dfree(e, e->pair_src); dfree(e, e->tap_coef); dfree(e, e->pair_coef);
+      e->pair_cap = 0;
+      e->tap_ia = dalloc<int>(e, cap); e->pair_cell = dalloc<int>(e, cap); e->pair_src = dalloc<int>(e, cap);
+      e->tap_coef = dalloc<float>(e, cap); e->pair_coef = dalloc<float>(e, cap);
       if (!e->pair_coef || !e->tap_ia || !e->pair_cell || !e->pair_src || !e->tap_coef) rc = -1;
+      else e->pair_cap = cap;
     }
     if (!rc && (cudaMalloc(&tap_chan, (size_t)A * K * sizeof(int)) != cudaSuccess || cudaMalloc(&tap_w, (size_t)A * K * sizeof(float)) != cudaSuccess)) rc = -1;
     if (!rc) {
@@ -1092,6 +1155,7 @@ static int set_case_native_impl(vv_engine* e, const float* xb_dev, const float* 
   e->n_obs = total;
   e->obs_coeff = obs_coeff;
   e->have_case = true;
+  e->generation++;
   return 0;
 }
 
@@ -1145,6 +1209,17 @@ VV_API int vv_metrics(vv_engine* e, const float* x_phys_dev, const float* gt_phy
 VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs) {
   VV_CHECK(e && n_obs, "null argument");
   *n_obs = e->n_obs;
+  return 0;
+}
+
+VV_API int vv_ln_fold_health(vv_engine* e, uint32_t counts_host[2]) {
+  VV_CHECK(e && counts_host, "null argument");
+  counts_host[0] = counts_host[1] = 0;
+  if (!e->ln_health) return 0;
+  VV_CUDA(cudaStreamSynchronize(e->stream));
+  VV_CUDA(cudaDeviceSynchronize());
+  VV_CUDA(cudaMemcpy(counts_host, e->ln_health, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  VV_CUDA(cudaMemset(e->ln_health, 0, 2 * sizeof(uint32_t)));
   return 0;
 }
 
@@ -1258,7 +1333,8 @@ VV_API int vv_test_obs(vv_engine* e, const float* xn_dev, double* J_obs_dev, flo
 
 VV_API int vv_last_launch_count(vv_engine* e) { return e ? e->last_launches : 0; }
 
-VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap) {
+VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap,
+                          int flush_l2) {
   VV_CHECK(e && ms_out && kind_out && reps >= 1, "bad argument");
   int rc = build_plans(e);
   if (rc) return rc;
@@ -1267,17 +1343,35 @@ VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_ou
   cudaEvent_t e0, e1;
   VV_CUDA(cudaEventCreate(&e0)); VV_CUDA(cudaEventCreate(&e1));
   cudaStream_t s = e->stream;
+  // flush_l2: every timed launch starts on a cold L2 (a 256 MiB scratch is overwritten first, outside the timed events) -- the
+  // HBM-bound kernels are then rated on DRAM traffic, not on a working set that stayed in the 126 MB L2 between repetitions.
+  const size_t FLUSH = (size_t)256 << 20;
+  void* scratch = nullptr;
+  if (flush_l2) VV_CUDA(cudaMalloc(&scratch, FLUSH));
   e->fwd[app].run(s);                       // make sure the stash holds finite values
   int k = 0;
   for (const Op& o : P.ops) {
     Plan one; one.ops.push_back(o);
     one.run(s);
-    cudaEventRecord(e0, s);
-    for (int r = 0; r < reps; ++r) one.run(s);
-    cudaEventRecord(e1, s);
-    cudaEventSynchronize(e1);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    if (flush_l2) {
+      for (int r = 0; r < reps; ++r) {
+        cudaMemsetAsync(scratch, r & 0xff, FLUSH, s);
+        cudaEventRecord(e0, s);
+        one.run(s);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e0, e1);
+        ms += t;
+      }
+    } else {
+      cudaEventRecord(e0, s);
+      for (int r = 0; r < reps; ++r) one.run(s);
+      cudaEventRecord(e1, s);
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1);
+    }
     if (k < cap) {
       ms_out[k] = ms / reps;
       kind_out[k] = (int)o.kind;
@@ -1292,6 +1386,7 @@ VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_ou
     ++k;
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (scratch) cudaFree(scratch);
   VV_CUDA(cudaGetLastError());
   return k;
 }
@@ -1319,12 +1414,14 @@ VV_API int vv_test_gemm(const void* A, const void* B, const float* bias, const f
   return 0;
 }
 
-// Folded-LayerNorm GEMM hook: out = epi( LN(x) W^T + b ) computed as rstd (x W'^T - mean s) + c from the raw 16-bit x (A),
-// the folded operand W' (B), c (bias), s (colsum) and per-row (sum, sumsq) statistics [batch][parts][M] float2.  stats_out /
-// out_f32: when given, the GEMM also acts as a statistics producer for its fp32 output (partials [batch][2*n_tiles][M]).
+// Folded-LayerNorm GEMM hook: out = epi( LN(x) W^T + b ) computed as rstd ((x - shift) W'^T - (mean - shift) s) + c from the centred
+// 16-bit copy x - shift (A), the folded operand W' (B), c (bias), s (colsum) and the per-row (mean, M2) partials [batch][parts][M]
+// float2 a producer with tile width prod_bn left (prod_bn = 0: one partial over the whole row).  stats_out / out_f32: when given,
+// the GEMM acts as the statistics PRODUCER for its fp32 output instead (partials [batch][2 * n_tiles][M]; its 16-bit copy is
+// centred on `shift`); parts_out[0] = partials per row, parts_out[1] = its tile width.  shift: [batch][M] or null; health: 2 counters.
 VV_API int vv_test_gemm_ln(const void* A, const void* B, const float* cbias, const float* colsum, const float* stats, int parts, int C,
                     float eps, void* out_16, void* aux_16, float* out_f32, float* stats_out, int* parts_out, int M, int N, int K,
-                    int batch, int epi, void* stream) {
+                    int batch, int epi, const float* shift, int prod_bn, uint32_t* health, const float* res, void* stream) {
   GemmArgs g{};
   g.f16 = (epi >> 4) & 1; g.aux_f16 = g.f16;
   epi &= 15;
@@ -1332,8 +1429,11 @@ VV_API int vv_test_gemm_ln(const void* A, const void* B, const float* cbias, con
   g.bias = cbias; g.bias_bs = N;
   if (stats) {
     g.ln_stats = stats; g.ln_parts = parts; g.ln_stats_bs = (long long)parts * M * 2; g.ln_colsum = colsum;
+    g.ln_prod_bn = prod_bn; g.ln_c = C; g.ln_health = health;
     g.ln_inv_c = 1.0f / (float)C; g.ln_eps = eps;
   }
+  g.ln_shift = shift;
+  g.res = res; g.ld_res = N; g.res_bs = (long long)M * N;
   if (epi == EPI_GELU) g.aux_out = (bf16*)aux_16;
   g.ld_aux = N; g.aux_bs = (long long)M * N;
   g.out_bf16 = (bf16*)out_16; g.ld_bf16 = N; g.bf16_bs = (long long)M * N;
@@ -1344,8 +1444,18 @@ VV_API int vv_test_gemm_ln(const void* A, const void* B, const float* cbias, con
   VV_CHECK(!er, "%s", er);
   const int po = 2 * ((N + d.bn - 1) / d.bn);
   d.a.stats_out_bs = (long long)po * M * 2;
-  if (parts_out) *parts_out = po;
+  if (parts_out) { parts_out[0] = po; parts_out[1] = d.bn; }
   launch_gemm(d, (cudaStream_t)stream);
+  VV_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Statistics pass of a stage input (the LayerNorm kernel's statistics-only mode): x (rows, C) fp32 -> centred 16-bit copy, (mean, M2)
+// per row (float2) and the row shifts.
+VV_API int vv_test_ln_stats(const float* x, void* out_16, float* stats, float* shift, int rows, int C, int f16, void* stream) {
+  VV_CHECK(ln_supported(MAP_PLAIN, C), "LayerNorm width %d not instantiated", C);
+  LnArgs a{rows, C, 1, MAP_PLAIN, 0, 0, 0.f, x, C, 0, nullptr, nullptr, 0, (bf16*)out_16, C, 0, nullptr, 0, 0, f16, stats, shift};
+  launch_ln_fwd(a, (cudaStream_t)stream);
   VV_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1363,7 +1473,7 @@ VV_API int vv_test_layernorm(const float* x, const float* gamma, const float* be
                       float eps, void* stream) {
   VV_CHECK(ln_supported(MAP_PLAIN, C), "LayerNorm width %d not instantiated", C);
   if (y) {
-    LnArgs a{rows, C, 1, MAP_PLAIN, 0, 0, eps, x, C, 0, gamma, beta, 0, nullptr, 0, 0, y, C, 0, 0};
+    LnArgs a{rows, C, 1, MAP_PLAIN, 0, 0, eps, x, C, 0, gamma, beta, 0, nullptr, 0, 0, y, C, 0, 0, nullptr, nullptr};
     launch_ln_fwd(a, (cudaStream_t)stream);
   }
   if (dy && dx) {

@@ -92,6 +92,8 @@ struct vv_engine {
   std::vector<long long> obs_off;   // [T+1]
   float obs_coeff = 1.f;
   bool have_case = false;
+  unsigned long long generation = 0;   // bumped by every vv_set_case* / vv_set_constants: cached evaluations of an older case are stale
+  unsigned int* ln_health = nullptr;       // [2] device counters of the folded LayerNorms (GemmArgs::ln_health)
   double *partials = nullptr, *dots = nullptr, *dot_scratch = nullptr, *Jbuf = nullptr;
   float* met_w = nullptr; double* met_part = nullptr;     // diagnostics scratch (latitude weights, block partials)
   int met_w_cap = 0;

@@ -160,6 +160,7 @@ static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, 
   if (args.epi == EPI_DGELU && (args.ln_stats || args.stats_out)) return "GEMM: GELU' epilogue with LayerNorm folding is not supported";
   if (args.ln_stats && args.stats_out) return "GEMM: a LayerNorm consumer cannot also be a statistics producer";
   if (args.stats_out && args.epi != EPI_LINEAR) return "GEMM: statistics are produced by linear epilogues only";
+  if (args.stats_out && args.N % GEMM_EC) return "GEMM: a statistics producer needs N to be a multiple of 32";
   d->a = args;
   const bool b_contig = ldb == args.K && (args.batch == 1 || b_bs == (long long)args.N * args.K);
   d->b_ptr = b_contig ? B : nullptr;

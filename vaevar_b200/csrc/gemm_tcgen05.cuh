@@ -57,13 +57,25 @@ struct GemmArgs {
   long long split_stride;
   // LayerNorm folded into the GEMM (forward pass).  With W' = W o gamma, s_n = sum_k W'[n,k], c_n = b_n + sum_k beta_k W[n,k]:
   //   LN(x) W^T + b = rstd_r (x W'^T - mean_r s_n) + c_n
-  // so the GEMM runs on the RAW 16-bit copy of x and the epilogue applies the per-row (mean, rstd) it derives from the
-  // (sum, sum of squares) partials a PRODUCER GEMM (or the stats kernel) left in ln_stats; c_n travels as `bias`.
-  const float* ln_stats;      // consumer: [batch][ln_parts][M] float2 (sum, sumsq) partials of the A rows; null = plain GEMM
+  // so the GEMM runs on a 16-bit copy of x and the epilogue applies the per-row (mean, rstd) it derives from the statistics
+  // partials a PRODUCER GEMM (or the stats kernel) left in ln_stats; c_n travels as `bias`.
+  // Numerics (what makes the fold safe for residual streams with |mean| >> sigma):
+  //  * the 16-bit copy holds x - shift_r, shift_r = the row's mean at the input of the stage (ln_shift, written by the stats
+  //    kernel), so the operand rounding error is relative to the row's spread, not to its offset; the consumer then applies
+  //    mean_r - shift_r;
+  //  * a partial is (mean_p, M2_p) = (mean, sum of squared deviations from it) of the columns it covers, accumulated around
+  //    the partial's first value and combined with Chan's pairwise update -- no E[x^2] - mean^2 cancellation anywhere;
+  //  * rows whose remaining offset or magnitude still endangers the 16-bit operand are counted in ln_health.
+  const float* ln_stats;      // consumer: [batch][ln_parts][M] float2 (mean_p, M2_p) partials of the A rows; null = plain GEMM
   int ln_parts;
+  int ln_prod_bn;             // consumer: tile width of the GEMM that produced the partials (partial 2 nt + h covers the 32-column
+                              // chunks h, h + 2, ... of n-tile nt); 0 = one partial over the whole row (stats kernel)
+  int ln_c;                   // consumer: row length C of the normalised rows
   long long ln_stats_bs;      // batch stride in floats
   const float* ln_colsum;     // consumer: s_n, [batch][N] (batch stride = bias_bs)
-  float ln_inv_c, ln_eps;     // 1 / row length of the normalised rows, epsilon
+  float ln_inv_c, ln_eps;     // 1 / C, epsilon
+  const float* ln_shift;      // consumer and producer: per-row shift [batch][M] (batch stride M); null = 0
+  unsigned int* ln_health;    // consumer: [0] += rows with |mean - shift| > 32 sigma, [1] += rows near fp16 saturation; null = off
   float* stats_out;           // producer: [batch][2 * n_tiles][M] float2 partials of the rows of the fp32 output; null = none
   long long stats_out_bs;     // batch stride in floats
   const void* pf_ptr;         // weights of the NEXT GEMM in the plan: prefetched into L2 by the idle producer warp (null = none)
@@ -119,11 +131,13 @@ VV_DEVINL float2 unpack16(uint32_t w, bool f16) {
 
 // One 32-row x 32-column chunk of the epilogue, executed by one warp (thread = row).  r[] holds the fp32 accumulators,
 // bv[] the bias of the 32 columns; slot A / slot B are this warp's staging slabs (see GEMM_SLOT_*).
-// ln_a scales the accumulator (the row's rstd when a LayerNorm is folded into this GEMM, else 1); rs / rq accumulate the
-// row's sum and sum of squares of the final fp32 values when this GEMM produces LayerNorm statistics for its consumer.
+// ln_a scales the accumulator (the row's rstd when a LayerNorm is folded into this GEMM, else 1).  When this GEMM produces
+// LayerNorm statistics for its consumer, rs / rq accumulate sum (v - piv) and sum (v - piv)^2 of the final fp32 values around
+// the pivot `piv` (the first value this thread saw in the tile; set here when `first`), and the 16-bit copy holds v - shift.
 template <int EPI, bool F16, int LNX>
 VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float (&bv)[32], uint8_t* SA, uint8_t* SB, int lane,
-                              bool has_res, bool has_auxin, bool has_auxout, float ln_a, float& rs, float& rq) {
+                              bool has_res, bool has_auxin, bool has_auxout, float ln_a, float& rs, float& rq, float& piv,
+                              bool first, float shift) {
   const uint32_t sw128 = static_cast<uint32_t>(lane & 7);          // 128B swizzle: 16-byte chunk c of row r lives at c ^ (r & 7)
   const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);    // 64B swizzle: chunk c of row r lives at c ^ ((r >> 1) & 3)
   uint8_t* rowA = SA + lane * 128;
@@ -175,15 +189,23 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
       v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
       v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
     }
-    if (LNX == LN_PRODUCE && p.stats_out) {   // two independent partial chains per statistic
-      rs += (v[0] + v[1]) + (v[2] + v[3]) + ((v[4] + v[5]) + (v[6] + v[7]));
-      rq += fmaf(v[0], v[0], v[1] * v[1]) + fmaf(v[2], v[2], v[3] * v[3]) + (fmaf(v[4], v[4], v[5] * v[5]) + fmaf(v[6], v[6], v[7] * v[7]));
+    if (LNX == LN_PRODUCE && p.stats_out) {   // deviations from the pivot; two independent partial chains per statistic
+      if (first && g == 0) piv = v[0];
+      float dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dv[i] = v[i] - piv;
+      rs += (dv[0] + dv[1]) + (dv[2] + dv[3]) + ((dv[4] + dv[5]) + (dv[6] + dv[7]));
+      rq += fmaf(dv[0], dv[0], dv[1] * dv[1]) + fmaf(dv[2], dv[2], dv[3] * dv[3]) + (fmaf(dv[4], dv[4], dv[5] * dv[5]) + fmaf(dv[6], dv[6], dv[7] * dv[7]));
     }
     if (p.out_f32) {
       *reinterpret_cast<float4*>(rowA + cA0) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(rowA + cA1) = make_float4(v[4], v[5], v[6], v[7]);
     }
     if (p.out_bf16) {
+      if (LNX == LN_PRODUCE) {                 // the copy a folded LayerNorm consumes is centred on the row's shift
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] -= shift;
+      }
       uint4 w;
       w.x = pack16<F16>(v[0], v[1]); w.y = pack16<F16>(v[2], v[3]);
       w.z = pack16<F16>(v[4], v[5]); w.w = pack16<F16>(v[6], v[7]);
@@ -386,25 +408,46 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (has_auxin) tma_load_3d(slab + buf * GEMM_BUF + GEMM_SLOT_A, &io.aux_in, &ldbar[buf], col, mrow, b);
     };
 
-    // folded LayerNorm: the first six (sum, sumsq) partials of this thread's row, fetched one tile ahead (a dependent global
-    // round trip per tile would dominate the small-K tower GEMMs)
+    // folded LayerNorm: the first six (mean, M2) partials of this thread's row and the row's shift, fetched one tile ahead (a
+    // dependent global round trip per tile would dominate the small-K tower GEMMs)
     float2 stat_nx[6];
+    float shift_nx = 0.f;
     const float2* stats2 = reinterpret_cast<const float2*>(p.ln_stats);
     const long long stats_bs2 = p.ln_stats_bs >> 1;
     auto load_stats = [&](const Coord& c) {
 #pragma unroll
       for (int j = 0; j < 6; ++j) stat_nx[j] = make_float2(0.f, 0.f);
+      shift_nx = 0.f;
       if (c.tile >= total_tiles) return;
       const int row = row0_of(c) + lane;
       if (row >= p.M) return;
+      if (p.ln_shift) shift_nx = __ldg(p.ln_shift + (long long)c.b * p.M + row);
+      if (LNX != LN_CONSUME) return;
       const float2* st = stats2 + c.b * stats_bs2 + row;
 #pragma unroll
       for (int j = 0; j < 6; ++j)
         if (j < p.ln_parts) stat_nx[j] = __ldg(st + j * p.M);
     };
+    // columns covered by partial j (see GemmArgs::ln_prod_bn)
+    auto part_cols = [&](int j) {
+      if (p.ln_prod_bn <= 0) return (float)p.ln_c;
+      const int nt = j >> 1, h = j & 1;
+      const int ncol = min(p.ln_prod_bn, p.ln_c - nt * p.ln_prod_bn);
+      const int nch = (ncol + GEMM_EC - 1) / GEMM_EC;
+      return (float)(GEMM_EC * ((nch - h + 1) >> 1));
+    };
+    // Chan's update: fold partial (nb, mb, qb) into the running (na, ma, qa)
+    auto chan = [&](float& na, float& ma, float& qa, float nb, float mb, float qb) {
+      if (nb <= 0.f) return;
+      const float n = na + nb, dm = mb - ma, f = __fdividef(nb, n);
+      ma = fmaf(dm, f, ma);
+      qa += fmaf(dm * dm, na * f, qb);
+      na = n;
+    };
     Coord cur{pair, pair % n_tiles, (pair / n_tiles) % pair_rows, pair / (n_tiles * pair_rows)};
     const bool ln_on = LNX == LN_CONSUME && p.ln_stats != nullptr;
-    if (ln_on) load_stats(cur);
+    const bool shift_on = ln_on || (LNX == LN_PRODUCE && p.ln_shift != nullptr);
+    if (shift_on) load_stats(cur);
     uint32_t it = 0;
     bool pre_issued = false;                                 // the loads of this warp's first chunk of the coming tile are in flight
     if (has_loads && cur.tile < total_tiles && half < nch_of(cur)) {
@@ -420,11 +463,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc = ti & 1;
       const float* bias = p.bias ? p.bias + (long long)b * p.bias_bs : nullptr;
       const float* colsum = ln_on ? p.ln_colsum + (long long)b * p.bias_bs : nullptr;
-      float ln_a = 1.f, ln_b = 0.f, rs = 0.f, rq = 0.f;
-      if (ln_on) {                                 // this thread's row: mean / rstd from the producer's partial sums
-        float sm = 0.f, sq = 0.f;
+      float ln_a = 1.f, ln_b = 0.f, rs = 0.f, rq = 0.f, piv = 0.f;
+      const float shift = shift_nx;
+      if (ln_on) {                                 // this thread's row: mean / rstd from the producer's partials
+        float na = 0.f, ma = 0.f, qa = 0.f;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) { sm += stat_nx[j].x; sq += stat_nx[j].y; }
+        for (int j = 0; j < 6; ++j)
+          if (j < p.ln_parts) chan(na, ma, qa, part_cols(j), stat_nx[j].x, stat_nx[j].y);
         if (p.ln_parts > 6 && nch > 0 && mrow + lane < p.M) {
           const float2* st = stats2 + b * stats_bs2 + mrow + lane;
           for (int q0 = 6; q0 < p.ln_parts; q0 += 6) {                     // six independent loads in flight per round trip
@@ -432,14 +477,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 6; ++j) t2[j] = q0 + j < p.ln_parts ? __ldg(st + (q0 + j) * p.M) : make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) { sm += t2[j].x; sq += t2[j].y; }
+            for (int j = 0; j < 6; ++j)
+              if (q0 + j < p.ln_parts) chan(na, ma, qa, part_cols(q0 + j), t2[j].x, t2[j].y);
           }
         }
         load_stats(nxt);                           // the next tile's partials travel while this tile is processed
-        const float mean = sm * p.ln_inv_c;
-        const float var = fmaxf(fmaf(sq, p.ln_inv_c, -mean * mean), 0.f);
+        const float var = qa * p.ln_inv_c;
+        const float mres = ma - shift;             // what is left of the mean in the centred 16-bit copy
         ln_a = rsqrtf(var + p.ln_eps);
-        ln_b = ln_a * mean;
+        ln_b = ln_a * mres;
+        if (p.ln_health && cur.nt == 0 && half == 0 && nch > 0 && mrow + lane < p.M) {
+          const float m2 = mres * mres;
+          if (m2 > 1024.f * (var + p.ln_eps)) atomicAdd(p.ln_health, 1u);            // |mean - shift| > 32 sigma
+          if (F16 && var + m2 > 1.0e8f) atomicAdd(p.ln_health + 1, 1u);              // rms of the copy > 1e4: fp16 range at risk
+        }
+      } else if (shift_on) {
+        load_stats(nxt);
       }
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       tc_fence_after();
@@ -499,7 +552,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ld_phase ^= 1u << buf;
         }
         // (4) fused math, results staged in place
-        epilogue_chunk<EPI, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq);
+        epilogue_chunk<EPI, F16, LNX>(p, r, bv, SA, SB, lane, has_res, has_auxin, has_auxout, ln_a, rs, rq, piv, c == half, shift);
         // (5) bulk stores
         fence_proxy_async();
         __syncwarp();
@@ -513,9 +566,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
-      if (LNX == LN_PRODUCE && p.stats_out && mrow + lane < p.M) {      // partial (sum, sumsq) of this warp's columns of the row; zeros if it had none
+      if (LNX == LN_PRODUCE && p.stats_out && mrow + lane < p.M) {      // partial (mean, M2) of this warp's columns of the row; zeros if it had none
         float2* so = reinterpret_cast<float2*>(p.stats_out + (long long)b * p.stats_out_bs);
-        so[(long long)(2 * cur.nt + half) * p.M + mrow + lane] = make_float2(rs, rq);
+        const int ncols = nch > half ? GEMM_EC * ((nch - half + 1) >> 1) : 0;
+        float2 st = make_float2(0.f, 0.f);
+        if (ncols > 0) {
+          const float inv = 1.0f / (float)ncols;
+          st = make_float2(fmaf(rs, inv, piv), fmaxf(fmaf(-rs * inv, rs, rq), 0.f));
+        }
+        so[(long long)(2 * cur.nt + half) * p.M + mrow + lane] = st;
       }
       // this warp no longer needs accumulator stage `acc`: tell the leader's MMA thread
       tc_fence_before();

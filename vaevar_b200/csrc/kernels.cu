@@ -81,12 +81,17 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   }
   const float qc = row_sum<LANES>(q);
   if (!live) return;
-  if (a.stats_out) {                               // statistics-only mode: raw 16-bit copy + (sum, sumsq) of the row
-    if (sl == 0)
-      reinterpret_cast<float2*>(a.stats_out)[(long long)b * a.rows + r] = make_float2(mean * a.C, fmaf(mean * a.C, mean, qc));
+  if (a.stats_out) {                               // statistics-only mode: (mean, M2) of the row, the row's shift (= its mean) and
+    if (sl == 0) {                                 // the CENTRED 16-bit copy x - mean a folded LayerNorm consumes (GemmArgs::ln_stats)
+      reinterpret_cast<float2*>(a.stats_out)[(long long)b * a.rows + r] = make_float2(mean, qc);
+      if (a.shift_out) a.shift_out[(long long)b * a.rows + r] = mean;
+    }
+    const float sh = a.shift_out ? mean : 0.f;
 #pragma unroll
-    for (int k = 0; k < NV; ++k)
-      st4_16(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + 4 * (sl + LANES * k), v[k], a.out_f16 != 0);
+    for (int k = 0; k < NV; ++k) {
+      const float4 c4 = make_float4(v[k].x - sh, v[k].y - sh, v[k].z - sh, v[k].w - sh);
+      st4_16(a.out_bf16 + (long long)b * a.ob_bs + (long long)r * a.ld_ob + 4 * (sl + LANES * k), c4, a.out_f16 != 0);
+    }
     return;
   }
   const float rstd = rsqrtf(qc / a.C + a.eps);

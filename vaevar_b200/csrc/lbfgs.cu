@@ -44,6 +44,7 @@ struct vv_lbfgs {
   double acc_J3[3] = {0, 0, 0};           // ... of the point z currently sits on (what cal_loss(z) would return)
   std::vector<std::array<double, 4>> ls_log;   // (t, J, J_reg, J_obs) of the current line search's trials
   bool reuse_entry = true, have_last = false;
+  unsigned long long last_generation = 0;   // engine case / constants generation the stored evaluation belongs to
   double last_loss = 0.0;
   long long skipped_evals = 0;
   float* z_last = nullptr;
@@ -416,7 +417,7 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   double loss, gmax, gl1;
   o->hist_t.push_back(0.0);
   bool reused = false;
-  if (o->reuse_entry && o->have_last) {
+  if (o->reuse_entry && o->have_last && (!o->e || o->e->generation == o->last_generation)) {
     launch_axpby(o->x_init, z, nullptr, 1.0, nullptr, 0.0, n, s);                     // x_init is scratch here: z - z_last
     launch_axpby(o->x_init, o->z_last, nullptr, -1.0, nullptr, 1.0, n, s);
     double dmax0;
@@ -515,6 +516,7 @@ VV_API int vv_lbfgs_step(vv_lbfgs* o, float* z, double* info, void* stream) {
   }
   if (copy_vec(o, o->z_last, z, s)) return -1;
   o->last_loss = loss; o->have_last = true;
+  o->last_generation = o->e ? o->e->generation : 0;
   LB_CUDA(cudaStreamSynchronize(s));
   if (info) {
     info[0] = orig_loss; info[1] = loss; info[2] = current_evals; info[3] = (double)o->n_iter_total;

@@ -83,10 +83,12 @@ __global__ void __launch_bounds__(256) compact_write_kernel(const float* H, cons
                                                             const int* offsets, int* idx, float* y, float* rinv) {
   const long long base = (long long)blockIdx.x * CHUNK + threadIdx.x * 4;
   bool nz[4];
+  float hv[4];
   int c = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    nz[k] = base + k < n && H[base + k] != 0.f;
+    hv[k] = base + k < n ? H[base + k] : 0.f;
+    nz[k] = hv[k] != 0.f;
     c += nz[k];
   }
   // exclusive scan of c over the block (thread order == index order)
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) compact_write_kernel(const float* H, cons
     if (nz[k]) {
       idx[pos] = (int)(base + k);
       y[pos] = yo[base + k];
-      rinv[pos] = 1.0f / R[base + k];
+      rinv[pos] = hv[k] / R[base + k];      // H / R: the reference's sum(H (x - yo)^2 / R) for ANY weight H (da_4dvar.py:1207); == 1 / R bit for bit when H = 1
       ++pos;
     }
   }

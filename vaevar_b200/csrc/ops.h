@@ -61,7 +61,9 @@ struct LnArgs {
   float* out_f32; long long ld_of, of_bs;
   int out_f16;                                     // 1: the 16-bit output is IEEE fp16 (forward pass), 0: bf16
   float* stats_out;                                // non-null: "statistics only" mode for a LayerNorm folded into the next GEMM --
-                                                   // out_bf16 receives the RAW row, stats_out[batch][rows] float2 = (sum, sumsq)
+                                                   // stats_out[batch][rows] float2 = (mean, sum of squared deviations)
+  float* shift_out;                                // statistics-only mode: [batch][rows] row shift (= mean); out_bf16 receives x - shift
+                                                   // (null: shift 0, the raw row)
 };
 struct LnBwdArgs {
   int rows, C, batch, map, gh, gw;

@@ -49,7 +49,7 @@ class Engine:
 
     def __init__(self, dec: NetConfig, flow: Optional[NetConfig] = None, T: int = 1, recompute: bool = False,
                  use_graph: bool = True, device: str = "cuda:0", flow_keep: int = 69, dec_keep: int = 0,
-                 forward_fp16: bool = True):
+                 forward_fp16: bool = True, ln_fold: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("vaevar_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -65,6 +65,8 @@ class Engine:
         cfg.has_flow = int(flow is not None)
         cfg.T, cfg.recompute, cfg.use_graph = T, int(recompute), int(use_graph)
         cfg.forward_fp16 = int(forward_fp16)     # fp16 forward / bf16 gradients (include/vaevar.h: vv_config.forward_fp16)
+        cfg.no_ln_fold = int(not ln_fold)        # False: LayerNorm kernels + plain GEMMs (include/vaevar.h: vv_config.no_ln_fold)
+        self.ln_fold = bool(ln_fold)
         self._h = C.c_void_p()
         _lib.check(self.lib.vv_engine_create(C.byref(cfg), C.byref(self._h)))
         self.n_state = dec_keep or dec.out_chans
@@ -92,6 +94,16 @@ class Engine:
     def set_constants(self, mean, std, stdtr):
         a = [np.ascontiguousarray(np.asarray(x, np.float32)) for x in (mean, std, stdtr)]
         _lib.check(self.lib.vv_set_constants(self._h, *[x.ctypes.data_as(C.c_void_p) for x in a]))
+
+    def ln_fold_health(self, raise_on_risk: bool = False):
+        """Counters of the folded LayerNorms since the last call: rows whose mean drifted > 32 sigma from their stage-input mean
+        (`far_mean`) or whose centred values approach the fp16 range (`near_saturation`).  Non-zero = use Engine(ln_fold=False)."""
+        c = (C.c_uint32 * 2)()
+        _lib.check(self.lib.vv_ln_fold_health(self._h, c))
+        out = {"far_mean": int(c[0]), "near_saturation": int(c[1])}
+        if raise_on_risk and (out["far_mean"] or out["near_saturation"]):
+            raise _lib.VVError(f"folded LayerNorm at risk for these weights / inputs ({out}): construct the engine with ln_fold=False")
+        return out
 
     # -- case -----------------------------------------------------------------------------------
     def set_case(self, xb, yo, H, R, obs_coeff: float = 1.0):
@@ -183,11 +195,12 @@ class Engine:
         _lib.check(self.lib.vv_test_obs(self._h, _ptr(xn.contiguous()), _ptr(J), _ptr(g), _stream()))
         return J, g
 
-    def profile_ops(self, app: int, bwd: bool, reps: int = 20):
-        """Steady-state CUDA-event time of every launch of one application plan: list of dicts."""
+    def profile_ops(self, app: int, bwd: bool, reps: int = 20, flush_l2: bool = False):
+        """CUDA-event time of every launch of one application plan: list of dicts.  flush_l2=False: launches back to back (steady
+        state, warm L2); True: every timed launch starts on a cold L2 (what an HBM roofline fraction has to be measured on)."""
         cap = 4096
         ms = (C.c_float * cap)(); kind = (C.c_int * cap)(); fl = (C.c_double * cap)(); mnk = (C.c_int * (4 * cap))()
-        n = self.lib.vv_profile_ops(self._h, app, int(bwd), reps, ms, kind, fl, mnk, cap)
+        n = self.lib.vv_profile_ops(self._h, app, int(bwd), reps, ms, kind, fl, mnk, cap, int(flush_l2))
         if n < 0:
             _lib.check(n)
         names = ["gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "p2t", "t2p"]
