@@ -51,6 +51,13 @@ class Case:
         self.T = self.yo.shape[0]
         self.obs_coeff = obs_coeff
 
+    def to(self, device):
+        """Move every captured tensor (bench.py's informational eager-GPU leg runs this same restatement on the B200)."""
+        for k, v in list(vars(self).items()):
+            if isinstance(v, torch.Tensor):
+                setattr(self, k, v.to(device))
+        return self
+
 
 class OracleNets:
     """The two network applications of the loop as callables: `decode` = VAE_lr.decoder
@@ -137,11 +144,11 @@ def loss_terms(z, c, nets):
 
 def cost_and_grad(z_np: np.ndarray, c: Case, nets):
     """One closure() call: returns (J, J_reg, J_obs, grad_z) as python floats / numpy."""
-    z = torch.from_numpy(np.ascontiguousarray(z_np)).clone().requires_grad_(True)
+    z = torch.from_numpy(np.ascontiguousarray(z_np)).clone().to(c.xb.device).requires_grad_(True)
     j_reg, j_obs = loss_terms(z, c, nets)
     J = j_reg + c.obs_coeff * j_obs
     J.backward()
-    return float(J.detach()), float(j_reg.detach()), float(j_obs.detach()), z.grad.detach().numpy()
+    return float(J.detach()), float(j_reg.detach()), float(j_obs.detach()), z.grad.detach().cpu().numpy()
 
 
 # ---- metrics (utils/metrics.py) ------------------------------------------------------------

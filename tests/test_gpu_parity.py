@@ -680,3 +680,26 @@ def test_residual_stream_with_large_row_offsets(chk, ln_fold):
     assert ey < 1e-2 and ed < 2e-2
     assert health == {"far_mean": 0, "near_saturation": 0}
     e.close()
+
+
+def test_case_results_do_not_depend_on_the_rank_that_runs_them(chk):
+    """"N cases on N GPUs == the same cases on 1 GPU, bit-identical".  A case's result may depend on nothing but
+    its seed: the same case run third in a sequence on one engine, and run alone on a fresh engine (what another rank would do),
+    gives bit-identical records (final J, z500 WRMSE, checksum of the analysis).  tools/run_cases.py --check does the same
+    comparison between real N-GPU and 1-GPU runs (profiles/r2_cases_*.json)."""
+    from vaevar_b200.config import DECODER_FULL, FLOW_FULL, small
+    from vaevar_b200.da import VaeVar4D
+    from vaevar_b200.dist import run_cases
+    from vaevar_b200.synth import make_case, make_state_dict
+    ds, fs = small(DECODER_FULL), small(FLOW_FULL)
+    mk = lambda i: make_case(2, *ds.img_size, obs_frac=0.1, seed=i)
+
+    def records(n_cases, rank, world):
+        agent = VaeVar4D(ds, fs, make_state_dict(ds, seed=0), make_state_dict(fs, seed=1), da_win=2, Nit=2, verbose=False)
+        r = run_cases(agent, n_cases, mk, rank, world, "cuda:0")
+        agent.engine.close()
+        return r["case_records"]
+    serial = records(3, 0, 1)                     # cases 0, 1, 2 on one "rank"
+    r0, r1 = records(3, 0, 2), records(3, 1, 2)   # the same cases dealt to two "ranks": 0 -> {0, 2}, 1 -> {1}
+    assert r0[0] == serial[0] and r0[2] == serial[2] and r1[1] == serial[1]
+    assert all(v[0] > 0 and v[2] != 0 for v in serial)

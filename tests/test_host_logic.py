@@ -82,7 +82,8 @@ def _cases_worker(rank, world, port, q):
     a.history = []
     mk = lambda i: {k: torch.full((1, 3, 4, 8), float(i)) for k in ("gt", "yo", "H", "R")} | {"xb": torch.full((3, 4, 8), float(i))}
     r = run_cases(a, 5, mk, rank, world, "cpu")
-    q.put((rank, {k: r[k] for k in ("n_cases", "mean_J", "mean_gmax", "rms_wrmse", "mean_bias", "cases_on_this_rank", "world")}))
+    q.put((rank, {k: r[k] for k in ("n_cases", "mean_J", "mean_gmax", "rms_wrmse", "mean_bias", "cases_on_this_rank", "world", "case_records",
+                                    "seconds_per_rank", "imbalance")}))
     dist.destroy_process_group()
 
 
@@ -101,6 +102,10 @@ def test_run_cases_world2_gloo():
         assert abs(g["mean_J"] - (10.0 + 2.0)) < 1e-12 and abs(g["mean_gmax"] - 1.0) < 1e-12
         assert np.allclose(g["rms_wrmse"], np.sqrt((0 + 1 + 4 + 9 + 16) / 5.0)) and np.allclose(g["mean_bias"], -2.0)
     assert got[0]["rms_wrmse"] == got[1]["rms_wrmse"]
+    # per-case records (final J, z500 WRMSE, checksum of the analysis) are the same on every rank and are those of a serial run:
+    # what `tools/run_cases.py --check` compares bit for bit between an N-GPU and a 1-GPU run
+    assert got[0]["case_records"] == got[1]["case_records"] == [[10.0 + i, float(i), 96.0 * i] for i in range(5)]
+    assert len(got[0]["seconds_per_rank"]) == 2 and got[0]["imbalance"] >= 1.0
 
 
 def test_metric_reduction_world2_gloo():

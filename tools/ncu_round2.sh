@@ -1,17 +1,23 @@
 #!/bin/bash
-# Round-2 profiling pass: ncu --set full captures of the kernels VERDICT r1 names (tower GEMMs, N=1152 trunk GEMMs, window
-# attention, LayerNorm backward) out of ONE eager decoder evaluation (T=1).  Each capture only after the plain command ran clean.
+# Round-2 profiling pass over ONE eager decoder evaluation (T=1, 271 launches): a sections-level capture of every launch
+# (exported to CSV on the box -- the .ncu-rep files are too large to travel) and source-level captures of two kernels.
 #     gpurun --timeout 900 -- 'bash tools/ncu_round2.sh r2_base'
 set -u
 tag=${1:-r2}
 out=gpurun_out
-mkdir -p $out
+tmp=/tmp/ncu_$tag
+mkdir -p $out $tmp
 python tools/profile_step.py --T 1 > $out/${tag}_plain.log 2>&1 || { tail -5 $out/${tag}_plain.log; exit 1; }
 tail -1 $out/${tag}_plain.log
-N="ncu --profile-from-start off --set full --clock-control none"
-$N -k regex:gemm_pair_kernel -c 26 -o $out/${tag}_gemm_fwd -f python tools/profile_step.py --T 1 > $out/${tag}_ncu1.log 2>&1; tail -1 $out/${tag}_ncu1.log
-$N --import-source on -k regex:gemm_pair_kernel -c 4 -o $out/${tag}_gemm_fwd_src -f python tools/profile_step.py --T 1 > $out/${tag}_ncu1s.log 2>&1
-$N -k regex:gemm_pair_kernel -s 87 -c 14 -o $out/${tag}_gemm_bwd -f python tools/profile_step.py --T 1 > $out/${tag}_ncu2.log 2>&1
-$N --import-source on -k "regex:attn_kernel|ln_bwd_kernel|ln_fwd_kernel|p2t_kernel|t2p_kernel" -c 14 -o $out/${tag}_misc_fwd -f python tools/profile_step.py --T 1 > $out/${tag}_ncu3.log 2>&1
-$N --import-source on -k "regex:attn_kernel|ln_bwd_kernel|ln_fwd_kernel|p2t_kernel|t2p_kernel" -s 30 -c 16 -o $out/${tag}_misc_bwd -f python tools/profile_step.py --T 1 > $out/${tag}_ncu4.log 2>&1
-ls -la $out/${tag}_*.ncu-rep
+SEC="--section SpeedOfLight --section WarpStateStats --section SchedulerStats --section LaunchStats --section Occupancy --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section InstructionStats"
+ncu --profile-from-start off $SEC --clock-control none -o $tmp/all -f python tools/profile_step.py --T 1 > $out/${tag}_ncu_all.log 2>&1
+tail -1 $out/${tag}_ncu_all.log
+ncu -i $tmp/all.ncu-rep --page raw --csv > $out/${tag}_all_raw.csv 2>/dev/null; wc -c $out/${tag}_all_raw.csv
+# source-level: the batched tower fc1 GEMM (LN-consume + GELU; 3rd GEMM launch) and the first trunk attention forward
+ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:gemm_pair_kernel -s 2 -c 1 -o $tmp/fc1 -f \
+    python tools/profile_step.py --T 1 > $out/${tag}_ncu_fc1.log 2>&1
+ncu -i $tmp/fc1.ncu-rep --page source --csv > $out/${tag}_fc1_source.csv 2>/dev/null
+ncu -i $tmp/fc1.ncu-rep --page raw --csv > $out/${tag}_fc1_raw.csv 2>/dev/null
+wc -c $out/${tag}_fc1_source.csv
+gzip -f $out/${tag}_fc1_source.csv
+ls -la $out/${tag}_*

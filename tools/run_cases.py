@@ -25,6 +25,8 @@ ap.add_argument("--T", type=int, default=6)
 ap.add_argument("--nit", type=int, default=1)
 ap.add_argument("--obs-frac", type=float, default=0.10)
 ap.add_argument("--small", action="store_true", help="shrunken networks on a 32x64 grid (smoke test)")
+ap.add_argument("--out", default="", help="write the JSON result (with the per-case records) to this file as well")
+ap.add_argument("--check", default="", help="a result file of another run (e.g. 1 GPU): the per-case records must be bit-identical")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
 torch.cuda.set_device(local)
@@ -41,8 +43,16 @@ for v in agent.metrics_list.values():
     v.clear()
 r = run_cases(agent, a.cases, mk, rank, world, dev)
 if rank == 0:
-    r.update(T=a.T, nit=a.nit, obs_frac=a.obs_frac, small=a.small, rms_wrmse_z500=r["rms_wrmse"][11])
+    r.update(T=a.T, nit=a.nit, obs_frac=a.obs_frac, small=a.small, rms_wrmse_z500=r["rms_wrmse"][11], config="BASELINE.json configs[3]")
     r.pop("rms_wrmse"); r.pop("mean_bias")
-    print(json.dumps(r))
+    if a.check:          # "N cases on N GPUs == the same cases on 1 GPU", per case, bit for bit
+        other = json.loads(pathlib.Path(a.check).read_text())["case_records"]
+        n = min(len(other), len(r["case_records"]))
+        r["identical_to"] = {"file": a.check, "cases_compared": n, "bit_identical": r["case_records"][:n] == other[:n]}
+    if a.out:
+        pathlib.Path(a.out).parent.mkdir(parents=True, exist_ok=True)
+        pathlib.Path(a.out).write_text(json.dumps(r))
+    brief = dict(r); brief["case_records"] = brief["case_records"][:2] + ["..."]
+    print(json.dumps(brief))
 if world > 1:
     dist.destroy_process_group()

@@ -48,23 +48,36 @@ def run_cases(agent, n_cases: int, make_case_fn: Callable[[int], Dict], rank: in
     the elapsed time is the maximum over ranks.  Returns the summary with `cases_per_hour` (identical on every rank)."""
     acc = MetricAccumulator(agent.nchannel, device)
     cuda = torch.device(device).type == "cuda"
-    if dist.is_available() and dist.is_initialized() and world > 1:
+    multi = dist.is_available() and dist.is_initialized() and world > 1
+    if multi:
         dist.barrier()
     if cuda:
         torch.cuda.synchronize()
     t0 = time.time()
     mine = shard_cases(n_cases, rank, world)
+    records = torch.zeros(n_cases, 3, dtype=torch.float64, device=device)       # per case: final J, z500 analysis WRMSE, checksum of xa
     for i in mine:
         c = make_case_fn(i)
-        agent.one_step_DA(c["gt"], c["xb"], c["yo"], c["H"], c["R"], "vae4dvar")
+        xa = agent.one_step_DA(c["gt"], c["xb"], c["yo"], c["H"], c["R"], "vae4dvar")
         info = agent.history[-1]
         acc.add(float(info["loss"]), float(info["gmax"]), agent.metrics_list["ana_wrmse"][-1], agent.metrics_list["ana_bias"][-1])
+        records[i, 0] = float(info["loss"])
+        records[i, 1] = float(agent.metrics_list["ana_wrmse"][-1][min(11, agent.nchannel - 1)])      # z500 (da_4dvar.py:1253)
+        records[i, 2] = float(torch.as_tensor(xa).double().sum())
     if cuda:
         torch.cuda.synchronize()
-    el = torch.tensor([time.time() - t0], dtype=torch.float64, device=device)
-    if dist.is_available() and dist.is_initialized() and world > 1:
+    mine_s = time.time() - t0
+    el = torch.tensor([mine_s], dtype=torch.float64, device=device)
+    per_rank = torch.zeros(world, dtype=torch.float64, device=device)
+    per_rank[rank] = mine_s
+    if multi:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        dist.all_reduce(records, op=dist.ReduceOp.SUM)          # every case was written by exactly one rank
     acc.reduce()
     out = acc.summary()
-    out.update(seconds=float(el), cases_per_hour=3600.0 * out["n_cases"] / max(float(el), 1e-9), world=world, cases_on_this_rank=len(mine))
+    pr = per_rank.tolist()
+    out.update(seconds=float(el), cases_per_hour=3600.0 * out["n_cases"] / max(float(el), 1e-9), world=world, cases_on_this_rank=len(mine),
+               seconds_per_rank=pr, imbalance=(max(pr) / max(min(pr), 1e-9)) if pr else 1.0,
+               case_records=[[float(v) for v in r] for r in records.cpu()])
     return out
