@@ -231,6 +231,48 @@ VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_ou
 /* Number of kernel launches the last vv_cost_grad enqueued (for bench.py's gpu_launches). */
 VV_API int vv_last_launch_count(vv_engine* e);
 
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * The forecast network LGUnet_all_1 (networks/LGUnet_all.py:743-777; da_4dvar.py:555 builds it, :1329 applies it once per cycle
+ * through integrate(xa, forecast_model, 1), :666-681).  Forward only -- the DA loop never differentiates it (detach=True).
+ * Its own handle: the network lives on the reference's native 721x1440 grid with patch (3, 2) / stride 2, three tower levels,
+ * SD_attn (2-D RoPE, wh x ww windows, 0 / -inf latitude shift mask; networks/utils/Attention.py:467-664) and a first trunk stage
+ * that attends over the whole token grid.
+ * ------------------------------------------------------------------------------------------------------------------------------ */
+#define VV_NET1_MAX_LEVELS 4
+typedef struct {
+  int img_h, img_w;              /* img_size; must be covered exactly by the (3, 2) kernel at stride 2 (721x1440 -> 360x720) */
+  int n_groups;
+  int in_chans[VV_MAX_GROUPS];   /* inchans_list  */
+  int out_chans[VV_MAX_GROUPS];  /* outchans_list (mean | std halves per group) */
+  int enc_dim, embed_dim;
+  int win_h, win_w;              /* window_size */
+  int n_levels;                  /* len(enc_depths) */
+  int enc_depth[VV_NET1_MAX_LEVELS], enc_heads[VV_NET1_MAX_LEVELS];
+  int n_lg;
+  int lg_depth[VV_MAX_LG], lg_heads[VV_MAX_LG];
+  int keep_out;                  /* leading output channels produced (69 for `model(x)[:, :69]`, da_4dvar.py:674); 0 = all */
+} vv_net1_config;
+typedef struct vv_net1 vv_net1;
+
+/* init_model_forecast (da_4dvar.py:548-569): LGUnet_all_1(**params), load_state_dict by name, eval(). */
+VV_API int vv_net1_create(const vv_net1_config* cfg, vv_net1** out);
+VV_API void vv_net1_destroy(vv_net1* n);
+VV_API int vv_net1_set_weight(vv_net1* n, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+VV_API int vv_net1_finalize(vv_net1* n);
+/* LGUnet_all_1.forward (networks/LGUnet_all.py:772-777) on one sample: in (sum in_chans, H, W) -> out (keep_out, H, W), fp32. */
+VV_API int vv_net1_forward(vv_net1* n, const float* in_dev, float* out_dev, void* stream);
+/* get_model_mean_std (da_4dvar.py:640-647) for vv_net1_integrate: host pointers, sum(in_chans) floats each. */
+VV_API int vv_net1_set_constants(vv_net1* n, const float* mean, const float* std);
+/* cyclic_4dvar.integrate(xa, forecast_model, steps) (da_4dvar.py:666-681, interpolation=False): physical state in -> physical
+ * state out, (x - mean) / std -> model(.)[:, :C] `steps` times -> * std + mean. */
+VV_API int vv_net1_integrate(vv_net1* n, const float* x_in_dev, float* x_out_dev, int steps, void* stream);
+VV_API int vv_net1_last_launch_count(vv_net1* n);
+VV_API long long vv_net1_device_bytes(vv_net1* n);
+/* Kernel-level hook: rope2 (positional_encodings.py:255-268; skipped when table_dev is null) + the SD_attn core
+ * (Attention.py:560-640) on a packed fp16 qkv buffer [gh * gw][3 * heads * hd] -> out fp16 [gh * gw][heads * hd]. */
+VV_API int vv_test_attn1(void* qkv_dev, void* out_dev, const float* table_dev, int gh, int gw, int wh, int ww, int sh, int sw, int heads, int hd,
+                         int mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

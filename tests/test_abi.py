@@ -76,3 +76,22 @@ def test_seam_index_tables_follow_the_reference_rule(lib, gold, lr, hr):
         assert lo[0] == 0 and lo[n] == n and (np.diff(lo) >= 0).all()
         for r in range(n):
             assert (tab[lo[r]:lo[r + 1]] == r).all() and (tab[:lo[r]] < r).all() and (tab[lo[r + 1]:] > r).all()
+
+
+def test_net1_config_struct_layout_matches_header():
+    from vaevar_b200 import _lib
+    # img_h, img_w, n_groups | in 8 | out 8 | enc_dim, embed_dim, win_h, win_w, n_levels | depth 4 | heads 4 | n_lg | 8 | 8 | keep_out
+    assert ctypes.sizeof(_lib.Net1ConfigC) == 4 * (3 + 8 + 8 + 5 + 4 + 4 + 1 + 8 + 8 + 1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_forecast_net_has_no_fallback_without_gpu():
+    from vaevar_b200.config import FORECAST_MID
+    from vaevar_b200.forecast import ForecastNet
+    from vaevar_b200.modules import LGUnet_all_1
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ForecastNet(FORECAST_MID)
+    m = LGUnet_all_1(**FORECAST_MID.to_reference_kwargs())
+    assert len(list(m.state_dict())) == 1079
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 69, 97, 192))

@@ -183,3 +183,24 @@ def test_lgunet_all_1_oracle_matches_reference(gold):
     m = shift_mask(24, 48, (6, 12), (3, 6))
     assert m.shape == (16, 72, 72) and float(m[:12].abs().sum()) == 0.0
     assert all(torch.equal(m[12], m[k]) for k in range(13, 16)) and set(np.unique(m[12].numpy())) == {-np.inf, 0.0}
+
+
+def test_lgunet_all_1_oracle_matches_reference_mid(gold):
+    """The mid-size fixture the CUDA path is checked against (head widths 32 / 32 / 64 / 192, a 288-token whole-grid stage, shifted
+    and masked windows on every level): the oracle agrees with the reference module's own output, and the product's parameter list
+    (names, shapes, order) is the reference module's state_dict."""
+    from oracle.lgunet1 import lgunet1_forward
+    from vaevar_b200.config import FORECAST_MID
+    from vaevar_b200.synth import make_state_dict_net1, net1_param_shapes
+    g = gold("net1_mid.npz")
+    shapes = net1_param_shapes(FORECAST_MID)
+    assert [str(n) for n in g["names"]] == list(shapes)
+    assert [tuple(eval(str(s))) for s in g["shapes"]] == [tuple(v) for v in shapes.values()]
+    sd = {k: torch.from_numpy(v) for k, v in make_state_dict_net1(FORECAST_MID, seed=int(g["seed"]), rich=True).items()}
+    x = torch.from_numpy(np.random.Generator(np.random.PCG64(int(g["x_seed"]))).standard_normal((1, 69, *FORECAST_MID.img_size), dtype=np.float32))
+    with torch.no_grad():
+        y = lgunet1_forward(x, sd, FORECAST_MID).numpy()
+    assert tuple(y.shape) == tuple(g["y_shape"]) == (1, 138, 97, 192)
+    y69 = y[0, :69]
+    np.testing.assert_allclose(y69.ravel()[g["y_idx"]], g["y_val"], rtol=5e-4, atol=5e-5)
+    assert abs(np.abs(y69.astype(np.float64)).sum() / float(g["y_abs"]) - 1) < 1e-5

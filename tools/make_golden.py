@@ -226,6 +226,36 @@ def golden_lgunet1():
     print(f"net1_small: {len(shapes)} tensors, {sum(int(np.prod(s)) for s in shapes.values())} params, |y|_1={np.abs(y).sum():.6g}")
 
 
+def golden_lgunet1_mid():
+    """LGUnet_all_1 at a mid-size configuration the CUDA path supports (enc_dim 96, head widths 32 / 32 / 64 / 192, three tower levels,
+    6 x 12 windows with 2 x 2 or more windows per level, a 288-token whole-grid trunk stage), run by the reference module itself on
+    weights of vaevar_b200.synth.make_state_dict_net1 (rich: no silent parameter).  Stores sampled outputs of the first 69 channels
+    (what `model(x)[:, :69]` keeps, da_4dvar.py:674) and of the whole output."""
+    from networks.LGUnet_all import LGUnet_all_1
+    from vaevar_b200.config import FORECAST_MID
+    from vaevar_b200.synth import make_state_dict_net1
+    cfg = FORECAST_MID
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = LGUnet_all_1(**cfg.to_reference_kwargs()).eval()
+    sd = make_state_dict_net1(cfg, seed=11, rich=True)
+    ref_shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert list(ref_shapes.items()) == [(k, tuple(v.shape)) for k, v in sd.items()], "net1_param_shapes disagrees with the reference module"
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    rng = np.random.Generator(np.random.PCG64(321))
+    x = rng.standard_normal((1, 69, *cfg.img_size), dtype=np.float32)
+    t0 = time.time()
+    with torch.no_grad():
+        y = net(torch.from_numpy(x)).numpy()
+    y69 = np.ascontiguousarray(y[0, :69])
+    iy = sample_idx(y69.size, 16384, seed=13)
+    np.savez_compressed(GOLD / "net1_mid.npz", names=np.array(list(ref_shapes)), shapes=np.array([str(list(s)) for s in ref_shapes.values()]),
+                        seed=11, x_seed=321, y_idx=iy, y_val=y69.ravel()[iy], y_abs=np.float64(np.abs(y69.astype(np.float64)).sum()),
+                        y_max=np.float64(np.abs(y69).max()), y_rms=np.float64(np.sqrt((y69.astype(np.float64) ** 2).mean())),
+                        y_chan_rms=np.sqrt((y69.astype(np.float64) ** 2).mean(axis=(1, 2))), y_shape=np.array(y.shape))
+    print(f"net1_mid: {len(sd)} tensors, {sum(v.size for v in sd.values())} params, |y|_1={np.abs(y69).sum():.6g} rms={np.sqrt((y69 ** 2).mean()):.4g} "
+          f"max={np.abs(y69).max():.4g} ({time.time() - t0:.1f} s)")
+
+
 def golden_metrics():
     from utils.metrics import Metrics
     rng = np.random.Generator(np.random.PCG64(5))
@@ -271,6 +301,7 @@ if __name__ == "__main__":
         "cost_native_T3_rich": lambda: golden_cost_native("native_T3_rich", ds, fs, 3, (181, 360), 0.10, 4, 3.0, True),
         "obs_interp": golden_obs_interp,
         "net1_small": golden_lgunet1,
+        "net1_mid": golden_lgunet1_mid,
         "cost_realobs_T2": lambda: golden_real_obs("realobs_T2", ds, fs, 2, ds.img_size, 5),
         "cost_realobs_native_T2": lambda: golden_real_obs("realobs_native_T2", ds, fs, 2, (181, 360), 6),
         "cost_native_T3_plain": lambda: golden_cost_native("native_T3_plain", ds, fs, 3, (181, 360), 0.10, 0, 1.0, False),

@@ -24,6 +24,17 @@ class ConfigC(C.Structure):
                 ("recompute", C.c_int), ("use_graph", C.c_int), ("forward_fp16", C.c_int), ("no_ln_fold", C.c_int)]
 
 
+VV_NET1_MAX_LEVELS = 4
+
+
+class Net1ConfigC(C.Structure):
+    _fields_ = [("img_h", C.c_int), ("img_w", C.c_int), ("n_groups", C.c_int),
+                ("in_chans", C.c_int * VV_MAX_GROUPS), ("out_chans", C.c_int * VV_MAX_GROUPS),
+                ("enc_dim", C.c_int), ("embed_dim", C.c_int), ("win_h", C.c_int), ("win_w", C.c_int), ("n_levels", C.c_int),
+                ("enc_depth", C.c_int * VV_NET1_MAX_LEVELS), ("enc_heads", C.c_int * VV_NET1_MAX_LEVELS), ("n_lg", C.c_int),
+                ("lg_depth", C.c_int * VV_MAX_LG), ("lg_heads", C.c_int * VV_MAX_LG), ("keep_out", C.c_int)]
+
+
 _P = C.c_void_p
 _SIGS = {
     "vv_last_error": (C.c_char_p, []),
@@ -74,6 +85,16 @@ _SIGS = {
     "vv_obs_term_work_doubles": (C.c_int64, []),
     "vv_debug_seam_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vv_obs_term": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, _P, _P, C.c_int64, _P, _P]),
+    "vv_net1_create": (C.c_int, [C.POINTER(Net1ConfigC), C.POINTER(_P)]),
+    "vv_net1_destroy": (None, [_P]),
+    "vv_net1_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "vv_net1_finalize": (C.c_int, [_P]),
+    "vv_net1_forward": (C.c_int, [_P, _P, _P, _P]),
+    "vv_net1_set_constants": (C.c_int, [_P, _P, _P]),
+    "vv_net1_integrate": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "vv_net1_last_launch_count": (C.c_int, [_P]),
+    "vv_net1_device_bytes": (C.c_longlong, [_P]),
+    "vv_test_attn1": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 EXPORTED = tuple(_SIGS)
 

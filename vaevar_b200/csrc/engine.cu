@@ -82,6 +82,14 @@ __global__ void finalize_J_kernel(const double* dots, const double* jobs, float 
   out[0] = jr + (double)coeff * jobs[0];
 }
 
+void launch_pack_w(bf16* dst, bf16* dstT, const float* src, int rows, int cols, int f16) {
+  pack_w_kernel<<<592, 256>>>(dst, dstT, src, rows, cols, f16);
+}
+void launch_fold_ln(bf16* dst, float* colsum, float* cbias, const float* W, const float* gamma, const float* beta, const float* bias,
+                    int rows, int cols, int f16) {
+  fold_ln_kernel<<<(rows + 7) / 8, 256>>>(dst, colsum, cbias, W, gamma, beta, bias, rows, cols, f16);
+}
+
 int Plan::run(cudaStream_t s) const {
   for (const Op& o : ops) {
     switch (o.kind) {
@@ -92,12 +100,15 @@ int Plan::run(cudaStream_t s) const {
       case Op::ATT_B: launch_attn_bwd(o.att, s); break;
       case Op::P2T: launch_p2t(o.patch, s); break;
       case Op::T2P: launch_t2p(o.patch, s); break;
+      case Op::ROPE: launch_rope(o.rope, s); break;
+      case Op::ATT1: launch_attn1(o.att1, s); break;
+      case Op::PE32: launch_patch32(o.pe32, s); break;
+      case Op::CT32: launch_convt32(o.ct32, s); break;
     }
   }
   return (int)ops.size();
 }
 
-bool ln_supported(int map, int C);
 bool p2t_supported(int D);
 
 }  // namespace vv

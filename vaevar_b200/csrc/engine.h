@@ -10,14 +10,23 @@
 namespace vv {
 
 void set_error(const char* fmt, ...);
+// weight packing shared by engine.cu and net1.cu (definitions in engine.cu)
+void launch_pack_w(bf16* dst, bf16* dstT, const float* src, int rows, int cols, int f16);
+void launch_fold_ln(bf16* dst, float* colsum, float* cbias, const float* W, const float* gamma, const float* beta, const float* bias,
+                    int rows, int cols, int f16);
+bool ln_supported(int map, int C);
 
 struct Op {
-  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P } kind;
+  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P, ROPE, ATT1, PE32, CT32 } kind;
   GemmDesc gemm;
   LnArgs lnf;
   LnBwdArgs lnb;
   AttnArgs att;
   PatchArgs patch;
+  RopeArgs rope;         // the last four: forecast network LGUnet_all_1 (net1.cu)
+  Attn1Args att1;
+  Patch32Args pe32;
+  ConvT32Args ct32;
 };
 struct Plan {
   std::vector<Op> ops;

@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       case 288: VV_LN_CASE(KERNEL, ARGS, 32, 9, MAP_PLAIN); break;    /* C = 1152 */     \
       case 1064: VV_LN_CASE(KERNEL, ARGS, 32, 2, MAP_MERGE); break;   /* C = 256  */     \
       case 1096: VV_LN_CASE(KERNEL, ARGS, 32, 3, MAP_MERGE); break;   /* C = 384  */     \
+      case 1192: VV_LN_CASE(KERNEL, ARGS, 32, 6, MAP_MERGE); break;   /* C = 768  */     \
+      case 2048: VV_LN_CASE(KERNEL, ARGS, 16, 3, MAP_EXPAND); break;  /* C = 192  */     \
       case 2016: VV_LN_CASE(KERNEL, ARGS, 8, 2, MAP_EXPAND); break;   /* C = 64   */     \
       case 2024: VV_LN_CASE(KERNEL, ARGS, 8, 3, MAP_EXPAND); break;   /* C = 96   */     \
       default: break;                                                                    \
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 bool ln_supported(int map, int C) {
   if (C % 32) return false;
   switch (map * 1000 + C / 4) {
-    case 16: case 24: case 32: case 48: case 96: case 288: case 1064: case 1096: case 2016: case 2024: return true;
+    case 16: case 24: case 32: case 48: case 96: case 288: case 1064: case 1096: case 1192: case 2016: case 2024: case 2048: return true;
     default: return false;
   }
 }

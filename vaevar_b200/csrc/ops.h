@@ -156,3 +156,58 @@ void launch_metrics(const float* x, const float* gt, const float* mean, const fl
 int reduce_blocks();  // number of blocks the reduction kernels use (size of scratch in doubles * 4)
 
 }  // namespace vv
+
+// =================================================================================================
+// Forecast network LGUnet_all_1 (networks/LGUnet_all.py:743-777), forward only -- kernels it needs beyond the ones above.
+// =================================================================================================
+namespace vv {
+
+// rope2 (networks/utils/positional_encodings.py:230-268) applied in place to the q and k thirds of a 16-bit qkv buffer.
+// A token's position is its (row, col) inside its (shifted) window; table[pos][j] = (cos, sin) of the angle of pair j < hd / 2
+// (pairs j < hd / 4 rotate with the row, the others with the column); the pair is (x[j], x[hd / 2 + j]).
+struct RopeArgs {
+  int gh, gw, wh, ww, sh, sw, heads, hd, batch;
+  bf16* qkv; long long ld_qkv, qkv_bs;
+  const float2* table;         // [wh * ww][hd / 2]
+};
+void launch_rope(const RopeArgs& a, cudaStream_t s);
+
+// SD_attn (networks/utils/Attention.py:551-650, dilation 1) on rotated q, k: softmax(scale q k^T + mask) v over windows of
+// wh x ww tokens of the rolled frame (roll by -(sh, sw), Attention.py:560), any window size up to the whole grid (the first
+// LG stage, networks/LGUnet_all.py:689), flash-style (online softmax over key tiles).  mask: 0 / -inf between the two latitude
+// bands of the last window row of a shifted frame (create_mask, Attention.py:520-548; longitude never masks).
+struct Attn1Args {
+  int gh, gw, wh, ww, sh, sw, heads, hd, batch, mask;
+  const bf16* qkv; long long ld_qkv, qkv_bs;     // fp16 [batch][gh * gw][3 * heads * hd]
+  bf16* out; long long ld_o, o_bs;               // fp16 [batch][gh * gw][heads * hd]
+  float scale;
+};
+void launch_attn1(const Attn1Args& a, cudaStream_t s);
+bool attn1_supported(int hd);
+
+// PatchEmbed with a 3 x 2 kernel and stride 2 (networks/LGUnet_all.py:14-50) + absolute position embedding (:396-400):
+// tok[g][i * w0 + j][c] = bias[g][c] + ape[g][tok][c] + sum_{ci, kr, kc} W[g][(ci * 3 + kr) * 2 + kc][c] img[chan(g, ci)][2 i + kr][2 j + kc]
+struct Patch32Args {
+  int H, W, h0, w0, G, D;
+  const int* kcnt; const int* cbase;             // channels per group, first NCHW channel of the group (device)
+  const float* Wp;                               // [sum_g kcnt[g] * 6][D], rows of group g start at cbase[g] * 6
+  const float* bias;                             // [G][D]
+  const float* ape;                              // [G][h0 * w0][D]
+  const float* img; float* tok;
+  int max_cnt;
+};
+void launch_patch32(const Patch32Args& a, cudaStream_t s);
+
+// The ConvTranspose2d head, kernel 3 x 2 / stride 2 (networks/LGUnet_all.py:606-650): adjacent patch rows overlap-add on even
+// image rows.  img[chan[slot]][y][x] = bias[slot] + sum_c sum_{(i, kr): 2 i + kr = y} tok[g][i * w0 + x / 2][c] Wt[slot][kr][x % 2][c]
+struct ConvT32Args {
+  int H, W, h0, w0, G, D;
+  const int* kcnt; const int* cbase; const int* chan;   // per group: output slots, first slot; NCHW channel of every slot (device)
+  const float* Wt;                               // [slots][3][2][D]
+  const float* bias;                             // [slots]
+  const float* tok; float* img;
+  int max_cnt;
+};
+void launch_convt32(const ConvT32Args& a, cudaStream_t s);
+
+}  // namespace vv

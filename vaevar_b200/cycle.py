@@ -5,9 +5,9 @@
     save_eval_result / load_eval_ckpts  da_4dvar.py:704-727   (metric .npy dumps)
     get_obs_info ("free" observations)  da_4dvar.py:758-805, 276-292, 442-450
 
-The reference fetches the truth from an S3 store (data_reader.get_state, da_4dvar.py:148-166) and forecasts with the 0.25-degree
-LGUnet_all_1; neither exists offline, so here the observation source is pluggable (`ObsSource`) and the forecast step is the flow
-model applied on the engine grid (stated, not hidden).  `TwinObs` is the identical-twin source the synthetic
+The reference fetches the truth from an S3 store (data_reader.get_state, da_4dvar.py:148-166), which does not exist offline, so the
+observation source is pluggable (`ObsSource`).  The forecast step is `agent.forecast_model` (an `LGUnet_all_1` shell on the analysis
+grid, da_4dvar.py:484, 1329) when the agent has one, else the flow model applied on the engine grid.  `TwinObs` is the identical-twin source the synthetic
 configs use: a truth run advanced by the same flow model, observed noise-free through a fixed random column mask.
 """
 from __future__ import annotations
@@ -153,7 +153,7 @@ class CycledDA:
             t0 = time.time()
             xa = a.one_step_DA(gt, self.xb, yo, H, R, "vae4dvar")
             self.save_eval_result(xa)
-            self.xb = a.integrate(xa, None, self.forecast_steps)
+            self.xb = a.integrate(xa, getattr(a, "forecast_model", None), self.forecast_steps)     # da_4dvar.py:1329
             if torch.device(a.device).type == "cuda":
                 torch.cuda.synchronize()
             self.current_cycle += 1

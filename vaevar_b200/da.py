@@ -75,7 +75,8 @@ class VaeVar4D:
     def __init__(self, dec_cfg: NetConfig, flow_cfg: Optional[NetConfig], dec_sd: Dict, flow_sd: Optional[Dict],
                  da_win: int = 1, Nit: int = 4, obs_coeff: float = 1.0, device: str = "cuda:0",
                  recompute: bool = False, use_graph: bool = True, verbose: bool = True, engine: Optional[Engine] = None,
-                 obs_type: str = "free", interp_dim: int = 40):
+                 obs_type: str = "free", interp_dim: int = 40, forecast_model=None):
+        self.forecast_model = forecast_model                                 # da_4dvar.py:484: LGUnet_all_1 on the analysis grid, or None
         self.obs_type = obs_type                                             # da_4dvar.py:476; "real..." selects the augmented obs space
         self.obs_interp = obs_interpolater(13, interp_dim)                   # da_4dvar.py:493
         self.da_win, self.Nit, self.obs_coeff, self.verbose = da_win, Nit, obs_coeff, verbose
@@ -106,11 +107,13 @@ class VaeVar4D:
         `interpolation` the field is brought to the network grid and back with the reference's nearest rule (:670-671, 678-679);
         the per-channel (de)normalisation commutes with that index map, so it stays inside the engine call."""
         xa = xa.to(self.device, torch.float32)
+        if model is not None and hasattr(model, "integrate") and not interpolation:
+            # run_assimilation's forecast: the native-resolution LGUnet_all_1 applied to the analysis on its own grid (da_4dvar.py:1329)
+            return model.integrate(xa, step)
         if tuple(xa.shape[-2:]) == (self.nlat, self.nlon):
             return self.engine.integrate(xa, step)
         if not interpolation and self.verbose:
-            # run_assimilation forecasts with a native-resolution model (LGUnet_all_1, da_4dvar.py:1329); until that network lands
-            # the forecast of a native-resolution analysis is the flow model behind the two seams
+            # no forecast model on the analysis grid was given: the flow model behind the two seams stands in for it
             print("integrate: field is on the analysis grid, resampling to the network grid and back", flush=True)
         from .seams import resample_nearest
         x = self.engine.integrate(resample_nearest(xa, (self.nlat, self.nlon)), step)

@@ -1,6 +1,7 @@
 """Drop-in shells with the reference's module call surface, backed by the CUDA engine.
 
     LGUnet_all   networks_old/transformer.py:716-752   (constructor keywords :717-718, forward :747-752)
+    LGUnet_all_1 networks/LGUnet_all.py:743-777        (the 0.25-degree forecast model; forward only, da_4dvar.py:555, 1329)
     VAE_lr       nf_model/vae.py:53-102                (encoder/decoder/decoder_hr/forward, .enc / .dec)
 
 Parameters live in ordinary nn.Parameters under the reference's state_dict names (so reference checkpoints load
@@ -16,9 +17,10 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from .config import DECODER_FULL, ENCODER_FULL, NetConfig
+from .config import DECODER_FULL, ENCODER_FULL, Net1Config, NetConfig
 from .engine import Engine
-from .synth import make_state_dict
+from .forecast import ForecastNet
+from .synth import make_state_dict, make_state_dict_net1
 
 
 class _Node(nn.Module):
@@ -98,6 +100,63 @@ class LGUnet_all(nn.Module):
     def forward(self, data: torch.Tensor) -> torch.Tensor:
         """(B, sum C_in, H, W) -> (B, sum C_out, H, W); transformer.py:747-752."""
         return _NetFn.apply(data, self)
+
+
+class LGUnet_all_1(nn.Module):
+    """networks/LGUnet_all.py:743-777.  The DA driver builds it in init_model_forecast (da_4dvar.py:548-569), keeps it in eval
+    mode under no_grad semantics (`integrate(..., detach=True)`, :666-681) and reads `model(x)[:, :69]`; the shell therefore
+    produces no gradients at all.  `keep_out` (default: every output channel) lets a caller that only wants the mean channels skip
+    the std half of the ConvTranspose2d head."""
+
+    def __init__(self, img_size=(32, 64), patch_size=(1, 1, 1), stride=(2, 2), in_chans=20, out_chans=20, enc_depths=(2, 2),
+                 enc_heads=(3, 6), lg_depths=(), lg_heads=(), inchans_list=(20,), outchans_list=(20,), enc_dim=96, embed_dim=768,
+                 window_size=(4, 8), Weather_T=16, drop_rate=0., attn_drop_rate=0., drop_path=0., use_checkpoint=False, channel_num=37,
+                 inp_length=1, use_mlp=False, pre_norm=True, seed: int = 0, keep_out: int = 0):
+        super().__init__()
+        if tuple(patch_size)[-2:] != (3, 2) or tuple(stride) != (2, 2) or inp_length != 1:
+            raise NotImplementedError("only patch (3, 2) / stride (2, 2) / inp_length 1 (model_0.25degree/training_options.yaml:64-119) is built")
+        if drop_rate or attn_drop_rate or drop_path:
+            raise NotImplementedError("dropout / drop-path are training-only; the DA path runs in eval mode")
+        if use_mlp or not pre_norm:
+            raise NotImplementedError("use_mlp / post-norm blocks are not part of the shipped forecast model")
+        self.cfg = Net1Config(img_size=tuple(img_size), patch_size=tuple(patch_size)[-2:], stride=tuple(stride),
+                              inchans_list=tuple(inchans_list), outchans_list=tuple(outchans_list), enc_dim=enc_dim, embed_dim=embed_dim,
+                              window_size=tuple(window_size), enc_depths=tuple(enc_depths), enc_heads=tuple(enc_heads),
+                              lg_depths=tuple(lg_depths), lg_heads=tuple(lg_heads))
+        self.keep_out = int(keep_out)
+        for k, v in make_state_dict_net1(self.cfg, seed=seed).items():
+            _install(self, k, torch.from_numpy(v))
+        self._eng: Optional[ForecastNet] = None
+        self._eng_version = None
+
+    def _version(self):
+        return tuple(p._version for p in self.parameters()) + (str(next(self.parameters()).device),)
+
+    def _engine(self) -> ForecastNet:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("vaevar_b200.LGUnet_all_1 runs on a CUDA device only (no CPU fallback): call .to('cuda') first")
+        v = self._version()
+        if self._eng is None or v != self._eng_version:
+            if self._eng is not None:
+                self._eng.close()
+            eng = ForecastNet(self.cfg, keep_out=self.keep_out, device=str(dev))
+            eng.load_state_dict({k: p.data for k, p in self.named_parameters()})
+            eng.finalize()
+            self._eng, self._eng_version = eng, v
+        return self._eng
+
+    def forward(self, data: torch.Tensor, **kwargs) -> torch.Tensor:
+        """(B, sum C_in, H, W) -> (B, keep_out or sum C_out, H, W); networks/LGUnet_all.py:772-777.  No autograd graph."""
+        eng = self._engine()
+        with torch.no_grad():
+            return torch.stack([eng.forward(data[b].float()) for b in range(data.shape[0])], 0)
+
+    def integrate(self, xa: torch.Tensor, steps: int = 1) -> torch.Tensor:
+        """cyclic_4dvar.integrate(xa, self, steps) in one library call (da_4dvar.py:666-681): physical (69, H, W) in and out."""
+        if self.keep_out != self.cfg.in_chans:
+            raise RuntimeError("integrate needs keep_out == number of state channels (69): the model must map the state onto itself")
+        return self._engine().integrate(xa, steps)
 
 
 def _yaml_config(param_path: str) -> Dict[str, Dict]:

@@ -170,3 +170,86 @@ def make_real_obs(gt: np.ndarray, interp: np.ndarray, frac: float = 0.02, seed: 
     var = obs_variance(obs_std, 2).astype(np.float32).reshape(1, 69, 1, 1)
     R = np.broadcast_to(aug(np.broadcast_to(var, (T, 69, 1, 1))), gt_aug.shape).copy()
     return dict(yo=(gt_aug * H).astype(np.float32), H=H, R=R)
+
+
+def net1_param_shapes(cfg) -> Dict[str, tuple]:
+    """state_dict names and shapes of `LGUnet_all_1` (networks/LGUnet_all.py:743-777), in the reference's registration order per
+    module; pinned to the reference module's own state_dict by tests/test_host_logic.py (fixture tests/golden/net1_mid.npz)."""
+    sh: Dict[str, tuple] = {}
+    G, D, E = cfg.groups, cfg.enc_dim, cfg.embed_dim
+    nl = len(cfg.enc_depths)
+    h0, w0 = cfg.patches
+    kh, kw = cfg.patch_size
+
+    def block(p, d):
+        sh[p + ".norm.weight"] = (d,); sh[p + ".norm.bias"] = (d,)
+        sh[p + ".attn.qkv.weight"] = (3 * d, d); sh[p + ".attn.qkv.bias"] = (3 * d,)
+        sh[p + ".attn.proj.weight"] = (d, d); sh[p + ".attn.proj.bias"] = (d,)
+        sh[p + ".norm2.weight"] = (d,); sh[p + ".norm2.bias"] = (d,)
+        sh[p + ".mlp.fc1.weight"] = (4 * d, d); sh[p + ".mlp.fc1.bias"] = (4 * d,)
+        sh[p + ".mlp.fc2.weight"] = (d, 4 * d); sh[p + ".mlp.fc2.bias"] = (d,)
+
+    for g in range(G):
+        p = f"enc.enc_list.{g}"
+        sh[p + ".absolute_pos_embed"] = (1, h0 * w0, D)
+        sh[p + ".patch_embed.proj.weight"] = (D, cfg.inchans_list[g], kh, kw)
+        sh[p + ".patch_embed.proj.bias"] = (D,)
+        for l in range(nl):
+            d = D << l
+            for b in range(cfg.enc_depths[l]):
+                block(f"{p}.layers.{l}.blocks.{b}", d)
+            if l > 0:
+                sh[f"{p}.layers.{l}.downsample.reduction.weight"] = (d, 2 * d)
+                sh[f"{p}.layers.{l}.downsample.norm.weight"] = (2 * d,); sh[f"{p}.layers.{l}.downsample.norm.bias"] = (2 * d,)
+        sh[p + ".norm.weight"] = (D << (nl - 1),); sh[p + ".norm.bias"] = (D << (nl - 1),)
+    top = D << (nl - 1)
+    sh["enc.proj.weight"] = (E, G * top); sh["enc.proj.bias"] = (E,)
+    ht, wt = cfg.level_grid(nl - 1)
+    sh["net.pos_embed"] = (1, ht * wt, E)
+    for s, depth in enumerate(cfg.lg_depths):
+        for b in range(depth):
+            block(f"net.layers.{s}.blocks.{b}", E)
+    for g in range(G):
+        p = f"dec.dec_list.{g}"
+        for inx in range(nl):
+            d = D << (nl - 1 - inx)
+            for b in range(cfg.enc_depths[nl - 1 - inx]):
+                block(f"{p}.layers_up.{inx}.blocks.{b}", d)
+            if inx < nl - 1:
+                sh[f"{p}.layers_up.{inx}.upsample.expand.weight"] = (2 * d, d)
+                sh[f"{p}.layers_up.{inx}.upsample.norm.weight"] = (d // 2,); sh[f"{p}.layers_up.{inx}.upsample.norm.bias"] = (d // 2,)
+        for inx in range(nl):
+            d = D << (nl - 1 - inx)
+            sh[f"{p}.concat_back_dim.{inx}.weight"] = (d, 2 * d); sh[f"{p}.concat_back_dim.{inx}.bias"] = (d,)
+        sh[p + ".norm_up.weight"] = (D,); sh[p + ".norm_up.bias"] = (D,)
+    for g in range(G):
+        sh[f"dec.final_proj_list.{g}.weight"] = (D, cfg.outchans_list[g], kh, kw)
+        sh[f"dec.final_proj_list.{g}.bias"] = (cfg.outchans_list[g],)
+    sh["dec.proj.weight"] = (G * top, E); sh["dec.proj.bias"] = (G * top,)
+    return sh
+
+
+def make_state_dict_net1(cfg, seed: int = 0, rich: bool = False) -> Dict[str, np.ndarray]:
+    """Random-init weights of `LGUnet_all_1` by reference name: Linear N(0, 0.02) with zero bias and LayerNorm (1, 0) as
+    `_init_weights` leaves them (networks/LGUnet_all.py:763-770), embeddings N(0, 0.02), convolutions U(+-1/sqrt(fan_in)).
+    rich: LayerNorm affines around (1, 0), non-zero biases and 4x larger Linear weights, so that no parameter is silent."""
+    rng = np.random.Generator(np.random.PCG64(7000 + seed))
+    sd: Dict[str, np.ndarray] = {}
+    shapes = net1_param_shapes(cfg)
+    for name, shape in shapes.items():
+        r = rng.standard_normal(shape, dtype=np.float32)
+        conv_w = name[: -len("bias")] + "weight" if name.endswith("bias") else name
+        if len(shapes.get(conv_w, ())) == 4:                     # Conv2d / ConvTranspose2d weight and bias: default uniform init
+            w = shapes[conv_w]
+            fan = w[1] * w[2] * w[3]
+            v = (rng.random(shape, dtype=np.float32) * 2 - 1) / np.float32(np.sqrt(fan))
+        elif name.endswith("embed"):
+            v = 0.02 * r
+        elif name.endswith("weight") and len(shape) == 1:        # LayerNorm weight
+            v = 1.0 + (0.1 if rich else 0.0) * r
+        elif name.endswith("weight"):                            # Linear weight
+            v = (0.08 if rich else 0.02) * r
+        else:                                                    # Linear / LayerNorm bias
+            v = (0.05 if rich else 0.0) * r
+        sd[name] = np.ascontiguousarray(v, dtype=np.float32)
+    return sd
