@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--recompute", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inflight", action="store_true", help="skip the several-cases-in-flight-per-GPU measurement")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
@@ -255,6 +256,58 @@ def main():
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = float(t2)
+
+    # ---- "one or more cases per GPU" (SURVEY 8e): S independent cases in flight on this GPU, one engine + stream + host thread each;
+    # aggregate cost+grad evaluations per second of the GPU.  The headline `value` stays the single-case latency. ----
+    inflight = {"1": {"evals_per_s_per_gpu": 1e3 * args.steps / total_ms, "ms_per_eval_per_case": total_ms / args.steps}}
+    extra_engs = []
+    if T > 1 and not args.no_inflight:
+        try:
+            import threading
+            for k in (1, 2):
+                c2 = build_inputs(T, args.obs_frac, seed=1000 + 17 * rank + k)[4]
+                e2 = Engine(dcfg, fcfg, T=T, recompute=bool(args.recompute), use_graph=not args.no_graph, device=f"cuda:{local}")
+                e2.load_state_dict(0, sd_d); e2.load_state_dict(1, sd_f); e2.finalize()
+                e2.set_case(c2["xb"], c2["yo"], c2["H"], c2["R"], 1.0)
+                extra_engs.append((e2, torch.from_numpy(c2["z"]).to(dev)))
+            pool = [(eng, z)] + extra_engs
+            for S in (2, 3):
+                gate = threading.Barrier(S + 1)
+                errs = []
+
+                def worker(e_, z_):
+                    try:
+                        torch.cuda.set_device(local)
+                        with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                            J_ = torch.empty(3, dtype=torch.float64, device=dev); g_ = torch.empty_like(z_)
+                            for _ in range(args.warmup):
+                                e_.cost_grad(z_, J_, g_)
+                            torch.cuda.current_stream().synchronize()
+                            gate.wait()
+                            for _ in range(args.steps):
+                                e_.cost_grad(z_, J_, g_)
+                            torch.cuda.current_stream().synchronize()
+                            gate.wait()
+                    except Exception as ex:          # never leave the main thread waiting at the gate
+                        errs.append(repr(ex)); gate.abort()
+
+                th = [threading.Thread(target=worker, args=pool[i]) for i in range(S)]
+                for t_ in th:
+                    t_.start()
+                gate.wait(); t0 = time.perf_counter()
+                gate.wait(); dt = time.perf_counter() - t0
+                for t_ in th:
+                    t_.join()
+                if errs:
+                    raise RuntimeError(errs[0])
+                inflight[str(S)] = {"evals_per_s_per_gpu": S * args.steps / dt, "ms_per_eval_per_case": 1e3 * dt / args.steps}
+            torch.cuda.synchronize()
+        except Exception as ex:
+            inflight["error"] = repr(ex)
+        for e2, _ in extra_engs:
+            e2.close()
+        extra_engs = []
+        torch.cuda.empty_cache()
 
     # ---- one REAL analysis-forecast cycle through the cycle driver (da_4dvar.py:1314-1342 with the shipped script's Nit=4,
     # da_4dvar_script.sh:14): 4 x LBFGS.step(max_iter=10) + 5 diagnostic sweeps + the forecast step, every rank its own case ----
@@ -428,6 +481,7 @@ def main():
         "engine": {"recompute": int(args.recompute), "cuda_graph": not args.no_graph, "ln_fold": True, "n_obs": int(eng.n_obs),
                    "parallelism": f"replicas x{world} (independent cases, no data-path collective)"},
         "evals_per_s": 1e3 * args.steps * world / total_ms,
+        "cases_in_flight_per_gpu": inflight,
         "da_cycles_per_hour": (cycles_per_hour_gpu * world) if cycles_per_hour_gpu else None,
         "da_cycle": {"measured": bool(cyc_s), "seconds_per_cycle": cyc_s, "closure_evals": cyc_evals,
                      "definition": "one analysis-forecast cycle through vaevar_b200.cycle.CycledDA: Nit=4 x LBFGS.step(max_iter=10, "

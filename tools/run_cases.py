@@ -25,6 +25,7 @@ ap.add_argument("--T", type=int, default=6)
 ap.add_argument("--nit", type=int, default=1)
 ap.add_argument("--obs-frac", type=float, default=0.10)
 ap.add_argument("--small", action="store_true", help="shrunken networks on a 32x64 grid (smoke test)")
+ap.add_argument("--in-flight", type=int, default=1, help="independent cases in flight per GPU (one engine, stream and host thread each)")
 ap.add_argument("--out", default="", help="write the JSON result (with the per-case records) to this file as well")
 ap.add_argument("--check", default="", help="a result file of another run (e.g. 1 GPU): the per-case records must be bit-identical")
 a = ap.parse_args()
@@ -34,14 +35,16 @@ dev = f"cuda:{local}"
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(dev))
 dcfg, fcfg = (small(DECODER_FULL), small(FLOW_FULL)) if a.small else (DECODER_FULL, FLOW_FULL)
-agent = VaeVar4D(dcfg, fcfg if a.T > 1 else None, make_state_dict(dcfg, seed=0), make_state_dict(fcfg, seed=1) if a.T > 1 else None,
-                 da_win=a.T, Nit=a.nit, device=dev, verbose=False)
+sd_d, sd_f = make_state_dict(dcfg, seed=0), make_state_dict(fcfg, seed=1) if a.T > 1 else None
+agents = [VaeVar4D(dcfg, fcfg if a.T > 1 else None, sd_d, sd_f, da_win=a.T, Nit=a.nit, device=dev, verbose=False) for _ in range(a.in_flight)]
 mk = lambda i: make_case(a.T, *dcfg.img_size, obs_frac=a.obs_frac, seed=i)
 c0 = mk(0)
-agent.one_step_DA(c0["gt"], c0["xb"], c0["yo"], c0["H"], c0["R"], "vae4dvar")      # warm-up: graph capture, lazy loads
-for v in agent.metrics_list.values():
-    v.clear()
-r = run_cases(agent, a.cases, mk, rank, world, dev)
+for agent in agents:
+    agent.one_step_DA(c0["gt"], c0["xb"], c0["yo"], c0["H"], c0["R"], "vae4dvar")      # warm-up: graph capture, lazy loads
+    for v in agent.metrics_list.values():
+        v.clear()
+    agent.history.clear()
+r = run_cases(agents if len(agents) > 1 else agents[0], a.cases, mk, rank, world, dev)
 if rank == 0:
     r.update(T=a.T, nit=a.nit, obs_frac=a.obs_frac, small=a.small, rms_wrmse_z500=r["rms_wrmse"][11], config="BASELINE.json configs[3]")
     r.pop("rms_wrmse"); r.pop("mean_bias")

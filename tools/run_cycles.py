@@ -1,17 +1,21 @@
 """BASELINE.json configs[4]: cycled data assimilation -- `--cycles` consecutive analysis-forecast cycles per
 chain (da_4dvar.py:1314-1342: observations of the window, one_step_DA with Nit = 4 x LBFGS.step(max_iter=10), diagnostics, save,
-forecast to the next window start), one independent chain per GPU (different truth / background / mask seeds), no data-path
+forecast to the next window start), one or more independent chains per GPU (different truth / background / mask seeds; with
+--chains-per-gpu S every chain has its own engine, CUDA stream and host thread, so their kernels interleave), no data-path
 collective; at the end one NCCL sum of the metric accumulator and of the per-rank timings.
     python tools/run_cycles.py --cycles 30
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29612 tools/run_cycles.py --cycles 30
 At 128x256 the forecast operator of the cycle is the flow model (the 0.25-degree LGUnet_all_1 needs the 721x1440 grid); stated in
 the output.  Rank 0 prints one JSON line (cycles/hour over the whole job, per-rank seconds, WRMSE of the first / last cycle)."""
 import argparse
+import contextlib
 import json
 import os
 import pathlib
 import sys
 import tempfile
+import threading
+import time
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
@@ -31,6 +35,7 @@ ap.add_argument("--T", type=int, default=6)
 ap.add_argument("--nit", type=int, default=4)
 ap.add_argument("--obs-frac", type=float, default=0.10)
 ap.add_argument("--small", action="store_true")
+ap.add_argument("--chains-per-gpu", type=int, default=1, help="independent cycle chains in flight on every GPU (one engine, stream and host thread each)")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
@@ -39,31 +44,66 @@ dev = f"cuda:{local}"
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(dev))
 dcfg, fcfg = (small(DECODER_FULL), small(FLOW_FULL)) if a.small else (DECODER_FULL, FLOW_FULL)
-agent = VaeVar4D(dcfg, fcfg, make_state_dict(dcfg, seed=0), make_state_dict(fcfg, seed=1), da_win=a.T, Nit=a.nit, device=dev, verbose=False)
-case = make_case(a.T, *dcfg.img_size, obs_frac=a.obs_frac, seed=100 + rank)           # chain `rank`: its own truth and background
-with tempfile.TemporaryDirectory() as tmp:
-    warm = CycledDA(agent, TwinObs(agent, torch.from_numpy(case["gt"][0]), obs_frac=a.obs_frac, seed=rank), torch.from_numpy(case["xb"]),
-                    name=f"warm{rank}", root=tmp, n_cycles=1, resume=False)
-    warm.run_assimilation()                          # graph capture, lazy loads: not part of the measured chain
-    for v in agent.metrics_list.values():
-        v.clear()
-    agent.history.clear()
-    run = CycledDA(agent, TwinObs(agent, torch.from_numpy(case["gt"][0]), obs_frac=a.obs_frac, seed=rank), torch.from_numpy(case["xb"]),
-                   name=f"chain{rank}", root=tmp, n_cycles=a.cycles, resume=False)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    r = run.run_assimilation()
-    torch.cuda.synchronize()
-    files = sorted(p.name for p in (pathlib.Path(tmp) / f"chain{rank}").iterdir())
+S = a.chains_per_gpu
+sd_d, sd_f = make_state_dict(dcfg, seed=0), make_state_dict(fcfg, seed=1)
+agents = [VaeVar4D(dcfg, fcfg, sd_d, sd_f, da_win=a.T, Nit=a.nit, device=dev, verbose=False) for _ in range(S)]
+tmpdir = tempfile.TemporaryDirectory()
+tmp = tmpdir.name
+runs, files = [None] * S, [None] * S
+gate = threading.Barrier(S + 1)
+errors = []
+
+
+def chain_worker(k):
+    """Chain `rank * S + k`: its own truth, background and mask seeds; warm-up cycle (graph capture, lazy loads), then the measured chain."""
+    try:
+        torch.cuda.set_device(local)
+        cid = rank * S + k
+        agent = agents[k]
+        with torch.cuda.stream(torch.cuda.Stream(device=dev)) if S > 1 else contextlib.nullcontext():
+            case = make_case(a.T, *dcfg.img_size, obs_frac=a.obs_frac, seed=100 + cid)
+            mk = lambda name, n: CycledDA(agent, TwinObs(agent, torch.from_numpy(case["gt"][0]), obs_frac=a.obs_frac, seed=cid),
+                                          torch.from_numpy(case["xb"]), name=name, root=tmp, n_cycles=n, resume=False)
+            mk(f"warm{cid}", 1).run_assimilation()
+            for v in agent.metrics_list.values():
+                v.clear()
+            agent.history.clear()
+            runs[k] = mk(f"chain{cid}", a.cycles)
+            torch.cuda.current_stream().synchronize()
+            gate.wait()
+            runs[k].run_assimilation()
+            torch.cuda.current_stream().synchronize()
+            gate.wait()
+            files[k] = sorted(p.name for p in (pathlib.Path(tmp) / f"chain{cid}").iterdir())
+    except Exception as ex:
+        errors.append(repr(ex))
+        gate.abort()
+
+
+threads = [threading.Thread(target=chain_worker, args=(k,)) for k in range(S)]
+for t in threads:
+    t.start()
+gate.wait()                                          # every chain of this rank is warmed up
+if world > 1:
+    dist.barrier()
+t0 = time.time()
+gate.wait()
+rank_seconds = time.time() - t0
+for t in threads:
+    t.join()
+if errors:
+    raise RuntimeError(errors[0])
 acc = MetricAccumulator(69, dev)
-bg = torch.stack(agent.metrics_list["bg_wrmse"]); an = torch.stack(agent.metrics_list["ana_wrmse"]); bi = torch.stack(agent.metrics_list["ana_bias"])
-for k in range(an.shape[0]):
-    acc.add(float(agent.history[(k + 1) * a.nit - 1]["loss"]), float(agent.history[(k + 1) * a.nit - 1]["gmax"]), an[k], bi[k])
-secs = torch.zeros(world, dtype=torch.float64, device=dev); secs[rank] = sum(run.cycle_seconds)
-z500 = torch.zeros(world, 4, dtype=torch.float64, device=dev)
-z500[rank] = torch.tensor([float(bg[0, 11]), float(an[0, 11]), float(bg[-1, 11]), float(an[-1, 11])], dtype=torch.float64)
-evals = torch.zeros(world, dtype=torch.float64, device=dev); evals[rank] = sum(h["func_evals"] if "func_evals" in h else h["n_evals"] for h in agent.history[-a.nit:])
+secs = torch.zeros(world, dtype=torch.float64, device=dev); secs[rank] = rank_seconds
+z500 = torch.zeros(world * S, 4, dtype=torch.float64, device=dev)
+evals = torch.zeros(world * S, dtype=torch.float64, device=dev)
+for k, agent in enumerate(agents):
+    bg = torch.stack(agent.metrics_list["bg_wrmse"]); an = torch.stack(agent.metrics_list["ana_wrmse"]); bi = torch.stack(agent.metrics_list["ana_bias"])
+    for c in range(an.shape[0]):
+        h = agent.history[(c + 1) * a.nit - 1]
+        acc.add(float(h["loss"]), float(h["gmax"]), an[c], bi[c])
+    z500[rank * S + k] = torch.tensor([float(bg[0, 11]), float(an[0, 11]), float(bg[-1, 11]), float(an[-1, 11])], dtype=torch.float64)
+    evals[rank * S + k] = sum(h["func_evals"] if "func_evals" in h else h["n_evals"] for h in agent.history[-a.nit:])
 if world > 1:
     for t in (secs, z500, evals):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -71,17 +111,19 @@ acc.reduce()
 if rank == 0:
     s = acc.summary()
     per = secs.tolist()
-    out = {"config": "BASELINE.json configs[4]: cycled DA, %d consecutive analysis-forecast cycles per chain, %d chains (one per GPU)" % (a.cycles, world),
-           "T": a.T, "nit": a.nit, "obs_frac": a.obs_frac, "small": a.small, "world": world, "cycles_per_chain": a.cycles,
+    out = {"config": "BASELINE.json configs[4]: cycled DA, %d consecutive analysis-forecast cycles per chain, %d chains (%d in flight per GPU)"
+                     % (a.cycles, world * S, S),
+           "T": a.T, "nit": a.nit, "obs_frac": a.obs_frac, "small": a.small, "world": world, "chains_per_gpu": S, "cycles_per_chain": a.cycles,
            "cycles_total": s["n_cases"], "seconds_per_rank": per, "imbalance": max(per) / max(min(per), 1e-9),
-           "seconds_per_cycle": max(per) / a.cycles, "da_cycles_per_hour": 3600.0 * s["n_cases"] / max(per),
-           "da_cycles_per_hour_per_gpu": 3600.0 * a.cycles / max(per),
-           "forecast_operator": "flow model on the 128x256 engine grid (da_4dvar.py:1329 uses LGUnet_all_1 at 721x1440)",
+           "seconds_per_cycle_per_chain": max(per) / a.cycles, "da_cycles_per_hour": 3600.0 * s["n_cases"] / max(per),
+           "da_cycles_per_hour_per_gpu": 3600.0 * a.cycles * S / max(per),
+           "forecast_operator": "flow model on the 128x256 engine grid (da_4dvar.py:1329 uses LGUnet_all_1 at 721x1440: tests/test_gpu_net1.py)",
            "z500_wrmse_per_chain[bg first, ana first, bg last, ana last]": z500.tolist(), "rms_ana_wrmse_z500": s["rms_wrmse"][11],
-           "mean_J_final": s["mean_J"], "files_per_chain": files, "func_evals_last_cycle_rank0": float(evals[0])}
+           "mean_J_final": s["mean_J"], "files_per_chain": files[0], "func_evals_last_cycle_per_chain": evals.tolist()}
     if a.out:
         pathlib.Path(a.out).parent.mkdir(parents=True, exist_ok=True)
         pathlib.Path(a.out).write_text(json.dumps(out))
     print(json.dumps(out))
+tmpdir.cleanup()
 if world > 1:
     dist.destroy_process_group()

@@ -149,13 +149,13 @@ class CycledDA:
         while self.current_cycle < self.n_cycles:
             yo, H, R, gt = self.obs.window(self.current_cycle)          # the data source is not part of the timed cycle
             if torch.device(a.device).type == "cuda":
-                torch.cuda.synchronize()
+                torch.cuda.current_stream().synchronize()     # this chain only: other chains may share the GPU
             t0 = time.time()
             xa = a.one_step_DA(gt, self.xb, yo, H, R, "vae4dvar")
             self.save_eval_result(xa)
             self.xb = a.integrate(xa, getattr(a, "forecast_model", None), self.forecast_steps)     # da_4dvar.py:1329
             if torch.device(a.device).type == "cuda":
-                torch.cuda.synchronize()
+                torch.cuda.current_stream().synchronize()     # this chain only: other chains may share the GPU
             self.current_cycle += 1
             if epoch % self.save_interval == 0:
                 self.save_ckpt()

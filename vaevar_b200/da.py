@@ -159,7 +159,7 @@ class VaeVar4D:
             if kk < self.Nit:
                 self.history.append(opt.step(z))                            # lbfgs.step(closure), da_4dvar.py:1298-1299
         xa = self.engine.decode_native(z) if self._native else self.engine.decode(z)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()       # this case's stream only: other cases may be in flight on the same GPU
         if self.verbose:
             print("DA finished. Time consumed: %.3f (s)" % (time.time() - t0), flush=True)
         self.z = z
