@@ -8,6 +8,8 @@
 
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "engine.h"
 #include "seams.cuh"
 
@@ -90,8 +92,38 @@ void launch_fold_ln(bf16* dst, float* colsum, float* cbias, const float* W, cons
   fold_ln_kernel<<<(rows + 7) / 8, 256>>>(dst, colsum, cbias, W, gamma, beta, bias, rows, cols, f16);
 }
 
+bool nvtx_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VV_NVTX");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+void nvtx_push(const char* name) { if (nvtx_enabled()) nvtxRangePushA(name); }
+void nvtx_pop() { if (nvtx_enabled()) nvtxRangePop(); }
+static const char* op_family(Op::Kind k) {
+  switch (k) {
+    case Op::GEMM: return "gemm (tcgen05)";
+    case Op::LN_F: return "layernorm fwd";
+    case Op::LN_B: return "layernorm bwd";
+    case Op::ATT_F: return "window attention fwd";
+    case Op::ATT_B: return "window attention bwd";
+    case Op::P2T: return "patch pixels->tokens";
+    case Op::T2P: return "patch tokens->pixels";
+    case Op::ROPE: return "rope2";
+    case Op::ATT1: return "SD_attn";
+    case Op::PE32: return "patch embed (3,2)";
+    case Op::CT32: return "conv-transpose head (3,2)";
+  }
+  return "op";
+}
+
 int Plan::run(cudaStream_t s) const {
+  const bool nv = nvtx_enabled();
+  if (nv && !label.empty()) nvtxRangePushA(label.c_str());
   for (const Op& o : ops) {
+    if (nv) nvtxRangePushA(op_family(o.kind));
     switch (o.kind) {
       case Op::GEMM: launch_gemm(o.gemm, s); break;
       case Op::LN_F: launch_ln_fwd(o.lnf, s); break;
@@ -105,7 +137,9 @@ int Plan::run(cudaStream_t s) const {
       case Op::PE32: launch_patch32(o.pe32, s); break;
       case Op::CT32: launch_convt32(o.ct32, s); break;
     }
+    if (nv) nvtxRangePop();
   }
+  if (nv && !label.empty()) nvtxRangePop();
   return (int)ops.size();
 }
 
@@ -756,6 +790,9 @@ static int build_plans(vv_engine* e) {
       B.net_bwd(e->bwd[a], e->stash[a], e->Gb[a % 2], e->Gb[(a - 1) % 2]);
     }
     VV_CHECK(!B.err, "plan construction failed: %s", B.err);
+    const std::string who = a == 0 ? std::string("decoder") : "flow[" + std::to_string(a) + "]";
+    e->fwd[a].label = who + " forward";
+    e->bwd[a].label = who + " backward (input-VJP)";
   }
   // Chain the GEMMs in execution order (fwd[0..napp-1], then bwd[napp-1..0], wrapping around to the next evaluation): each
   // one prefetches the weights of its successor into L2 while its own epilogue drains.
@@ -804,6 +841,7 @@ static int enqueue_forward(vv_engine* e, cudaStream_t s, bool with_obs) {
     }
   }
   if (with_obs) {
+    nvtx_push("observation term + J");
     if (e->taps)
       launch_obs_taps_misfit(e->XF, e->tap_ia, e->tap_coef, e->taps, e->yobs, e->rinv, e->n_obs, e->obs_coeff, e->resid, e->partials,
                              reduce_blocks(), s);
@@ -815,6 +853,7 @@ static int enqueue_forward(vv_engine* e, cudaStream_t s, bool with_obs) {
     launch_multi_dot(dp, (long long)e->Zc * e->HW, e->dots, e->dot_scratch, s);
     finalize_J_kernel<<<1, 1, 0, s>>>(e->dots, e->Jbuf + 3, e->obs_coeff, e->Jbuf);
     launches += 5;
+    nvtx_pop();
   }
   (void)CHW;
   return launches;

@@ -30,8 +30,13 @@ struct Op {
 };
 struct Plan {
   std::vector<Op> ops;
+  std::string label;               // NVTX range around the plan (VV_NVTX=1): "decoder forward", "flow[3] backward", ...
   int run(cudaStream_t s) const;   // returns number of launches
 };
+// NVTX ranges (VV_NVTX=1): one per application plan and one per launch, named after the kernel family -- for nsys / ncu --nvtx timelines.
+bool nvtx_enabled();
+void nvtx_push(const char* name);
+void nvtx_pop();
 
 // One stack of G identically shaped Swin blocks (G towers batched, or G = 1 for the trunk).
 struct BlockW {

@@ -513,6 +513,7 @@ int net1_build_plan(vv_net1* n) {
   o.ct32 = ConvT32Args{n->H, n->W, n->gh[0], n->gw[0], G, D, n->ct_kcnt, n->ct_cbase, n->ct_chan, n->ct_W, n->ct_bias, NU, n->OUT, n->ct_max};
   n->plan.ops.push_back(o);
   N1_CHECK(!B.err, "plan construction failed: %s", B.err);
+  n->plan.label = "LGUnet_all_1 forward";
   n->plan_built = true;
   return 0;
 }
