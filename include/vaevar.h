@@ -268,6 +268,10 @@ VV_API int vv_net1_set_constants(vv_net1* n, const float* mean, const float* std
 VV_API int vv_net1_integrate(vv_net1* n, const float* x_in_dev, float* x_out_dev, int steps, void* stream);
 VV_API int vv_net1_last_launch_count(vv_net1* n);
 VV_API long long vv_net1_device_bytes(vv_net1* n);
+/* Steady-state time of every launch of the forward plan (each `reps` times between CUDA events).  kind: 0 GEMM, 1 LayerNorm, 7 rope2,
+ * 8 SD_attn, 9 patch embedding, 10 ConvTranspose2d head; flop_out: 2 M N K batch (GEMM) / 4 N^2 hd per window and head (attention);
+ * mnk_out: 4 ints per op (GEMM: M, N, K, batch; attention: tokens, window tokens, head width, heads x batch).  Returns the op count. */
+VV_API int vv_net1_profile_ops(vv_net1* n, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap);
 /* Kernel-level hook: rope2 (positional_encodings.py:255-268; skipped when table_dev is null) + the SD_attn core
  * (Attention.py:560-640) on a packed fp16 qkv buffer [gh * gw][3 * heads * hd] -> out fp16 [gh * gw][heads * hd]. */
 VV_API int vv_test_attn1(void* qkv_dev, void* out_dev, const float* table_dev, int gh, int gw, int wh, int ww, int sh, int sw, int heads, int hd,

@@ -619,6 +619,50 @@ VV_API int vv_net1_integrate(vv_net1* n, const float* x_in_dev, float* x_out_dev
 
 VV_API int vv_net1_last_launch_count(vv_net1* n) { return n ? n->last_launches : 0; }
 
+// Steady-state time of every launch of the forward plan (each op `reps` times between CUDA events, on whatever the buffers hold
+// after one full application).  kind: Op::Kind (0 GEMM, 1 LayerNorm, 7 rope2, 8 SD_attn, 9 patch embed, 10 conv-transpose head);
+// flop_out: 2 M N K batch for GEMMs, 4 N^2 hd per (window, head) for attention; mnk_out: 4 ints per op.  Returns the op count.
+VV_API int vv_net1_profile_ops(vv_net1* n, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap) {
+  N1_CHECK(n && ms_out && kind_out && reps >= 1, "bad argument");
+  int rc = net1_build_plan(n);
+  if (rc) return rc;
+  cudaStream_t s = nullptr;
+  N1_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  N1_CUDA(cudaEventCreate(&e0)); N1_CUDA(cudaEventCreate(&e1));
+  n->plan.run(s);
+  int k = 0;
+  for (const Op& o : n->plan.ops) {
+    Plan one; one.ops.push_back(o);
+    one.run(s);
+    cudaEventRecord(e0, s);
+    for (int r = 0; r < reps; ++r) one.run(s);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (k < cap) {
+      ms_out[k] = ms / reps;
+      kind_out[k] = (int)o.kind;
+      double fl = 0.0;
+      int m4[4] = {0, 0, 0, 0};
+      if (o.kind == Op::GEMM) { fl = 2.0 * o.gemm.a.M * o.gemm.a.N * o.gemm.a.K * o.gemm.a.batch; m4[0] = o.gemm.a.M; m4[1] = o.gemm.a.N; m4[2] = o.gemm.a.K; m4[3] = o.gemm.a.batch; }
+      else if (o.kind == Op::ATT1) {
+        const double N = (double)o.att1.wh * o.att1.ww, nwin = (double)(o.att1.gh / o.att1.wh) * (o.att1.gw / o.att1.ww);
+        fl = 4.0 * N * N * o.att1.hd * o.att1.heads * nwin * o.att1.batch;
+        m4[0] = o.att1.gh * o.att1.gw; m4[1] = o.att1.wh * o.att1.ww; m4[2] = o.att1.hd; m4[3] = o.att1.batch * o.att1.heads;
+      } else if (o.kind == Op::LN_F) { m4[0] = o.lnf.rows; m4[1] = o.lnf.C; m4[3] = o.lnf.batch; }
+      else if (o.kind == Op::ROPE) { m4[0] = o.rope.gh * o.rope.gw; m4[1] = o.rope.wh * o.rope.ww; m4[2] = o.rope.hd; m4[3] = o.rope.batch * o.rope.heads; }
+      if (flop_out) flop_out[k] = fl;
+      if (mnk_out) for (int j = 0; j < 4; ++j) mnk_out[4 * k + j] = m4[j];
+    }
+    ++k;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+  N1_CUDA(cudaGetLastError());
+  return k;
+}
+
 VV_API long long vv_net1_device_bytes(vv_net1* n) {
   return n ? n->bytes : 0;
 }

@@ -228,6 +228,202 @@ static void launch_attn1_t(const Attn1Args& a, cudaStream_t s) {
   const long long items = (long long)(a.gh / a.wh) * (a.gw / a.ww) * a.heads * nq;
   launch_kernel(attn1_kernel<HD, WARPS, KT>, dim3((unsigned)items, a.batch), dim3(WARPS * 32), L::BYTES, s, a);
 }
+// =============================================================================================
+// Long windows (the whole-grid first LG stage: 16 200 tokens): the same online-softmax attention with the operand traffic of a
+// flash kernel -- one CTA = one (window, head, 128 query rows), eight warps of 16 rows; keys / values stream through a
+// double-buffered cp.async ring of 64-token tiles (the loads of tile i + 1 fly while tile i is multiplied); Q, K fragments come
+// from ldmatrix.x4 (one shared-memory instruction per two MMAs), V fragments from ldmatrix.x4.trans.
+// =============================================================================================
+VV_DEVINL void ldsm_x4(uint32_t (&r)[4], const void* smem_row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row_ptr)));
+}
+
+template <int HD>
+struct Attn1LongSmem {
+  static constexpr int WARPS = 8, QR = 128, KT = 64;
+  static constexpr int RS = HD / 2 + 4;
+  static constexpr int WORDS = (QR + 4 * KT) * RS;              // Q, K[2], V[2]
+  static constexpr int BYTES = WORDS * 4;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(256, 1) attn1_long_kernel(const Attn1Args a) {
+  using L = Attn1LongSmem<HD>;
+  constexpr int RS = L::RS, QR = L::QR, KT = L::KT, CH = HD / 8;
+  extern __shared__ __align__(16) uint32_t at1l_sm[];
+  uint32_t* Qs = at1l_sm;
+  uint32_t* KV = Qs + QR * RS;                                   // stage b: K at KV + b * 2 * KT * RS, V right behind it
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int N = a.wh * a.ww;
+  const int nq = (N + QR - 1) / QR;
+  const int nww = a.gw / a.ww;
+  int item = blockIdx.x;
+  const int qt = item % nq; item /= nq;
+  const int h = item % a.heads; const int win = item / a.heads;
+  const int wi = win / nww, wj = win - wi * nww;
+  const int b = blockIdx.y;
+  const int d = a.heads * HD;
+  pdl_launch_dependents();
+  pdl_wait();
+  const __half* qkv = reinterpret_cast<const __half*>(a.qkv) + (long long)b * a.qkv_bs;
+  auto tok_of = [&](int n) {
+    const int r = n / a.ww, c = n - r * a.ww;
+    int row = wi * a.wh + r + a.sh; if (row >= a.gh) row -= a.gh;
+    int col = wj * a.ww + c + a.sw; if (col >= a.gw) col -= a.gw;
+    return row * a.gw + col;
+  };
+  auto stage = [&](uint32_t* dst, int m, int n0, int rows) {
+    for (int idx = threadIdx.x; idx < rows * CH; idx += 256) {
+      const int r = idx / CH, ch = idx - r * CH;
+      uint32_t* sp = dst + r * RS + 4 * ch;
+      if (n0 + r < N) {
+        const __half* src = qkv + (long long)tok_of(n0 + r) * a.ld_qkv + m * d + h * HD + 8 * ch;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sp)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(sp) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+  const int q0 = qt * QR;
+  const int nkt = (N + KT - 1) / KT;
+  stage(Qs, 0, q0, QR);
+  stage(KV, 1, 0, KT);
+  stage(KV + KT * RS, 2, 0, KT);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int m0 = warp * 16;
+  const bool masked = a.mask && a.sh > 0 && wi == a.gh / a.wh - 1;
+  const int band_row = a.wh - a.sh;
+  const int qi0 = q0 + m0 + g, qi1 = qi0 + 8;
+  const int qb0 = (qi0 / a.ww) < band_row ? 0 : 1, qb1 = (qi1 / a.ww) < band_row ? 0 : 1;
+  const bool warp_live = q0 + m0 < N;                           // a warp whose 16 rows all lie beyond N only helps with the loads
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float mrun0 = -INFINITY, mrun1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const float sc = a.scale * 1.4426950408889634f;
+  // ldmatrix lane addressing: A fragments of Q (rows m0.., 16 x 16 block at k-step ks) and B fragments of K (two 8-key n-tiles)
+  const uint32_t* q_lane = Qs + (m0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 4 * (lane >> 4);
+  const int k_lane = ((lane & 7) + 8 * (lane >> 4)) * RS + 4 * ((lane >> 3) & 1);
+  const int lm = lane >> 3, lr = lane & 7;
+  const int v_lane = ((lm & 1) * 8 + lr) * RS + (lm >> 1) * 4;
+
+  for (int it = 0; it < nkt; ++it) {
+    const int kv0 = it * KT;
+    uint32_t* Ks = KV + (it & 1) * 2 * KT * RS;
+    uint32_t* Vs = Ks + KT * RS;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // tile `it` has landed for everyone; tile it - 1 is no longer read
+    if (it + 1 < nkt) {
+      uint32_t* Kn = KV + ((it + 1) & 1) * 2 * KT * RS;
+      stage(Kn, 1, kv0 + KT, KT);
+      stage(Kn + KT * RS, 2, kv0 + KT, KT);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (!warp_live) continue;
+    // ---- S = Q K^T ----
+    float s[KT / 8][4];
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t af[4];
+      ldsm_x4(af, q_lane + ks * 8);
+#pragma unroll
+      for (int j = 0; j < KT / 8; j += 2) {
+        uint32_t kb[4];
+        ldsm_x4(kb, Ks + j * 8 * RS + k_lane + ks * 8);
+        mma_f16(s[j], af, kb[0], kb[1]);
+        mma_f16(s[j + 1], af, kb[2], kb[3]);
+      }
+    }
+    // ---- scale, mask, online softmax ----
+    const bool ragged = kv0 + KT > N;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float v0 = s[j][e] * sc, v1 = s[j][2 + e] * sc;
+        if (ragged || masked) {
+          const int kn = kv0 + 8 * j + 2 * t + e;
+          bool dead0 = kn >= N, dead1 = dead0;
+          if (masked && !dead0) {
+            const int kb = (kn / a.ww) < band_row ? 0 : 1;
+            dead0 = kb != qb0; dead1 = kb != qb1;
+          }
+          if (dead0) v0 = -INFINITY;
+          if (dead1) v1 = -INFINITY;
+        }
+        s[j][e] = v0; s[j][2 + e] = v1;
+        mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(mrun0, mx0), mn1 = fmaxf(mrun1, mx1);
+    const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;
+    const float c0 = ex2_approx(mrun0 - ms0), c1 = ex2_approx(mrun1 - ms1);
+    mrun0 = mn0; mrun1 = mn1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < KT / 8; ++j) {
+      s[j][0] = ex2_approx(s[j][0] - ms0); s[j][1] = ex2_approx(s[j][1] - ms0);
+      s[j][2] = ex2_approx(s[j][2] - ms1); s[j][3] = ex2_approx(s[j][3] - ms1);
+      ps0 += s[j][0] + s[j][1]; ps1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * c0 + ps0; l1 = l1 * c1 + ps1;
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kb = 0; kb < KT / 16; ++kb) {
+      const uint32_t pa[4] = {pack_h2(s[2 * kb][0], s[2 * kb][1]), pack_h2(s[2 * kb][2], s[2 * kb][3]),
+                              pack_h2(s[2 * kb + 1][0], s[2 * kb + 1][1]), pack_h2(s[2 * kb + 1][2], s[2 * kb + 1][3])};
+#pragma unroll
+      for (int c16 = 0; c16 < HD / 16; ++c16) {
+        uint32_t vb[4];
+        ldsm_x4_trans(vb, Vs + 16 * kb * RS + v_lane + c16 * 8);
+        mma_f16(o[2 * c16], pa, vb[0], vb[1]);
+        mma_f16(o[2 * c16 + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+  // ---- normalise, stage through this warp's Q rows, store ----
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    Qs[(m0 + g) * RS + n * 4 + t] = pack_h2(o[n][0] * i0, o[n][1] * i0);
+    Qs[(m0 + g + 8) * RS + n * 4 + t] = pack_h2(o[n][2] * i1, o[n][3] * i1);
+  }
+  __syncwarp();
+  __half* out = reinterpret_cast<__half*>(a.out) + (long long)b * a.o_bs;
+  for (int idx = lane; idx < 16 * CH; idx += 32) {
+    const int r = idx / CH, ch = idx - r * CH;
+    const int qi = q0 + m0 + r;
+    if (qi < N)
+      *reinterpret_cast<uint4*>(out + (long long)tok_of(qi) * a.ld_o + h * HD + 8 * ch) = *reinterpret_cast<const uint4*>(Qs + (m0 + r) * RS + 4 * ch);
+  }
+}
+
+template <int HD>
+static void launch_attn1_long_t(const Attn1Args& a, cudaStream_t s) {
+  using L = Attn1LongSmem<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn1_long_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    attr_set = true;
+  }
+  const int N = a.wh * a.ww, nq = (N + L::QR - 1) / L::QR;
+  const long long items = (long long)(a.gh / a.wh) * (a.gw / a.ww) * a.heads * nq;
+  launch_kernel(attn1_long_kernel<HD>, dim3((unsigned)items, a.batch), dim3(256), L::BYTES, s, a);
+}
+
 bool attn1_supported(int hd) { return hd == 32 || hd == 64 || hd == 192; }
 void launch_attn1(const Attn1Args& a, cudaStream_t s) {
   const int N = a.wh * a.ww;
@@ -235,10 +431,10 @@ void launch_attn1(const Attn1Args& a, cudaStream_t s) {
     if (a.hd == 32) launch_attn1_t<32, 5, 80>(a, s);
     else if (a.hd == 64) launch_attn1_t<64, 5, 80>(a, s);
     else if (a.hd == 192) launch_attn1_t<192, 5, 80>(a, s);
-  } else {                            // long windows (the whole-grid first LG stage): 64-row query tiles, 64-key tiles
-    if (a.hd == 32) launch_attn1_t<32, 4, 64>(a, s);
-    else if (a.hd == 64) launch_attn1_t<64, 4, 64>(a, s);
-    else if (a.hd == 192) launch_attn1_t<192, 4, 64>(a, s);
+  } else {                            // long windows (the whole-grid first LG stage): 128-row query tiles, 64-key tiles, double-buffered
+    if (a.hd == 32) launch_attn1_long_t<32>(a, s);
+    else if (a.hd == 64) launch_attn1_long_t<64>(a, s);
+    else if (a.hd == 192) launch_attn1_long_t<192>(a, s);
   }
 }
 

@@ -94,6 +94,16 @@ class ForecastNet:
         _lib.check(self.lib.vv_net1_integrate(self._h, _ptr(xa), _ptr(out), int(steps), _stream()))
         return out
 
+    def profile_ops(self, reps: int = 3):
+        """Per-launch steady-state times of one application: list of dicts (kind, ms, flop, shape)."""
+        cap = 4096
+        ms = (C.c_float * cap)(); kind = (C.c_int * cap)(); fl = (C.c_double * cap)(); mnk = (C.c_int * (4 * cap))()
+        n = self.lib.vv_net1_profile_ops(self._h, int(reps), ms, kind, fl, mnk, cap)
+        if n < 0:
+            _lib.check(n)
+        names = {0: "gemm", 1: "ln_fwd", 7: "rope2", 8: "sd_attn", 9: "patch_embed32", 10: "convt_head32"}
+        return [{"kind": names.get(kind[i], str(kind[i])), "ms": ms[i], "flop": fl[i], "shape": [mnk[4 * i + j] for j in range(4)]} for i in range(min(n, cap))]
+
     @property
     def last_launch_count(self) -> int:
         return int(self.lib.vv_net1_last_launch_count(self._h))
