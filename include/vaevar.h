@@ -273,9 +273,10 @@ VV_API long long vv_net1_device_bytes(vv_net1* n);
  * mnk_out: 4 ints per op (GEMM: M, N, K, batch; attention: tokens, window tokens, head width, heads x batch).  Returns the op count. */
 VV_API int vv_net1_profile_ops(vv_net1* n, int reps, float* ms_out, int* kind_out, double* flop_out, int* mnk_out, int cap);
 /* Kernel-level hook: rope2 (positional_encodings.py:255-268; skipped when table_dev is null) + the SD_attn core
- * (Attention.py:560-640) on a packed fp16 qkv buffer [gh * gw][3 * heads * hd] -> out fp16 [gh * gw][heads * hd]. */
+ * (Attention.py:560-640) on a packed fp16 qkv buffer [gh * gw][3 * heads * hd] -> out fp16 [gh * gw][heads * hd].
+ * use_tc = 1: insist on the tcgen05 kernel of the whole-grid stage (error if the shape is not eligible); 0: the mma.sync kernels. */
 VV_API int vv_test_attn1(void* qkv_dev, void* out_dev, const float* table_dev, int gh, int gw, int wh, int ww, int sh, int sw, int heads, int hd,
-                         int mask, void* stream);
+                         int mask, int use_tc, void* stream);
 
 #ifdef __cplusplus
 }

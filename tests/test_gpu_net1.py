@@ -60,15 +60,18 @@ def _rope_table(win, hd, dev):
     return torch.stack([cs, sn], -1).float().contiguous().to(dev)
 
 
-@pytest.mark.parametrize("gh,gw,win,shifted,heads,hd", [
-    (12, 24, (6, 12), False, 3, 32), (12, 24, (6, 12), True, 3, 32), (12, 24, (6, 12), True, 2, 64), (12, 24, (6, 12), True, 2, 192),
-    (6, 24, (6, 12), True, 2, 32),          # a single window row: every window is a masked one
-    (6, 12, (6, 12), True, 1, 32),          # the window spans the whole width: rolled, but never masked (Attention.py:553)
-    (12, 24, (12, 24), False, 2, 192),      # whole-grid stage, 288 tokens: the online-softmax path
-    (18, 36, (18, 36), False, 1, 64),       # 648 tokens: key and query tiles with a ragged tail
-    (30, 60, (30, 60), False, 2, 32),       # 1800 tokens
+@pytest.mark.parametrize("gh,gw,win,shifted,heads,hd,tc", [
+    (12, 24, (6, 12), False, 3, 32, False), (12, 24, (6, 12), True, 3, 32, False), (12, 24, (6, 12), True, 2, 64, False), (12, 24, (6, 12), True, 2, 192, False),
+    (6, 24, (6, 12), True, 2, 32, False),          # a single window row: every window is a masked one
+    (6, 12, (6, 12), True, 1, 32, False),          # the window spans the whole width: rolled, but never masked (Attention.py:553)
+    (12, 24, (12, 24), False, 2, 192, False),      # whole-grid stage, 288 tokens: the online-softmax path
+    (18, 36, (18, 36), False, 1, 64, False),       # 648 tokens: key and query tiles with a ragged tail
+    (30, 60, (30, 60), False, 2, 32, False),       # 1800 tokens
+    (18, 36, (18, 36), False, 1, 192, True),    # the tcgen05 kernel of the whole-grid stage: 648 tokens = 2.5 query blocks, 10.1 key tiles
+    (30, 60, (30, 60), False, 2, 192, True),    # 1800 tokens, two heads
+    (45, 90, (45, 90), False, 6, 192, True),    # 4050 tokens, six heads (the shipped trunk width 1152)
 ])
-def test_sd_attn_core_against_oracle(lib, gh, gw, win, shifted, heads, hd):
+def test_sd_attn_core_against_oracle(lib, gh, gw, win, shifted, heads, hd, tc):
     from vaevar_b200 import _lib
     dev = "cuda:0"
     g = torch.Generator(device="cpu").manual_seed(gh * 1000 + gw + hd + heads)
@@ -81,11 +84,11 @@ def test_sd_attn_core_against_oracle(lib, gh, gw, win, shifted, heads, hd):
     work = qkv.clone()                       # rope2 rotates q and k in place
     mask = int(shift[1] > 0 and win[1] != gw)
     _lib.check(lib.vv_test_attn1(C.c_void_p(work.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(tab.data_ptr()), gh, gw, win[0], win[1],
-                                 shift[0], shift[1], heads, hd, mask, None))
+                                 shift[0], shift[1], heads, hd, mask, int(tc), None))
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     err = _rel(out.float(), ref)
-    print(f"SD_attn {gh}x{gw} win {win} shift {shift} heads {heads} hd {hd}: rel {err:.2e}")
+    print(f"SD_attn {gh}x{gw} win {win} shift {shift} heads {heads} hd {hd}{' [tcgen05]' if tc else ''}: rel {err:.2e}")
     assert err < 5e-3             # fp16 q / k after the rotation, fp16 P and output; fp32 softmax and accumulation
     assert torch.equal(work[:, 2 * d:], qkv[:, 2 * d:])           # v is untouched
 

@@ -95,7 +95,7 @@ _SIGS = {
     "vv_net1_last_launch_count": (C.c_int, [_P]),
     "vv_net1_device_bytes": (C.c_longlong, [_P]),
     "vv_net1_profile_ops": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int]),
-    "vv_test_attn1": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vv_test_attn1": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 EXPORTED = tuple(_SIGS)
 

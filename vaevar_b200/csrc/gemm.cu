@@ -53,6 +53,12 @@ static const char* encode_map_t(CUtensorMap* tm, const void* base, bool f32, lon
   return nullptr;
 }
 
+// 2-D map over a row-major [rows][cols] matrix of 16-bit elements with row stride ld (elements), 128B-swizzled boxes of
+// box_cols (= 64) x box_rows; used by the tcgen05 attention of the forecast network (net1_kernels.cu).
+const char* encode_tma_2d_16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
+  return encode_map_t(tm, base, false, cols, rows, 1, ld, 0, box_cols, box_rows);
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {

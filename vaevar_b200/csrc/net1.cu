@@ -183,6 +183,7 @@ float2* rope_table(vv_net1* n, int wh, int ww, int hd) {
 
 struct Scratch {
   bf16 *h, *qkv, *ao, *a;       // LayerNorm output, qkv, attention output, MLP hidden (sized for the widest stage)
+  bf16* vt; long long vt_ld;    // V^T of the whole-grid trunk stage for the tcgen05 attention ([embed_dim][round_up(tokens, 64)])
 };
 
 struct N1Builder {
@@ -222,7 +223,8 @@ struct N1Builder {
     n->plan.ops.push_back(o);
     o = Op{}; o.kind = Op::ATT1;
     const int mask = (sw > 0 && ww != gw) ? 1 : 0;                 // Attention.py:553: no mask when the window spans the whole width
-    o.att1 = Attn1Args{gh, gw, wh, ww, sh, sw, w.heads, hd, G, mask, t.qkv, 3LL * d, 3 * rd, t.ao, (long long)d, rd, 1.0f / sqrtf((float)hd)};
+    o.att1 = Attn1Args{gh, gw, wh, ww, sh, sw, w.heads, hd, G, mask, t.qkv, 3LL * d, 3 * rd, t.ao, (long long)d, rd, 1.0f / sqrtf((float)hd),
+                       (G == 1 && d == n->E) ? t.vt : nullptr, t.vt_ld};
     n->plan.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = x1; g.ld_f32 = d; g.f32_bs = rd;
@@ -431,6 +433,10 @@ int net1_build_plan(vv_net1* n) {
   for (int l = 0; l < nl; ++l) m_rd = std::max<size_t>(m_rd, (size_t)G * n->L[l] * n->dl[l]);
   Scratch t{};
   t.h = n1_alloc<bf16>(n, m_rd); t.qkv = n1_alloc<bf16>(n, 3 * m_rd); t.ao = n1_alloc<bf16>(n, m_rd); t.a = n1_alloc<bf16>(n, 4 * m_rd);
+  t.vt_ld = (n->L[top] + 63) / 64 * 64;
+  t.vt = n1_alloc<bf16>(n, (size_t)E * t.vt_ld);
+  if (!t.vt) return -1;
+  cudaMemset(t.vt, 0, (size_t)E * t.vt_ld * sizeof(bf16));
   std::vector<float*> XA(nl), XB(nl); std::vector<bf16*> CAT(nl);
   for (int l = 0; l < nl; ++l) {
     const size_t sz = (size_t)G * n->L[l] * n->dl[l];
@@ -671,7 +677,7 @@ VV_API long long vv_net1_device_bytes(vv_net1* n) {
 // SD_attn core on a packed fp16 qkv buffer [gh * gw][3 * heads * hd] (Attention.py:560-640): rope2 on q, k in place, then the
 // windowed softmax(scale q k^T + mask) v into out [gh * gw][heads * hd].  table_host: [wh * ww][hd / 2] (cos, sin) pairs.
 VV_API int vv_test_attn1(void* qkv_dev, void* out_dev, const float* table_dev, int gh, int gw, int wh, int ww, int sh, int sw, int heads, int hd,
-                         int mask, void* stream) {
+                         int mask, int use_tc, void* stream) {
   N1_CHECK(qkv_dev && out_dev && attn1_supported(hd), "bad argument / head width %d not instantiated", hd);
   N1_CHECK(gh % wh == 0 && gw % ww == 0, "grid is not a multiple of the window");
   cudaStream_t s = (cudaStream_t)stream;
@@ -680,8 +686,17 @@ VV_API int vv_test_attn1(void* qkv_dev, void* out_dev, const float* table_dev, i
     RopeArgs r{gh, gw, wh, ww, sh, sw, heads, hd, 1, (bf16*)qkv_dev, 3 * d, 0, (const float2*)table_dev};
     launch_rope(r, s);
   }
-  Attn1Args a{gh, gw, wh, ww, sh, sw, heads, hd, 1, mask, (const bf16*)qkv_dev, 3 * d, 0, (bf16*)out_dev, d, 0, 1.0f / sqrtf((float)hd)};
+  Attn1Args a{gh, gw, wh, ww, sh, sw, heads, hd, 1, mask, (const bf16*)qkv_dev, 3 * d, 0, (bf16*)out_dev, d, 0, 1.0f / sqrtf((float)hd), nullptr, 0};
+  bf16* vt = nullptr;
+  if (use_tc) {                                   // scratch for V^T: the whole-grid tcgen05 path (synchronises: test hook only)
+    a.vt_ld = ((long long)gh * gw + 63) / 64 * 64;
+    N1_CUDA(cudaMalloc(&vt, (size_t)d * a.vt_ld * sizeof(bf16)));
+    N1_CUDA(cudaMemsetAsync(vt, 0, (size_t)d * a.vt_ld * sizeof(bf16), s));
+    a.vt = vt;
+    if (!attn1_tc_eligible(a)) { cudaFree(vt); set_error("shape not eligible for the tcgen05 attention (unshifted whole-grid window, head width 192, >= 512 tokens)"); return -2; }
+  }
   launch_attn1(a, s);
+  if (vt) { cudaStreamSynchronize(s); cudaFree(vt); }
   N1_CUDA(cudaGetLastError());
   return 0;
 }

@@ -424,9 +424,307 @@ static void launch_attn1_long_t(const Attn1Args& a, cudaStream_t s) {
   launch_kernel(attn1_long_kernel<HD>, dim3((unsigned)items, a.batch), dim3(256), L::BYTES, s, a);
 }
 
+// =============================================================================================
+// The whole-grid stage on the 5th-generation tensor cores (tcgen05 / TMEM / TMA): 16 200 queries x 16 200 keys x 6 heads of width 192
+// is 1.2 TFLOP per block -- the dominant cost of one forecast.
+//
+// One CTA = one head x 256 query rows (two 128-row blocks a, b that ping-pong on the tensor pipe), keys / values stream in 64-token
+// tiles.  warp 0: TMA producer (Q once; a two-stage ring of K tiles [64 keys][192] and V^T tiles [192][64 keys]); warp 1: issues
+// tcgen05.mma.cta_group::1 (S_x = Q_x K^T: M 128, N 64, K 192; O_x += P_x V: M 128, N 192, K 64) and owns TMEM (O_a, O_b: 2 x 192
+// columns, S_a, S_b: 2 x 64); warps 2-5 / 6-9: softmax of block a / b, thread = query row (tcgen05.ld gives a thread its row's 64
+// scores: row maximum and sum need no shuffles), P written as fp16 into a 128B-swizzled K-major tile the second MMA reads.
+// The running maximum is LAZY: P = exp2(s - m_ref) with m_ref raised (and O, l rescaled through tcgen05.ld / tcgen05.st) only when
+// a row's maximum exceeds it by more than 2^8 -- after the first tiles that is rare, so O stays in TMEM untouched.
+// V is transposed once per launch into vt[head * 192 + c][key] so that both MMA operands are K-major TMA tiles.
+// =============================================================================================
+constexpr int TC_HD = 192, TC_QB = 128, TC_KT = 64;
+constexpr int TC_Q_BYTES = TC_QB * TC_HD * 2;        // 48 KB: three 64-column swizzle atoms of 128 rows x 128 B
+constexpr int TC_K_BYTES = TC_KT * TC_HD * 2;        // 24 KB: three atoms of 64 rows x 128 B
+constexpr int TC_V_BYTES = TC_HD * TC_KT * 2;        // 24 KB: one atom column, 192 rows x 128 B
+constexpr int TC_P_BYTES = TC_QB * TC_KT * 2;        // 16 KB: 128 rows x 128 B
+constexpr int TC_OFF_K = 2 * TC_Q_BYTES, TC_OFF_V = TC_OFF_K + 2 * TC_K_BYTES, TC_OFF_P = TC_OFF_V + 2 * TC_V_BYTES;
+constexpr int TC_OFF_BAR = TC_OFF_P + 2 * TC_P_BYTES;
+constexpr int TC_SMEM = TC_OFF_BAR + 16 * 8 + 16 + 1024;
+static_assert(TC_SMEM <= 232448, "shared memory budget");
+constexpr int TC_THREADS = 320;
+constexpr float TC_LAZY = 8.0f;                      // rescale when a row maximum exceeds the reference by more than 2^8
+
+struct Attn1TcParams {
+  int N, heads, d;                                   // tokens (= keys = queries of the one window), heads, heads * 192
+  bf16* out; long long ld_o;
+  float sc;                                          // scale * log2(e)
+};
+
+__global__ void __launch_bounds__(256) vt_transpose_kernel(const bf16* __restrict__ qkv, long long ld_qkv, int N, int d, bf16* __restrict__ vt, long long vt_ld) {
+  __shared__ uint16_t tile[64][66];
+  const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(qkv) + 2 * d + c0;
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {       // 64 tokens x 32 channel pairs
+    const int r = idx >> 5, cp = idx & 31;
+    uint32_t v = 0;
+    if (n0 + r < N) v = *reinterpret_cast<const uint32_t*>(src + (long long)(n0 + r) * ld_qkv + 2 * cp);
+    tile[r][2 * cp] = (uint16_t)(v & 0xffff); tile[r][2 * cp + 1] = (uint16_t)(v >> 16);
+  }
+  __syncthreads();
+  uint16_t* dst = reinterpret_cast<uint16_t*>(vt);
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {       // 64 channels x 32 token pairs
+    const int c = idx >> 5, np = idx & 31;
+    const uint32_t v = (uint32_t)tile[2 * np][c] | ((uint32_t)tile[2 * np + 1][c] << 16);
+    *reinterpret_cast<uint32_t*>(dst + (long long)(c0 + c) * vt_ld + n0 + 2 * np) = v;      // vt_ld >= round_up(N, 64): in bounds
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn1_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                const Attn1TcParams p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+  uint64_t* q_full = bars;              // [1]
+  uint64_t* kv_full = bars + 1;         // [2]
+  uint64_t* kv_empty = bars + 3;        // [2]
+  uint64_t* s_full = bars + 5;          // [2]  (block a, b)
+  uint64_t* s_empty = bars + 7;         // [2]
+  uint64_t* p_full = bars + 9;          // [2]
+  uint64_t* pv_done = bars + 11;        // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int nqb = (p.N + 2 * TC_QB - 1) / (2 * TC_QB);
+  const int h = blockIdx.x / nqb, qblk = blockIdx.x - h * nqb;
+  const int q0 = qblk * 2 * TC_QB;
+  const int nkt = (p.N + TC_KT - 1) / TC_KT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * TC_Q_BYTES);
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int at = 0; at < 3; ++at)
+          tma_load_3d(smem + x * TC_Q_BYTES + at * (TC_QB * 128), &tmQ, q_full, h * TC_HD + at * 64, q0 + x * TC_QB, 0);
+    }
+    __syncwarp();
+    for (int i = 0; i < nkt; ++i) {
+      const int st = i & 1;
+      mbar_wait(&kv_empty[st], ((i >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&kv_full[st], TC_K_BYTES + TC_V_BYTES);
+#pragma unroll
+        for (int at = 0; at < 3; ++at)
+          tma_load_3d(smem + TC_OFF_K + st * TC_K_BYTES + at * (TC_KT * 128), &tmK, &kv_full[st], p.d + h * TC_HD + at * 64, i * TC_KT, 0);
+        tma_load_3d(smem + TC_OFF_V + st * TC_V_BYTES, &tmV, &kv_full[st], i * TC_KT, h * TC_HD, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc_s = make_idesc_16(TC_QB, TC_KT, true);
+    const uint32_t idesc_o = make_idesc_16(TC_QB, TC_HD, true);
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t tO[2] = {tmem_base, tmem_base + TC_HD};
+    const uint32_t tS[2] = {tmem_base + 2 * TC_HD, tmem_base + 2 * TC_HD + TC_KT};
+    auto issue_s = [&](int x, int i) {               // S_x(i) = Q_x K(i)^T
+      const int st = i & 1;
+      mbar_wait(&s_empty[x], (i & 1) ^ 1);             // the softmax warps hold S_x(i - 1) in registers
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int at = 0; at < 3; ++at) {
+          const uint64_t da = make_smem_desc_sw128(sb + x * TC_Q_BYTES + at * (TC_QB * 128));
+          const uint64_t db = make_smem_desc_sw128(sb + TC_OFF_K + st * TC_K_BYTES + at * (TC_KT * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tS[x], da + 2 * k, db + 2 * k, idesc_s, (at | k) ? 1u : 0u);
+        }
+        umma_commit(&s_full[x]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int x, int i) {              // O_x += P_x(i) V(i)
+      const int st = i & 1;
+      mbar_wait(&p_full[x], i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = make_smem_desc_sw128(sb + TC_OFF_P + x * TC_P_BYTES);
+        const uint64_t db = make_smem_desc_sw128(sb + TC_OFF_V + st * TC_V_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tO[x], da + 2 * k, db + 2 * k, idesc_o, (i | k) ? 1u : 0u);
+        umma_commit(&pv_done[x]);
+        if (x == 1) umma_commit(&kv_empty[st]);        // the last reader of this K / V stage
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    for (int i = 0; i < nkt; ++i) {
+      const bool more = i + 1 < nkt;
+      if (more) { mbar_wait(&kv_full[(i + 1) & 1], ((i + 1) >> 1) & 1); tc_fence_after(); }
+      issue_pv(0, i);
+      if (more) issue_s(0, i + 1);
+      issue_pv(1, i);
+      if (more) issue_s(1, i + 1);
+    }
+  } else {
+    // ===== softmax warps: block x, TMEM lane quarter q, thread = query row =====
+    const int x = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                    // row of the 128-row block = TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tO = tmem_base + x * TC_HD + lane_base;
+    const uint32_t tS = tmem_base + 2 * TC_HD + x * TC_KT + lane_base;
+    uint8_t* prow = smem + TC_OFF_P + x * TC_P_BYTES + row * 128;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    float m_ref = -INFINITY, l = 0.f;
+    for (int i = 0; i < nkt; ++i) {
+      mbar_wait(&s_full[x], i & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tS, r0);
+      tmem_ld32(tS + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&s_empty[x]);       // S_x may be overwritten by the next tile's MMA
+      const int live = p.N - i * TC_KT;                // keys of this tile that exist (TMA zero-filled the others)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float a0 = __uint_as_float(r0[j]) * p.sc, a1 = __uint_as_float(r1[j]) * p.sc;
+        if (j >= live) a0 = -INFINITY;
+        if (32 + j >= live) a1 = -INFINITY;
+        r0[j] = __float_as_uint(a0); r1[j] = __float_as_uint(a1);
+        mx = fmaxf(mx, fmaxf(a0, a1));
+      }
+      // O_x and the P_x buffer are stable once PV_x(i - 1) has retired
+      mbar_wait(&pv_done[x], (i & 1) ^ 1);
+      tc_fence_after();
+      const bool bump = mx > m_ref + TC_LAZY;          // first tile: m_ref = -inf -> true
+      if (__any_sync(0xffffffffu, bump)) {
+        const float m_new = bump ? mx : m_ref;
+        const float f = (m_ref == -INFINITY) ? 0.f : ex2_approx(m_ref - m_new);     // 1 for rows that keep their reference
+        if (i > 0) {                                    // rescale the accumulator of every row of this quarter (f = 1: unchanged)
+#pragma unroll 1
+          for (int c = 0; c < TC_HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
+            tmem_st32(tO + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        l *= f;
+        m_ref = m_new;
+      }
+      float ps = 0.f;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {                  // 8 keys = one 16-byte chunk of the P row
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = c8 * 8 + 2 * e;
+          const float e0 = ex2_approx(__uint_as_float(j < 32 ? r0[j] : r1[j - 32]) - m_ref);
+          const float e1 = ex2_approx(__uint_as_float(j + 1 < 32 ? r0[j + 1] : r1[j + 1 - 32]) - m_ref);
+          ps += e0 + e1;
+          w[e] = pack_h2(e0, e1);
+        }
+        *reinterpret_cast<uint4*>(prow + ((static_cast<uint32_t>(c8) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l += ps;
+      fence_proxy_async();                              // P (generic proxy) -> the MMA's async-proxy reads
+      tc_fence_before();                                // and the rescaled O (tcgen05.st) before the next accumulate
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&p_full[x]);
+    }
+    // ---- O / l -> global ----
+    mbar_wait(&pv_done[x], (nkt - 1) & 1);
+    tc_fence_after();
+    const int qi = q0 + x * TC_QB + row;
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    __half* orow = reinterpret_cast<__half*>(p.out) + (long long)qi * p.ld_o + h * TC_HD;
+#pragma unroll 1
+    for (int c = 0; c < TC_HD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tO + c * 32, o);
+      tmem_ld_wait();
+      if (qi < p.N) {
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          uint4 w;
+          w.x = pack_h2(__uint_as_float(o[8 * g4]) * inv, __uint_as_float(o[8 * g4 + 1]) * inv);
+          w.y = pack_h2(__uint_as_float(o[8 * g4 + 2]) * inv, __uint_as_float(o[8 * g4 + 3]) * inv);
+          w.z = pack_h2(__uint_as_float(o[8 * g4 + 4]) * inv, __uint_as_float(o[8 * g4 + 5]) * inv);
+          w.w = pack_h2(__uint_as_float(o[8 * g4 + 6]) * inv, __uint_as_float(o[8 * g4 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + 8 * g4) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool attn1_tc_eligible(const Attn1Args& a) {
+  return a.vt != nullptr && a.hd == TC_HD && a.wh == a.gh && a.ww == a.gw && a.sh == 0 && a.sw == 0 && a.mask == 0 && a.batch == 1 &&
+         a.gh * a.gw >= 512 && a.vt_ld >= ((a.gh * a.gw + 63) / 64) * 64 && (a.ld_qkv % 8) == 0 && (a.ld_o % 8) == 0 && (a.vt_ld % 8) == 0;
+}
+static const char* launch_attn1_tc(const Attn1Args& a, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    attr_set = true;
+  }
+  const int N = a.gh * a.gw, d = a.heads * a.hd;
+  CUtensorMap tmQ, tmK, tmV;
+  const char* e;
+  if ((e = encode_tma_2d_16(&tmQ, a.qkv, 3LL * d, N, a.ld_qkv, 64, TC_QB))) return e;
+  if ((e = encode_tma_2d_16(&tmK, a.qkv, 3LL * d, N, a.ld_qkv, 64, TC_KT))) return e;
+  if ((e = encode_tma_2d_16(&tmV, a.vt, N, (long long)d, a.vt_ld, 64, TC_HD))) return e;
+  launch_kernel(vt_transpose_kernel, dim3((N + 63) / 64, d / 64), dim3(256), 0, s, a.qkv, a.ld_qkv, N, d, a.vt, a.vt_ld);
+  Attn1TcParams p{N, a.heads, d, a.out, a.ld_o, a.scale * 1.4426950408889634f};
+  const int nqb = (N + 2 * TC_QB - 1) / (2 * TC_QB);
+  launch_kernel(attn1_tc_kernel, dim3(a.heads * nqb), dim3(TC_THREADS), TC_SMEM, s, tmQ, tmK, tmV, p);
+  return nullptr;
+}
+
 bool attn1_supported(int hd) { return hd == 32 || hd == 64 || hd == 192; }
 void launch_attn1(const Attn1Args& a, cudaStream_t s) {
   const int N = a.wh * a.ww;
+  if (attn1_tc_eligible(a) && !getenv("VV_NO_TC_ATTN")) {
+    if (!launch_attn1_tc(a, s)) return;               // (a descriptor that cannot be encoded falls through to the mma.sync kernel)
+  }
   if (N <= 80) {                      // one key tile, five query warps: the 6 x 12 windows (72 tokens)
     if (a.hd == 32) launch_attn1_t<32, 5, 80>(a, s);
     else if (a.hd == 64) launch_attn1_t<64, 5, 80>(a, s);

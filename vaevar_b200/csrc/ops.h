@@ -43,6 +43,7 @@ struct GemmDesc {
 const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb,
                            long long b_bs, const GemmArgs& args);
 void launch_gemm(const GemmDesc& d, cudaStream_t s);
+const char* encode_tma_2d_16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long ld, int box_cols, int box_rows);
 void set_gemm_debug_mode(int mode);                 // debug: 1 = MMA only, 2 = TMA feed only (results are garbage)
 void set_gemm_trace(unsigned long long* dev_ptr);   // debug: GEMM descriptors built afterwards stamp clocks into dev_ptr (null = off)
 
@@ -181,8 +182,11 @@ struct Attn1Args {
   const bf16* qkv; long long ld_qkv, qkv_bs;     // fp16 [batch][gh * gw][3 * heads * hd]
   bf16* out; long long ld_o, o_bs;               // fp16 [batch][gh * gw][heads * hd]
   float scale;
+  bf16* vt; long long vt_ld;                     // optional scratch [heads * hd][vt_ld >= round_up(gh * gw, 64)] fp16: with it, an unshifted
+                                                 // whole-grid window of head width 192 (the first LG stage) runs on the tcgen05 kernel
 };
 void launch_attn1(const Attn1Args& a, cudaStream_t s);
+bool attn1_tc_eligible(const Attn1Args& a);
 bool attn1_supported(int hd);
 
 // PatchEmbed with a 3 x 2 kernel and stride 2 (networks/LGUnet_all.py:14-50) + absolute position embedding (:396-400):
