@@ -108,6 +108,40 @@ def test_run_cases_world2_gloo():
     assert len(got[0]["seconds_per_rank"]) == 2 and got[0]["imbalance"] >= 1.0
 
 
+def test_run_cases_with_several_agents_in_flight():
+    """"One or more cases per GPU" (SURVEY 8e): the cases of a rank dealt to several agents, one host thread each -- every case is
+    computed once, and the per-case records and the reduced metrics are those of the single-agent run, whatever the interleaving."""
+    import threading
+    import time as _time
+    from vaevar_b200.dist import run_cases
+    seen = []
+
+    class Agent(_FakeAgent):
+        def one_step_DA(self, gt, xb, yo, H, R, mode="vae4dvar"):
+            seed = float(xb.flatten()[0])
+            _time.sleep(0.002 * ((int(seed) * 7) % 5))                 # uneven case lengths: the threads interleave
+            seen.append((int(seed), threading.get_ident()))
+            self.metrics_list["ana_wrmse"].append(torch.full((self.nchannel,), seed))
+            self.metrics_list["ana_bias"].append(torch.full((self.nchannel,), -seed))
+            self.history.append({"loss": 10.0 + seed, "gmax": 0.5 * seed})
+            return xb
+
+    def agents(n):
+        out = [Agent() for _ in range(n)]
+        for a in out:
+            a.history = []
+        return out
+
+    mk = lambda i: {k: torch.full((1, 3, 4, 8), float(i)) for k in ("gt", "yo", "H", "R")} | {"xb": torch.full((3, 4, 8), float(i))}
+    one = run_cases(agents(1)[0], 11, mk, 0, 1, "cpu")
+    seen.clear()
+    three = run_cases(agents(3), 11, mk, 0, 1, "cpu")
+    assert sorted(c for c, _ in seen) == list(range(11)) and len({t for _, t in seen}) == 3
+    assert three["cases_in_flight_per_gpu"] == 3 and one["cases_in_flight_per_gpu"] == 1
+    for k in ("n_cases", "mean_J", "mean_gmax", "rms_wrmse", "mean_bias", "case_records"):
+        assert one[k] == three[k], k
+
+
 def test_metric_reduction_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

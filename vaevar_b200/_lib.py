@@ -4,8 +4,11 @@ from __future__ import annotations
 import ctypes as C
 import pathlib
 
+import os
+
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libvaevar.so"
+# VV_LIB: an experimental build of the same library (tools/build_variant.sh) -- A/B measurements only
+LIB_PATH = pathlib.Path(os.environ["VV_LIB"]).resolve() if os.environ.get("VV_LIB") else _HERE / "libvaevar.so"
 
 VV_MAX_GROUPS = 8
 VV_MAX_LG = 8

@@ -91,6 +91,9 @@ struct alignas(64) GemmStoreMaps {
   CUtensorMap res, aux_in;      // loads
 };
 
+#ifndef VV_EPI_GW
+#define VV_EPI_GW 8                 // columns of an epilogue chunk processed together (8, 16 or 32)
+#endif
 constexpr int GEMM_BM = 128;        // rows per CTA (256 per pair)
 constexpr int GEMM_BK = 64;         // K elements per pipeline stage = one 128-byte swizzle row
 constexpr int GEMM_THREADS = 320;
@@ -143,75 +146,97 @@ VV_DEVINL void epilogue_chunk(const GemmArgs& p, uint32_t (&r)[32], const float 
   uint8_t* rowA = SA + lane * 128;
   uint8_t* rowA16 = SA + lane * 64;                                // slot A used as a 16-bit slab (saved pre-activation)
   uint8_t* rowB = SB + lane * 64;
+  // GW columns are in flight together: the dependent chains of the epilogue math (GELU: ~10 deep, two MUFU each) are hidden by
+  // the GW / 2 independent column pairs of a group, so wider groups stall less on fixed-latency dependencies (VV_EPI_GW).
+  constexpr int GW = VV_EPI_GW, NS = GW / 8;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {                                    // 4 groups of 8 columns
-    float v[8];
+  for (int g0 = 0; g0 < 32 / GW; ++g0) {
+    float v[GW];
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {                                 // packed fp32: two columns per instruction
-      const float2 a2 = make_float2(__uint_as_float(r[g * 8 + i]), __uint_as_float(r[g * 8 + i + 1]));
-      const float2 b2 = make_float2(bv[g * 8 + i], bv[g * 8 + i + 1]);
+    for (int i = 0; i < GW; i += 2) {                                // packed fp32: two columns per instruction
+      const float2 a2 = make_float2(__uint_as_float(r[g0 * GW + i]), __uint_as_float(r[g0 * GW + i + 1]));
+      const float2 b2 = make_float2(bv[g0 * GW + i], bv[g0 * GW + i + 1]);
       const float2 o2 = LNX == LN_CONSUME ? fma2(splat2(ln_a), a2, b2) : add2(a2, b2);
       v[i] = o2.x; v[i + 1] = o2.y;
     }
-    uint4 u16 = make_uint4(0, 0, 0, 0);
+    uint4 u16[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) u16[s] = make_uint4(0, 0, 0, 0);
     if (EPI == EPI_GELU) {
       if (has_auxout) {                      // gelu and gelu' share their transcendental work; the backward pass needs only gelu'(u)
-        float d[8];
+        float d[GW];
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
+        for (int i = 0; i < GW; i += 2) {
           float2 y2, d2;
+#ifdef VV_EXP_NOGELU
+          y2 = make_float2(v[i], v[i + 1]); d2 = y2;
+#else
           gelu_erf_both2(make_float2(v[i], v[i + 1]), &y2, &d2);
+#endif
           v[i] = y2.x; v[i + 1] = y2.y; d[i] = d2.x; d[i + 1] = d2.y;
         }
-        u16.x = pack16<F16>(d[0], d[1]); u16.y = pack16<F16>(d[2], d[3]);
-        u16.z = pack16<F16>(d[4], d[5]); u16.w = pack16<F16>(d[6], d[7]);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          u16[s].x = pack16<F16>(d[8 * s], d[8 * s + 1]); u16[s].y = pack16<F16>(d[8 * s + 2], d[8 * s + 3]);
+          u16[s].z = pack16<F16>(d[8 * s + 4], d[8 * s + 5]); u16[s].w = pack16<F16>(d[8 * s + 6], d[8 * s + 7]);
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
+        for (int i = 0; i < GW; i += 2) {
           const float2 y2 = gelu_erf2(make_float2(v[i], v[i + 1]));
           v[i] = y2.x; v[i + 1] = y2.y;
         }
       }
     } else if (EPI == EPI_DGELU) {
       if (has_auxin) {                       // aux = gelu'(u) saved by the forward GEMM
-        const uint4 w = *reinterpret_cast<const uint4*>(rowB + ((static_cast<uint32_t>(g) ^ sw64) << 4));
         const bool af = p.aux_f16 != 0;
-        const float2 u0 = unpack16(w.x, af), u1 = unpack16(w.y, af), u2 = unpack16(w.z, af), u3 = unpack16(w.w, af);
-        const float2 m0 = mul2(make_float2(v[0], v[1]), u0), m1 = mul2(make_float2(v[2], v[3]), u1);
-        const float2 m2 = mul2(make_float2(v[4], v[5]), u2), m3 = mul2(make_float2(v[6], v[7]), u3);
-        v[0] = m0.x; v[1] = m0.y; v[2] = m1.x; v[3] = m1.y; v[4] = m2.x; v[5] = m2.y; v[6] = m3.x; v[7] = m3.y;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          const int g = g0 * NS + s;
+          const uint4 w = *reinterpret_cast<const uint4*>(rowB + ((static_cast<uint32_t>(g) ^ sw64) << 4));
+          const float2 u0 = unpack16(w.x, af), u1 = unpack16(w.y, af), u2 = unpack16(w.z, af), u3 = unpack16(w.w, af);
+          float* vs = v + 8 * s;
+          const float2 m0 = mul2(make_float2(vs[0], vs[1]), u0), m1 = mul2(make_float2(vs[2], vs[3]), u1);
+          const float2 m2 = mul2(make_float2(vs[4], vs[5]), u2), m3 = mul2(make_float2(vs[6], vs[7]), u3);
+          vs[0] = m0.x; vs[1] = m0.y; vs[2] = m1.x; vs[3] = m1.y; vs[4] = m2.x; vs[5] = m2.y; vs[6] = m3.x; vs[7] = m3.y;
+        }
       }
     }
-    const uint32_t cA0 = (static_cast<uint32_t>(2 * g) ^ sw128) << 4, cA1 = (static_cast<uint32_t>(2 * g + 1) ^ sw128) << 4;
-    if (has_res) {
-      const float4 r0 = *reinterpret_cast<const float4*>(rowA + cA0);
-      const float4 r1 = *reinterpret_cast<const float4*>(rowA + cA1);
-      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-    }
-    if (LNX == LN_PRODUCE && p.stats_out) {   // deviations from the pivot; two independent partial chains per statistic
-      if (first && g == 0) piv = v[0];
-      float dv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dv[i] = v[i] - piv;
-      rs += (dv[0] + dv[1]) + (dv[2] + dv[3]) + ((dv[4] + dv[5]) + (dv[6] + dv[7]));
-      rq += fmaf(dv[0], dv[0], dv[1] * dv[1]) + fmaf(dv[2], dv[2], dv[3] * dv[3]) + (fmaf(dv[4], dv[4], dv[5] * dv[5]) + fmaf(dv[6], dv[6], dv[7] * dv[7]));
-    }
-    if (p.out_f32) {
-      *reinterpret_cast<float4*>(rowA + cA0) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(rowA + cA1) = make_float4(v[4], v[5], v[6], v[7]);
-    }
-    if (p.out_bf16) {
-      if (LNX == LN_PRODUCE) {                 // the copy a folded LayerNorm consumes is centred on the row's shift
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] -= shift;
+    for (int s = 0; s < NS; ++s) {
+      const int g = g0 * NS + s;                                     // 8-column subgroup = one 16-byte chunk of the 16-bit slabs
+      float* vs = v + 8 * s;
+      const uint32_t cA0 = (static_cast<uint32_t>(2 * g) ^ sw128) << 4, cA1 = (static_cast<uint32_t>(2 * g + 1) ^ sw128) << 4;
+      if (has_res) {
+        const float4 r0 = *reinterpret_cast<const float4*>(rowA + cA0);
+        const float4 r1 = *reinterpret_cast<const float4*>(rowA + cA1);
+        vs[0] += r0.x; vs[1] += r0.y; vs[2] += r0.z; vs[3] += r0.w;
+        vs[4] += r1.x; vs[5] += r1.y; vs[6] += r1.z; vs[7] += r1.w;
       }
-      uint4 w;
-      w.x = pack16<F16>(v[0], v[1]); w.y = pack16<F16>(v[2], v[3]);
-      w.z = pack16<F16>(v[4], v[5]); w.w = pack16<F16>(v[6], v[7]);
-      *reinterpret_cast<uint4*>(rowB + ((static_cast<uint32_t>(g) ^ sw64) << 4)) = w;
+      if (LNX == LN_PRODUCE && p.stats_out) {   // deviations from the pivot; two independent partial chains per statistic
+        if (first && g == 0) piv = vs[0];
+        float dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[i] = vs[i] - piv;
+        rs += (dv[0] + dv[1]) + (dv[2] + dv[3]) + ((dv[4] + dv[5]) + (dv[6] + dv[7]));
+        rq += fmaf(dv[0], dv[0], dv[1] * dv[1]) + fmaf(dv[2], dv[2], dv[3] * dv[3]) + (fmaf(dv[4], dv[4], dv[5] * dv[5]) + fmaf(dv[6], dv[6], dv[7] * dv[7]));
+      }
+      if (p.out_f32) {
+        *reinterpret_cast<float4*>(rowA + cA0) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+        *reinterpret_cast<float4*>(rowA + cA1) = make_float4(vs[4], vs[5], vs[6], vs[7]);
+      }
+      if (p.out_bf16) {
+        if (LNX == LN_PRODUCE) {                 // the copy a folded LayerNorm consumes is centred on the row's shift
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vs[i] -= shift;
+        }
+        uint4 w;
+        w.x = pack16<F16>(vs[0], vs[1]); w.y = pack16<F16>(vs[2], vs[3]);
+        w.z = pack16<F16>(vs[4], vs[5]); w.w = pack16<F16>(vs[6], vs[7]);
+        *reinterpret_cast<uint4*>(rowB + ((static_cast<uint32_t>(g) ^ sw64) << 4)) = w;
+      }
+      if (EPI == EPI_GELU && has_auxout) *reinterpret_cast<uint4*>(rowA16 + ((static_cast<uint32_t>(g) ^ sw64) << 4)) = u16[s];
     }
-    if (EPI == EPI_GELU && has_auxout) *reinterpret_cast<uint4*>(rowA16 + ((static_cast<uint32_t>(g) ^ sw64) << 4)) = u16;
   }
 }
 
@@ -514,11 +539,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef VV_EXP_NOBIAS
           if (bias && col + 4 * j < p.N) t = __ldg(reinterpret_cast<const float4*>(bias + col + 4 * j));
+#endif
           bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
           if (LNX == LN_CONSUME) {
             svv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef VV_EXP_NOBIAS
             if (colsum && col + 4 * j < p.N) svv[j] = __ldg(reinterpret_cast<const float4*>(colsum + col + 4 * j));
+#endif
           }
         }
         // (3) prefetch the residual / pre-activation of this warp's NEXT chunk into the other buffer
