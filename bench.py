@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inflight", action="store_true", help="skip the several-cases-in-flight-per-GPU measurement")
+    ap.add_argument("--no-forecast", action="store_true", help="skip the LGUnet_all_1 (721x1440 forecast network) measurement")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
@@ -471,6 +472,40 @@ def main():
         except Exception as ex:
             native = {"error": repr(ex), "restore_failed": True}
 
+    # ---- the cycle's forecast operator at the reference's size: one LGUnet_all_1 application on 69 x 721 x 1440,
+    # random-init weights of the shipped architecture; algorithmic flops = its Linears + attention. Diagnostics only. ----
+    forecast = None
+    if world == 1 and not args.no_forecast:
+        try:
+            from vaevar_b200.config import FORECAST_FULL
+            from vaevar_b200.forecast import ForecastNet
+            from vaevar_b200.synth import make_state_dict_net1
+            fnet = ForecastNet(FORECAST_FULL, keep_out=69, device=f"cuda:{local}")
+            fnet.load_state_dict(make_state_dict_net1(FORECAST_FULL, seed=1)); fnet.finalize()
+            xf = torch.randn(69, *FORECAST_FULL.img_size, device=dev)
+            for _ in range(2):
+                yf = fnet.forward(xf)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                yf = fnet.forward(xf)
+            e1.record(); torch.cuda.synchronize()
+            ms_f = e0.elapsed_time(e1) / 5
+            ops_f = fnet.profile_ops(2)
+            fl_f = sum(o["flop"] for o in ops_f) / 1e12
+            att = [o for o in ops_f if o["kind"] == "sd_attn" and o["shape"][0] == o["shape"][1]]
+            forecast = {"model": "LGUnet_all_1 (networks/LGUnet_all.py:743-777), 69x721x1440, forward only", "ms_per_application": ms_f,
+                        "launches": fnet.last_launch_count, "device_GiB": round(fnet.device_bytes / 2**30, 2), "algorithmic_tflop": round(fl_f, 2),
+                        "TFLOP/s": round(fl_f / (ms_f * 1e-3), 1), "frac_of_sustained": round(fl_f / (ms_f * 1e-3) / sustained, 3),
+                        "whole_grid_attention": {"kernel": "attn1_tc_kernel (tcgen05, TMEM, TMA)", "launches": len(att), "ms": round(sum(o["ms"] for o in att), 3),
+                                                 "TFLOP/s": round(sum(o["flop"] for o in att) / max(sum(o["ms"] for o in att), 1e-9) / 1e9, 1)},
+                        "finite": bool(torch.isfinite(yf).all())}
+            fnet.close()
+            del xf, yf
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            forecast = {"error": repr(ex)}
+
     cycles_per_hour_gpu = (3600.0 / cyc_s) if cyc_s else None
     line = {
         # weak scaling: the per-replica time of one cost+grad (max over ranks); the whole-job aggregate is evals_per_s
@@ -507,6 +542,7 @@ def main():
                           "algorithmic_tflop": tflop, "peak_source": f"{src} sustained"},
         "roofline_hbm": {"peak": hbm, "unit": "GB/s", "peak_source": src, "l2": "flushed before every timed launch", "kernels": hbm_rows},
         "native_geometry": native,
+        "forecast_net": forecast,
         "J": [float(v) for v in Jb.cpu()],
         "hbm_used_gb": hbm_used,
     }

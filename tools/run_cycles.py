@@ -36,6 +36,8 @@ ap.add_argument("--nit", type=int, default=4)
 ap.add_argument("--obs-frac", type=float, default=0.10)
 ap.add_argument("--small", action="store_true")
 ap.add_argument("--chains-per-gpu", type=int, default=1, help="independent cycle chains in flight on every GPU (one engine, stream and host thread each)")
+ap.add_argument("--native", action="store_true", help="the reference's real geometry: fields, observations and analysis on the 69x721x1440 grid "
+                "(decoder_hr / integrate(interpolation=True) composed into the engine) and the forecast step by LGUnet_all_1 at 721x1440")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
@@ -47,6 +49,14 @@ dcfg, fcfg = (small(DECODER_FULL), small(FLOW_FULL)) if a.small else (DECODER_FU
 S = a.chains_per_gpu
 sd_d, sd_f = make_state_dict(dcfg, seed=0), make_state_dict(fcfg, seed=1)
 agents = [VaeVar4D(dcfg, fcfg, sd_d, sd_f, da_win=a.T, Nit=a.nit, device=dev, verbose=False) for _ in range(S)]
+grid = dcfg.img_size
+if a.native:
+    from vaevar_b200.config import FORECAST_FULL
+    from vaevar_b200.modules import LGUnet_all_1
+    grid = FORECAST_FULL.img_size
+    fmodel = LGUnet_all_1(**FORECAST_FULL.to_reference_kwargs(), keep_out=69).to(dev).eval()        # random-init weights of the shipped architecture
+    for ag in agents:
+        ag.forecast_model = fmodel
 tmpdir = tempfile.TemporaryDirectory()
 tmp = tmpdir.name
 runs, files = [None] * S, [None] * S
@@ -61,7 +71,7 @@ def chain_worker(k):
         cid = rank * S + k
         agent = agents[k]
         with torch.cuda.stream(torch.cuda.Stream(device=dev)) if S > 1 else contextlib.nullcontext():
-            case = make_case(a.T, *dcfg.img_size, obs_frac=a.obs_frac, seed=100 + cid)
+            case = make_case(1, *grid, obs_frac=a.obs_frac, seed=100 + cid) if a.native else make_case(a.T, *dcfg.img_size, obs_frac=a.obs_frac, seed=100 + cid)
             mk = lambda name, n: CycledDA(agent, TwinObs(agent, torch.from_numpy(case["gt"][0]), obs_frac=a.obs_frac, seed=cid),
                                           torch.from_numpy(case["xb"]), name=name, root=tmp, n_cycles=n, resume=False)
             mk(f"warm{cid}", 1).run_assimilation()
@@ -103,7 +113,7 @@ for k, agent in enumerate(agents):
         h = agent.history[(c + 1) * a.nit - 1]
         acc.add(float(h["loss"]), float(h["gmax"]), an[c], bi[c])
     z500[rank * S + k] = torch.tensor([float(bg[0, 11]), float(an[0, 11]), float(bg[-1, 11]), float(an[-1, 11])], dtype=torch.float64)
-    evals[rank * S + k] = sum(h["func_evals"] if "func_evals" in h else h["n_evals"] for h in agent.history[-a.nit:])
+    evals[rank * S + k] = sum(h["n_evals"] for h in agent.history[-a.nit:])
 if world > 1:
     for t in (secs, z500, evals):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -117,9 +127,11 @@ if rank == 0:
            "cycles_total": s["n_cases"], "seconds_per_rank": per, "imbalance": max(per) / max(min(per), 1e-9),
            "seconds_per_cycle_per_chain": max(per) / a.cycles, "da_cycles_per_hour": 3600.0 * s["n_cases"] / max(per),
            "da_cycles_per_hour_per_gpu": 3600.0 * a.cycles * S / max(per),
-           "forecast_operator": "flow model on the 128x256 engine grid (da_4dvar.py:1329 uses LGUnet_all_1 at 721x1440: tests/test_gpu_net1.py)",
+           "analysis_grid": list(grid),
+           "forecast_operator": ("LGUnet_all_1 at 721x1440 (da_4dvar.py:1329), random-init weights of the shipped architecture" if a.native else
+                                 "flow model on the 128x256 engine grid (da_4dvar.py:1329 uses LGUnet_all_1 at 721x1440: --native)"),
            "z500_wrmse_per_chain[bg first, ana first, bg last, ana last]": z500.tolist(), "rms_ana_wrmse_z500": s["rms_wrmse"][11],
-           "mean_J_final": s["mean_J"], "files_per_chain": files[0], "func_evals_last_cycle_per_chain": evals.tolist()}
+           "mean_J_final": s["mean_J"], "files_per_chain": files[0], "closure_evals_last_cycle_per_chain": evals.tolist()}
     if a.out:
         pathlib.Path(a.out).parent.mkdir(parents=True, exist_ok=True)
         pathlib.Path(a.out).write_text(json.dumps(out))

@@ -38,7 +38,9 @@ class TwinObs:
         self.agent, self.steps = agent, steps_per_cycle
         self.truth = truth0.to(agent.device, torch.float32)
         self._cycle = 0
-        T, C, nlat, nlon = agent.da_win, agent.nchannel, agent.nlat, agent.nlon
+        # the observation grid is the truth's: the network grid, or a finer analysis grid (the reference's 721x1440)
+        T, C, nlat, nlon = agent.da_win, agent.nchannel, int(truth0.shape[-2]), int(truth0.shape[-1])
+        self.native = (nlat, nlon) != (agent.nlat, agent.nlon)
         rng = np.random.Generator(np.random.PCG64(2000 + seed))
         cols = rng.choice(nlat * nlon, int(obs_frac * nlat * nlon), replace=False)
         mask = np.zeros(nlat * nlon, np.float32)
@@ -48,12 +50,13 @@ class TwinObs:
         self.R = torch.from_numpy(np.broadcast_to(var, (T, C, nlat, nlon)).copy()).to(agent.device)
 
     def truth_window(self, cycle: int) -> torch.Tensor:
-        while self._cycle < cycle:                         # advance the truth run to the start of this window
-            self.truth = self.agent.integrate(self.truth, None, self.steps)
+        native = getattr(self, "native", False)
+        while self._cycle < cycle:                         # advance the truth run to the start of this window: the cycle's own forecast
+            self.truth = self.agent.integrate(self.truth, getattr(self.agent, "forecast_model", None), self.steps)      # operator (identical twin)
             self._cycle += 1
         gt = [self.truth]
-        for _ in range(self.agent.da_win - 1):
-            gt.append(self.agent.integrate(gt[-1], None, 1))
+        for _ in range(self.agent.da_win - 1):             # inside the window: the flow model, as the closure applies it (da_4dvar.py:1191)
+            gt.append(self.agent.integrate(gt[-1], None, 1, interpolation=native))
         return torch.stack(gt)
 
     def window(self, cycle: int):
