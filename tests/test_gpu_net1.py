@@ -192,6 +192,7 @@ def test_forecast_network_at_the_reference_size(lib):
     y0 = net.forward(x)
     torch.cuda.synchronize()
     t_setup = time.time() - t0
+    net.forward(x)                      # the timed application is the third: allocator and clocks have settled
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     y1 = net.forward(x)

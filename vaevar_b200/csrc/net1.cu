@@ -218,13 +218,18 @@ struct N1Builder {
     GemmArgs g = ga(rows, 3 * d, d, G);
     g.bias = w.bqkv; g.bias_bs = 3 * d; g.out_bf16 = t.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd;
     gemm(t.h, d, rd, w.Wqkv, d, 3LL * d * d, g);
-    Op o{}; o.kind = Op::ROPE;
-    o.rope = RopeArgs{gh, gw, wh, ww, sh, sw, w.heads, hd, G, t.qkv, 3LL * d, 3 * rd, rope_table(n, wh, ww, hd)};
-    n->plan.ops.push_back(o);
+    const float2* rtab = rope_table(n, wh, ww, hd);
+    const bool fused_rope = attn1_fuses_rope(wh, ww);             // short windows rotate q, k inside the attention kernel
+    Op o{};
+    if (!fused_rope) {
+      o.kind = Op::ROPE;
+      o.rope = RopeArgs{gh, gw, wh, ww, sh, sw, w.heads, hd, G, t.qkv, 3LL * d, 3 * rd, rtab};
+      n->plan.ops.push_back(o);
+    }
     o = Op{}; o.kind = Op::ATT1;
     const int mask = (sw > 0 && ww != gw) ? 1 : 0;                 // Attention.py:553: no mask when the window spans the whole width
     o.att1 = Attn1Args{gh, gw, wh, ww, sh, sw, w.heads, hd, G, mask, t.qkv, 3LL * d, 3 * rd, t.ao, (long long)d, rd, 1.0f / sqrtf((float)hd),
-                       (G == 1 && d == n->E) ? t.vt : nullptr, t.vt_ld};
+                       (G == 1 && d == n->E) ? t.vt : nullptr, t.vt_ld, fused_rope ? rtab : nullptr};
     n->plan.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = x1; g.ld_f32 = d; g.f32_bs = rd;
@@ -275,7 +280,7 @@ int net1_init(vv_net1& n, const vv_net1_config& c) {
   for (int s = 0; s < c.n_lg; ++s)
     N1_CHECK(c.lg_heads[s] >= 1 && n.E % c.lg_heads[s] == 0 && attn1_supported(n.E / c.lg_heads[s]), "trunk head width not built (32, 64, 192)");
   N1_CHECK(ln_supported(MAP_PLAIN, n.E), "LayerNorm width %d not instantiated", n.E);
-  N1_CHECK(n.D <= 128, "enc_dim too large for the patch kernels");
+  N1_CHECK(patch32_supported(n.D), "enc_dim %d not supported by the patch kernels (32, 64, 96, 128)", n.D);
   n.cin = n.cout = 0;
   for (int g = 0; g < n.G; ++g) {
     N1_CHECK(c.in_chans[g] >= 1 && c.out_chans[g] >= 2 && c.out_chans[g] % 2 == 0 && c.in_chans[g] <= 32 && c.out_chans[g] <= 64, "bad channel lists");
@@ -682,11 +687,13 @@ VV_API int vv_test_attn1(void* qkv_dev, void* out_dev, const float* table_dev, i
   N1_CHECK(gh % wh == 0 && gw % ww == 0, "grid is not a multiple of the window");
   cudaStream_t s = (cudaStream_t)stream;
   const long long d = (long long)heads * hd;
-  if (table_dev) {
+  const bool fused_rope = table_dev && attn1_fuses_rope(wh, ww);    // then q, k stay unrotated in qkv_dev
+  if (table_dev && !fused_rope) {
     RopeArgs r{gh, gw, wh, ww, sh, sw, heads, hd, 1, (bf16*)qkv_dev, 3 * d, 0, (const float2*)table_dev};
     launch_rope(r, s);
   }
-  Attn1Args a{gh, gw, wh, ww, sh, sw, heads, hd, 1, mask, (const bf16*)qkv_dev, 3 * d, 0, (bf16*)out_dev, d, 0, 1.0f / sqrtf((float)hd), nullptr, 0};
+  Attn1Args a{gh, gw, wh, ww, sh, sw, heads, hd, 1, mask, (const bf16*)qkv_dev, 3 * d, 0, (bf16*)out_dev, d, 0, 1.0f / sqrtf((float)hd), nullptr, 0,
+              fused_rope ? (const float2*)table_dev : nullptr};
   bf16* vt = nullptr;
   if (use_tc) {                                   // scratch for V^T: the whole-grid tcgen05 path (synchronises: test hook only)
     a.vt_ld = ((long long)gh * gw + 63) / 64 * 64;

@@ -18,6 +18,15 @@ VV_DEVINL void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row_ptr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(smem_row_ptr)));
 }
+VV_DEVINL void ldsm_x4(uint32_t (&r)[4], const void* smem_row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row_ptr)));
+}
+VV_DEVINL uint32_t pack_h2_rn(float a, float b) {        // the two roundings of __float2half_rn, packed (a in the low half)
+  const __half2 h = __halves2half2(__float2half_rn(a), __float2half_rn(b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 VV_DEVINL uint32_t pack_h2(float a, float b) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
@@ -62,101 +71,122 @@ void launch_rope(const RopeArgs& a, cudaStream_t s) {
 }
 
 // =============================================================================================
-// Attention over windows of any size: one CTA = one (window, head, query tile of 16 x WARPS rows); keys / values stream through
-// shared memory in tiles of KT tokens; S = Q K^T and O += P V are m16n8k16 tensor-core tiles (fp16 operands, fp32 accumulation),
-// the softmax is the online (running max / running sum) form, so a window may be the whole 90 x 180 grid.
+// The 6 x 12 windows (72 tokens <= 80: one key tile, plain softmax) as a PERSISTENT kernel: a CTA of five warps (16 query rows each)
+// walks over (window, head) items and stages item i + 1 (cp.async, second buffer) while it multiplies item i -- a window is ~1 us
+// of work behind several dependent global-memory latencies, so one-item CTAs were latency-bound at a fifth of the HBM roofline.
+// rope2 is applied to the staged q, k rows in shared memory when a.rope is set.
 // =============================================================================================
-template <int HD, int WARPS, int KT>
-struct Attn1Smem {
-  static constexpr int QR = 16 * WARPS;
-  static constexpr int RS = HD / 2 + 4;           // padded row stride in 32-bit words (16-byte aligned, conflict-free fragments)
-  static constexpr int WORDS = (QR + 2 * KT) * RS;
-  static constexpr int BYTES = WORDS * 4;
+template <int HD>
+struct Attn1WinSmem {
+  static constexpr int WARPS = 5, ROWS = 80;
+  static constexpr int RS = HD / 2 + 4;
+  static constexpr int BUF_WORDS = 3 * ROWS * RS;               // Q, K, V of one item
+  static constexpr int NBUF = (2 * BUF_WORDS * 4 <= 100 * 1024) ? 2 : 1;      // head width 192: one buffer (96 KB), no prefetch
+  static constexpr int BYTES = NBUF * BUF_WORDS * 4;
 };
 
-template <int HD, int WARPS, int KT>
-__global__ void __launch_bounds__(WARPS * 32) attn1_kernel(const Attn1Args a) {
-  using L = Attn1Smem<HD, WARPS, KT>;
-  constexpr int RS = L::RS, QR = L::QR, CH = HD / 8;            // CH: 16-byte chunks per row
-  extern __shared__ __align__(16) uint32_t at1_sm[];
-  uint32_t* Qs = at1_sm;
-  uint32_t* Ks = Qs + QR * RS;
-  uint32_t* Vs = Ks + KT * RS;
+template <int HD>
+__global__ void __launch_bounds__(160) attn1_win_kernel(const Attn1Args a) {
+  using L = Attn1WinSmem<HD>;
+  constexpr int RS = L::RS, ROWS = L::ROWS, CH = HD / 8, NB = L::NBUF;
+  extern __shared__ __align__(16) uint32_t at1w_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int N = a.wh * a.ww;
-  const int nq = (N + QR - 1) / QR;
   const int nww = a.gw / a.ww;
-  int item = blockIdx.x;
-  const int qt = item % nq; item /= nq;
-  const int h = item % a.heads; const int win = item / a.heads;
-  const int wi = win / nww, wj = win - wi * nww;
+  const int items = (a.gh / a.wh) * nww * a.heads;
   const int b = blockIdx.y;
   const int d = a.heads * HD;
   pdl_launch_dependents();
   pdl_wait();
   const __half* qkv = reinterpret_cast<const __half*>(a.qkv) + (long long)b * a.qkv_bs;
-  auto tok_of = [&](int n) {
+  __half* out = reinterpret_cast<__half*>(a.out) + (long long)b * a.o_bs;
+  auto tok_of = [&](int wi, int wj, int n) {
     const int r = n / a.ww, c = n - r * a.ww;
     int row = wi * a.wh + r + a.sh; if (row >= a.gh) row -= a.gh;
     int col = wj * a.ww + c + a.sw; if (col >= a.gw) col -= a.gw;
     return row * a.gw + col;
   };
-  // rows [n0, n0 + rows) of matrix m (0 q, 1 k, 2 v) -> dst; rows beyond N are zero-filled
-  auto stage = [&](uint32_t* dst, int m, int n0, int rows) {
-    for (int idx = threadIdx.x; idx < rows * CH; idx += WARPS * 32) {
+  auto stage_item = [&](uint32_t* buf, int item) {              // Q, K, V rows of one (window, head); rows beyond N are zero-filled
+    const int h = item % a.heads, win = item / a.heads, wi = win / nww, wj = win - wi * nww;
+    for (int idx = threadIdx.x; idx < ROWS * CH; idx += 160) {
       const int r = idx / CH, ch = idx - r * CH;
-      uint32_t* sp = dst + r * RS + 4 * ch;
-      if (n0 + r < N) {
-        const __half* src = qkv + (long long)tok_of(n0 + r) * a.ld_qkv + m * d + h * HD + 8 * ch;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sp)), "l"(src) : "memory");
+      uint32_t* sp = buf + r * RS + 4 * ch;
+      if (r < N) {
+        const __half* src = qkv + (long long)tok_of(wi, wj, r) * a.ld_qkv + h * HD + 8 * ch;
+#pragma unroll
+        for (int m = 0; m < 3; ++m)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sp + m * ROWS * RS)), "l"(src + m * d) : "memory");
       } else {
-        *reinterpret_cast<uint4*>(sp) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) *reinterpret_cast<uint4*>(sp + m * ROWS * RS) = make_uint4(0, 0, 0, 0);
       }
     }
   };
-  const int q0 = qt * QR;
-  stage(Qs, 0, q0, QR);
-  const int m0 = warp * 16;
-  // latitude bands of a masked window (the last window row of a shifted frame): local rows < wh - sh vs the rest
-  const bool masked = a.mask && a.sh > 0 && wi == a.gh / a.wh - 1;
-  const int band_row = a.wh - a.sh;
-  const int qi0 = q0 + m0 + g, qi1 = qi0 + 8;                    // this thread's two query rows (window-local indices)
-  const int qb0 = (qi0 / a.ww) < band_row ? 0 : 1, qb1 = (qi1 / a.ww) < band_row ? 0 : 1;
-
-  float o[HD / 8][4];
-#pragma unroll
-  for (int n = 0; n < HD / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
-  float mrun0 = -INFINITY, mrun1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   const float sc = a.scale * 1.4426950408889634f;              // softmax in base 2
-
-  for (int kv0 = 0; kv0 < N; kv0 += KT) {
-    __syncthreads();                                            // the previous tile's K / V are no longer read
-    stage(Ks, 1, kv0, KT);
-    stage(Vs, 2, kv0, KT);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const int band_row = a.wh - a.sh;
+  const int m0 = warp * 16;
+  const int lm = lane >> 3, lr = lane & 7;
+  int item = blockIdx.x, cur = 0;
+  if (item < items) stage_item(at1w_sm, item);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (; item < items; item += gridDim.x) {
+    uint32_t* Qs = at1w_sm + cur * L::BUF_WORDS;
+    uint32_t* Ks = Qs + ROWS * RS;
+    uint32_t* Vs = Ks + ROWS * RS;
+    const int nxt = item + gridDim.x;
+    if (NB == 2) {
+      if (nxt < items) stage_item(at1w_sm + (cur ^ 1) * L::BUF_WORDS, nxt);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
-    // ---- S = Q K^T ----
-    float s[KT / 8][4];
+    const int h = item % a.heads, win = item / a.heads, wi = win / nww, wj = win - wi * nww;
+    if (a.rope) {
+      // rope2 (positional_encodings.py:255-268) on the staged q and k rows: pair (x[j], x[hd / 2 + j]) of window-local token n turns
+      // by table[n][j]; two adjacent pairs per step, fp32 arithmetic, rounded back to fp16 exactly as the stand-alone kernel does
+      constexpr int HP = HD / 4;
+      for (int idx = threadIdx.x; idx < 2 * N * HP; idx += 160) {
+        const int rr = idx / HP, jp = idx - rr * HP;
+        const int n = rr < N ? rr : rr - N;
+        uint32_t* row = (rr < N ? Qs : Ks) + n * RS;
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(a.rope + (long long)n * (HD / 2) + 2 * jp));
+        const float2 x1 = __half22float2(*reinterpret_cast<__half2*>(&row[jp]));
+        const float2 x2 = __half22float2(*reinterpret_cast<__half2*>(&row[HD / 4 + jp]));
+        row[jp] = pack_h2_rn(x1.x * cs.x - x2.x * cs.y, x1.y * cs.z - x2.y * cs.w);
+        row[HD / 4 + jp] = pack_h2_rn(x2.x * cs.x + x1.x * cs.y, x2.y * cs.z + x1.y * cs.w);
+      }
+      __syncthreads();
+    }
+    // ---- S = Q K^T: this warp's 16 query rows against the 80 key rows ----
+    float s[ROWS / 8][4];
 #pragma unroll
-    for (int j = 0; j < KT / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+    for (int j = 0; j < ROWS / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < HD / 16; ++ks) {
-      const int w = ks * 8 + t;
-      const uint32_t af[4] = {Qs[(m0 + g) * RS + w], Qs[(m0 + g + 8) * RS + w], Qs[(m0 + g) * RS + w + 4], Qs[(m0 + g + 8) * RS + w + 4]};
+      uint32_t af[4];
+      ldsm_x4(af, Qs + (m0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * RS + 4 * (lane >> 4) + ks * 8);
 #pragma unroll
-      for (int j = 0; j < KT / 8; ++j) mma_f16(s[j], af, Ks[(8 * j + g) * RS + w], Ks[(8 * j + g) * RS + w + 4]);
+      for (int j = 0; j < ROWS / 8; j += 2) {
+        uint32_t kb[4];
+        ldsm_x4(kb, Ks + (j * 8 + (lane & 7) + 8 * (lane >> 4)) * RS + 4 * ((lane >> 3) & 1) + ks * 8);
+        mma_f16(s[j], af, kb[0], kb[1]);
+        mma_f16(s[j + 1], af, kb[2], kb[3]);
+      }
     }
-    // ---- scale, mask, online softmax ----
+    // ---- scale, mask (the two latitude bands of the last window row of a shifted frame), softmax ----
+    const bool masked = a.mask && a.sh > 0 && wi == a.gh / a.wh - 1;
+    const int qi0 = m0 + g, qi1 = qi0 + 8;
+    const int qb0 = (qi0 / a.ww) < band_row ? 0 : 1, qb1 = (qi1 / a.ww) < band_row ? 0 : 1;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < KT / 8; ++j) {
+    for (int j = 0; j < ROWS / 8; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int kn = kv0 + 8 * j + 2 * t + e;
-        bool dead = kn >= N;
-        bool dead0 = dead, dead1 = dead;
-        if (masked && !dead) {
+        const int kn = 8 * j + 2 * t + e;
+        bool dead0 = kn >= N, dead1 = dead0;
+        if (masked && !dead0) {
           const int kb = (kn / a.ww) < band_row ? 0 : 1;
           dead0 = kb != qb0; dead1 = kb != qb1;
         }
@@ -167,78 +197,81 @@ __global__ void __launch_bounds__(WARPS * 32) attn1_kernel(const Attn1Args a) {
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(mrun0, mx0), mn1 = fmaxf(mrun1, mx1);
-    const float ms0 = mn0 == -INFINITY ? 0.f : mn0, ms1 = mn1 == -INFINITY ? 0.f : mn1;     // a row that has seen no live key yet
-    const float c0 = ex2_approx(mrun0 - ms0), c1 = ex2_approx(mrun1 - ms1);                 // exp2(-inf) = 0
-    mrun0 = mn0; mrun1 = mn1;
-    float ps0 = 0.f, ps1 = 0.f;
+    if (mx0 == -INFINITY) mx0 = 0.f;
+    if (mx1 == -INFINITY) mx1 = 0.f;
+    float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < KT / 8; ++j) {
-      s[j][0] = ex2_approx(s[j][0] - ms0); s[j][1] = ex2_approx(s[j][1] - ms0);
-      s[j][2] = ex2_approx(s[j][2] - ms1); s[j][3] = ex2_approx(s[j][3] - ms1);
-      ps0 += s[j][0] + s[j][1]; ps1 += s[j][2] + s[j][3];
+    for (int j = 0; j < ROWS / 8; ++j) {
+      s[j][0] = ex2_approx(s[j][0] - mx0); s[j][1] = ex2_approx(s[j][1] - mx0);
+      s[j][2] = ex2_approx(s[j][2] - mx1); s[j][3] = ex2_approx(s[j][3] - mx1);
+      l0 += s[j][0] + s[j][1]; l1 += s[j][2] + s[j][3];
     }
-    l0 = l0 * c0 + ps0; l1 = l1 * c1 + ps1;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+    // ---- O = P V, normalised, staged through this warp's own Q rows (read by no other warp), stored ----
+    uint32_t pa[ROWS / 16][4];
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
-    // ---- O += P V ----
-    const int lm = lane >> 3, lr = lane & 7;
+    for (int kb = 0; kb < ROWS / 16; ++kb) {
+      pa[kb][0] = pack_h2(s[2 * kb][0], s[2 * kb][1]); pa[kb][1] = pack_h2(s[2 * kb][2], s[2 * kb][3]);
+      pa[kb][2] = pack_h2(s[2 * kb + 1][0], s[2 * kb + 1][1]); pa[kb][3] = pack_h2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+    }
+    __syncwarp();
 #pragma unroll
-    for (int kb = 0; kb < KT / 16; ++kb) {
-      const uint32_t pa[4] = {pack_h2(s[2 * kb][0], s[2 * kb][1]), pack_h2(s[2 * kb][2], s[2 * kb][3]),
-                              pack_h2(s[2 * kb + 1][0], s[2 * kb + 1][1]), pack_h2(s[2 * kb + 1][2], s[2 * kb + 1][3])};
+    for (int c16 = 0; c16 < HD / 16; ++c16) {
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c16 = 0; c16 < HD / 16; ++c16) {
+      for (int kb = 0; kb < ROWS / 16; ++kb) {
         uint32_t vb[4];
         ldsm_x4_trans(vb, Vs + (16 * kb + (lm & 1) * 8 + lr) * RS + c16 * 8 + (lm >> 1) * 4);
-        mma_f16(o[2 * c16], pa, vb[0], vb[1]);
-        mma_f16(o[2 * c16 + 1], pa, vb[2], vb[3]);
+        mma_f16(o0, pa[kb], vb[0], vb[1]);
+        mma_f16(o1, pa[kb], vb[2], vb[3]);
       }
+      Qs[(m0 + g) * RS + c16 * 8 + t] = pack_h2(o0[0] * i0, o0[1] * i0);
+      Qs[(m0 + g + 8) * RS + c16 * 8 + t] = pack_h2(o0[2] * i1, o0[3] * i1);
+      Qs[(m0 + g) * RS + c16 * 8 + 4 + t] = pack_h2(o1[0] * i0, o1[1] * i0);
+      Qs[(m0 + g + 8) * RS + c16 * 8 + 4 + t] = pack_h2(o1[2] * i1, o1[3] * i1);
     }
-  }
-  // ---- normalise, stage through this warp's Q rows, store ----
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
-  __syncwarp();
-#pragma unroll
-  for (int n = 0; n < HD / 8; ++n) {
-    Qs[(m0 + g) * RS + n * 4 + t] = pack_h2(o[n][0] * i0, o[n][1] * i0);
-    Qs[(m0 + g + 8) * RS + n * 4 + t] = pack_h2(o[n][2] * i1, o[n][3] * i1);
-  }
-  __syncwarp();
-  __half* out = reinterpret_cast<__half*>(a.out) + (long long)b * a.o_bs;
-  for (int idx = lane; idx < 16 * CH; idx += 32) {
-    const int r = idx / CH, ch = idx - r * CH;
-    const int qi = q0 + m0 + r;
-    if (qi < N)
-      *reinterpret_cast<uint4*>(out + (long long)tok_of(qi) * a.ld_o + h * HD + 8 * ch) = *reinterpret_cast<const uint4*>(Qs + (m0 + r) * RS + 4 * ch);
+    __syncwarp();
+    for (int idx = lane; idx < 16 * CH; idx += 32) {
+      const int r = idx / CH, ch = idx - r * CH;
+      const int qi = m0 + r;
+      if (qi < N)
+        *reinterpret_cast<uint4*>(out + (long long)tok_of(wi, wj, qi) * a.ld_o + h * HD + 8 * ch) = *reinterpret_cast<const uint4*>(Qs + (m0 + r) * RS + 4 * ch);
+    }
+    __syncthreads();                                            // the buffer may be refilled (prefetch of the item after next / the next item)
+    if (NB == 2) cur ^= 1;
+    else {
+      if (nxt < items) stage_item(at1w_sm, nxt);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
   }
 }
 
-template <int HD, int WARPS, int KT>
-static void launch_attn1_t(const Attn1Args& a, cudaStream_t s) {
-  using L = Attn1Smem<HD, WARPS, KT>;
+template <int HD>
+static void launch_attn1_win_t(const Attn1Args& a, cudaStream_t s) {
+  using L = Attn1WinSmem<HD>;
   static bool attr_set = false;
+  static int per_sm = 1;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn1_kernel<HD, WARPS, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    cudaFuncSetAttribute(attn1_win_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, attn1_win_kernel<HD>, 160, L::BYTES) != cudaSuccess || per_sm < 1) per_sm = 1;
     attr_set = true;
   }
-  const int N = a.wh * a.ww, nq = (N + L::QR - 1) / L::QR;
-  const long long items = (long long)(a.gh / a.wh) * (a.gw / a.ww) * a.heads * nq;
-  launch_kernel(attn1_kernel<HD, WARPS, KT>, dim3((unsigned)items, a.batch), dim3(WARPS * 32), L::BYTES, s, a);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)(a.gh / a.wh) * (a.gw / a.ww) * a.heads;
+  const long long grid = std::min<long long>(items, std::max(1LL, (long long)sms * per_sm / std::max(1, a.batch)));
+  launch_kernel(attn1_win_kernel<HD>, dim3((unsigned)grid, a.batch), dim3(160), L::BYTES, s, a);
 }
+
 // =============================================================================================
 // Long windows (the whole-grid first LG stage: 16 200 tokens): the same online-softmax attention with the operand traffic of a
 // flash kernel -- one CTA = one (window, head, 128 query rows), eight warps of 16 rows; keys / values stream through a
 // double-buffered cp.async ring of 64-token tiles (the loads of tile i + 1 fly while tile i is multiplied); Q, K fragments come
 // from ldmatrix.x4 (one shared-memory instruction per two MMAs), V fragments from ldmatrix.x4.trans.
 // =============================================================================================
-VV_DEVINL void ldsm_x4(uint32_t (&r)[4], const void* smem_row_ptr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(smem_row_ptr)));
-}
 
 template <int HD>
 struct Attn1LongSmem {
@@ -720,15 +753,16 @@ static const char* launch_attn1_tc(const Attn1Args& a, cudaStream_t s) {
 }
 
 bool attn1_supported(int hd) { return hd == 32 || hd == 64 || hd == 192; }
+bool attn1_fuses_rope(int wh, int ww) { return wh * ww <= 80; }
 void launch_attn1(const Attn1Args& a, cudaStream_t s) {
   const int N = a.wh * a.ww;
   if (attn1_tc_eligible(a) && !getenv("VV_NO_TC_ATTN")) {
     if (!launch_attn1_tc(a, s)) return;               // (a descriptor that cannot be encoded falls through to the mma.sync kernel)
   }
   if (N <= 80) {                      // one key tile, five query warps: the 6 x 12 windows (72 tokens)
-    if (a.hd == 32) launch_attn1_t<32, 5, 80>(a, s);
-    else if (a.hd == 64) launch_attn1_t<64, 5, 80>(a, s);
-    else if (a.hd == 192) launch_attn1_t<192, 5, 80>(a, s);
+    if (a.hd == 32) launch_attn1_win_t<32>(a, s);
+    else if (a.hd == 64) launch_attn1_win_t<64>(a, s);
+    else if (a.hd == 192) launch_attn1_win_t<192>(a, s);
   } else {                            // long windows (the whole-grid first LG stage): 128-row query tiles, 64-key tiles, double-buffered
     if (a.hd == 32) launch_attn1_long_t<32>(a, s);
     else if (a.hd == 64) launch_attn1_long_t<64>(a, s);
@@ -739,8 +773,14 @@ void launch_attn1(const Attn1Args& a, cudaStream_t s) {
 // =============================================================================================
 // Patch embedding, 3 x 2 kernel / stride 2
 // =============================================================================================
+// One CTA = 64 tokens x D channels of one group.  The patch tile is staged as [k][token] (image rows are read as coalesced float2
+// pixel pairs), the group's weights as [k][D]; a thread accumulates 4 tokens x NC channels in registers (one LDS.128 of patch values
+// and NC / 2 LDS.64 of weights per 4 NC FMAs), so the kernel runs on the FMA pipe instead of the shared-memory pipe.
 constexpr int P32_TOK = 64;
+template <int D>
 __global__ void __launch_bounds__(256) patch32_kernel(const Patch32Args a) {
+  constexpr int CG = 16, NC = D / CG;                 // 16 channel groups of NC channels x 16 token groups of 4 tokens = 256 threads
+  static_assert(D % 32 == 0 && NC % 2 == 0, "D");
   extern __shared__ __align__(16) float p32_sm[];
   const int g = blockIdx.y;
   const int L0 = a.h0 * a.w0;
@@ -749,103 +789,167 @@ __global__ void __launch_bounds__(256) patch32_kernel(const Patch32Args a) {
   pdl_wait();
   const int cnt = a.kcnt[g], cb = a.cbase[g];
   const int K = cnt * 6;
-  float* patch = p32_sm;                         // [P32_TOK][K + 1]
-  float* Ws = patch + P32_TOK * (K + 1);         // [K][D]
+  float* patch = p32_sm;                         // [K][P32_TOK]
+  float* Ws = patch + a.max_cnt * 6 * P32_TOK;   // [K][D]
   const long long HW = (long long)a.H * a.W;
-  for (int idx = threadIdx.x; idx < P32_TOK * K; idx += 256) {
-    const int k = idx / P32_TOK, tk = idx - k * P32_TOK;          // consecutive threads -> consecutive tokens (stride-2 pixels)
-    const int ci = k / 6, kr = (k - ci * 6) >> 1, kc = k & 1;
+  for (int idx = threadIdx.x; idx < cnt * 3 * P32_TOK; idx += 256) {
+    const int tk = idx % P32_TOK, rk = idx / P32_TOK, ci = rk / 3, kr = rk - ci * 3;
     const int tok = t0 + tk;
-    float v = 0.f;
+    float2 v = make_float2(0.f, 0.f);
     if (tok < L0) {
       const int i = tok / a.w0, j = tok - i * a.w0;
-      v = a.img[(cb + ci) * HW + (long long)(2 * i + kr) * a.W + 2 * j + kc];
+      v = *reinterpret_cast<const float2*>(a.img + (cb + ci) * HW + (long long)(2 * i + kr) * a.W + 2 * j);     // W even: 8-byte aligned
     }
-    patch[tk * (K + 1) + k] = v;
+    patch[(rk * 2) * P32_TOK + tk] = v.x;
+    patch[(rk * 2 + 1) * P32_TOK + tk] = v.y;
   }
-  const float* wsrc = a.Wp + (long long)cb * 6 * a.D;
-  for (int idx = threadIdx.x; idx < K * a.D; idx += 256) Ws[idx] = wsrc[idx];
+  const float* wsrc = a.Wp + (long long)cb * 6 * D;
+  for (int idx = threadIdx.x; idx < K * D / 4; idx += 256) reinterpret_cast<float4*>(Ws)[idx] = __ldg(reinterpret_cast<const float4*>(wsrc) + idx);
   __syncthreads();
-  for (int idx = threadIdx.x; idx < P32_TOK * a.D; idx += 256) {
-    const int tk = idx / a.D, c = idx - tk * a.D;
-    const int tok = t0 + tk;
+  const int cq = threadIdx.x % CG, tq = threadIdx.x / CG;
+  float acc[4][NC];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[t][c] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float4 pv = *reinterpret_cast<const float4*>(patch + k * P32_TOK + 4 * tq);
+    float w[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c += 2) {
+      const float2 w2 = *reinterpret_cast<const float2*>(Ws + k * D + NC * cq + c);
+      w[c] = w2.x; w[c + 1] = w2.y;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      acc[0][c] = fmaf(pv.x, w[c], acc[0][c]); acc[1][c] = fmaf(pv.y, w[c], acc[1][c]);
+      acc[2][c] = fmaf(pv.z, w[c], acc[2][c]); acc[3][c] = fmaf(pv.w, w[c], acc[3][c]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int tok = t0 + 4 * tq + t;
     if (tok >= L0) continue;
-    float acc = a.bias[g * a.D + c];
-    const float* pr = patch + tk * (K + 1);
-    for (int k = 0; k < K; ++k) acc = fmaf(pr[k], Ws[k * a.D + c], acc);
-    const long long o = ((long long)g * L0 + tok) * a.D + c;
-    a.tok[o] = acc + a.ape[o];
+    const long long o = ((long long)g * L0 + tok) * D + NC * cq;
+#pragma unroll
+    for (int c = 0; c < NC; c += 2) {
+      const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bias + g * D + NC * cq + c));
+      const float2 e2 = __ldg(reinterpret_cast<const float2*>(a.ape + o + c));
+      *reinterpret_cast<float2*>(a.tok + o + c) = make_float2(acc[t][c] + b2.x + e2.x, acc[t][c + 1] + b2.y + e2.y);
+    }
   }
 }
-void launch_patch32(const Patch32Args& a, cudaStream_t s) {
+template <int D>
+static void launch_patch32_t(const Patch32Args& a, cudaStream_t s) {
   const int K = a.max_cnt * 6;
-  const size_t smem = (size_t)(P32_TOK * (K + 1) + K * a.D) * sizeof(float);
+  const size_t smem = (size_t)(K * P32_TOK + K * D) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
-    cudaFuncSetAttribute(patch32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(patch32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
   const int L0 = a.h0 * a.w0;
-  launch_kernel(patch32_kernel, dim3((L0 + P32_TOK - 1) / P32_TOK, a.G), dim3(256), smem, s, a);
+  launch_kernel(patch32_kernel<D>, dim3((L0 + P32_TOK - 1) / P32_TOK, a.G), dim3(256), smem, s, a);
+}
+bool patch32_supported(int D) { return D == 32 || D == 64 || D == 96 || D == 128; }
+void launch_patch32(const Patch32Args& a, cudaStream_t s) {
+  switch (a.D) {
+    case 32: launch_patch32_t<32>(a, s); break;
+    case 64: launch_patch32_t<64>(a, s); break;
+    case 96: launch_patch32_t<96>(a, s); break;
+    case 128: launch_patch32_t<128>(a, s); break;
+    default: break;
+  }
 }
 
 // =============================================================================================
 // ConvTranspose2d head, 3 x 2 kernel / stride 2: output-stationary (no atomics) -- a CTA owns image rows 2 i and 2 i + 1 over 64
 // patch columns of one group and reads patch rows i (kernel rows 0, 1) and i - 1 (kernel row 2, the overlap onto row 2 i).
+// A thread owns two patch columns (four pixels) x two output slots x both image rows: 24 FMAs per channel against two LDS.64 of
+// token values and six LDS.64 of weights ([slot][channel][kernel row][kernel column] in shared memory).
 // =============================================================================================
 constexpr int CT_TOK = 64;
 __global__ void __launch_bounds__(256) convt32_kernel(const ConvT32Args a) {
   extern __shared__ __align__(16) float ct_sm[];
-  const int g = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * CT_TOK;
-  const int D = a.D, DS = D + 1;
+  const int nblk = (a.max_cnt + 15) / 16;         // blocks of 16 output slots per group
+  const int g = blockIdx.z / nblk, sb = blockIdx.z - g * nblk, i = blockIdx.y, j0 = blockIdx.x * CT_TOK;
+  const int D = a.D;
+  constexpr int XS = CT_TOK + 2;                  // row stride of the transposed token tiles: 8-byte aligned pairs, 2-way store conflicts
   pdl_launch_dependents();
   pdl_wait();
-  const int cnt = a.kcnt[g], cb = a.cbase[g];
-  float* X0 = ct_sm;                              // [CT_TOK][D + 1] patch row i      (zeros if i == h0)
-  float* X1 = X0 + CT_TOK * DS;                   // [CT_TOK][D + 1] patch row i - 1  (zeros if i == 0)
-  float* Ws = X1 + CT_TOK * DS;                   // [cnt][3][2][D]
+  const int cnt = a.kcnt[g] - 16 * sb, cb = a.cbase[g] + 16 * sb;      // this CTA's slots: cb .. cb + min(cnt, 16)
+  if (cnt <= 0) return;
+  float* X0 = ct_sm;                              // [D][XS] patch row i      (zeros if i == h0)
+  float* X1 = X0 + D * XS;                        // [D][XS] patch row i - 1  (zeros if i == 0)
+  float* Ws = X1 + D * XS;                        // [16 slots][D][3][2] (slots >= cnt: zeros)
   const long long L0 = (long long)a.h0 * a.w0;
   for (int idx = threadIdx.x; idx < CT_TOK * D; idx += 256) {
-    const int tk = idx / D, c = idx - tk * D;
+    const int tk = idx / D, c = idx - tk * D;     // consecutive threads -> consecutive channels of a token (coalesced reads)
     const int j = j0 + tk;
     float v0 = 0.f, v1 = 0.f;
     if (j < a.w0) {
       if (i < a.h0) v0 = a.tok[((long long)g * L0 + (long long)i * a.w0 + j) * D + c];
       if (i > 0) v1 = a.tok[((long long)g * L0 + (long long)(i - 1) * a.w0 + j) * D + c];
     }
-    X0[tk * DS + c] = v0; X1[tk * DS + c] = v1;
+    X0[c * XS + tk] = v0; X1[c * XS + tk] = v1;
   }
-  const float* wsrc = a.Wt + (long long)cb * 6 * D;
-  for (int idx = threadIdx.x; idx < cnt * 6 * D; idx += 256) Ws[idx] = wsrc[idx];
+  const float* wsrc = a.Wt + (long long)cb * 6 * D;            // [slot][3][2][D]
+  for (int idx = threadIdx.x; idx < 16 * 6 * D; idx += 256) {
+    const int slot = idx / (6 * D), rem = idx - slot * 6 * D, kk = rem / D, c = rem - kk * D;
+    Ws[(slot * D + c) * 6 + kk] = slot < cnt ? __ldg(wsrc + idx) : 0.f;
+  }
   __syncthreads();
-  const long long HW = (long long)a.H * a.W;
-  const int npx = 2 * CT_TOK;
-  // outputs of this CTA: cnt slots x 2 image rows x 128 pixels
-  for (int idx = threadIdx.x; idx < cnt * 2 * npx; idx += 256) {
-    const int px = idx % npx, rest = idx / npx, par = rest & 1, slot = rest >> 1;
-    const int tk = px >> 1, kc = px & 1;
-    const int x = 2 * j0 + px, y = 2 * i + par;
-    if (x >= a.W || y >= a.H) continue;
-    float acc = a.bias[cb + slot];
-    const float* w = Ws + (long long)slot * 6 * D;
-    if (par == 0) {                                // even row: kernel row 0 of patch row i, kernel row 2 of patch row i - 1
-      const float *wa = w + (0 * 2 + kc) * D, *wb = w + (2 * 2 + kc) * D, *xa = X0 + tk * DS, *xb = X1 + tk * DS;
-      for (int c = 0; c < D; ++c) acc = fmaf(xa[c], wa[c], fmaf(xb[c], wb[c], acc));
-    } else {                                       // odd row: kernel row 1 of patch row i
-      const float *wa = w + (1 * 2 + kc) * D, *xa = X0 + tk * DS;
-      for (int c = 0; c < D; ++c) acc = fmaf(xa[c], wa[c], acc);
+  const int tp = threadIdx.x & 31, sg = threadIdx.x >> 5;      // token pair (2 tp, 2 tp + 1), slot pair (2 sg, 2 sg + 1)
+  float ev[2][2][2], od[2][2][2];                              // [slot][token][kernel column]: even / odd image row
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) ev[s][t][0] = ev[s][t][1] = od[s][t][0] = od[s][t][1] = 0.f;
+  if (2 * sg < cnt) {
+    for (int c = 0; c < D; ++c) {
+      const float2 x0 = *reinterpret_cast<const float2*>(X0 + c * XS + 2 * tp);
+      const float2 x1 = *reinterpret_cast<const float2*>(X1 + c * XS + 2 * tp);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float* w = Ws + ((2 * sg + s) * D + c) * 6;
+        const float2 k0 = *reinterpret_cast<const float2*>(w), k1 = *reinterpret_cast<const float2*>(w + 2), k2 = *reinterpret_cast<const float2*>(w + 4);
+        ev[s][0][0] = fmaf(x0.x, k0.x, fmaf(x1.x, k2.x, ev[s][0][0])); ev[s][0][1] = fmaf(x0.x, k0.y, fmaf(x1.x, k2.y, ev[s][0][1]));
+        ev[s][1][0] = fmaf(x0.y, k0.x, fmaf(x1.y, k2.x, ev[s][1][0])); ev[s][1][1] = fmaf(x0.y, k0.y, fmaf(x1.y, k2.y, ev[s][1][1]));
+        od[s][0][0] = fmaf(x0.x, k1.x, od[s][0][0]); od[s][0][1] = fmaf(x0.x, k1.y, od[s][0][1]);
+        od[s][1][0] = fmaf(x0.y, k1.x, od[s][1][0]); od[s][1][1] = fmaf(x0.y, k1.y, od[s][1][1]);
+      }
     }
-    a.img[a.chan[cb + slot] * HW + (long long)y * a.W + x] = acc;
+  }
+  const long long HW = (long long)a.H * a.W;
+  const int x = 2 * (j0 + 2 * tp);                             // first of this thread's four pixels
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int slot = 2 * sg + s;
+    if (slot >= cnt || x >= a.W) continue;
+    const float b = a.bias[cb + slot];
+    float* base = a.img + a.chan[cb + slot] * HW;
+    const bool four = x + 3 < a.W;                             // W even: a thread has four pixels or two
+    if (2 * i < a.H) {
+      float* p = base + (long long)(2 * i) * a.W + x;
+      *reinterpret_cast<float2*>(p) = make_float2(ev[s][0][0] + b, ev[s][0][1] + b);
+      if (four) *reinterpret_cast<float2*>(p + 2) = make_float2(ev[s][1][0] + b, ev[s][1][1] + b);
+    }
+    if (2 * i + 1 < a.H) {
+      float* p = base + (long long)(2 * i + 1) * a.W + x;
+      *reinterpret_cast<float2*>(p) = make_float2(od[s][0][0] + b, od[s][0][1] + b);
+      if (four) *reinterpret_cast<float2*>(p + 2) = make_float2(od[s][1][0] + b, od[s][1][1] + b);
+    }
   }
 }
 void launch_convt32(const ConvT32Args& a, cudaStream_t s) {
-  const size_t smem = (size_t)(2 * CT_TOK * (a.D + 1) + a.max_cnt * 6 * a.D) * sizeof(float);
+  const size_t smem = (size_t)(2 * (CT_TOK + 2) * a.D + 16 * 6 * a.D) * sizeof(float);
   static size_t attr = 0;
   if (smem > attr) {
     cudaFuncSetAttribute(convt32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  launch_kernel(convt32_kernel, dim3((a.w0 + CT_TOK - 1) / CT_TOK, a.h0 + 1, a.G), dim3(256), smem, s, a);
+  const int nblk = (a.max_cnt + 15) / 16;
+  launch_kernel(convt32_kernel, dim3((a.w0 + CT_TOK - 1) / CT_TOK, a.h0 + 1, a.G * nblk), dim3(256), smem, s, a);
 }
 
 }  // namespace vv

@@ -184,7 +184,10 @@ struct Attn1Args {
   float scale;
   bf16* vt; long long vt_ld;                     // optional scratch [heads * hd][vt_ld >= round_up(gh * gw, 64)] fp16: with it, an unshifted
                                                  // whole-grid window of head width 192 (the first LG stage) runs on the tcgen05 kernel
+  const float2* rope;                            // optional rope2 table [wh * ww][hd / 2] (cos, sin): windows of <= 80 tokens rotate q and k
+                                                 // on their way through shared memory (qkv is then left unrotated); null = q, k are rotated already
 };
+bool attn1_fuses_rope(int wh, int ww);
 void launch_attn1(const Attn1Args& a, cudaStream_t s);
 bool attn1_tc_eligible(const Attn1Args& a);
 bool attn1_supported(int hd);
@@ -201,6 +204,7 @@ struct Patch32Args {
   int max_cnt;
 };
 void launch_patch32(const Patch32Args& a, cudaStream_t s);
+bool patch32_supported(int D);
 
 // The ConvTranspose2d head, kernel 3 x 2 / stride 2 (networks/LGUnet_all.py:606-650): adjacent patch rows overlap-add on even
 // image rows.  img[chan[slot]][y][x] = bias[slot] + sum_c sum_{(i, kr): 2 i + kr = y} tok[g][i * w0 + x / 2][c] Wt[slot][kr][x % 2][c]
