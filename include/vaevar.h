@@ -208,6 +208,20 @@ VV_API int vv_test_gemm_ln(const void* A_16_dev, const void* B_16_dev, const flo
                     int parts, int C, float eps, void* out_16_dev, void* aux_16_dev, float* out_f32_dev, float* stats_out_dev,
                     int* parts_out_host, int M, int N, int K, int batch, int epi, const float* shift_dev, int prod_bn,
                     uint32_t* health_dev, const float* res_f32_dev, void* stream);
+/* Fused tower MLP (the second half of a Swin block, swinblock.py:13-29, 304-307) as ONE kernel per direction; D in {64, 96, 128, 192},
+ * rows a multiple of 128.  Forward: out = x1 + fc2(gelu(fc1(normalise(x1)))) where W1 (batch, 4D, D) / b1 (batch, 4D) are fc1 with norm2's
+ * gamma / beta folded in (W o gamma, b + W beta), W2 (batch, D, 4D), b2 (batch, D); u_out (batch, rows, 4D) receives gelu'(u) for the
+ * backward pass; optional: out_16 = out - shift (shift (batch, rows) or null) and stats_out (batch, rows) float2 = (mean, M2) of the
+ * output rows (what the next block's folded norm1 consumes).  16-bit buffers are fp16 if f16 != 0, else bf16. */
+VV_API int vv_test_mlp_fwd(const float* x1_dev, const void* W1_16_dev, const void* W2_16_dev, const float* b1_dev, const float* b2_dev, int rows,
+                    int batch, int D, int f16, float eps, void* u_out_16_dev, float* out_f32_dev, void* out_16_dev, const float* shift_dev,
+                    float* stats_out_dev, void* stream);
+/* Its input-VJP: dx = LN^T((dy W2 . u) W1) + dres with dy (batch, rows, D) bf16, u = the saved gelu'(u) (fp16 if f16 != 0), W2T (batch, 4D, D)
+ * = fc2.weight^T and W1T (batch, D, 4D) = fc1.weight^T in bf16 (unfolded), gamma (batch, D) = norm2.weight, x1 the forward input, dres
+ * the fp32 gradient arriving over the residual branch; writes dx fp32 and its bf16 copy. */
+VV_API int vv_test_mlp_bwd(const void* dy_bf16_dev, const void* u_16_dev, const float* x1_dev, const void* W2T_bf16_dev, const void* W1T_bf16_dev,
+                    const float* gamma_dev, const float* dres_dev, int rows, int batch, int D, int f16, float eps, float* dx_dev,
+                    void* dx_bf16_dev, void* stream);
 /* Statistics pass at a stage input: x (rows, C) fp32 -> out_16 = x - mean (16-bit), stats (rows) float2 = (mean, M2), shift = mean. */
 VV_API int vv_test_ln_stats(const float* x_dev, void* out_16_dev, float* stats_dev, float* shift_dev, int rows, int C, int f16, void* stream);
 /* Debug: GEMM launches built after this call stamp per-CTA clock64 values into trace_dev (64 x uint64 per CTA; layout in

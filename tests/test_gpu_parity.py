@@ -23,7 +23,7 @@ def chk():
     return gpu_check
 
 
-@pytest.mark.parametrize("stage", ["gemm", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small"])
+@pytest.mark.parametrize("stage", ["gemm", "mlp", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small"])
 def test_stage(chk, stage):
     assert getattr(chk, "stage_" + stage)(), f"stage {stage} has failing checks (see stdout)"
 

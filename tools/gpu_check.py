@@ -12,7 +12,7 @@ import time
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
-STAGES = ["gemm", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
+STAGES = ["gemm", "mlp", "ln", "attn", "obs", "lbfgs_testfn", "net_small", "cost_small", "lbfgs_small", "net_full", "cost_full"]
 
 
 def rel(a, b):
@@ -111,6 +111,88 @@ def stage_gemm():
             e1.record(); torch.cuda.synchronize()
             line.append(f"{name} {e0.elapsed_time(e1)/30*1e3:.1f}us")
         print(f"[gemm] time epilogues {M}x{N}x{K}x{B}: " + " | ".join(line), flush=True)
+    return ok
+
+
+def stage_mlp():
+    """Fused tower MLP (mlp_fused.cuh) against fp32 torch: forward out / saved gelu' / statistics / centred 16-bit copy, backward dx."""
+    import ctypes as C
+    import torch
+    import torch.nn.functional as F
+    from vaevar_b200 import _lib
+    lib = _lib.load()
+    dev = "cuda:0"
+    ok = True
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    eps = 1e-5
+    for (rows, D, B) in [(128, 64, 1), (512, 64, 6), (128, 128, 6), (256, 96, 2), (8192, 96, 6), (2048, 192, 6), (128 * 150, 96, 1)]:
+        for f16 in (1, 0):
+            dt = torch.float16 if f16 else torch.bfloat16
+            tol16 = 8e-4 if f16 else 5e-3
+            tag = f"{rows}x{D}x{B} {'f16' if f16 else 'bf16'}"
+            g = torch.Generator(device=dev).manual_seed(rows + D + B)
+            x1 = torch.randn(B, rows, D, device=dev, generator=g) * 1.5 + 0.7 + torch.randn(B, rows, 1, device=dev, generator=g) * 3.0
+            W1 = (torch.randn(B, 4 * D, D, device=dev, generator=g) * 0.08).to(dt)
+            W2 = (torch.randn(B, D, 4 * D, device=dev, generator=g) * 0.05).to(dt)
+            b1 = torch.randn(B, 4 * D, device=dev, generator=g) * 0.3
+            b2 = torch.randn(B, D, device=dev, generator=g) * 0.3
+            shift = x1.mean(-1) + 0.1
+            u = torch.empty(B, rows, 4 * D, device=dev, dtype=dt)
+            out = torch.empty(B, rows, D, device=dev)
+            o16 = torch.empty(B, rows, D, device=dev, dtype=dt)
+            stats = torch.empty(B, rows, 2, device=dev)
+            _lib.check(lib.vv_test_mlp_fwd(P(x1), P(W1), P(W2), P(b1), P(b2), rows, B, D, f16, eps, P(u), P(out), P(o16), P(shift), P(stats), st))
+            torch.cuda.synchronize()
+            xn = F.layer_norm(x1, (D,), eps=eps)
+            pre = torch.einsum("brk,bnk->brn", xn.to(dt).float(), W1.float()) + b1[:, None, :]
+            pre.requires_grad_(True)
+            hid = F.gelu(pre)
+            hid.sum().backward()
+            ref = x1 + torch.einsum("brk,bnk->brn", hid.detach().to(dt).float(), W2.float()) + b2[:, None, :]
+            ok &= report("mlp", f"fwd out {tag}", rel(out, ref), 3e-5 if f16 else 5e-5)
+            ok &= report("mlp", f"fwd gelu' {tag}", rel(u.float(), pre.grad), tol16)
+            ok &= report("mlp", f"fwd 16-bit copy {tag}", rel(o16.float(), ref - shift[..., None]), tol16)
+            ok &= report("mlp", f"fwd stats mean {tag}", rel(stats[..., 0], ref.mean(-1)), 2e-6)
+            ok &= report("mlp", f"fwd stats M2 {tag}", rel(stats[..., 1], ((ref - ref.mean(-1, keepdim=True)) ** 2).sum(-1)), 2e-5)
+            # backward: dx = LN^T((dy W2 . u) W1) + dres, bf16 operands, u as saved by the forward kernel
+            dy = torch.randn(B, rows, D, device=dev, generator=g)
+            dyb = dy.bfloat16()
+            gamma = 1.0 + 0.2 * torch.randn(B, D, device=dev, generator=g)
+            W2T = (W2.float().transpose(1, 2).contiguous()).bfloat16()       # [B][4D][D]
+            W1T = (W1.float().transpose(1, 2).contiguous()).bfloat16()       # [B][D][4D]
+            dx = torch.empty(B, rows, D, device=dev); dxb = torch.empty(B, rows, D, device=dev, dtype=torch.bfloat16)
+            _lib.check(lib.vv_test_mlp_bwd(P(dyb), P(u), P(x1), P(W2T), P(W1T), P(gamma), P(dy), rows, B, D, f16, eps, P(dx), P(dxb), st))
+            torch.cuda.synchronize()
+            du = (torch.einsum("brd,bnd->brn", dyb.float(), W2T.float()) * u.float()).bfloat16().float()
+            dh = torch.einsum("brn,bdn->brd", du, W1T.float())
+            xr = x1.clone().requires_grad_(True)
+            (F.layer_norm(xr, (D,), eps=eps) * gamma[:, None, :] * dh).sum().backward()
+            refdx = xr.grad + dy
+            ok &= report("mlp", f"bwd dx {tag}", rel(dx, refdx), 6e-3)
+            ok &= report("mlp", f"bwd dx bf16 {tag}", rel(dxb.float(), dx), 4e-3)
+    # timing at the engine's shapes
+    for (rows, D, B) in [(8192, 96, 6), (2048, 192, 6)]:
+        dt = torch.float16
+        x1 = torch.randn(B, rows, D, device=dev); W1 = (torch.randn(B, 4 * D, D, device=dev) * 0.08).to(dt); W2 = (torch.randn(B, D, 4 * D, device=dev) * 0.05).to(dt)
+        b1 = torch.randn(B, 4 * D, device=dev); b2 = torch.randn(B, D, device=dev); shift = x1.mean(-1).contiguous()
+        u = torch.empty(B, rows, 4 * D, device=dev, dtype=dt); out = torch.empty(B, rows, D, device=dev); o16 = torch.empty(B, rows, D, device=dev, dtype=dt)
+        stats = torch.empty(B, rows, 2, device=dev)
+        dyb = torch.randn(B, rows, D, device=dev).bfloat16(); dres = torch.randn(B, rows, D, device=dev); gamma = torch.ones(B, D, device=dev)
+        W2T = W2.float().transpose(1, 2).contiguous().bfloat16(); W1T = W1.float().transpose(1, 2).contiguous().bfloat16()
+        dx = torch.empty(B, rows, D, device=dev); dxb = torch.empty(B, rows, D, device=dev, dtype=torch.bfloat16)
+        fw = lambda: lib.vv_test_mlp_fwd(P(x1), P(W1), P(W2), P(b1), P(b2), rows, B, D, 1, eps, P(u), P(out), P(o16), P(shift), P(stats), st)
+        bw = lambda: lib.vv_test_mlp_bwd(P(dyb), P(u), P(x1), P(W2T), P(W1T), P(gamma), P(dres), rows, B, D, 1, eps, P(dx), P(dxb), st)
+        for name, fn in (("fwd", fw), ("bwd", bw)):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(30):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 30 * 1e3
+            print(f"[mlp] time {name} {rows}x{D}x{B}: {us:.1f} us = {16.0 * rows * D * D * B / us / 1e6:.0f} TFLOP/s", flush=True)
     return ok
 
 

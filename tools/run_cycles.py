@@ -38,6 +38,8 @@ ap.add_argument("--small", action="store_true")
 ap.add_argument("--chains-per-gpu", type=int, default=1, help="independent cycle chains in flight on every GPU (one engine, stream and host thread each)")
 ap.add_argument("--native", action="store_true", help="the reference's real geometry: fields, observations and analysis on the 69x721x1440 grid "
                 "(decoder_hr / integrate(interpolation=True) composed into the engine) and the forecast step by LGUnet_all_1 at 721x1440")
+ap.add_argument("--chain-base", type=int, default=0, help="first chain id of this job (chain ids seed the truth, background and mask)")
+ap.add_argument("--verbose", action="store_true", help="print the per-cycle z500 WRMSE of every chain of rank 0")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
@@ -68,7 +70,7 @@ def chain_worker(k):
     """Chain `rank * S + k`: its own truth, background and mask seeds; warm-up cycle (graph capture, lazy loads), then the measured chain."""
     try:
         torch.cuda.set_device(local)
-        cid = rank * S + k
+        cid = a.chain_base + rank * S + k
         agent = agents[k]
         with torch.cuda.stream(torch.cuda.Stream(device=dev)) if S > 1 else contextlib.nullcontext():
             case = make_case(1, *grid, obs_frac=a.obs_frac, seed=100 + cid) if a.native else make_case(a.T, *dcfg.img_size, obs_frac=a.obs_frac, seed=100 + cid)
@@ -112,6 +114,11 @@ for k, agent in enumerate(agents):
     for c in range(an.shape[0]):
         h = agent.history[(c + 1) * a.nit - 1]
         acc.add(float(h["loss"]), float(h["gmax"]), an[c], bi[c])
+    if a.verbose and rank == 0:
+        print(f"chain {a.chain_base + k}: z500 WRMSE per cycle (bg -> ana): " + " ".join(f"{float(bg[c, 11]):.4g}->{float(an[c, 11]):.4g}" for c in range(an.shape[0])),
+              flush=True)
+        print(f"chain {a.chain_base + k}: closure evals per L-BFGS step: " + " ".join(str(h["n_evals"]) for h in agent.history), flush=True)
+        print(f"chain {a.chain_base + k}: final J per step: " + " ".join(f"{h['loss']:.4g}" for h in agent.history), flush=True)
     z500[rank * S + k] = torch.tensor([float(bg[0, 11]), float(an[0, 11]), float(bg[-1, 11]), float(an[-1, 11])], dtype=torch.float64)
     evals[rank * S + k] = sum(h["n_evals"] for h in agent.history[-a.nit:])
 if world > 1:

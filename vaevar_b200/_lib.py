@@ -76,6 +76,8 @@ _SIGS = {
     "vv_test_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vv_test_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, C.POINTER(C.c_int), C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "vv_test_mlp_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "vv_test_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     "vv_test_ln_stats": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "vv_debug_gemm_trace": (C.c_int, [_P]),
     "vv_debug_gemm_mode": (C.c_int, [C.c_int]),

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libvaevar.so"
-SOURCES = ["gemm.cu", "kernels.cu", "obs_lbfgs.cu", "engine.cu", "lbfgs.cu", "seams.cu", "net1_kernels.cu", "net1.cu"]
+SOURCES = ["gemm.cu", "kernels.cu", "obs_lbfgs.cu", "engine.cu", "lbfgs.cu", "seams.cu", "net1_kernels.cu", "net1.cu", "mlp_fused.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -115,6 +115,8 @@ static const char* op_family(Op::Kind k) {
     case Op::ATT1: return "SD_attn";
     case Op::PE32: return "patch embed (3,2)";
     case Op::CT32: return "conv-transpose head (3,2)";
+    case Op::MLP_F: return "fused tower MLP fwd (tcgen05)";
+    case Op::MLP_B: return "fused tower MLP bwd (tcgen05)";
   }
   return "op";
 }
@@ -136,6 +138,7 @@ int Plan::run(cudaStream_t s) const {
       case Op::ATT1: launch_attn1(o.att1, s); break;
       case Op::PE32: launch_patch32(o.pe32, s); break;
       case Op::CT32: launch_convt32(o.ct32, s); break;
+      case Op::MLP_F: case Op::MLP_B: launch_mlp(o.mlp, s); break;
     }
     if (nv) nvtxRangePop();
   }
@@ -445,6 +448,14 @@ struct Builder {
   vv_engine* e; Net* n; Temps t; const char* err = nullptr;
   int f16 = 0;        // forward activations / weights in fp16 (gradients always bf16)
   bool fold = true;   // norm1 / norm2 folded into the qkv / fc1 GEMMs (vv_config::no_ln_fold)
+  bool fuse_mlp = true;   // tower blocks: norm2 + fc1 + GELU + fc2 + residual (and its input-VJP) as one kernel (VV_NO_FUSED_MLP=1: off)
+  bool mlp_fused(const BlockW& w, int rows) const { return fuse_mlp && fold && mlp_fused_supported(w.d, rows); }
+  void mlp(Plan& P, bool bwd, int D, const bf16* W1, const bf16* W2, const bf16* u, const bf16* dy16, const MlpArgs& a) {
+    Op o{}; o.kind = bwd ? Op::MLP_B : Op::MLP_F;
+    const char* er = make_mlp_desc(&o.mlp, D, bwd, W1, W2, u, dy16, a);
+    if (er && !err) err = er;
+    P.ops.push_back(o);
+  }
 
   void gemm(Plan& P, const bf16* A, long long lda, long long a_bs, const bf16* B, long long ldb, long long b_bs, GemmArgs g) {
     Op o{}; o.kind = Op::GEMM;
@@ -528,6 +539,21 @@ struct Builder {
     P.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = st.x1; g.ld_f32 = d; g.f32_bs = rd;
+    if (mlp_fused(w, rows)) {
+      // the MLP half as one kernel: norm2 is computed from x1 inside it, so proj only has to leave the fp32 residual stream
+      gemm(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g);
+      MlpArgs m{};
+      m.rows = rows; m.batch = G; m.f16 = f16; m.eps = 1e-5f; m.x1 = st.x1; m.b1 = w.c1; m.b2 = w.b2; m.out_f32 = x_out; m.u_out = st.u;
+      if (emit_next) {
+        m.out16 = t.h; m.ld16 = d; m.bs16 = rd; m.shift = t.lnshift; m.stats_out = t.lnst;
+        parts = 1; prod_bn = 0;
+      } else {
+        if (copy_b) { m.out16 = copy_b; m.ld16 = ld_c; m.bs16 = bs_c; }
+        parts = 0;
+      }
+      mlp(P, false, d, w.W1, w.W2, st.u, nullptr, m);
+      return;
+    }
     int parts2 = 0, bn2 = 0;
     if (fold) parts2 = gemm_with_stats(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g, d, bn2);
     else gemm(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g);
@@ -556,13 +582,20 @@ struct Builder {
   void block_bwd(Plan& P, const BlockW& w, int gh, int gw, int shift, const float* x, BlkStash& st, float* g32, bf16* g16) {
     const int G = w.G, d = w.d, rows = gh * gw;
     const long long rd = (long long)rows * d;
-    GemmArgs g = gb(rows, 4 * d, d, G);                       // d(gelu out) = dy W2 ; du = . * gelu'(u)
-    g.epi = EPI_DGELU; g.aux_in = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd; g.out_bf16 = t.du; g.ld_bf16 = 4 * d; g.bf16_bs = 4 * rd;
-    gemm(P, g16, d, rd, w.W2T, d, 4LL * d * d, g);
-    g = gb(rows, d, 4 * d, G);                                // d(LN2 out) = du W1
-    g.out_bf16 = t.dhb; g.ld_bf16 = d; g.bf16_bs = rd;        // bf16 like every other gradient that enters a GEMM / LayerNorm adjoint
-    gemm(P, t.du, 4 * d, 4 * rd, w.W1T, 4 * d, 4LL * d * d, g);
-    ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, nullptr, d, rd, g32, d, rd, t.dx1, d, rd, t.dx1b, d, rd, t.dhb);
+    GemmArgs g{};
+    if (mlp_fused(w, rows)) {                                 // dx1 = LN2^T((dy W2 . gelu'(u)) W1) + dy in one kernel
+      MlpArgs m{};
+      m.rows = rows; m.batch = G; m.f16 = f16; m.eps = 1e-5f; m.x1 = st.x1; m.gamma = w.g2; m.dres = g32; m.dx = t.dx1; m.dx16 = t.dx1b;
+      mlp(P, true, d, w.W2T, w.W1T, st.u, g16, m);
+    } else {
+      g = gb(rows, 4 * d, d, G);                              // d(gelu out) = dy W2 ; du = . * gelu'(u)
+      g.epi = EPI_DGELU; g.aux_in = st.u; g.ld_aux = 4 * d; g.aux_bs = 4 * rd; g.out_bf16 = t.du; g.ld_bf16 = 4 * d; g.bf16_bs = 4 * rd;
+      gemm(P, g16, d, rd, w.W2T, d, 4LL * d * d, g);
+      g = gb(rows, d, 4 * d, G);                              // d(LN2 out) = du W1
+      g.out_bf16 = t.dhb; g.ld_bf16 = d; g.bf16_bs = rd;      // bf16 like every other gradient that enters a GEMM / LayerNorm adjoint
+      gemm(P, t.du, 4 * d, 4 * rd, w.W1T, 4 * d, 4LL * d * d, g);
+      ln_b(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, st.x1, d, rd, w.g2, nullptr, d, rd, g32, d, rd, t.dx1, d, rd, t.dx1b, d, rd, t.dhb);
+    }
     g = gb(rows, d, d, G);                                    // d(attn out) = dx1 Wproj
     g.out_bf16 = t.dao; g.ld_bf16 = d; g.bf16_bs = rd;
     gemm(P, t.dx1b, d, rd, w.WprojT, d, (long long)d * d, g);
@@ -782,6 +815,7 @@ static int build_plans(vv_engine* e) {
     Builder B{e, &n, t};
     B.f16 = e->cfg.forward_fp16 ? 1 : 0;
     B.fold = e->cfg.no_ln_fold == 0;
+    B.fuse_mlp = getenv("VV_NO_FUSED_MLP") == nullptr;
     if (a == 0) {
       B.net_fwd(e->fwd[a], e->stash[a], e->Z, e->DOUT);
       B.net_bwd(e->bwd[a], e->stash[a], e->GD, e->GZ);
@@ -1425,8 +1459,12 @@ VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_ou
     if (k < cap) {
       ms_out[k] = ms / reps;
       kind_out[k] = (int)o.kind;
-      if (flop_out) flop_out[k] = o.kind == Op::GEMM ? 2.0 * o.gemm.a.M * o.gemm.a.N * o.gemm.a.K * o.gemm.a.batch : 0.0;
-      if (mnk_out) {
+      const bool is_mlp = o.kind == Op::MLP_F || o.kind == Op::MLP_B;
+      if (flop_out) flop_out[k] = o.kind == Op::GEMM ? 2.0 * o.gemm.a.M * o.gemm.a.N * o.gemm.a.K * o.gemm.a.batch
+                                  : is_mlp ? 16.0 * o.mlp.a.rows * o.mlp.D * o.mlp.D * o.mlp.a.batch : 0.0;      // two GEMMs of rows x 4D x D
+      if (mnk_out && is_mlp) {
+        mnk_out[4 * k] = o.mlp.a.rows; mnk_out[4 * k + 1] = 4 * o.mlp.D; mnk_out[4 * k + 2] = o.mlp.D; mnk_out[4 * k + 3] = o.mlp.a.batch;
+      } else if (mnk_out) {
         mnk_out[4 * k] = o.kind == Op::GEMM ? o.gemm.a.M : (o.kind == Op::LN_F ? o.lnf.rows : o.kind == Op::LN_B ? o.lnb.rows : 0);
         mnk_out[4 * k + 1] = o.kind == Op::GEMM ? o.gemm.a.N : (o.kind == Op::LN_F ? o.lnf.C : o.kind == Op::LN_B ? o.lnb.C : (o.kind == Op::ATT_F || o.kind == Op::ATT_B) ? o.att.hd : 0);
         mnk_out[4 * k + 2] = o.kind == Op::GEMM ? o.gemm.a.K : 0;

@@ -17,7 +17,7 @@ void launch_fold_ln(bf16* dst, float* colsum, float* cbias, const float* W, cons
 bool ln_supported(int map, int C);
 
 struct Op {
-  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P, ROPE, ATT1, PE32, CT32 } kind;
+  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P, ROPE, ATT1, PE32, CT32, MLP_F, MLP_B } kind;
   GemmDesc gemm;
   LnArgs lnf;
   LnBwdArgs lnb;
@@ -27,6 +27,7 @@ struct Op {
   Attn1Args att1;
   Patch32Args pe32;
   ConvT32Args ct32;
+  MlpDesc mlp;           // fused tower MLP (mlp_fused.cuh), forward / backward
 };
 struct Plan {
   std::vector<Op> ops;

@@ -27,14 +27,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 3-D map over a [batch][rows][cols] tensor of 2-byte (fp16 / bf16 storage) or 4-byte elements, box = (box_cols x box_rows x 1).
-// The box row must span 128 bytes (128B swizzle) or 64 bytes (64B swizzle); OOB -> zeros on loads / clipped on stores.
+// The box row must span 128 bytes (128B swizzle), 64 bytes (64B swizzle) or 32 bytes (no swizzle); OOB -> zeros on loads / clipped on stores.
 static const char* encode_map_t(CUtensorMap* tm, const void* base, bool f32, long long K, long long rows, long long batch,
                                 long long ld, long long bs, int box_cols, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return "cuTensorMapEncodeTiled entry point not available";
   const int es = f32 ? 4 : 2;
   const int row_bytes = box_cols * es;
-  if (row_bytes != 128 && row_bytes != 64) return "GEMM tensor-map box row must be 64 or 128 bytes";
+  if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32) return "GEMM tensor-map box row must be 32, 64 or 128 bytes";
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * es) & 15) || (batch > 1 && ((bs * es) & 15))) return "GEMM operand not 16-byte aligned";
   cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t gstr[2] = {(cuuint64_t)ld * es, (cuuint64_t)(batch > 1 ? bs : ld * rows) * es};
@@ -42,7 +42,8 @@ static const char* encode_map_t(CUtensorMap* tm, const void* base, bool f32, lon
   cuuint32_t estr[3] = {1, 1, 1};
   // the 16-bit payload is opaque to TMA (no arithmetic, OOB fill is zero bits): fp16 data uses the same map type as bf16
   CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[160];
@@ -59,7 +60,14 @@ const char* encode_tma_2d_16(CUtensorMap* tm, const void* base, long long cols, 
   return encode_map_t(tm, base, false, cols, rows, 1, ld, 0, box_cols, box_rows);
 }
 
-static int num_sms() {
+// 3-D map over a [batch][rows][cols] tensor of 16-bit elements (row stride ld, batch stride bs, in elements); the box row decides
+// the swizzle: 128 B -> 128B, 64 B -> 64B, 32 B -> none (dense rows).  Used by the fused tower MLP (mlp_fused.cu).
+const char* encode_tma_3d_16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch, long long ld, long long bs,
+                             int box_cols, int box_rows) {
+  return encode_map_t(tm, base, false, cols, rows, batch, ld, bs, box_cols, box_rows);
+}
+
+int num_sms() {
   static int n = 0;
   if (!n) {
     int dev = 0;

@@ -1,0 +1,592 @@
+// The MLP half of a tower Swin block in ONE kernel per direction (swinblock.py:13-29 Mlp, :304-307 x + mlp(norm2(x))):
+//
+//   forward    out = x1 + fc2( gelu( fc1( LN2(x1) ) ) )            saves gelu'(u) for the backward pass
+//   backward   dx1 = LN2^T( (dy W2 . gelu'(u)) W1 ) + dy            (input-VJP; weights are frozen, da_4dvar.py:590-603)
+//
+// The towers (d = 96 / 192, six variable groups batched) are K = 96 / 192 GEMMs: as four separate launches their cost was the
+// epilogue and the HBM round trips of the 4d-wide hidden activation (27 % of the step for 12 % of the flops).
+// Here the hidden activation never leaves the SM: a CTA owns a 128-token tile and walks over the 4d hidden columns in chunks of 64,
+//
+//   GEMM 1 (chunk c)   acc1[c & 1] = A (128 x d)  *  W1[c]^T (64 x d)          tcgen05.mma.cta_group::1, M 128, N 64
+//   epilogue 1         h = gelu(acc1 + b1)  (backward: acc1 * gelu'(u))  -> 16-bit, 128B-swizzled K-major tile in shared memory
+//   GEMM 2 (chunk c)   acc2 += h (128 x 64) * W2[:, c]^T (d x 64)               M 128, N d
+//
+// with acc1 double-buffered in TMEM so that GEMM 1 of chunk c + 1 runs under epilogue 1 of chunk c.  Both directions have this
+// shape (backward: A = dy, "W1" = W2^T, "W2" = W1^T), so one kernel template serves both.
+//   warp 0        TMA producer: a ring of weight chunks (W1[c] | W2[:, c]); backward also the dy tile and the saved gelu'(u) chunks,
+//                 which land in the very buffer epilogue 1 then overwrites with du
+//   warp 1        tcgen05.mma issuer, TMEM owner
+//   warps 2..17   sixteen epilogue warps (four per TMEM lane quarter, 16 hidden columns each per chunk; thread = token row).
+//                 Forward prologue: LayerNorm of the x1 tile (two-pass fp32, lanes across channels) straight into the swizzled
+//                 A operand -- norm2 is neither a launch nor a folded epilogue here, and the operand is the normalised value.
+//                 Final epilogue: acc2 is transposed through shared memory (thread = row -> lanes across channels) so that every
+//                 global access of the residual add / LayerNorm statistics / LayerNorm backward is coalesced.
+// Shared memory: weight ring | A tile | two hidden chunks | (forward) per-warp staging of the gelu' chunks for their TMA stores;
+// the transposition buffer of the final epilogue aliases A | hidden | staging, which are idle by then.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace vv {
+
+struct MlpArgs {
+  int rows, batch;               // token rows per batch entry (a multiple of 128), batch entries (variable groups)
+  int f16;                       // forward: operands and the saved gelu' are IEEE fp16 (1) or bf16 (0); backward: format of the saved gelu'
+  float eps;
+  const float* x1;               // [batch][rows][D] fp32: the residual stream after the attention half (input of norm2)
+  // forward
+  const float* b1;               // [batch][4D]: fc1 bias with norm2's beta folded in (c_n = b_n + sum_k beta_k W[n,k]); W1 carries gamma
+  const float* b2;               // [batch][D]
+  float* out_f32;                // [batch][rows][D] block output
+  __nv_bfloat16* out16;          // optional 16-bit copy of (out - shift)
+  long long ld16, bs16;
+  const float* shift;            // optional [batch][rows]: centre of the 16-bit copy (GemmArgs::ln_shift)
+  float* stats_out;              // optional [batch][rows] float2 (mean, M2) of the output rows: the next block's folded norm1
+  __nv_bfloat16* u_out;          // [batch][rows][4D] gelu'(u), through the store map
+  // backward
+  const float* gamma;            // [batch][D] norm2 weight
+  const float* dres;             // [batch][rows][D] fp32 gradient of the block output (the residual branch)
+  float* dx;                     // [batch][rows][D] gradient of x1
+  __nv_bfloat16* dx16;           // bf16 copy of dx
+};
+
+constexpr int MLP_THREADS = 576;
+constexpr int MLP_EPI_WARPS = 16;
+constexpr int MLP_HC = 64;       // hidden columns per chunk
+
+template <int D, bool BWD>
+struct MlpSmem {
+  static constexpr int KSD = (D + 63) / 64;                 // 64-column swizzle slabs of a K = D operand
+  static constexpr int NCH = 4 * D / MLP_HC;
+  static constexpr int W1C = MLP_HC * 128 * KSD;            // W1 chunk: 64 rows x KSD slabs of 128 B
+  static constexpr int W2C = D * 128;                       // W2 chunk: D rows x one slab
+  static constexpr int STAGE = W1C + W2C;
+  static constexpr int NST = D <= 96 ? 4 : D <= 128 ? 3 : 2;
+  static constexpr int A_BYTES = KSD * 16384;
+  static constexpr int HID = 16384;
+  static constexpr int GP = BWD ? 0 : MLP_EPI_WARPS * 2 * 1024;   // per warp: two slabs of 32 rows x 32 B
+  static constexpr int OFF_A = NST * STAGE;
+  static constexpr int OFF_HID = OFF_A + A_BYTES;
+  static constexpr int OFF_GP = OFF_HID + 2 * HID;
+  static constexpr int OFF_CONST = OFF_GP + GP;             // forward: b1 (4D floats) | b2 (D floats)
+  static constexpr int CONST_BYTES = BWD ? 0 : 5 * D * 4;
+  static constexpr int OFF_BAR = OFF_CONST + CONST_BYTES;
+  static constexpr int NBAR = 2 * NST + 16;
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+  static constexpr int STG_STRIDE = BWD ? 2 * D + 16 : 4 * D + 16;     // transposition buffer: bf16 (backward) / fp32 (forward) rows
+  static_assert(128 * STG_STRIDE <= A_BYTES + 2 * HID + GP, "transposition buffer must fit into A | hidden | staging");
+  static_assert(STAGE % 1024 == 0 && W1C % 1024 == 0, "swizzle atoms need 1024-byte alignment");
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+VV_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+VV_DEVINL void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// named barrier of the sixteen epilogue warps
+VV_DEVINL void mlp_epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int D, bool BWD, bool F16>
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmA,
+                 const __grid_constant__ CUtensorMap tmU, const MlpArgs p) {
+  using L = MlpSmem<D, BWD>;
+  constexpr int KSD = L::KSD, NCH = L::NCH, NST = L::NST, HC = MLP_HC;
+  constexpr int D4 = D / 4;                       // float4 per row
+  constexpr int NV = (D4 + 31) / 32;              // float4 per lane of a row spread over a warp
+  constexpr int FW = D / 4;                       // acc2 columns per epilogue warp (four warps per lane quarter)
+  static_assert(D % 32 == 0 && D >= 64 && D <= 192, "token width");
+  constexpr bool OPF16 = BWD ? false : F16;       // MMA operand format (gradients are always bf16)
+
+  extern __shared__ uint8_t mlp_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mlp_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* w_full = bars;                        // [NST]
+  uint64_t* w_empty = bars + NST;                 // [NST]
+  uint64_t* a_full = bars + 2 * NST;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* acc1_full = a_full + 2;               // [2]
+  uint64_t* acc1_empty = a_full + 4;              // [2]
+  uint64_t* hid_full = a_full + 6;                // [2]
+  uint64_t* hid_empty = a_full + 8;               // [2]
+  uint64_t* u_full = a_full + 10;                 // [2] backward: the saved gelu' chunk has landed in the hidden buffer
+  uint64_t* acc2_full = a_full + 12;
+  uint64_t* acc2_empty = a_full + 13;
+  uint64_t* fin_done = a_full + 14;               // backward: the transposition buffer (aliases A | hidden) has been read
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NBAR);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tpb = p.rows >> 7;                    // 128-row tiles per batch entry
+  const int total_tiles = tpb * p.batch;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmU);
+    if (BWD) tma_prefetch_desc(&tmA);
+    for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(a_full, BWD ? 1 : MLP_EPI_WARPS);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], MLP_EPI_WARPS);
+      mbar_init(&hid_full[i], MLP_EPI_WARPS); mbar_init(&hid_empty[i], 1);
+      mbar_init(&u_full[i], 1);
+    }
+    mbar_init(acc2_full, 1); mbar_init(acc2_empty, MLP_EPI_WARPS);
+    mbar_init(fin_done, MLP_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    uint32_t st = 0, st_n = 0, gc = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
+      for (int c = 0; c < NCH; ++c, ++gc) {
+        mbar_wait(&w_empty[st], (st_n & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* sp = smem + st * L::STAGE;
+          mbar_expect_tx(&w_full[st], L::STAGE);
+#pragma unroll
+          for (int j = 0; j < KSD; ++j) tma_load_3d(sp + j * (HC * 128), &tmW1, &w_full[st], 64 * j, c * HC, g);
+          tma_load_3d(sp + L::W1C, &tmW2, &w_full[st], c * HC, 0, g);
+        }
+        __syncwarp();
+        if (++st == NST) { st = 0; ++st_n; }
+        if (BWD) {
+          if (c == 0) {
+            if (ti > 0) mbar_wait(fin_done, (ti - 1) & 1);        // A | hidden double as the previous tile's transposition buffer
+            mbar_wait(a_empty, (ti & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(a_full, L::A_BYTES);
+#pragma unroll
+              for (int j = 0; j < KSD; ++j) tma_load_3d(smem + L::OFF_A + j * 16384, &tmA, a_full, 64 * j, row0, g);
+            }
+            __syncwarp();
+          }
+          const uint32_t b = gc & 1, n = gc >> 1;
+          mbar_wait(&hid_empty[b], (n & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&u_full[b], L::HID);
+            tma_load_3d(smem + L::OFF_HID + b * L::HID, &tmU, &u_full[b], c * HC, row0, g);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc1 = make_idesc_16(128, HC, OPF16);
+    const uint32_t idesc2 = make_idesc_16(128, D, OPF16);
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t tacc2 = tmem_base + 2 * HC;
+    uint32_t gc0 = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, gc0 += NCH) {
+      mbar_wait(a_full, ti & 1);
+      tc_fence_after();
+      for (int c = 0; c <= NCH; ++c) {
+        if (c < NCH) {                                               // GEMM 1 of chunk c
+          const uint32_t x = gc0 + c, b = x & 1, n = x >> 1, s = x % NST, sn = x / NST;
+          mbar_wait(&w_full[s], sn & 1);
+          mbar_wait(&acc1_empty[b], (n & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < D / 16; ++k) {
+              const uint64_t da = make_smem_desc_sw128(sb + L::OFF_A + (k >> 2) * 16384) + 2 * (k & 3);
+              const uint64_t db = make_smem_desc_sw128(sb + s * L::STAGE + (k >> 2) * (HC * 128)) + 2 * (k & 3);
+              umma_bf16(tmem_base + b * HC, da, db, idesc1, k ? 1u : 0u);
+            }
+            umma_commit(&acc1_full[b]);
+            if (c == NCH - 1) umma_commit(a_empty);                  // every GEMM 1 of the tile has read A
+          }
+          __syncwarp();
+        }
+        if (c > 0) {                                                 // GEMM 2 of chunk c - 1
+          const uint32_t x = gc0 + c - 1, b = x & 1, n = x >> 1, s = x % NST;
+          if (c == 1) mbar_wait(acc2_empty, (ti & 1) ^ 1);           // the previous tile's acc2 has been drained
+          mbar_wait(&hid_full[b], n & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc_sw128(sb + L::OFF_HID + b * L::HID);
+            const uint64_t db = make_smem_desc_sw128(sb + s * L::STAGE + L::W1C);
+#pragma unroll
+            for (int k = 0; k < HC / 16; ++k) umma_bf16(tacc2, da + 2 * k, db + 2 * k, idesc2, (c > 1 || k) ? 1u : 0u);
+            umma_commit(&hid_empty[b]);
+            umma_commit(&w_empty[s]);
+            if (c == NCH) umma_commit(acc2_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int ew = warp - 2;
+    const int q = warp & 3;                                          // TMEM lane quarter
+    const int cp = ew >> 2;                                          // which 16 of a chunk's 64 columns / which quarter of acc2's columns
+    const int row = q * 32 + lane;                                   // thread = token row of the tile
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    float* consts = reinterpret_cast<float*>(smem + L::OFF_CONST);
+    uint8_t* stg = smem + L::OFF_A;                                  // transposition buffer of the final epilogue
+    uint8_t* gslab = smem + L::OFF_GP + ew * 2048;
+    int g_cur = -1;
+    float4 gam[NV];                                                  // backward: norm2 weight of this lane's channels
+#pragma unroll
+    for (int t = 0; t < NV; ++t) gam[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t gc = 0, ti = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
+      const long long rbase = (long long)g * p.rows + row0;          // first token row of the tile in [batch * rows]
+      if (!BWD) {
+        mlp_epi_sync();                                              // everybody has left the previous tile's buffers
+        if (g != g_cur) {
+          for (int i = threadIdx.x - 64; i < 5 * D; i += 512)
+            consts[i] = i < 4 * D ? __ldg(p.b1 + (long long)g * 4 * D + i) : __ldg(p.b2 + (long long)g * D + (i - 4 * D));
+        }
+        // ---- prologue: LayerNorm of rows ew * 8 .. + 8 into the swizzled A operand ----
+        mbar_wait(a_empty, (ti & 1) ^ 1);
+        const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
+        float4 xv[8][NV];
+        float s[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] = 0.f;
+#pragma unroll
+          for (int t = 0; t < NV; ++t) {
+            const int j = lane + 32 * t;
+            xv[i][t] = j < D4 ? __ldg(xr + i * D4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s[i] += (xv[i][t].x + xv[i][t].y) + (xv[i][t].z + xv[i][t].w);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+        float sq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float mean = s[i] * (1.0f / D);
+          sq[i] = 0.f;
+#pragma unroll
+          for (int t = 0; t < NV; ++t) {
+            if (lane + 32 * t < D4) {
+              xv[i][t].x -= mean; xv[i][t].y -= mean; xv[i][t].z -= mean; xv[i][t].w -= mean;
+              sq[i] += fmaf(xv[i][t].x, xv[i][t].x, xv[i][t].y * xv[i][t].y) + fmaf(xv[i][t].z, xv[i][t].z, xv[i][t].w * xv[i][t].w);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float rstd = rsqrtf(sq[i] * (1.0f / D) + p.eps);
+#pragma unroll
+          for (int t = 0; t < NV; ++t) {
+            const int j = lane + 32 * t;
+            if (j < D4) {
+              const int k = 4 * j, kk = k & 63;
+              uint8_t* dst = smem + L::OFF_A + (k >> 6) * 16384 + (ew * 8 + i) * 128 + ((static_cast<uint32_t>(kk >> 3) ^ static_cast<uint32_t>(i)) << 4) +
+                             ((kk >> 2) & 1) * 8;
+              uint2 w;
+              w.x = pack16<OPF16>(xv[i][t].x * rstd, xv[i][t].y * rstd);
+              w.y = pack16<OPF16>(xv[i][t].z * rstd, xv[i][t].w * rstd);
+              *reinterpret_cast<uint2*>(dst) = w;
+            }
+          }
+        }
+        fence_proxy_async();
+        mlp_epi_sync();                                              // the biases are in place for every warp
+        if (elect_one()) mbar_arrive(a_full);
+        g_cur = g;
+      } else if (g != g_cur) {
+#pragma unroll
+        for (int t = 0; t < NV; ++t)
+          if (lane + 32 * t < D4) gam[t] = __ldg(reinterpret_cast<const float4*>(p.gamma + (long long)g * D) + lane + 32 * t);
+        g_cur = g;
+      }
+
+      // ---- epilogue 1, chunk by chunk ----
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++gc, ++it) {
+        const uint32_t b = gc & 1, n = gc >> 1;
+        mbar_wait(&acc1_full[b], n & 1);
+        tc_fence_after();
+        uint32_t r[16];
+        tmem_ld16(tmem_base + lane_base + b * HC + cp * 16, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (elect_one()) mbar_arrive(&acc1_empty[b]);
+        uint8_t* hrow = smem + L::OFF_HID + b * L::HID + row * 128;
+        const uint32_t o0 = (static_cast<uint32_t>(2 * cp) ^ sw) << 4, o1 = (static_cast<uint32_t>(2 * cp + 1) ^ sw) << 4;
+        if (!BWD) {
+          const float4* bs = reinterpret_cast<const float4*>(consts + c * HC + cp * 16);
+          float y[16], d[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 bb = bs[i4];
+            float2 y2, d2;
+            gelu_erf_both2(add2(make_float2(__uint_as_float(r[4 * i4]), __uint_as_float(r[4 * i4 + 1])), make_float2(bb.x, bb.y)), &y2, &d2);
+            y[4 * i4] = y2.x; y[4 * i4 + 1] = y2.y; d[4 * i4] = d2.x; d[4 * i4 + 1] = d2.y;
+            gelu_erf_both2(add2(make_float2(__uint_as_float(r[4 * i4 + 2]), __uint_as_float(r[4 * i4 + 3])), make_float2(bb.z, bb.w)), &y2, &d2);
+            y[4 * i4 + 2] = y2.x; y[4 * i4 + 3] = y2.y; d[4 * i4 + 2] = d2.x; d[4 * i4 + 3] = d2.y;
+          }
+          // gelu'(u): this warp's 32 x 16 piece -> its own staging slab -> TMA store
+          uint8_t* slab = gslab + (it & 1) * 1024;
+          if (elect_one()) tma_store_wait_read1();                   // the store issued two chunks ago has read this slab
+          __syncwarp();
+          *reinterpret_cast<uint4*>(slab + lane * 32) =
+              make_uint4(pack16<F16>(d[0], d[1]), pack16<F16>(d[2], d[3]), pack16<F16>(d[4], d[5]), pack16<F16>(d[6], d[7]));
+          *reinterpret_cast<uint4*>(slab + lane * 32 + 16) =
+              make_uint4(pack16<F16>(d[8], d[9]), pack16<F16>(d[10], d[11]), pack16<F16>(d[12], d[13]), pack16<F16>(d[14], d[15]));
+          mbar_wait(&hid_empty[b], (n & 1) ^ 1);                      // GEMM 2 of chunk gc - 2 has read this hidden buffer
+          *reinterpret_cast<uint4*>(hrow + o0) =
+              make_uint4(pack16<F16>(y[0], y[1]), pack16<F16>(y[2], y[3]), pack16<F16>(y[4], y[5]), pack16<F16>(y[6], y[7]));
+          *reinterpret_cast<uint4*>(hrow + o1) =
+              make_uint4(pack16<F16>(y[8], y[9]), pack16<F16>(y[10], y[11]), pack16<F16>(y[12], y[13]), pack16<F16>(y[14], y[15]));
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_3d(&tmU, slab, c * HC + cp * 16, row0 + q * 32, g);
+            tma_store_commit();
+            mbar_arrive(&hid_full[b]);
+          }
+        } else {
+          mbar_wait(&u_full[b], n & 1);                               // gelu'(u) of this chunk sits where du goes
+          const bool uf = p.f16 != 0;
+          const uint4 u0 = *reinterpret_cast<const uint4*>(hrow + o0), u1 = *reinterpret_cast<const uint4*>(hrow + o1);
+          const uint32_t uw[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 m = mul2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), unpack16(uw[i], uf));
+            w[i] = pack_bf16(m.x, m.y);
+          }
+          *reinterpret_cast<uint4*>(hrow + o0) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(hrow + o1) = make_uint4(w[4], w[5], w[6], w[7]);
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one()) mbar_arrive(&hid_full[b]);
+        }
+      }
+
+      // ---- final epilogue: acc2 (thread = row) -> transposition buffer -> coalesced global traffic ----
+      mbar_wait(acc2_full, ti & 1);
+      tc_fence_after();
+      if (!BWD) {
+        if (elect_one()) tma_store_wait_read0();                     // the staging slabs are part of the transposition buffer
+        __syncwarp();
+        mlp_epi_sync();
+      }
+      {
+        uint32_t a[FW];
+#pragma unroll
+        for (int i = 0; i < FW / 8; ++i) tmem_ld8(tmem_base + lane_base + 2 * HC + cp * FW + 8 * i, a + 8 * i);
+        tmem_ld_wait();
+        tc_fence_before();
+        uint8_t* srow = stg + row * L::STG_STRIDE;
+        if (!BWD) {
+          const float4* b2s = reinterpret_cast<const float4*>(consts + 4 * D + cp * FW);
+#pragma unroll
+          for (int i = 0; i < FW / 4; ++i) {
+            const float4 bb = b2s[i];
+            *reinterpret_cast<float4*>(srow + (cp * FW + 4 * i) * 4) =
+                make_float4(__uint_as_float(a[4 * i]) + bb.x, __uint_as_float(a[4 * i + 1]) + bb.y, __uint_as_float(a[4 * i + 2]) + bb.z,
+                            __uint_as_float(a[4 * i + 3]) + bb.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < FW / 8; ++i)
+            *reinterpret_cast<uint4*>(srow + (cp * FW + 8 * i) * 2) =
+                make_uint4(pack_bf16(__uint_as_float(a[8 * i]), __uint_as_float(a[8 * i + 1])), pack_bf16(__uint_as_float(a[8 * i + 2]), __uint_as_float(a[8 * i + 3])),
+                           pack_bf16(__uint_as_float(a[8 * i + 4]), __uint_as_float(a[8 * i + 5])), pack_bf16(__uint_as_float(a[8 * i + 6]), __uint_as_float(a[8 * i + 7])));
+        }
+      }
+      __syncwarp();
+      if (elect_one()) mbar_arrive(acc2_empty);
+      mlp_epi_sync();
+      // rows ew * 8 .. + 8, lanes across channels
+      if (!BWD) {
+        const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
+        float4* orow = reinterpret_cast<float4*>(p.out_f32 + (rbase + ew * 8) * D);
+        float4 v[8][NV];
+        float s[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] = 0.f;
+#pragma unroll
+          for (int t = 0; t < NV; ++t) {
+            const int j = lane + 32 * t;
+            v[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < D4) {
+              const float4 x = __ldg(xr + i * D4 + j);
+              const float4 y = *reinterpret_cast<const float4*>(stg + (ew * 8 + i) * L::STG_STRIDE + 16 * j);
+              v[i][t] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+              orow[i * D4 + j] = v[i][t];
+            }
+            s[i] += (v[i][t].x + v[i][t].y) + (v[i][t].z + v[i][t].w);
+          }
+        }
+        if (p.stats_out || p.out16) {
+          float sq[8];
+          if (p.stats_out) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float mean = s[i] * (1.0f / D);
+              s[i] = mean;
+              sq[i] = 0.f;
+#pragma unroll
+              for (int t = 0; t < NV; ++t) {
+                if (lane + 32 * t < D4) {
+                  const float dx = v[i][t].x - mean, dy = v[i][t].y - mean, dz = v[i][t].z - mean, dw = v[i][t].w - mean;
+                  sq[i] += fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+            if (lane < 8) {
+              float m = s[0], qq = sq[0];
+#pragma unroll
+              for (int i = 1; i < 8; ++i) if (lane == i) { m = s[i]; qq = sq[i]; }
+              reinterpret_cast<float2*>(p.stats_out)[rbase + ew * 8 + lane] = make_float2(m, qq);
+            }
+          }
+          if (p.out16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float sh = p.shift ? __ldg(p.shift + rbase + ew * 8 + i) : 0.f;
+              __nv_bfloat16* crow = p.out16 + (long long)g * p.bs16 + (long long)(row0 + ew * 8 + i) * p.ld16;
+#pragma unroll
+              for (int t = 0; t < NV; ++t) {
+                const int j = lane + 32 * t;
+                if (j < D4) {
+                  uint2 w;
+                  w.x = pack16<F16>(v[i][t].x - sh, v[i][t].y - sh);
+                  w.y = pack16<F16>(v[i][t].z - sh, v[i][t].w - sh);
+                  *reinterpret_cast<uint2*>(crow + 4 * j) = w;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // LayerNorm backward (norm2) + the residual branch:  dx = rstd (g - mean(g) - xhat mean(g xhat)) + dres,  g = dh gamma
+        const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
+        const float4* rr = reinterpret_cast<const float4*>(p.dres + (rbase + ew * 8) * D);
+        float4* orow = reinterpret_cast<float4*>(p.dx + (rbase + ew * 8) * D);
+        __nv_bfloat16* o16 = p.dx16 + (rbase + ew * 8) * D;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                                // four rows at a time
+          float4 xc[4][NV], gg[4][NV];
+          float s[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            s[i] = 0.f;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+              const int j = lane + 32 * t;
+              xc[i][t] = make_float4(0.f, 0.f, 0.f, 0.f); gg[i][t] = xc[i][t];
+              if (j < D4) {
+                xc[i][t] = __ldg(xr + (4 * h + i) * D4 + j);
+                const uint2 w = *reinterpret_cast<const uint2*>(stg + (ew * 8 + 4 * h + i) * L::STG_STRIDE + 8 * j);
+                const float2 d0 = unpack_bf16(w.x), d1 = unpack_bf16(w.y);
+                gg[i][t] = make_float4(d0.x * gam[t].x, d0.y * gam[t].y, d1.x * gam[t].z, d1.y * gam[t].w);
+              }
+              s[i] += (xc[i][t].x + xc[i][t].y) + (xc[i][t].z + xc[i][t].w);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+          float sa[4], sb2[4], sc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float mean = s[i] * (1.0f / D);
+            sa[i] = sb2[i] = sc[i] = 0.f;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+              if (lane + 32 * t < D4) {
+                float4& x = xc[i][t];
+                const float4 gq = gg[i][t];
+                x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+                sa[i] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+                sb2[i] += (gq.x + gq.y) + (gq.z + gq.w);
+                sc[i] += fmaf(gq.x, x.x, gq.y * x.y) + fmaf(gq.z, x.z, gq.w * x.w);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              sa[i] += __shfl_xor_sync(0xffffffffu, sa[i], o);
+              sb2[i] += __shfl_xor_sync(0xffffffffu, sb2[i], o);
+              sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
+            }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float rstd = rsqrtf(sa[i] * (1.0f / D) + p.eps);
+            const float mb = sb2[i] * (1.0f / D), mc = sc[i] * (1.0f / D) * rstd * rstd;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+              const int j = lane + 32 * t;
+              if (j < D4) {
+                const float4 x = xc[i][t], gq = gg[i][t];
+                const float4 dr = __ldg(rr + (4 * h + i) * D4 + j);
+                float4 o;
+                o.x = fmaf(rstd, gq.x - mb - x.x * mc, dr.x); o.y = fmaf(rstd, gq.y - mb - x.y * mc, dr.y);
+                o.z = fmaf(rstd, gq.z - mb - x.z * mc, dr.z); o.w = fmaf(rstd, gq.w - mb - x.w * mc, dr.w);
+                orow[(4 * h + i) * D4 + j] = o;
+                *reinterpret_cast<uint2*>(o16 + (4 * h + i) * D + 4 * j) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) mbar_arrive(fin_done);
+      }
+    }
+    if (!BWD) {
+      if (elect_one()) tma_store_wait_read0();
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace vv

@@ -10,6 +10,7 @@
 #include <utility>
 
 #include "gemm_tcgen05.cuh"
+#include "mlp_fused.cuh"
 
 namespace vv {
 
@@ -44,8 +45,22 @@ const char* make_gemm_desc(GemmDesc* d, const bf16* A, long long lda, long long 
                            long long b_bs, const GemmArgs& args);
 void launch_gemm(const GemmDesc& d, cudaStream_t s);
 const char* encode_tma_2d_16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long ld, int box_cols, int box_rows);
+const char* encode_tma_3d_16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch, long long ld, long long bs,
+                             int box_cols, int box_rows);
+int num_sms();
 void set_gemm_debug_mode(int mode);                 // debug: 1 = MMA only, 2 = TMA feed only (results are garbage)
 void set_gemm_trace(unsigned long long* dev_ptr);   // debug: GEMM descriptors built afterwards stamp clocks into dev_ptr (null = off)
+
+// ---- fused tower MLP (mlp_fused.cuh): norm2 + fc1 + GELU + fc2 + residual forward, its input-VJP backward --------------------
+struct MlpDesc {
+  CUtensorMap tmW1, tmW2, tmA, tmU;
+  MlpArgs a;
+  int D, bwd;
+};
+bool mlp_fused_supported(int D, int rows);
+const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const __nv_bfloat16* W1, const __nv_bfloat16* W2, const __nv_bfloat16* u,
+                          const __nv_bfloat16* dy16, const MlpArgs& args);
+void launch_mlp(const MlpDesc& d, cudaStream_t s);
 
 // ---- LayerNorm (one warp per row, fp32 statistics) -------------------------------------------
 enum RowMap : int {
