@@ -222,6 +222,9 @@ VV_API int vv_test_mlp_fwd(const float* x1_dev, const void* W1_16_dev, const voi
 VV_API int vv_test_mlp_bwd(const void* dy_bf16_dev, const void* u_16_dev, const float* x1_dev, const void* W2T_bf16_dev, const void* W1T_bf16_dev,
                     const float* gamma_dev, const float* dres_dev, int rows, int batch, int D, int f16, float eps, float* dx_dev,
                     void* dx_bf16_dev, void* stream);
+/* Debug: fused-MLP launches built after this call stamp clock64 values of CTA 0 into trace_dev (128 x uint64: slots 0..63 epilogue warp 0,
+ * 64..127 the MMA warp; tools/mlp_trace.py); null = off. */
+VV_API int vv_debug_mlp_trace(void* trace_dev);
 /* Statistics pass at a stage input: x (rows, C) fp32 -> out_16 = x - mean (16-bit), stats (rows) float2 = (mean, M2), shift = mean. */
 VV_API int vv_test_ln_stats(const float* x_dev, void* out_16_dev, float* stats_dev, float* shift_dev, int rows, int C, int f16, void* stream);
 /* Debug: GEMM launches built after this call stamp per-CTA clock64 values into trace_dev (64 x uint64 per CTA; layout in

@@ -9,6 +9,8 @@
 
 namespace vv {
 
+static unsigned long long* g_mlp_trace = nullptr;
+
 bool mlp_fused_supported(int D, int rows) {
   return (D == 64 || D == 96 || D == 128 || D == 192) && rows > 0 && rows % 128 == 0;
 }
@@ -18,6 +20,7 @@ bool mlp_fused_supported(int D, int rows) {
 const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const bf16* W1, const bf16* W2, const bf16* u, const bf16* dy16, const MlpArgs& args) {
   if (!mlp_fused_supported(D, args.rows)) return "fused MLP: token width / row count not supported";
   d->D = D; d->bwd = bwd ? 1 : 0; d->a = args;
+  d->a.trace = g_mlp_trace;
   const long long rows = args.rows, B = args.batch;
   const char* e;
   if ((e = encode_tma_3d_16(&d->tmW1, W1, D, 4LL * D, B, D, 4LL * D * D, 64, MLP_HC))) return e;
@@ -66,6 +69,12 @@ void launch_mlp(const MlpDesc& d, cudaStream_t s) {
 using namespace vv;
 
 extern "C" {
+
+// Debug: fused-MLP launches built after this call stamp clock64 values of CTA 0 into trace_dev (128 x uint64; tools/mlp_trace.py); null = off.
+VV_API int vv_debug_mlp_trace(void* trace_dev) {
+  g_mlp_trace = (unsigned long long*)trace_dev;
+  return 0;
+}
 
 // Kernel-level hook: out = x1 + fc2(gelu(fc1(normalise(x1)))) with W1 (4D x D) / b1 standing for the gamma- / beta-folded fc1; u_out
 // receives gelu'(u).  16-bit buffers are fp16 when f16 != 0, else bf16.

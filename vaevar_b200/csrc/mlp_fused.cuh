@@ -47,6 +47,7 @@ struct MlpArgs {
   const float* dres;             // [batch][rows][D] fp32 gradient of the block output (the residual branch)
   float* dx;                     // [batch][rows][D] gradient of x1
   __nv_bfloat16* dx16;           // bf16 copy of dx
+  unsigned long long* trace;     // debug: clock64 stamps of CTA 0 (128 slots, see tools/mlp_trace.py); null in production
 };
 
 constexpr int MLP_THREADS = 576;
@@ -60,20 +61,31 @@ struct MlpSmem {
   static constexpr int W1C = MLP_HC * 128 * KSD;            // W1 chunk: 64 rows x KSD slabs of 128 B
   static constexpr int W2C = D * 128;                       // W2 chunk: D rows x one slab
   static constexpr int STAGE = W1C + W2C;
-  static constexpr int NST = D <= 96 ? 4 : D <= 128 ? 3 : 2;
+  // PIPE: the transposition buffer of the final epilogue does not alias the A tile, so the next tile's A (forward: its LayerNorm
+  // prologue, backward: its TMA load) and first GEMMs run under the final epilogue of the current tile
+  static constexpr bool PIPE = D <= 96;
+  static constexpr int NST = BWD ? (D <= 64 ? 4 : D <= 128 ? 3 : 2) : (D <= 96 ? 4 : D <= 128 ? 3 : 2);
+  // hidden buffers: forward 2 (filled by epilogue 1); backward as many as fit -- they are the prefetch depth of the saved gelu'(u),
+  // which streams from HBM (37.7 MB per d = 96 launch) with ~1 us of latency per chunk
+  static constexpr int NH = BWD ? (D == 96 ? 5 : 4) : 2;
   static constexpr int A_BYTES = KSD * 16384;
   static constexpr int HID = 16384;
   static constexpr int GP = BWD ? 0 : MLP_EPI_WARPS * 2 * 1024;   // per warp: two slabs of 32 rows x 32 B
+  static constexpr int STG_STRIDE = BWD ? 2 * D + 16 : 4 * D + 16;     // transposition buffer: bf16 (backward) / fp32 (forward) rows
+  static constexpr int STG_BYTES = 128 * STG_STRIDE;
   static constexpr int OFF_A = NST * STAGE;
   static constexpr int OFF_HID = OFF_A + A_BYTES;
-  static constexpr int OFF_GP = OFF_HID + 2 * HID;
-  static constexpr int OFF_CONST = OFF_GP + GP;             // forward: b1 (4D floats) | b2 (D floats)
-  static constexpr int CONST_BYTES = BWD ? 0 : 5 * D * 4;
-  static constexpr int OFF_BAR = OFF_CONST + CONST_BYTES;
-  static constexpr int NBAR = 2 * NST + 16;
+  static constexpr int OFF_GP = OFF_HID + NH * HID;
+  static constexpr int OFF_STG_OWN = OFF_GP + GP;           // backward + PIPE: a buffer of its own
+  static constexpr bool STG_OWN = BWD && PIPE;
+  static constexpr int OFF_STG = STG_OWN ? OFF_STG_OWN : PIPE ? OFF_HID : OFF_A;
+  static constexpr int OFF_CONST = OFF_STG_OWN + (STG_OWN ? STG_BYTES : 0);   // forward: two sets of b1 (4D floats) | b2 (D floats)
+  static constexpr int CONST_SET = 5 * D * 4;
+  static constexpr int CONST_BYTES = BWD ? 0 : 2 * CONST_SET;
+  static constexpr int OFF_BAR = (OFF_CONST + CONST_BYTES + 15) / 16 * 16;
+  static constexpr int NBAR = 2 * NST + 3 * NH + 10;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
-  static constexpr int STG_STRIDE = BWD ? 2 * D + 16 : 4 * D + 16;     // transposition buffer: bf16 (backward) / fp32 (forward) rows
-  static_assert(128 * STG_STRIDE <= A_BYTES + 2 * HID + GP, "transposition buffer must fit into A | hidden | staging");
+  static_assert(STG_OWN || STG_BYTES <= (PIPE ? 0 : A_BYTES) + NH * HID + GP, "transposition buffer must fit into the buffers it aliases");
   static_assert(STAGE % 1024 == 0 && W1C % 1024 == 0, "swizzle atoms need 1024-byte alignment");
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
@@ -100,9 +112,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmU, const MlpArgs p) {
   using L = MlpSmem<D, BWD>;
-  constexpr int KSD = L::KSD, NCH = L::NCH, NST = L::NST, HC = MLP_HC;
+  constexpr int KSD = L::KSD, NCH = L::NCH, NST = L::NST, NH = L::NH, HC = MLP_HC;
+  constexpr bool PIPE = L::PIPE;
   constexpr int D4 = D / 4;                       // float4 per row
-  constexpr int NV = (D4 + 31) / 32;              // float4 per lane of a row spread over a warp
+  constexpr int LPR = D == 192 ? 16 : 8;          // row-wise phases: lanes per row,
+  constexpr int V = D4 / LPR;                     //   float4 per lane,
+  constexpr int RPW = 32 / LPR;                   //   rows per warp pass,
+  constexpr int NP = 8 / RPW;                     //   passes over a warp's 8 rows,
+  constexpr int PG = BWD ? (NP * V * 2 <= 12 ? NP : NP / 2) : NP;   // passes whose global loads are in flight together (registers)
+  static_assert(D4 % LPR == 0, "row split");
   constexpr int FW = D / 4;                       // acc2 columns per epilogue warp (four warps per lane quarter)
   static_assert(D % 32 == 0 && D >= 64 && D <= 192, "token width");
   constexpr bool OPF16 = BWD ? false : F16;       // MMA operand format (gradients are always bf16)
@@ -112,16 +130,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* w_full = bars;                        // [NST]
   uint64_t* w_empty = bars + NST;                 // [NST]
-  uint64_t* a_full = bars + 2 * NST;
+  uint64_t* hid_full = bars + 2 * NST;            // [NH]
+  uint64_t* hid_empty = hid_full + NH;            // [NH]
+  uint64_t* u_full = hid_full + 2 * NH;           // [NH] backward: the saved gelu' chunk has landed in the hidden buffer
+  uint64_t* a_full = hid_full + 3 * NH;
   uint64_t* a_empty = a_full + 1;
   uint64_t* acc1_full = a_full + 2;               // [2]
   uint64_t* acc1_empty = a_full + 4;              // [2]
-  uint64_t* hid_full = a_full + 6;                // [2]
-  uint64_t* hid_empty = a_full + 8;               // [2]
-  uint64_t* u_full = a_full + 10;                 // [2] backward: the saved gelu' chunk has landed in the hidden buffer
-  uint64_t* acc2_full = a_full + 12;
-  uint64_t* acc2_empty = a_full + 13;
-  uint64_t* fin_done = a_full + 14;               // backward: the transposition buffer (aliases A | hidden) has been read
+  uint64_t* acc2_full = a_full + 6;
+  uint64_t* acc2_empty = a_full + 7;
+  uint64_t* fin_done = a_full + 8;                // backward, not PIPE: the transposition buffer (aliases A | hidden) has been read
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NBAR);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -133,13 +151,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmU);
     if (BWD) tma_prefetch_desc(&tmA);
     for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NH; ++i) { mbar_init(&hid_full[i], MLP_EPI_WARPS); mbar_init(&hid_empty[i], 1); mbar_init(&u_full[i], 1); }
     mbar_init(a_full, BWD ? 1 : MLP_EPI_WARPS);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], MLP_EPI_WARPS);
-      mbar_init(&hid_full[i], MLP_EPI_WARPS); mbar_init(&hid_empty[i], 1);
-      mbar_init(&u_full[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], MLP_EPI_WARPS); }
     mbar_init(acc2_full, 1); mbar_init(acc2_empty, MLP_EPI_WARPS);
     mbar_init(fin_done, MLP_EPI_WARPS);
     fence_barrier_init();
@@ -157,10 +172,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 
   if (warp == 0) {
     // ===== TMA producer =====
-    uint32_t st = 0, st_n = 0, gc = 0, ti = 0;
+    uint32_t st = 0, st_n = 0, hb = 0, hn = 0, ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
-      for (int c = 0; c < NCH; ++c, ++gc) {
+      for (int c = 0; c < NCH; ++c) {
         mbar_wait(&w_empty[st], (st_n & 1) ^ 1);
         if (elect_one()) {
           uint8_t* sp = smem + st * L::STAGE;
@@ -173,7 +188,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         if (++st == NST) { st = 0; ++st_n; }
         if (BWD) {
           if (c == 0) {
-            if (ti > 0) mbar_wait(fin_done, (ti - 1) & 1);        // A | hidden double as the previous tile's transposition buffer
+            if (!PIPE && ti > 0) mbar_wait(fin_done, (ti - 1) & 1);   // A | hidden double as the previous tile's transposition buffer
             mbar_wait(a_empty, (ti & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(a_full, L::A_BYTES);
@@ -182,13 +197,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             }
             __syncwarp();
           }
-          const uint32_t b = gc & 1, n = gc >> 1;
-          mbar_wait(&hid_empty[b], (n & 1) ^ 1);
+          mbar_wait(&hid_empty[hb], (hn & 1) ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&u_full[b], L::HID);
-            tma_load_3d(smem + L::OFF_HID + b * L::HID, &tmU, &u_full[b], c * HC, row0, g);
+            mbar_expect_tx(&u_full[hb], L::HID);
+            tma_load_3d(smem + L::OFF_HID + hb * L::HID, &tmU, &u_full[hb], c * HC, row0, g);
           }
           __syncwarp();
+          if (++hb == NH) { hb = 0; ++hn; }
         }
       }
     }
@@ -198,43 +213,56 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const uint32_t idesc2 = make_idesc_16(128, D, OPF16);
     const uint32_t sb = smem_u32(smem);
     const uint32_t tacc2 = tmem_base + 2 * HC;
-    uint32_t gc0 = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti, gc0 += NCH) {
+    uint32_t gc = 0, ti = 0;                                           // gc: chunks whose GEMM 1 has been issued
+    uint32_t s1 = 0, s1n = 0;                                          // ring stage (and its use count) of the next GEMM 1
+    uint32_t s2 = 0, h2 = 0, h2n = 0;                                  // ring stage / hidden buffer (use count) of the next GEMM 2
+    unsigned long long* trc = (p.trace && blockIdx.x == 0 && lane == 0) ? p.trace + 64 : nullptr;           // MMA warp: slots 64..127
+    int tslot = 0;
+    auto stamp = [&]() { if (trc && tslot < 64) trc[tslot++] = clock64(); };
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      stamp();
       mbar_wait(a_full, ti & 1);
+      stamp();                                                         // A ready
       tc_fence_after();
       for (int c = 0; c <= NCH; ++c) {
         if (c < NCH) {                                               // GEMM 1 of chunk c
-          const uint32_t x = gc0 + c, b = x & 1, n = x >> 1, s = x % NST, sn = x / NST;
-          mbar_wait(&w_full[s], sn & 1);
+          const uint32_t b = gc & 1, n = gc >> 1;
+          mbar_wait(&w_full[s1], s1n & 1);
+          stamp();                                                     // GEMM 1: weights there
           mbar_wait(&acc1_empty[b], (n & 1) ^ 1);
+          stamp();                                                     // GEMM 1: accumulator free
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < D / 16; ++k) {
               const uint64_t da = make_smem_desc_sw128(sb + L::OFF_A + (k >> 2) * 16384) + 2 * (k & 3);
-              const uint64_t db = make_smem_desc_sw128(sb + s * L::STAGE + (k >> 2) * (HC * 128)) + 2 * (k & 3);
+              const uint64_t db = make_smem_desc_sw128(sb + s1 * L::STAGE + (k >> 2) * (HC * 128)) + 2 * (k & 3);
               umma_bf16(tmem_base + b * HC, da, db, idesc1, k ? 1u : 0u);
             }
             umma_commit(&acc1_full[b]);
             if (c == NCH - 1) umma_commit(a_empty);                  // every GEMM 1 of the tile has read A
           }
           __syncwarp();
+          ++gc;
+          if (++s1 == NST) { s1 = 0; ++s1n; }
         }
         if (c > 0) {                                                 // GEMM 2 of chunk c - 1
-          const uint32_t x = gc0 + c - 1, b = x & 1, n = x >> 1, s = x % NST;
           if (c == 1) mbar_wait(acc2_empty, (ti & 1) ^ 1);           // the previous tile's acc2 has been drained
-          mbar_wait(&hid_full[b], n & 1);
+          mbar_wait(&hid_full[h2], h2n & 1);
+          stamp();                                                     // GEMM 2: hidden chunk written
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = make_smem_desc_sw128(sb + L::OFF_HID + b * L::HID);
-            const uint64_t db = make_smem_desc_sw128(sb + s * L::STAGE + L::W1C);
+            const uint64_t da = make_smem_desc_sw128(sb + L::OFF_HID + h2 * L::HID);
+            const uint64_t db = make_smem_desc_sw128(sb + s2 * L::STAGE + L::W1C);
 #pragma unroll
             for (int k = 0; k < HC / 16; ++k) umma_bf16(tacc2, da + 2 * k, db + 2 * k, idesc2, (c > 1 || k) ? 1u : 0u);
-            umma_commit(&hid_empty[b]);
-            umma_commit(&w_empty[s]);
+            umma_commit(&hid_empty[h2]);
+            umma_commit(&w_empty[s2]);
             if (c == NCH) umma_commit(acc2_full);
           }
           __syncwarp();
+          if (++s2 == NST) s2 = 0;
+          if (++h2 == NH) { h2 = 0; ++h2n; }
         }
       }
     }
@@ -246,92 +274,113 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const int row = q * 32 + lane;                                   // thread = token row of the tile
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sw = static_cast<uint32_t>(row & 7);
-    float* consts = reinterpret_cast<float*>(smem + L::OFF_CONST);
-    uint8_t* stg = smem + L::OFF_A;                                  // transposition buffer of the final epilogue
+    uint8_t* stg = smem + L::OFF_STG;                                // transposition buffer of the final epilogue
     uint8_t* gslab = smem + L::OFF_GP + ew * 2048;
+    // Row-wise phases (LayerNorm prologue, residual add + statistics, LayerNorm backward): a warp owns rows ew * 8 .. + 8 of the tile
+    // and walks them RPW at a time, LPR lanes per row, V float4 per lane -- every lane busy, a row reduction is log2(LPR) shuffles
+    // shared by RPW rows, and a load / store instruction covers RPW full 128-byte (LPR = 8) or 256-byte segments.
+    const int sub = lane % LPR, rsel = lane / LPR;
     int g_cur = -1;
-    float4 gam[NV];                                                  // backward: norm2 weight of this lane's channels
+    float4 gam[V];                                                   // backward: norm2 weight of this lane's channels
 #pragma unroll
-    for (int t = 0; t < NV; ++t) gam[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t gc = 0, ti = 0, it = 0;
+    for (int v = 0; v < V; ++v) gam[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto row_sum = [&](float x) {
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      return x;
+    };
+
+    // forward prologue of tile `tile` (the ti-th of this CTA): biases of its group into constant set ti & 1, LayerNorm of this warp's
+    // rows into the swizzled A operand
+    auto prologue = [&](int tile, uint32_t ti) {
+      const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
+      float* cs = reinterpret_cast<float*>(smem + L::OFF_CONST + (PIPE ? (ti & 1) : 0) * L::CONST_SET);
+      for (int i = threadIdx.x - 64; i < 5 * D; i += 512)
+        cs[i] = i < 4 * D ? __ldg(p.b1 + (long long)g * 4 * D + i) : __ldg(p.b2 + (long long)g * D + (i - 4 * D));
+      const float4* xr = reinterpret_cast<const float4*>(p.x1 + ((long long)g * p.rows + row0 + ew * 8) * D);
+      float4 xv[NP][V];
+#pragma unroll
+      for (int pz = 0; pz < NP; ++pz)
+#pragma unroll
+        for (int v = 0; v < V; ++v) xv[pz][v] = __ldg(xr + (pz * RPW + rsel) * D4 + sub + LPR * v);
+      float rstd[NP];
+#pragma unroll
+      for (int pz = 0; pz < NP; ++pz) {
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) s += (xv[pz][v].x + xv[pz][v].y) + (xv[pz][v].z + xv[pz][v].w);
+        const float mean = row_sum(s) * (1.0f / D);
+        float sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          float4& x = xv[pz][v];
+          x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+          sq += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+        }
+        rstd[pz] = rsqrtf(row_sum(sq) * (1.0f / D) + p.eps);
+      }
+      mbar_wait(a_empty, (ti & 1) ^ 1);                              // the previous tile's GEMM 1s have read A
+#pragma unroll
+      for (int pz = 0; pz < NP; ++pz) {
+        const int r = ew * 8 + pz * RPW + rsel;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int k = 4 * (sub + LPR * v), kk = k & 63;
+          uint8_t* dst = smem + L::OFF_A + (k >> 6) * 16384 + r * 128 + ((static_cast<uint32_t>(kk >> 3) ^ static_cast<uint32_t>(r & 7)) << 4) + ((kk >> 2) & 1) * 8;
+          uint2 w;
+          w.x = pack16<OPF16>(xv[pz][v].x * rstd[pz], xv[pz][v].y * rstd[pz]);
+          w.y = pack16<OPF16>(xv[pz][v].z * rstd[pz], xv[pz][v].w * rstd[pz]);
+          *reinterpret_cast<uint2*>(dst) = w;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(a_full);
+    };
+    // pull the rows this warp will read at the start of a later phase (x1 of the next tile; backward also dres) towards L2
+    auto prefetch_rows = [&](int tile) {
+      if (tile >= total_tiles) return;
+      const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
+      const long long off = ((long long)g * p.rows + row0 + ew * 8) * D;
+      constexpr int LINES = 8 * D * 4 / 128;                         // 128-byte lines of 8 fp32 rows
+      for (int l = lane; l < LINES; l += 32) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x1 + off + l * 32));
+        if (BWD) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dres + off + l * 32));
+      }
+    };
+
+    unsigned long long* trc = (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0) ? p.trace : nullptr;     // epilogue warp 0: slots 0..63
+    int tslot = 0;
+    auto stamp = [&]() { if (trc && tslot < 64) trc[tslot++] = clock64(); };
+    if (!BWD && PIPE) {
+      if ((int)blockIdx.x < total_tiles) prologue(blockIdx.x, 0);
+      mlp_epi_sync();                                                // the first tile's biases are in place for every warp
+    }
+    uint32_t gc = 0, ti = 0, it = 0, hb = 0, hn = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      stamp();                                                       // tile start
       const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
       const long long rbase = (long long)g * p.rows + row0;          // first token row of the tile in [batch * rows]
-      if (!BWD) {
+      const float* consts = reinterpret_cast<const float*>(smem + L::OFF_CONST + (PIPE ? (ti & 1) : 0) * L::CONST_SET);
+      if (!BWD && !PIPE) {
         mlp_epi_sync();                                              // everybody has left the previous tile's buffers
-        if (g != g_cur) {
-          for (int i = threadIdx.x - 64; i < 5 * D; i += 512)
-            consts[i] = i < 4 * D ? __ldg(p.b1 + (long long)g * 4 * D + i) : __ldg(p.b2 + (long long)g * D + (i - 4 * D));
-        }
-        // ---- prologue: LayerNorm of rows ew * 8 .. + 8 into the swizzled A operand ----
-        mbar_wait(a_empty, (ti & 1) ^ 1);
-        const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
-        float4 xv[8][NV];
-        float s[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] = 0.f;
-#pragma unroll
-          for (int t = 0; t < NV; ++t) {
-            const int j = lane + 32 * t;
-            xv[i][t] = j < D4 ? __ldg(xr + i * D4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            s[i] += (xv[i][t].x + xv[i][t].y) + (xv[i][t].z + xv[i][t].w);
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-        float sq[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float mean = s[i] * (1.0f / D);
-          sq[i] = 0.f;
-#pragma unroll
-          for (int t = 0; t < NV; ++t) {
-            if (lane + 32 * t < D4) {
-              xv[i][t].x -= mean; xv[i][t].y -= mean; xv[i][t].z -= mean; xv[i][t].w -= mean;
-              sq[i] += fmaf(xv[i][t].x, xv[i][t].x, xv[i][t].y * xv[i][t].y) + fmaf(xv[i][t].z, xv[i][t].z, xv[i][t].w * xv[i][t].w);
-            }
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float rstd = rsqrtf(sq[i] * (1.0f / D) + p.eps);
-#pragma unroll
-          for (int t = 0; t < NV; ++t) {
-            const int j = lane + 32 * t;
-            if (j < D4) {
-              const int k = 4 * j, kk = k & 63;
-              uint8_t* dst = smem + L::OFF_A + (k >> 6) * 16384 + (ew * 8 + i) * 128 + ((static_cast<uint32_t>(kk >> 3) ^ static_cast<uint32_t>(i)) << 4) +
-                             ((kk >> 2) & 1) * 8;
-              uint2 w;
-              w.x = pack16<OPF16>(xv[i][t].x * rstd, xv[i][t].y * rstd);
-              w.y = pack16<OPF16>(xv[i][t].z * rstd, xv[i][t].w * rstd);
-              *reinterpret_cast<uint2*>(dst) = w;
-            }
-          }
-        }
-        fence_proxy_async();
+        prologue(tile, ti);
         mlp_epi_sync();                                              // the biases are in place for every warp
-        if (elect_one()) mbar_arrive(a_full);
-        g_cur = g;
-      } else if (g != g_cur) {
+      }
+      if (BWD && g != g_cur) {
 #pragma unroll
-        for (int t = 0; t < NV; ++t)
-          if (lane + 32 * t < D4) gam[t] = __ldg(reinterpret_cast<const float4*>(p.gamma + (long long)g * D) + lane + 32 * t);
+        for (int v = 0; v < V; ++v) gam[v] = __ldg(reinterpret_cast<const float4*>(p.gamma + (long long)g * D) + sub + LPR * v);
         g_cur = g;
       }
+      prefetch_rows(tile + gridDim.x);
+      if (BWD) prefetch_rows(tile);
 
       // ---- epilogue 1, chunk by chunk ----
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++gc, ++it) {
         const uint32_t b = gc & 1, n = gc >> 1;
         mbar_wait(&acc1_full[b], n & 1);
+        stamp();                                                     // chunk: accumulator seen
         tc_fence_after();
         uint32_t r[16];
         tmem_ld16(tmem_base + lane_base + b * HC + cp * 16, r);
@@ -339,7 +388,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (elect_one()) mbar_arrive(&acc1_empty[b]);
-        uint8_t* hrow = smem + L::OFF_HID + b * L::HID + row * 128;
+        uint8_t* hrow = smem + L::OFF_HID + hb * L::HID + row * 128;
         const uint32_t o0 = (static_cast<uint32_t>(2 * cp) ^ sw) << 4, o1 = (static_cast<uint32_t>(2 * cp + 1) ^ sw) << 4;
         if (!BWD) {
           const float4* bs = reinterpret_cast<const float4*>(consts + c * HC + cp * 16);
@@ -361,7 +410,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
               make_uint4(pack16<F16>(d[0], d[1]), pack16<F16>(d[2], d[3]), pack16<F16>(d[4], d[5]), pack16<F16>(d[6], d[7]));
           *reinterpret_cast<uint4*>(slab + lane * 32 + 16) =
               make_uint4(pack16<F16>(d[8], d[9]), pack16<F16>(d[10], d[11]), pack16<F16>(d[12], d[13]), pack16<F16>(d[14], d[15]));
-          mbar_wait(&hid_empty[b], (n & 1) ^ 1);                      // GEMM 2 of chunk gc - 2 has read this hidden buffer
+          stamp();                                                   // chunk: math done, gelu' staged
+          mbar_wait(&hid_empty[hb], (hn & 1) ^ 1);                    // GEMM 2 of the chunk that used this hidden buffer last has read it
+          stamp();                                                   // chunk: hidden buffer free
           *reinterpret_cast<uint4*>(hrow + o0) =
               make_uint4(pack16<F16>(y[0], y[1]), pack16<F16>(y[2], y[3]), pack16<F16>(y[4], y[5]), pack16<F16>(y[6], y[7]));
           *reinterpret_cast<uint4*>(hrow + o1) =
@@ -371,10 +422,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           if (elect_one()) {
             tma_store_3d(&tmU, slab, c * HC + cp * 16, row0 + q * 32, g);
             tma_store_commit();
-            mbar_arrive(&hid_full[b]);
+            mbar_arrive(&hid_full[hb]);
           }
         } else {
-          mbar_wait(&u_full[b], n & 1);                               // gelu'(u) of this chunk sits where du goes
+          stamp();
+          mbar_wait(&u_full[hb], hn & 1);                             // gelu'(u) of this chunk sits where du goes
+          stamp();
           const bool uf = p.f16 != 0;
           const uint4 u0 = *reinterpret_cast<const uint4*>(hrow + o0), u1 = *reinterpret_cast<const uint4*>(hrow + o1);
           const uint32_t uw[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
@@ -388,12 +441,32 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           *reinterpret_cast<uint4*>(hrow + o1) = make_uint4(w[4], w[5], w[6], w[7]);
           fence_proxy_async();
           __syncwarp();
-          if (elect_one()) mbar_arrive(&hid_full[b]);
+          if (elect_one()) mbar_arrive(&hid_full[hb]);
         }
+        if (++hb == NH) { hb = 0; ++hn; }
       }
 
-      // ---- final epilogue: acc2 (thread = row) -> transposition buffer -> coalesced global traffic ----
+      // forward, PIPE: the next tile's LayerNorm prologue comes BEFORE this tile's final epilogue -- its GEMM 1s then run under it
+      if (!BWD && PIPE && tile + (int)gridDim.x < total_tiles) prologue(tile + gridDim.x, ti + 1);
+
+      // ---- final epilogue: acc2 (thread = row) -> transposition buffer -> row-wise phase with coalesced global traffic ----
+      // what the row-wise phase needs from global memory is requested first: PG passes per group (register budget)
+      stamp();                                                       // chunks (and the next prologue) done
+      const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
+      const float4* rr = reinterpret_cast<const float4*>((BWD ? p.dres : p.x1) + (rbase + ew * 8) * D);
+      float4 xv[PG][V], dv[BWD ? PG : 1][V];
+      auto load_rows = [&](int pz0) {
+#pragma unroll
+        for (int pz = 0; pz < PG; ++pz)
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            xv[pz][v] = __ldg(xr + ((pz0 + pz) * RPW + rsel) * D4 + sub + LPR * v);
+            if (BWD) dv[pz][v] = __ldg(rr + ((pz0 + pz) * RPW + rsel) * D4 + sub + LPR * v);
+          }
+      };
+      load_rows(0);
       mbar_wait(acc2_full, ti & 1);
+      stamp();                                                       // acc2 complete
       tc_fence_after();
       if (!BWD) {
         if (elect_one()) tma_store_wait_read0();                     // the staging slabs are part of the transposition buffer
@@ -427,151 +500,90 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       __syncwarp();
       if (elect_one()) mbar_arrive(acc2_empty);
       mlp_epi_sync();
-      // rows ew * 8 .. + 8, lanes across channels
-      if (!BWD) {
-        const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
-        float4* orow = reinterpret_cast<float4*>(p.out_f32 + (rbase + ew * 8) * D);
-        float4 v[8][NV];
-        float s[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] = 0.f;
-#pragma unroll
-          for (int t = 0; t < NV; ++t) {
-            const int j = lane + 32 * t;
-            v[i][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < D4) {
-              const float4 x = __ldg(xr + i * D4 + j);
-              const float4 y = *reinterpret_cast<const float4*>(stg + (ew * 8 + i) * L::STG_STRIDE + 16 * j);
-              v[i][t] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
-              orow[i * D4 + j] = v[i][t];
-            }
-            s[i] += (v[i][t].x + v[i][t].y) + (v[i][t].z + v[i][t].w);
-          }
-        }
-        if (p.stats_out || p.out16) {
-          float sq[8];
-          if (p.stats_out) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float mean = s[i] * (1.0f / D);
-              s[i] = mean;
-              sq[i] = 0.f;
-#pragma unroll
-              for (int t = 0; t < NV; ++t) {
-                if (lane + 32 * t < D4) {
-                  const float dx = v[i][t].x - mean, dy = v[i][t].y - mean, dz = v[i][t].z - mean, dw = v[i][t].w - mean;
-                  sq[i] += fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
-                }
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
-            if (lane < 8) {
-              float m = s[0], qq = sq[0];
-#pragma unroll
-              for (int i = 1; i < 8; ++i) if (lane == i) { m = s[i]; qq = sq[i]; }
-              reinterpret_cast<float2*>(p.stats_out)[rbase + ew * 8 + lane] = make_float2(m, qq);
-            }
-          }
-          if (p.out16) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float sh = p.shift ? __ldg(p.shift + rbase + ew * 8 + i) : 0.f;
-              __nv_bfloat16* crow = p.out16 + (long long)g * p.bs16 + (long long)(row0 + ew * 8 + i) * p.ld16;
-#pragma unroll
-              for (int t = 0; t < NV; ++t) {
-                const int j = lane + 32 * t;
-                if (j < D4) {
-                  uint2 w;
-                  w.x = pack16<F16>(v[i][t].x - sh, v[i][t].y - sh);
-                  w.y = pack16<F16>(v[i][t].z - sh, v[i][t].w - sh);
-                  *reinterpret_cast<uint2*>(crow + 4 * j) = w;
-                }
-              }
-            }
-          }
-        }
-      } else {
-        // LayerNorm backward (norm2) + the residual branch:  dx = rstd (g - mean(g) - xhat mean(g xhat)) + dres,  g = dh gamma
-        const float4* xr = reinterpret_cast<const float4*>(p.x1 + (rbase + ew * 8) * D);
-        const float4* rr = reinterpret_cast<const float4*>(p.dres + (rbase + ew * 8) * D);
-        float4* orow = reinterpret_cast<float4*>(p.dx + (rbase + ew * 8) * D);
-        __nv_bfloat16* o16 = p.dx16 + (rbase + ew * 8) * D;
+      stamp();                                                       // transposed
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {                                // four rows at a time
-          float4 xc[4][NV], gg[4][NV];
-          float s[4];
+      for (int pz0 = 0; pz0 < NP; pz0 += PG) {
+        if (pz0 > 0) load_rows(pz0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            s[i] = 0.f;
+        for (int pz = 0; pz < PG; ++pz) {
+          const int r = ew * 8 + (pz0 + pz) * RPW + rsel;            // row of the tile this lane works on
+          const long long grow = rbase + r;
+          if (!BWD) {
+            float4* orow = reinterpret_cast<float4*>(p.out_f32 + grow * D);
+            float s = 0.f;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) {
-              const int j = lane + 32 * t;
-              xc[i][t] = make_float4(0.f, 0.f, 0.f, 0.f); gg[i][t] = xc[i][t];
-              if (j < D4) {
-                xc[i][t] = __ldg(xr + (4 * h + i) * D4 + j);
-                const uint2 w = *reinterpret_cast<const uint2*>(stg + (ew * 8 + 4 * h + i) * L::STG_STRIDE + 8 * j);
-                const float2 d0 = unpack_bf16(w.x), d1 = unpack_bf16(w.y);
-                gg[i][t] = make_float4(d0.x * gam[t].x, d0.y * gam[t].y, d1.x * gam[t].z, d1.y * gam[t].w);
-              }
-              s[i] += (xc[i][t].x + xc[i][t].y) + (xc[i][t].z + xc[i][t].w);
+            for (int v = 0; v < V; ++v) {
+              const int j = sub + LPR * v;
+              const float4 y = *reinterpret_cast<const float4*>(stg + r * L::STG_STRIDE + 16 * j);
+              float4& x = xv[pz][v];
+              x = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+              orow[j] = x;
+              s += (x.x + x.y) + (x.z + x.w);
             }
-          }
+            if (p.stats_out) {
+              const float mean = row_sum(s) * (1.0f / D);
+              float sq = 0.f;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
+              for (int v = 0; v < V; ++v) {
+                const float4 x = xv[pz][v];
+                const float dx = x.x - mean, dy = x.y - mean, dz = x.z - mean, dw = x.w - mean;
+                sq += fmaf(dx, dx, dy * dy) + fmaf(dz, dz, dw * dw);
+              }
+              sq = row_sum(sq);
+              if (sub == 0) reinterpret_cast<float2*>(p.stats_out)[grow] = make_float2(mean, sq);
+            }
+            if (p.out16) {
+              const float sh = p.shift ? __ldg(p.shift + grow) : 0.f;
+              __nv_bfloat16* crow = p.out16 + (long long)g * p.bs16 + (long long)(row0 + r) * p.ld16;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
-          float sa[4], sb2[4], sc[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float mean = s[i] * (1.0f / D);
-            sa[i] = sb2[i] = sc[i] = 0.f;
-#pragma unroll
-            for (int t = 0; t < NV; ++t) {
-              if (lane + 32 * t < D4) {
-                float4& x = xc[i][t];
-                const float4 gq = gg[i][t];
-                x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
-                sa[i] += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
-                sb2[i] += (gq.x + gq.y) + (gq.z + gq.w);
-                sc[i] += fmaf(gq.x, x.x, gq.y * x.y) + fmaf(gq.z, x.z, gq.w * x.w);
+              for (int v = 0; v < V; ++v) {
+                const float4 x = xv[pz][v];
+                *reinterpret_cast<uint2*>(crow + 4 * (sub + LPR * v)) = make_uint2(pack16<F16>(x.x - sh, x.y - sh), pack16<F16>(x.z - sh, x.w - sh));
               }
             }
-          }
+          } else {
+            // LayerNorm backward (norm2) + the residual branch:  dx = rstd (g - mean(g) - xhat mean(g xhat)) + dres,  g = dh gamma
+            float4 gg[V];
+            float s = 0.f;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              sa[i] += __shfl_xor_sync(0xffffffffu, sa[i], o);
-              sb2[i] += __shfl_xor_sync(0xffffffffu, sb2[i], o);
-              sc[i] += __shfl_xor_sync(0xffffffffu, sc[i], o);
+            for (int v = 0; v < V; ++v) {
+              const uint2 w = *reinterpret_cast<const uint2*>(stg + r * L::STG_STRIDE + 8 * (sub + LPR * v));
+              const float2 d0 = unpack_bf16(w.x), d1 = unpack_bf16(w.y);
+              gg[v] = make_float4(d0.x * gam[v].x, d0.y * gam[v].y, d1.x * gam[v].z, d1.y * gam[v].w);
+              s += (xv[pz][v].x + xv[pz][v].y) + (xv[pz][v].z + xv[pz][v].w);
             }
+            const float mean = row_sum(s) * (1.0f / D);
+            float sa = 0.f, sb2 = 0.f, sc = 0.f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float rstd = rsqrtf(sa[i] * (1.0f / D) + p.eps);
-            const float mb = sb2[i] * (1.0f / D), mc = sc[i] * (1.0f / D) * rstd * rstd;
+            for (int v = 0; v < V; ++v) {
+              float4& x = xv[pz][v];
+              const float4 gq = gg[v];
+              x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+              sa += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+              sb2 += (gq.x + gq.y) + (gq.z + gq.w);
+              sc += fmaf(gq.x, x.x, gq.y * x.y) + fmaf(gq.z, x.z, gq.w * x.w);
+            }
+            sa = row_sum(sa); sb2 = row_sum(sb2); sc = row_sum(sc);
+            const float rstd = rsqrtf(sa * (1.0f / D) + p.eps);
+            const float mb = sb2 * (1.0f / D), mc = sc * (1.0f / D) * rstd * rstd;
+            float4* orow = reinterpret_cast<float4*>(p.dx + grow * D);
+            __nv_bfloat16* o16 = p.dx16 + grow * D;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) {
-              const int j = lane + 32 * t;
-              if (j < D4) {
-                const float4 x = xc[i][t], gq = gg[i][t];
-                const float4 dr = __ldg(rr + (4 * h + i) * D4 + j);
-                float4 o;
-                o.x = fmaf(rstd, gq.x - mb - x.x * mc, dr.x); o.y = fmaf(rstd, gq.y - mb - x.y * mc, dr.y);
-                o.z = fmaf(rstd, gq.z - mb - x.z * mc, dr.z); o.w = fmaf(rstd, gq.w - mb - x.w * mc, dr.w);
-                orow[(4 * h + i) * D4 + j] = o;
-                *reinterpret_cast<uint2*>(o16 + (4 * h + i) * D + 4 * j) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-              }
+            for (int v = 0; v < V; ++v) {
+              const float4 x = xv[pz][v], gq = gg[v], dr = dv[pz][v];
+              float4 o;
+              o.x = fmaf(rstd, gq.x - mb - x.x * mc, dr.x); o.y = fmaf(rstd, gq.y - mb - x.y * mc, dr.y);
+              o.z = fmaf(rstd, gq.z - mb - x.z * mc, dr.z); o.w = fmaf(rstd, gq.w - mb - x.w * mc, dr.w);
+              orow[sub + LPR * v] = o;
+              *reinterpret_cast<uint2*>(o16 + 4 * (sub + LPR * v)) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
             }
           }
         }
+      }
+      stamp();                                                       // tile done
+      if (!BWD) {
+        if (PIPE) mlp_epi_sync();                                    // the transposition buffer aliases hidden | staging: everybody has read it
+      } else if (!PIPE) {
         __syncwarp();
         if (elect_one()) mbar_arrive(fin_done);
       }
