@@ -356,12 +356,14 @@ def main():
             for bwd in (False, True):
                 for o in eng.profile_ops(app, bwd, 5):
                     all_ms += o["ms"] * mult
-                    if o["kind"] != "gemm":
+                    if o["kind"] not in ("gemm", "mlp_fwd", "mlp_bwd"):       # the tensor-core kernels: the tcgen05 GEMM and the fused tower MLP
                         continue
                     gemm_ms += o["ms"] * mult; gemm_fl += o["flop"] * mult
                     M_, N_, K_, B_ = o["shape"]
-                    key = "trunk d=1152, N=1152 (proj, fc2, dgrads: 72 tiles on 74 SM pairs)" if (B_ == 1 and N_ == 1152) else \
-                          "trunk d=1152, N>=3456 (qkv, fc1, dgrad of fc2)" if B_ == 1 else "towers d=96/192 (batched over 6 variable groups)"
+                    key = "towers: fused MLP half of a block, norm2 + fc1 + GELU + fc2 + residual / its input-VJP (mlp_fused_kernel, tcgen05 cta_group::1)" \
+                          if o["kind"] != "gemm" else \
+                          "trunk d=1152, N=1152 (proj, fc2, dgrads: 72 tiles on 74 SM pairs)" if (B_ == 1 and N_ == 1152) else \
+                          "trunk d=1152, N>=3456 (qkv, fc1, dgrad of fc2)" if B_ == 1 else "towers d=96/192: qkv, proj, seams and their dgrads (batched over 6 variable groups)"
                     f_ = fam.setdefault(key, [0.0, 0.0, 0]); f_[0] += o["ms"] * mult; f_[1] += o["flop"] * mult; f_[2] += mult
     except Exception as ex:
         fam = {"error": [0.0, 0.0, repr(ex)]}
@@ -533,7 +535,7 @@ def main():
         "gpu_launches_per_step": launches,
         "roofline": {"bound": "tensor", "achieved": gemm_tfs, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tfs / sustained,
                      "traffic": None,
-                     "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, TMEM, TMA): ALL its launches of the step, time-weighted "
+                     "kernel": "gemm_pair_kernel (tcgen05 cta_group::2, TMEM, TMA) + mlp_fused_kernel (tcgen05 cta_group::1): ALL their launches of the step, time-weighted "
                                "(sum of algorithmic flops / sum of per-launch CUDA-event times, steady state)",
                      "gemm_share_of_step_time": gemm_ms / max(all_ms, 1e-9), "gemm_ms_per_step": gemm_ms,
                      "step_achieved": step_tfs, "step_frac": step_tfs / sustained, "step_frac_of_burst": step_tfs / burst,

@@ -5,7 +5,7 @@ set -eu
 tag=$1; shift
 cd "$(dirname "$0")/../vaevar_b200"
 mkdir -p build_$tag
-for f in gemm kernels obs_lbfgs engine lbfgs seams net1_kernels net1; do
+for f in gemm kernels obs_lbfgs engine lbfgs seams net1_kernels net1 mlp_fused; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden "$@" -c csrc/$f.cu -o build_$tag/$f.o &
 done
 wait

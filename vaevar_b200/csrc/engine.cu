@@ -256,8 +256,10 @@ static int build_blocks(vv_engine* e, WeightReader& R, std::vector<BlockW>& out,
     const size_t dd = (size_t)d * d;
     w.Wqkv = dalloc<bf16>(e, G * 3 * dd); w.WqkvT = dalloc<bf16>(e, G * 3 * dd);
     w.Wproj = dalloc<bf16>(e, G * dd); w.WprojT = dalloc<bf16>(e, G * dd);
-    w.W1 = dalloc<bf16>(e, G * 4 * dd); w.W1T = dalloc<bf16>(e, G * 4 * dd);
-    w.W2 = dalloc<bf16>(e, G * 4 * dd); w.W2T = dalloc<bf16>(e, G * 4 * dd);
+    // fc1 | fc2 (and fc2^T | fc1^T) share one allocation each: the fused tower MLP reads both, and the GEMM in front of it
+    // prefetches the pair into L2 as one region
+    w.W1 = dalloc<bf16>(e, G * 8 * dd); w.W2T = dalloc<bf16>(e, G * 8 * dd);
+    w.W2 = w.W1 ? w.W1 + G * 4 * dd : nullptr; w.W1T = w.W2T ? w.W2T + G * 4 * dd : nullptr;
     if (!w.Wqkv || !w.WqkvT || !w.Wproj || !w.WprojT || !w.W1 || !w.W1T || !w.W2 || !w.W2T) return -1;
     std::vector<float> bqkv, bproj, b1, b2, g1, be1, g2, be2, rb;
     auto app = [](std::vector<float>& dst, const std::vector<float>& src) { dst.insert(dst.end(), src.begin(), src.end()); };
@@ -841,6 +843,21 @@ static int build_plans(vv_engine* e) {
       chain[i]->a.pf_ptr = nx->b_ptr;
       chain[i]->a.pf_bytes = nx->b_ptr ? nx->b_bytes : 0;
     }
+    // a fused tower MLP streams fc1 | fc2 (backward: fc2^T | fc1^T, 1.8 / 7 MB for all six towers) through its weight ring from the first
+    // cycle on: the GEMM launched right before it pulls that region into L2 as well
+    auto mlp_prefetch = [](Plan& P) {
+      for (size_t i = 1; i < P.ops.size(); ++i) {
+        Op& o = P.ops[i];
+        if (o.kind != Op::MLP_F && o.kind != Op::MLP_B) continue;
+        for (size_t j = i; j-- > 0 && i - j <= 3;) {                  // the nearest GEMM in front of it (backward: behind a LayerNorm launch)
+          if (P.ops[j].kind != Op::GEMM) continue;
+          P.ops[j].gemm.a.pf2_ptr = o.mlp.w_ptr;
+          P.ops[j].gemm.a.pf2_bytes = o.mlp.w_bytes;
+          break;
+        }
+      }
+    };
+    for (int a = 0; a < napp; ++a) { mlp_prefetch(e->fwd[a]); mlp_prefetch(e->bwd[a]); }
   }
   e->plans_built = true;
   return 0;
@@ -1295,6 +1312,60 @@ VV_API int vv_num_obs(vv_engine* e, int64_t* n_obs) {
   *n_obs = e->n_obs;
   return 0;
 }
+
+}  // extern "C"
+
+// Debug (VV_NAN_PROBE=1, called by the optimiser the first time a closure returns a non-finite J): where along the window did the
+// first non-finite value appear?  Non-finite count and largest finite magnitude of the latent, the decoder output, every state of
+// the trajectory and every residual-stream buffer of every application's stash, in execution order, to stderr.
+__global__ void nan_probe_kernel(const float* x, long long n, unsigned int* out) {
+  unsigned int bad = 0, mx = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (isfinite(v)) mx = max(mx, __float_as_uint(fabsf(v))); else ++bad;
+  }
+  if (bad) atomicAdd(out, bad);
+  atomicMax(out + 1, mx);
+}
+namespace vv {
+void engine_nan_probe(vv_engine* e, const float* z) {
+  unsigned int* d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return;
+  auto probe = [&](const char* what, int app, int k, const float* x, size_t n) {
+    if (!x || !n) return;
+    cudaMemset(d, 0, 8);
+    nan_probe_kernel<<<592, 256, 0, e->stream>>>(x, (long long)n, d);
+    unsigned int h[2] = {0, 0};
+    cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+    float mx; memcpy(&mx, &h[1], 4);
+    fprintf(stderr, "[vaevar nan-probe] %-10s app %d #%d: non-finite %u of %zu, max |finite| %.4g\n", what, app, k, h[0], n, mx);
+  };
+  const size_t CHW = (size_t)e->C * e->HW;
+  probe("z", -1, 0, z, (size_t)e->Zc * e->HW);
+  for (size_t a = 0; a < e->stash.size(); ++a) {
+    Net& n = e->net[a == 0 ? 0 : 1];
+    Stash& S = e->stash[a];
+    if (a >= 1) probe("x_in", (int)a, 0, e->XN + (a - 1) * CHW, CHW);
+    struct { const char* nm; StageStash* st; size_t rows; } stages[5] = {{"enc0", &S.e0, (size_t)n.L0}, {"enc1", &S.e1, (size_t)n.L1}, {"trunk", &S.lg, (size_t)n.L1},
+                                                                            {"dec0", &S.u0, (size_t)n.L1}, {"dec1", &S.u1, (size_t)n.L0}};
+    const std::vector<BlockW>* ws[5] = {&n.e0, &n.e1, &n.lg, &n.u0, &n.u1};
+    for (int q = 0; q < 5; ++q) {
+      if (ws[q]->empty()) continue;
+      const size_t rd = (size_t)(*ws[q])[0].G * stages[q].rows * (*ws[q])[0].d;
+      for (size_t k = 0; k < stages[q].st->x.size(); ++k) {
+        probe(stages[q].nm, (int)a, (int)k, stages[q].st->x[k], rd);
+        if (k < stages[q].st->b.size()) probe("  .x1", (int)a, (int)k, stages[q].st->b[k].x1, rd);
+      }
+    }
+    if (a == 0) probe("D(z)", 0, 0, e->DOUT, CHW);
+    else probe("x_out", (int)a, 0, e->XN + a * CHW, CHW);
+  }
+  cudaFree(d);
+}
+}  // namespace vv
+
+extern "C" {
 
 VV_API int vv_ln_fold_health(vv_engine* e, uint32_t counts_host[2]) {
   VV_CHECK(e && counts_host, "null argument");

@@ -142,4 +142,6 @@ int engine_cost_grad(vv_engine* e, const float* z, double* Jout, float* grad, cu
 // Order the engine's private stream after `user` (fence_in) / `user` after the private stream (fence_out).
 int fence_in(vv_engine* e, cudaStream_t user);
 int fence_out(vv_engine* e, cudaStream_t user);
+// Debug: per-buffer non-finite counts of the window's trajectory and stashes to stderr (VV_NAN_PROBE=1).
+void engine_nan_probe(vv_engine* e, const float* z);
 }

@@ -138,7 +138,7 @@ static int tuned_bn(const bf16* A, long long lda, long long a_bs, const bf16* B,
     GemmArgs a2 = args;
     if (a2.stats_out) a2.stats_out_bs = 2LL * 2 * ((a2.N + cand[i] - 1) / cand[i]) * a2.M;
     if (make_gemm_desc_bn(&d, A, lda, a_bs, B, ldb, b_bs, a2, cand[i])) continue;
-    d.a.pf_ptr = nullptr; d.a.pf_bytes = 0; d.a.trace = nullptr; d.a.debug_mode = 0;
+    d.a.pf_ptr = nullptr; d.a.pf_bytes = 0; d.a.pf2_ptr = nullptr; d.a.pf2_bytes = 0; d.a.trace = nullptr; d.a.debug_mode = 0;
     d.a.stats_out_bs = a2.stats_out_bs;
     launch_gemm(d, 0); launch_gemm(d, 0);
     cudaEventRecord(e0, 0);
@@ -179,7 +179,7 @@ static const char* make_gemm_desc_bn(GemmDesc* d, const bf16* A, long long lda, 
   const bool b_contig = ldb == args.K && (args.batch == 1 || b_bs == (long long)args.N * args.K);
   d->b_ptr = b_contig ? B : nullptr;
   d->b_bytes = b_contig ? (unsigned long long)args.N * args.K * args.batch * 2 : 0;
-  d->a.pf_ptr = nullptr; d->a.pf_bytes = 0;
+  d->a.pf_ptr = nullptr; d->a.pf_bytes = 0; d->a.pf2_ptr = nullptr; d->a.pf2_bytes = 0;
   d->a.trace = g_gemm_trace;
   d->a.debug_mode = g_gemm_debug_mode;
   d->bn = force_bn > 0 ? force_bn : pick_bn(args.M, args.N, args.batch);

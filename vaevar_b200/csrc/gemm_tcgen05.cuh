@@ -80,6 +80,8 @@ struct GemmArgs {
   long long stats_out_bs;     // batch stride in floats
   const void* pf_ptr;         // weights of the NEXT GEMM in the plan: prefetched into L2 by the idle producer warp (null = none)
   unsigned long long pf_bytes;
+  const void* pf2_ptr;        // a second region to prefetch (the weights of a fused tower MLP launched next); null = none
+  unsigned long long pf2_bytes;
   int debug_mode;             // debug: 0 normal; 1 MMA only (no TMA, operands = whatever is in smem); 2 TMA only (no MMA)
   unsigned long long* trace;  // debug: per-CTA clock64 stamps (64 slots per CTA, see tools/gemm_trace.py); null in production
 };
@@ -335,14 +337,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // All operand loads of this CTA are in flight: use the idle producer warp to pull this CTA's slice of the NEXT GEMM's
     // weights from HBM into L2 (the 0.43 GB of weights per network never stay in the 126 MB L2 from one evaluation to the
     // next, so without this every GEMM starts on a DRAM-latency-bound pipeline fill).
-    if (p.pf_ptr) {
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      const void* pf = r ? p.pf2_ptr : p.pf_ptr;
+      const unsigned long long pfb = r ? p.pf2_bytes : p.pf_bytes;
+      if (!pf) continue;
       constexpr unsigned long long CH = 4096;
-      const unsigned long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
+      const unsigned long long per = ((pfb + gridDim.x - 1) / gridDim.x + CH - 1) / CH * CH;
       const unsigned long long beg = (unsigned long long)blockIdx.x * per;
-      const unsigned long long end = beg + per < p.pf_bytes ? beg + per : p.pf_bytes;
+      const unsigned long long end = beg + per < pfb ? beg + per : pfb;
       for (unsigned long long o = beg + lane * CH; o < end; o += 32 * CH) {
         const unsigned long long n = end - o < CH ? (end - o) & ~15ull : CH;
-        if (n) l2_prefetch_bulk(static_cast<const uint8_t*>(p.pf_ptr) + o, (uint32_t)n);
+        if (n) l2_prefetch_bulk(static_cast<const uint8_t*>(pf) + o, (uint32_t)n);
       }
     }
   } else if (warp == 1) {

@@ -111,6 +111,10 @@ int eval(vv_lbfgs* o, const float* z, float* gout, const float* dvec, double* f,
   if (gtd) *gtd = o->pinned[3];
   o->func_evals++;
   o->hist_loss.push_back(*f);
+  if (!std::isfinite(*f) && o->e) {
+    static bool probed = false;
+    if (!probed && getenv("VV_NAN_PROBE")) { probed = true; engine_nan_probe(o->e, z); }
+  }
   return 0;
 }
 
@@ -163,7 +167,10 @@ Sc cubic_interpolate(Sc x1, double f1, Sc g1, Sc x2, double f2, Sc g2, bool has_
       mp = op(x2, '-', op(op(x2, '-', x1), '*', op(op(op(g2, '+', d2), '-', d1), '/', op(op(g2, '-', g1), '+', op(py(2.0), '*', d2)))));
     else
       mp = op(x1, '-', op(op(x1, '-', x2), '*', op(op(op(g1, '+', d2), '-', d1), '/', op(op(g1, '-', g2), '+', op(py(2.0), '*', d2)))));
-    return pymin(pymax(mp, xmin), xmax);
+    // The one deliberate departure from lbfgs.py:12-37: in float32 d1 * d1 overflows once |3 (f1 - f2) / (x1 - x2)| exceeds 1.8e19 (losses
+    // of 1e10 over steps of 1e-10 -- the first trial steps of a cycle whose background is far from the observations); torch then gets
+    // inf / inf = NaN for the step and the NaN reaches z.  A non-finite minimiser is treated like a negative discriminant: bisection.
+    if (std::isfinite(mp.v)) return pymin(pymax(mp, xmin), xmax);
   }
   return op(op(xmin, '+', xmax), '/', py(2.0));
 }

@@ -21,6 +21,9 @@ const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const bf16* W1, const bf1
   if (!mlp_fused_supported(D, args.rows)) return "fused MLP: token width / row count not supported";
   d->D = D; d->bwd = bwd ? 1 : 0; d->a = args;
   d->a.trace = g_mlp_trace;
+  const unsigned long long wb = 4ull * D * D * args.batch * 2;                     // bytes of one of the two weight blocks
+  const bool adj = reinterpret_cast<const char*>(W2) == reinterpret_cast<const char*>(W1) + wb;
+  d->w_ptr = adj ? W1 : nullptr; d->w_bytes = adj ? 2 * wb : 0;
   const long long rows = args.rows, B = args.batch;
   const char* e;
   if ((e = encode_tma_3d_16(&d->tmW1, W1, D, 4LL * D, B, D, 4LL * D * D, 64, MLP_HC))) return e;

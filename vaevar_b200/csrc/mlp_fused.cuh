@@ -349,6 +349,71 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       }
     };
 
+    // backward: LayerNorm backward (norm2) of row r of the tile (global row grow) + the residual branch, from the transposition buffer:
+    //   dx = rstd (g - mean(g) - xhat mean(g xhat)) + dres,  g = dh gamma          x, dr: this lane's float4s of x1 / dres
+    auto ln_bwd_row = [&](int r, long long grow, float4 (&x4)[V], const float4 (&dr4)[V], const float4 (&gm)[V]) {
+      float4 gg[V];
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const uint2 w = *reinterpret_cast<const uint2*>(stg + r * L::STG_STRIDE + 8 * (sub + LPR * v));
+        const float2 d0 = unpack_bf16(w.x), d1 = unpack_bf16(w.y);
+        gg[v] = make_float4(d0.x * gm[v].x, d0.y * gm[v].y, d1.x * gm[v].z, d1.y * gm[v].w);
+        s += (x4[v].x + x4[v].y) + (x4[v].z + x4[v].w);
+      }
+      const float mean = row_sum(s) * (1.0f / D);
+      float sa = 0.f, sb2 = 0.f, sc = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float4& x = x4[v];
+        const float4 gq = gg[v];
+        x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
+        sa += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
+        sb2 += (gq.x + gq.y) + (gq.z + gq.w);
+        sc += fmaf(gq.x, x.x, gq.y * x.y) + fmaf(gq.z, x.z, gq.w * x.w);
+      }
+      sa = row_sum(sa); sb2 = row_sum(sb2); sc = row_sum(sc);
+      const float rstd = rsqrtf(sa * (1.0f / D) + p.eps);
+      const float mb = sb2 * (1.0f / D), mc = sc * (1.0f / D) * rstd * rstd;
+      float4* orow = reinterpret_cast<float4*>(p.dx + grow * D);
+      __nv_bfloat16* o16 = p.dx16 + grow * D;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float4 x = x4[v], gq = gg[v], dr = dr4[v];
+        float4 o;
+        o.x = fmaf(rstd, gq.x - mb - x.x * mc, dr.x); o.y = fmaf(rstd, gq.y - mb - x.y * mc, dr.y);
+        o.z = fmaf(rstd, gq.z - mb - x.z * mc, dr.z); o.w = fmaf(rstd, gq.w - mb - x.w * mc, dr.w);
+        orow[sub + LPR * v] = o;
+        *reinterpret_cast<uint2*>(o16 + 4 * (sub + LPR * v)) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    };
+    // backward, PIPE: the row-wise phase of a tile is DEFERRED into the chunk loop of the next one (the epilogue warps idle there:
+    // the loop runs at the pace of the MMA issue thread) -- pass pz at the top of chunk pz + 1, its loads one chunk earlier.  The
+    // transposition buffer has its own shared memory then; it is rewritten only after every warp has arrived for the next tile's last
+    // chunk, i.e. after its deferred passes.
+#ifdef VV_MLP_NODEFER
+    constexpr bool DEFER = false;
+#else
+    constexpr bool DEFER = BWD && PIPE && NP + 1 < NCH;
+#endif
+    bool pending = false;
+    long long rbase_prev = 0;
+    float4 xd[V], dd[V], gamd[V];                                  // gamd: norm2 weight of the deferred tile's group
+    auto deferred_load = [&](int pz) {
+      const float4* xq = reinterpret_cast<const float4*>(p.x1 + (rbase_prev + ew * 8 + pz * RPW + rsel) * D);
+      const float4* dq = reinterpret_cast<const float4*>(p.dres + (rbase_prev + ew * 8 + pz * RPW + rsel) * D);
+#pragma unroll
+      for (int v = 0; v < V; ++v) { xd[v] = __ldg(xq + sub + LPR * v); dd[v] = __ldg(dq + sub + LPR * v); }
+    };
+    auto deferred_step = [&](int c) {                                // called at the top of chunk c of the tile that follows
+      if (c >= 1 && c - 1 < NP) {
+        const int r = ew * 8 + (c - 1) * RPW + rsel;
+        ln_bwd_row(r, rbase_prev + r, xd, dd, gamd);
+      }
+      if (c < NP) deferred_load(c);
+      if (c == NP) pending = false;
+    };
+
     unsigned long long* trc = (p.trace && blockIdx.x == 0 && ew == 0 && lane == 0) ? p.trace : nullptr;     // epilogue warp 0: slots 0..63
     int tslot = 0;
     auto stamp = [&]() { if (trc && tslot < 64) trc[tslot++] = clock64(); };
@@ -372,13 +437,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         for (int v = 0; v < V; ++v) gam[v] = __ldg(reinterpret_cast<const float4*>(p.gamma + (long long)g * D) + sub + LPR * v);
         g_cur = g;
       }
+#ifndef VV_MLP_NOPF
       prefetch_rows(tile + gridDim.x);
       if (BWD) prefetch_rows(tile);
+#endif
 
       // ---- epilogue 1, chunk by chunk ----
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++gc, ++it) {
         const uint32_t b = gc & 1, n = gc >> 1;
+        if (DEFER && pending) deferred_step(c);
         mbar_wait(&acc1_full[b], n & 1);
         stamp();                                                     // chunk: accumulator seen
         tc_fence_after();
@@ -464,7 +532,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             if (BWD) dv[pz][v] = __ldg(rr + ((pz0 + pz) * RPW + rsel) * D4 + sub + LPR * v);
           }
       };
-      load_rows(0);
+      if (!DEFER) load_rows(0);
       mbar_wait(acc2_full, ti & 1);
       stamp();                                                       // acc2 complete
       tc_fence_after();
@@ -501,8 +569,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       if (elect_one()) mbar_arrive(acc2_empty);
       mlp_epi_sync();
       stamp();                                                       // transposed
+      if (DEFER) {
+        pending = true; rbase_prev = rbase;
+#pragma unroll
+        for (int v = 0; v < V; ++v) gamd[v] = gam[v];
+      }
 #pragma unroll 1
-      for (int pz0 = 0; pz0 < NP; pz0 += PG) {
+      for (int pz0 = 0; pz0 < (DEFER ? 0 : NP); pz0 += PG) {
         if (pz0 > 0) load_rows(pz0);
 #pragma unroll
         for (int pz = 0; pz < PG; ++pz) {
@@ -542,41 +615,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
               }
             }
           } else {
-            // LayerNorm backward (norm2) + the residual branch:  dx = rstd (g - mean(g) - xhat mean(g xhat)) + dres,  g = dh gamma
-            float4 gg[V];
-            float s = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const uint2 w = *reinterpret_cast<const uint2*>(stg + r * L::STG_STRIDE + 8 * (sub + LPR * v));
-              const float2 d0 = unpack_bf16(w.x), d1 = unpack_bf16(w.y);
-              gg[v] = make_float4(d0.x * gam[v].x, d0.y * gam[v].y, d1.x * gam[v].z, d1.y * gam[v].w);
-              s += (xv[pz][v].x + xv[pz][v].y) + (xv[pz][v].z + xv[pz][v].w);
-            }
-            const float mean = row_sum(s) * (1.0f / D);
-            float sa = 0.f, sb2 = 0.f, sc = 0.f;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              float4& x = xv[pz][v];
-              const float4 gq = gg[v];
-              x.x -= mean; x.y -= mean; x.z -= mean; x.w -= mean;
-              sa += fmaf(x.x, x.x, x.y * x.y) + fmaf(x.z, x.z, x.w * x.w);
-              sb2 += (gq.x + gq.y) + (gq.z + gq.w);
-              sc += fmaf(gq.x, x.x, gq.y * x.y) + fmaf(gq.z, x.z, gq.w * x.w);
-            }
-            sa = row_sum(sa); sb2 = row_sum(sb2); sc = row_sum(sc);
-            const float rstd = rsqrtf(sa * (1.0f / D) + p.eps);
-            const float mb = sb2 * (1.0f / D), mc = sc * (1.0f / D) * rstd * rstd;
-            float4* orow = reinterpret_cast<float4*>(p.dx + grow * D);
-            __nv_bfloat16* o16 = p.dx16 + grow * D;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              const float4 x = xv[pz][v], gq = gg[v], dr = dv[pz][v];
-              float4 o;
-              o.x = fmaf(rstd, gq.x - mb - x.x * mc, dr.x); o.y = fmaf(rstd, gq.y - mb - x.y * mc, dr.y);
-              o.z = fmaf(rstd, gq.z - mb - x.z * mc, dr.z); o.w = fmaf(rstd, gq.w - mb - x.w * mc, dr.w);
-              orow[sub + LPR * v] = o;
-              *reinterpret_cast<uint2*>(o16 + 4 * (sub + LPR * v)) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
-            }
+            if (BWD) ln_bwd_row(r, grow, xv[pz], dv[BWD ? pz : 0], gam);
           }
         }
       }
@@ -587,6 +626,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         __syncwarp();
         if (elect_one()) mbar_arrive(fin_done);
       }
+    }
+    if (DEFER && pending) {                                          // the last tile's row-wise phase
+#pragma unroll 1
+      for (int c = 0; c <= NP; ++c) deferred_step(c);
     }
     if (!BWD) {
       if (elect_one()) tma_store_wait_read0();

@@ -56,6 +56,8 @@ struct MlpDesc {
   CUtensorMap tmW1, tmW2, tmA, tmU;
   MlpArgs a;
   int D, bwd;
+  const void* w_ptr;            // W1 | W2 as one contiguous block (null if they are not adjacent): what the GEMM before it prefetches
+  unsigned long long w_bytes;
 };
 bool mlp_fused_supported(int D, int rows);
 const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const __nv_bfloat16* W1, const __nv_bfloat16* W2, const __nv_bfloat16* u,
