@@ -191,6 +191,13 @@ VV_API int vv_lbfgs_steps(vv_lbfgs* o, double* t_out_host, int cap);
  * optimiser's decisions with torch.optim.LBFGS on an identical objective. */
 VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, vv_lbfgs** out);
 
+/* Host-only (no device needed): the strong-Wolfe line search's cubic interpolation (torch/optim/lbfgs.py:12-37) with torch's scalar
+ * typing -- steps / directional derivatives are 0-dim float32 tensors when *_is_tensor, losses are Python floats.  Identical to torch
+ * except where torch's float32 arithmetic overflows to inf / inf = NaN: the bisection step of the negative-discriminant branch is
+ * returned instead (lbfgs.cu).  has_bounds = 0: bounds = (min(x1, x2), max(x1, x2)). */
+VV_API double vv_debug_cubic_interpolate(double x1, double f1, double g1, double x2, double f2, double g2, int x_is_tensor, int g_is_tensor,
+                                  int has_bounds, double lo, double hi);
+
 /* Kernel-level hooks used by tests/ and bench.py (roofline of the dominant kernel). */
 /* epi: 0 linear, 1 GELU (aux out = saved gelu'(u)), 2 multiply by aux (aux in = the saved gelu'(u)); | 16: operands, 16-bit outputs
  * and aux are fp16 instead of bf16. */

@@ -262,3 +262,30 @@ def test_real_simu_observation_source(gold):
                          yo_real=lambda cycle: ref + bad)
     _, Hq, _, _ = src_qc.window(0)
     assert float(Hq[:, 7].sum()) == 0.0 and torch.equal(Hq[:, :7], H[:, :7]) and torch.equal(Hq[:, 8:], H[:, 8:])
+
+
+def test_line_search_cubic_interpolation_matches_torch_and_survives_overflow():
+    """The controller's cubic interpolation (host code of libvaevar.so, no device needed) equals torch.optim.lbfgs._cubic_interpolate on
+    float32-tensor scalars, and where torch's float32 arithmetic overflows (losses ~1e10 over steps ~1e-11: d1 * d1 = inf, the step becomes
+    inf / inf = NaN and poisons z) it returns the finite bisection step instead -- the native-geometry chains hit exactly that."""
+    from torch.optim.lbfgs import _cubic_interpolate
+    from vaevar_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        x1, x2 = sorted(rng.uniform(1e-4, 2.0, size=2))
+        f1, f2 = rng.uniform(-5, 5, size=2)
+        g1, g2 = rng.uniform(-10, 10, size=2)
+        bounds = bool(rng.integers(0, 2))
+        lo, hi = (x2 + 0.01 * (x2 - x1), 10 * x2) if bounds else (0.0, 0.0)
+        T = lambda v: torch.tensor(v, dtype=torch.float32)
+        ref = _cubic_interpolate(T(x1), float(f1), T(g1), T(x2), float(f2), T(g2), bounds=(T(lo), T(hi)) if bounds else None)
+        got = lib.vv_debug_cubic_interpolate(x1, f1, g1, x2, f2, g2, 1, 1, int(bounds), lo, hi)
+        assert abs(got - float(ref)) <= 2e-6 * max(1.0, abs(float(ref))), (x1, f1, g1, x2, f2, g2, bounds, got, float(ref))
+    # the overflow case: torch yields NaN, the controller the midpoint of the bracket
+    x1, x2, f1, f2, g1, g2 = 0.0, 1e-11, 4.1e10, 2.9e10, -3.0e15, -2.5e15
+    T = lambda v: torch.tensor(v, dtype=torch.float32)
+    ref = _cubic_interpolate(T(x1), f1, T(g1), T(x2), f2, T(g2))
+    assert not torch.isfinite(torch.as_tensor(ref)), "torch's interpolation is expected to overflow here"
+    got = lib.vv_debug_cubic_interpolate(x1, f1, g1, x2, f2, g2, 1, 1, 0, 0.0, 0.0)
+    assert np.isfinite(got) and abs(got - 0.5e-11) <= 1e-17

@@ -336,6 +336,16 @@ VV_API int vv_lbfgs_create_testfn(long long n, int history_size, int max_iter, v
   return lbfgs_alloc(o, n, history_size, max_iter, out);
 }
 
+// Host-only hook (no device needed): the line search's cubic interpolation with torch's scalar typing (x / g are 0-dim float32 tensors
+// when *_is_tensor, losses are Python floats), for the CPU test that pins it to torch.optim.lbfgs._cubic_interpolate and checks the
+// overflow guard.  has_bounds = 0: bounds default to (min(x1, x2), max(x1, x2)).
+VV_API double vv_debug_cubic_interpolate(double x1, double f1, double g1, double x2, double f2, double g2, int x_is_tensor, int g_is_tensor,
+                                         int has_bounds, double lo, double hi) {
+  const Sc X1 = x_is_tensor ? tn(x1) : py(x1), X2 = x_is_tensor ? tn(x2) : py(x2);
+  const Sc G1 = g_is_tensor ? tn(g1) : py(g1), G2 = g_is_tensor ? tn(g2) : py(g2);
+  return cubic_interpolate(X1, f1, G1, X2, f2, G2, has_bounds != 0, x_is_tensor ? tn(lo) : py(lo), x_is_tensor ? tn(hi) : py(hi), 0.0).v;
+}
+
 VV_API int vv_lbfgs_history(vv_lbfgs* o, double* loss_out, int cap) {
   if (!o) return 0;
   const int k = (int)std::min<size_t>(o->hist_loss.size(), (size_t)cap);
