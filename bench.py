@@ -356,11 +356,11 @@ def main():
             for bwd in (False, True):
                 for o in eng.profile_ops(app, bwd, 5):
                     all_ms += o["ms"] * mult
-                    if o["kind"] not in ("gemm", "mlp_fwd", "mlp_bwd"):       # the tensor-core kernels: the tcgen05 GEMM and the fused tower MLP
+                    if o["kind"] not in ("gemm", "mlp_fwd", "mlp_bwd", "lin_fwd"):       # the tensor-core kernels: the tcgen05 GEMM and the fused tower MLP
                         continue
                     gemm_ms += o["ms"] * mult; gemm_fl += o["flop"] * mult
                     M_, N_, K_, B_ = o["shape"]
-                    key = "towers: fused MLP half of a block, norm2 + fc1 + GELU + fc2 + residual / its input-VJP (mlp_fused_kernel, tcgen05 cta_group::1)" \
+                    key = "towers: fused norm1 + qkv, and the MLP half of a block (norm2 + fc1 + GELU + fc2 + residual) / its input-VJP (mlp_fused_kernel, tcgen05 cta_group::1)" \
                           if o["kind"] != "gemm" else \
                           "trunk d=1152, N=1152 (proj, fc2, dgrads: 72 tiles on 74 SM pairs)" if (B_ == 1 and N_ == 1152) else \
                           "trunk d=1152, N>=3456 (qkv, fc1, dgrad of fc2)" if B_ == 1 else "towers d=96/192: qkv, proj, seams and their dgrads (batched over 6 variable groups)"

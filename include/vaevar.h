@@ -229,6 +229,11 @@ VV_API int vv_test_mlp_fwd(const float* x1_dev, const void* W1_16_dev, const voi
 VV_API int vv_test_mlp_bwd(const void* dy_bf16_dev, const void* u_16_dev, const float* x1_dev, const void* W2T_bf16_dev, const void* W1T_bf16_dev,
                     const float* gamma_dev, const float* dres_dev, int rows, int batch, int D, int f16, float eps, float* dx_dev,
                     void* dx_bf16_dev, void* stream);
+/* LayerNorm + ONE Linear on the same kernel (norm1 -> qkv of a tower block, swinblock.py:268-269 + :139): out_16 (batch, rows, n_out) =
+ * 16bit(normalise(x) W^T + bias) with W (batch, n_out, D) 16-bit carrying gamma and bias (batch, n_out) the folded beta; n_out a
+ * multiple of 16. */
+VV_API int vv_test_lin_fwd(const float* x_dev, const void* W_16_dev, const float* bias_dev, int rows, int batch, int D, int n_out, int f16,
+                    float eps, void* out_16_dev, void* stream);
 /* Debug: fused-MLP launches built after this call stamp clock64 values of CTA 0 into trace_dev (128 x uint64: slots 0..63 epilogue warp 0,
  * 64..127 the MMA warp; tools/mlp_trace.py); null = off. */
 VV_API int vv_debug_mlp_trace(void* trace_dev);

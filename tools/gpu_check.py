@@ -171,6 +171,32 @@ def stage_mlp():
             refdx = xr.grad + dy
             ok &= report("mlp", f"bwd dx {tag}", rel(dx, refdx), 6e-3)
             ok &= report("mlp", f"bwd dx bf16 {tag}", rel(dxb.float(), dx), 4e-3)
+    # LayerNorm + one Linear (norm1 -> qkv) on the same kernel
+    for (rows, D, B) in [(128, 64, 1), (256, 128, 6), (8192, 96, 6), (2048, 192, 6), (128 * 150, 96, 1)]:
+        for f16 in (1, 0):
+            dt = torch.float16 if f16 else torch.bfloat16
+            tol16 = 8e-4 if f16 else 5e-3
+            g = torch.Generator(device=dev).manual_seed(7 * rows + D + B)
+            x = torch.randn(B, rows, D, device=dev, generator=g) * 1.5 + 0.7 + torch.randn(B, rows, 1, device=dev, generator=g) * 3.0
+            W = (torch.randn(B, 3 * D, D, device=dev, generator=g) * 0.08).to(dt)
+            bias = torch.randn(B, 3 * D, device=dev, generator=g) * 0.3
+            out = torch.empty(B, rows, 3 * D, device=dev, dtype=dt)
+            _lib.check(lib.vv_test_lin_fwd(P(x), P(W), P(bias), rows, B, D, 3 * D, f16, eps, P(out), st))
+            torch.cuda.synchronize()
+            ref = torch.einsum("brk,bnk->brn", F.layer_norm(x, (D,), eps=eps).to(dt).float(), W.float()) + bias[:, None, :]
+            ok &= report("mlp", f"norm1+qkv {rows}x{D}x{B} {'f16' if f16 else 'bf16'}", rel(out.float(), ref), tol16)
+    for (rows, D, B) in [(8192, 96, 6), (2048, 192, 6)]:
+        x = torch.randn(B, rows, D, device=dev); W = (torch.randn(B, 3 * D, D, device=dev) * 0.08).half(); bias = torch.randn(B, 3 * D, device=dev)
+        out = torch.empty(B, rows, 3 * D, device=dev, dtype=torch.float16)
+        fn = lambda: lib.vv_test_lin_fwd(P(x), P(W), P(bias), rows, B, D, 3 * D, 1, eps, P(out), st)
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(30):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f"[mlp] time norm1+qkv {rows}x{D}x{B}: {e0.elapsed_time(e1) / 30 * 1e3:.1f} us", flush=True)
     # timing at the engine's shapes
     for (rows, D, B) in [(8192, 96, 6), (2048, 192, 6)]:
         dt = torch.float16

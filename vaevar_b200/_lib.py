@@ -78,6 +78,7 @@ _SIGS = {
                                   C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
     "vv_test_mlp_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P, _P]),
     "vv_test_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
+    "vv_test_lin_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "vv_debug_mlp_trace": (C.c_int, [_P]),
     "vv_debug_cubic_interpolate": (C.c_double, [C.c_double] * 6 + [C.c_int] * 3 + [C.c_double] * 2),
     "vv_test_ln_stats": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

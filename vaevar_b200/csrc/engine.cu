@@ -117,6 +117,7 @@ static const char* op_family(Op::Kind k) {
     case Op::CT32: return "conv-transpose head (3,2)";
     case Op::MLP_F: return "fused tower MLP fwd (tcgen05)";
     case Op::MLP_B: return "fused tower MLP bwd (tcgen05)";
+    case Op::LIN_F: return "fused tower norm1 + qkv (tcgen05)";
   }
   return "op";
 }
@@ -138,7 +139,7 @@ int Plan::run(cudaStream_t s) const {
       case Op::ATT1: launch_attn1(o.att1, s); break;
       case Op::PE32: launch_patch32(o.pe32, s); break;
       case Op::CT32: launch_convt32(o.ct32, s); break;
-      case Op::MLP_F: case Op::MLP_B: launch_mlp(o.mlp, s); break;
+      case Op::MLP_F: case Op::MLP_B: case Op::LIN_F: launch_mlp(o.mlp, s); break;
     }
     if (nv) nvtxRangePop();
   }
@@ -525,9 +526,17 @@ struct Builder {
                  bf16* copy_b, long long ld_c, long long bs_c, int& parts, int& prod_bn, bool emit_next) {
     const int G = w.G, d = w.d, rows = gh * gw;
     const long long rd = (long long)rows * d;
+    const bool fused = mlp_fused(w, rows);      // tower block: norm1 + qkv and the whole MLP half on mlp_fused_kernel
     GemmArgs g = ga(rows, 3 * d, d, G);
     g.out_bf16 = st.qkv; g.ld_bf16 = 3 * d; g.bf16_bs = 3 * rd; g.bias_bs = 3 * d;
-    if (fold) {
+    if (fused) {
+      MlpArgs q{};
+      q.rows = rows; q.batch = G; q.f16 = f16; q.eps = 1e-5f; q.x1 = x; q.b1 = w.cqkv; q.n_out = 3 * d;
+      Op o{}; o.kind = Op::LIN_F;
+      const char* er = make_lin_desc(&o.mlp, d, w.Wqkv, st.qkv, 3LL * d, 3 * rd, q);
+      if (er && !err) err = er;
+      P.ops.push_back(o);
+    } else if (fold) {
       if (parts == 0) { ln_stats(P, rows, d, G, x); parts = 1; prod_bn = 0; }
       g.bias = w.cqkv;
       fold_ln(g, parts, prod_bn, w.sqkv, d, 1e-5f);
@@ -535,24 +544,20 @@ struct Builder {
       ln_f(P, rows, d, G, MAP_PLAIN, gh, gw, 1e-5f, x, d, rd, w.g1, w.be1, t.h, d, rd, nullptr, 0, 0);
       g.bias = w.bqkv;
     }
-    gemm(P, t.h, d, rd, w.Wqkv, d, 3LL * d * d, g);
+    if (!fused) gemm(P, t.h, d, rd, w.Wqkv, d, 3LL * d * d, g);
     Op o{}; o.kind = Op::ATT_F;
     o.att = AttnArgs{gh, gw, w.heads, d / w.heads, shift, G, st.qkv, 3LL * d, 3 * rd, w.relbias, (long long)w.heads * 256, t.ao, d, rd, nullptr, nullptr, f16};
     P.ops.push_back(o);
     g = ga(rows, d, d, G);
     g.bias = w.bproj; g.bias_bs = d; g.res = x; g.ld_res = d; g.res_bs = rd; g.out_f32 = st.x1; g.ld_f32 = d; g.f32_bs = rd;
-    if (mlp_fused(w, rows)) {
-      // the MLP half as one kernel: norm2 is computed from x1 inside it, so proj only has to leave the fp32 residual stream
+    if (fused) {
+      // the MLP half as one kernel: norm2 is computed from x1 inside it, so proj only has to leave the fp32 residual stream; the next
+      // block's norm1 is computed inside its qkv kernel, so no statistics / centred copy of the output are needed either
       gemm(P, t.ao, d, rd, w.Wproj, d, (long long)d * d, g);
       MlpArgs m{};
       m.rows = rows; m.batch = G; m.f16 = f16; m.eps = 1e-5f; m.x1 = st.x1; m.b1 = w.c1; m.b2 = w.b2; m.out_f32 = x_out; m.u_out = st.u;
-      if (emit_next) {
-        m.out16 = t.h; m.ld16 = d; m.bs16 = rd; m.shift = t.lnshift; m.stats_out = t.lnst;
-        parts = 1; prod_bn = 0;
-      } else {
-        if (copy_b) { m.out16 = copy_b; m.ld16 = ld_c; m.bs16 = bs_c; }
-        parts = 0;
-      }
+      if (copy_b && !emit_next) { m.out16 = copy_b; m.ld16 = ld_c; m.bs16 = bs_c; }
+      parts = 0;
       mlp(P, false, d, w.W1, w.W2, st.u, nullptr, m);
       return;
     }
@@ -1530,11 +1535,12 @@ VV_API int vv_profile_ops(vv_engine* e, int app, int bwd, int reps, float* ms_ou
     if (k < cap) {
       ms_out[k] = ms / reps;
       kind_out[k] = (int)o.kind;
-      const bool is_mlp = o.kind == Op::MLP_F || o.kind == Op::MLP_B;
+      const bool is_lin = o.kind == Op::LIN_F, is_mlp = o.kind == Op::MLP_F || o.kind == Op::MLP_B || is_lin;
       if (flop_out) flop_out[k] = o.kind == Op::GEMM ? 2.0 * o.gemm.a.M * o.gemm.a.N * o.gemm.a.K * o.gemm.a.batch
+                                  : is_lin ? 2.0 * o.mlp.a.rows * o.mlp.a.n_out * o.mlp.D * o.mlp.a.batch
                                   : is_mlp ? 16.0 * o.mlp.a.rows * o.mlp.D * o.mlp.D * o.mlp.a.batch : 0.0;      // two GEMMs of rows x 4D x D
       if (mnk_out && is_mlp) {
-        mnk_out[4 * k] = o.mlp.a.rows; mnk_out[4 * k + 1] = 4 * o.mlp.D; mnk_out[4 * k + 2] = o.mlp.D; mnk_out[4 * k + 3] = o.mlp.a.batch;
+        mnk_out[4 * k] = o.mlp.a.rows; mnk_out[4 * k + 1] = is_lin ? o.mlp.a.n_out : 4 * o.mlp.D; mnk_out[4 * k + 2] = o.mlp.D; mnk_out[4 * k + 3] = o.mlp.a.batch;
       } else if (mnk_out) {
         mnk_out[4 * k] = o.kind == Op::GEMM ? o.gemm.a.M : (o.kind == Op::LN_F ? o.lnf.rows : o.kind == Op::LN_B ? o.lnb.rows : 0);
         mnk_out[4 * k + 1] = o.kind == Op::GEMM ? o.gemm.a.N : (o.kind == Op::LN_F ? o.lnf.C : o.kind == Op::LN_B ? o.lnb.C : (o.kind == Op::ATT_F || o.kind == Op::ATT_B) ? o.att.hd : 0);

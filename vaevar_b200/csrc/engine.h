@@ -17,7 +17,7 @@ void launch_fold_ln(bf16* dst, float* colsum, float* cbias, const float* W, cons
 bool ln_supported(int map, int C);
 
 struct Op {
-  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P, ROPE, ATT1, PE32, CT32, MLP_F, MLP_B } kind;
+  enum Kind { GEMM, LN_F, LN_B, ATT_F, ATT_B, P2T, T2P, ROPE, ATT1, PE32, CT32, MLP_F, MLP_B, LIN_F } kind;
   GemmDesc gemm;
   LnArgs lnf;
   LnBwdArgs lnb;

@@ -19,7 +19,7 @@ bool mlp_fused_supported(int D, int rows) {
 // u: [batch][rows][4D] saved gelu'(u) (written by the forward kernel, read by the backward one);  dy16: backward only, [batch][rows][D] bf16.
 const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const bf16* W1, const bf16* W2, const bf16* u, const bf16* dy16, const MlpArgs& args) {
   if (!mlp_fused_supported(D, args.rows)) return "fused MLP: token width / row count not supported";
-  d->D = D; d->bwd = bwd ? 1 : 0; d->a = args;
+  d->D = D; d->bwd = bwd ? 1 : 0; d->mode = bwd ? MLP_BWD : MLP_FWD; d->a = args;
   d->a.trace = g_mlp_trace;
   const unsigned long long wb = 4ull * D * D * args.batch * 2;                     // bytes of one of the two weight blocks
   const bool adj = reinterpret_cast<const char*>(W2) == reinterpret_cast<const char*>(W1) + wb;
@@ -38,23 +38,24 @@ const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const bf16* W1, const bf1
   return nullptr;
 }
 
-template <int D, bool BWD, bool F16>
+template <int D, int MODE, bool F16>
 static void launch_mlp_t(const MlpDesc& d, cudaStream_t s) {
-  using L = MlpSmem<D, BWD>;
+  using L = MlpSmem<D, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(mlp_fused_kernel<D, BWD, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaFuncSetAttribute(mlp_fused_kernel<D, MODE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     attr_set = true;
   }
   const int tiles = (d.a.rows / 128) * d.a.batch;
-  launch_kernel(mlp_fused_kernel<D, BWD, F16>, dim3(std::min(tiles, num_sms())), dim3(MLP_THREADS), L::TOTAL, s, d.tmW1, d.tmW2, d.tmA, d.tmU, d.a);
+  launch_kernel(mlp_fused_kernel<D, MODE, F16>, dim3(std::min(tiles, num_sms())), dim3(MLP_THREADS), L::TOTAL, s, d.tmW1, d.tmW2, d.tmA, d.tmU, d.a);
 }
 
 template <int D>
 static void launch_mlp_d(const MlpDesc& d, cudaStream_t s) {
-  if (d.bwd) launch_mlp_t<D, true, false>(d, s);
-  else if (d.a.f16) launch_mlp_t<D, false, true>(d, s);
-  else launch_mlp_t<D, false, false>(d, s);
+  if (d.mode == MLP_BWD) launch_mlp_t<D, MLP_BWD, false>(d, s);
+  else if (d.mode == MLP_LIN) { if (d.a.f16) launch_mlp_t<D, MLP_LIN, true>(d, s); else launch_mlp_t<D, MLP_LIN, false>(d, s); }
+  else if (d.a.f16) launch_mlp_t<D, MLP_FWD, true>(d, s);
+  else launch_mlp_t<D, MLP_FWD, false>(d, s);
 }
 
 void launch_mlp(const MlpDesc& d, cudaStream_t s) {
@@ -65,6 +66,22 @@ void launch_mlp(const MlpDesc& d, cudaStream_t s) {
     case 192: launch_mlp_d<192>(d, s); break;
     default: break;
   }
+}
+
+// LayerNorm + ONE Linear of a tower block (norm1 -> qkv, swinblock.py:268-269 + :139) on the same kernel: out16 [batch][rows][n_out] =
+// 16bit(normalise(x) W^T + bias) with W (batch, n_out, D) carrying gamma and bias the folded beta.
+const char* make_lin_desc(MlpDesc* d, int D, const bf16* W, bf16* out16, long long ld_out, long long out_bs, const MlpArgs& args) {
+  if (!mlp_fused_supported(D, args.rows)) return "fused LayerNorm + Linear: token width / row count not supported";
+  if (args.n_out <= 0 || args.n_out % 16 || args.n_out > 5 * D) return "fused LayerNorm + Linear: n_out must be a multiple of 16, at most 5 D";
+  d->D = D; d->bwd = 0; d->mode = MLP_LIN; d->a = args;
+  d->a.trace = nullptr;
+  const long long rows = args.rows, B = args.batch;
+  const char* e;
+  if ((e = encode_tma_3d_16(&d->tmW1, W, D, args.n_out, B, D, (long long)args.n_out * D, 64, MLP_HC))) return e;
+  d->tmW2 = d->tmW1; d->tmA = d->tmW1;                                                  // unused
+  if ((e = encode_tma_3d_16(&d->tmU, out16, args.n_out, rows, B, ld_out, out_bs, 16, 32))) return e;
+  d->w_ptr = W; d->w_bytes = (unsigned long long)args.n_out * D * B * 2;
+  return nullptr;
 }
 
 }  // namespace vv
@@ -106,6 +123,20 @@ VV_API int vv_test_mlp_bwd(const void* dy16, const void* u, const float* x1, con
   if (er) { set_error("%s", er); return -2; }
   launch_mlp(d, (cudaStream_t)stream);
   if (cudaGetLastError() != cudaSuccess) { set_error("vv_test_mlp_bwd: launch failed"); return -1; }
+  return 0;
+}
+
+// Kernel-level hook: out_16 (batch, rows, n_out) = 16bit(normalise(x) W^T + bias), W (batch, n_out, D) 16-bit, bias (batch, n_out) fp32.
+VV_API int vv_test_lin_fwd(const float* x, const void* W, const float* bias, int rows, int batch, int D, int n_out, int f16, float eps,
+                           void* out16, void* stream) {
+  if (!mlp_fused_supported(D, rows)) { set_error("vv_test_lin_fwd: D must be 64 / 96 / 128 / 192 and rows a multiple of 128"); return -2; }
+  MlpArgs a{};
+  a.rows = rows; a.batch = batch; a.f16 = f16; a.eps = eps; a.x1 = x; a.b1 = bias; a.n_out = n_out;
+  MlpDesc d;
+  const char* er = make_lin_desc(&d, D, (const bf16*)W, (bf16*)out16, n_out, (long long)rows * n_out, a);
+  if (er) { set_error("%s", er); return -2; }
+  launch_mlp(d, (cudaStream_t)stream);
+  if (cudaGetLastError() != cudaSuccess) { set_error("vv_test_lin_fwd: launch failed"); return -1; }
   return 0;
 }
 

@@ -31,6 +31,7 @@ namespace vv {
 struct MlpArgs {
   int rows, batch;               // token rows per batch entry (a multiple of 128), batch entries (variable groups)
   int f16;                       // forward: operands and the saved gelu' are IEEE fp16 (1) or bf16 (0); backward: format of the saved gelu'
+  int n_out;                     // MLP_LIN only: output columns of the one Linear (3D for qkv)
   float eps;
   const float* x1;               // [batch][rows][D] fp32: the residual stream after the attention half (input of norm2)
   // forward
@@ -50,29 +51,32 @@ struct MlpArgs {
   unsigned long long* trace;     // debug: clock64 stamps of CTA 0 (128 slots, see tools/mlp_trace.py); null in production
 };
 
+enum MlpMode : int { MLP_FWD = 0, MLP_BWD = 1, MLP_LIN = 2 };   // MLP_LIN: LayerNorm + ONE Linear (norm1 -> qkv of a tower block), forward
+
 constexpr int MLP_THREADS = 576;
 constexpr int MLP_EPI_WARPS = 16;
 constexpr int MLP_HC = 64;       // hidden columns per chunk
 
-template <int D, bool BWD>
+template <int D, int MODE>
 struct MlpSmem {
+  static constexpr bool BWD = MODE == MLP_BWD, LIN = MODE == MLP_LIN;
   static constexpr int KSD = (D + 63) / 64;                 // 64-column swizzle slabs of a K = D operand
-  static constexpr int NCH = 4 * D / MLP_HC;
+  static constexpr int NCH = LIN ? (3 * D + MLP_HC - 1) / MLP_HC : 4 * D / MLP_HC;
   static constexpr int W1C = MLP_HC * 128 * KSD;            // W1 chunk: 64 rows x KSD slabs of 128 B
-  static constexpr int W2C = D * 128;                       // W2 chunk: D rows x one slab
+  static constexpr int W2C = LIN ? 0 : D * 128;             // W2 chunk: D rows x one slab
   static constexpr int STAGE = W1C + W2C;
   // PIPE: the transposition buffer of the final epilogue does not alias the A tile, so the next tile's A (forward: its LayerNorm
-  // prologue, backward: its TMA load) and first GEMMs run under the final epilogue of the current tile
-  static constexpr bool PIPE = D <= 96;
-  static constexpr int NST = BWD ? (D <= 64 ? 4 : D <= 128 ? 3 : 2) : (D <= 96 ? 4 : D <= 128 ? 3 : 2);
+  // prologue, backward: its TMA load) and first GEMMs run under the final epilogue of the current tile.  MLP_LIN has no final epilogue.
+  static constexpr bool PIPE = LIN || D <= 96;
+  static constexpr int NST = LIN ? 4 : BWD ? (D <= 64 ? 4 : D <= 128 ? 3 : 2) : (D <= 96 ? 4 : D <= 128 ? 3 : 2);
   // hidden buffers: forward 2 (filled by epilogue 1); backward as many as fit -- they are the prefetch depth of the saved gelu'(u),
   // which streams from HBM (37.7 MB per d = 96 launch) with ~1 us of latency per chunk
-  static constexpr int NH = BWD ? (D == 96 ? 5 : 4) : 2;
+  static constexpr int NH = LIN ? 1 : BWD ? (D == 96 ? 5 : 4) : 2;
   static constexpr int A_BYTES = KSD * 16384;
-  static constexpr int HID = 16384;
+  static constexpr int HID = LIN ? 0 : 16384;
   static constexpr int GP = BWD ? 0 : MLP_EPI_WARPS * 2 * 1024;   // per warp: two slabs of 32 rows x 32 B
   static constexpr int STG_STRIDE = BWD ? 2 * D + 16 : 4 * D + 16;     // transposition buffer: bf16 (backward) / fp32 (forward) rows
-  static constexpr int STG_BYTES = 128 * STG_STRIDE;
+  static constexpr int STG_BYTES = LIN ? 0 : 128 * STG_STRIDE;
   static constexpr int OFF_A = NST * STAGE;
   static constexpr int OFF_HID = OFF_A + A_BYTES;
   static constexpr int OFF_GP = OFF_HID + NH * HID;
@@ -107,11 +111,12 @@ VV_DEVINL void tmem_ld8(uint32_t taddr, uint32_t* r) {
 // named barrier of the sixteen epilogue warps
 VV_DEVINL void mlp_epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-template <int D, bool BWD, bool F16>
+template <int D, int MODE, bool F16>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmU, const MlpArgs p) {
-  using L = MlpSmem<D, BWD>;
+  constexpr bool BWD = MODE == MLP_BWD, LIN = MODE == MLP_LIN;
+  using L = MlpSmem<D, MODE>;
   constexpr int KSD = L::KSD, NCH = L::NCH, NST = L::NST, NH = L::NH, HC = MLP_HC;
   constexpr bool PIPE = L::PIPE;
   constexpr int D4 = D / 4;                       // float4 per row
@@ -148,7 +153,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   const int total_tiles = tpb * p.batch;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmU);
+    tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmU);
+    if (!LIN) tma_prefetch_desc(&tmW2);
     if (BWD) tma_prefetch_desc(&tmA);
     for (int i = 0; i < NST; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < NH; ++i) { mbar_init(&hid_full[i], MLP_EPI_WARPS); mbar_init(&hid_empty[i], 1); mbar_init(&u_full[i], 1); }
@@ -182,7 +188,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           mbar_expect_tx(&w_full[st], L::STAGE);
 #pragma unroll
           for (int j = 0; j < KSD; ++j) tma_load_3d(sp + j * (HC * 128), &tmW1, &w_full[st], 64 * j, c * HC, g);
-          tma_load_3d(sp + L::W1C, &tmW2, &w_full[st], c * HC, 0, g);
+          if (!LIN) tma_load_3d(sp + L::W1C, &tmW2, &w_full[st], c * HC, 0, g);
         }
         __syncwarp();
         if (++st == NST) { st = 0; ++st_n; }
@@ -240,13 +246,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
               umma_bf16(tmem_base + b * HC, da, db, idesc1, k ? 1u : 0u);
             }
             umma_commit(&acc1_full[b]);
+            if (LIN) umma_commit(&w_empty[s1]);                      // no GEMM 2: the weight chunk is free once GEMM 1 has read it
             if (c == NCH - 1) umma_commit(a_empty);                  // every GEMM 1 of the tile has read A
           }
           __syncwarp();
           ++gc;
           if (++s1 == NST) { s1 = 0; ++s1n; }
         }
-        if (c > 0) {                                                 // GEMM 2 of chunk c - 1
+        if (!LIN && c > 0) {                                         // GEMM 2 of chunk c - 1
           if (c == 1) mbar_wait(acc2_empty, (ti & 1) ^ 1);           // the previous tile's acc2 has been drained
           mbar_wait(&hid_full[h2], h2n & 1);
           stamp();                                                     // GEMM 2: hidden chunk written
@@ -295,8 +302,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     auto prologue = [&](int tile, uint32_t ti) {
       const int g = tile / tpb, row0 = (tile - g * tpb) << 7;
       float* cs = reinterpret_cast<float*>(smem + L::OFF_CONST + (PIPE ? (ti & 1) : 0) * L::CONST_SET);
-      for (int i = threadIdx.x - 64; i < 5 * D; i += 512)
-        cs[i] = i < 4 * D ? __ldg(p.b1 + (long long)g * 4 * D + i) : __ldg(p.b2 + (long long)g * D + (i - 4 * D));
+      if (LIN) {
+        for (int i = threadIdx.x - 64; i < p.n_out; i += 512) cs[i] = __ldg(p.b1 + (long long)g * p.n_out + i);
+      } else {
+        for (int i = threadIdx.x - 64; i < 5 * D; i += 512)
+          cs[i] = i < 4 * D ? __ldg(p.b1 + (long long)g * 4 * D + i) : __ldg(p.b2 + (long long)g * D + (i - 4 * D));
+      }
       const float4* xr = reinterpret_cast<const float4*>(p.x1 + ((long long)g * p.rows + row0 + ew * 8) * D);
       float4 xv[NP][V];
 #pragma unroll
@@ -458,7 +469,33 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         if (elect_one()) mbar_arrive(&acc1_empty[b]);
         uint8_t* hrow = smem + L::OFF_HID + hb * L::HID + row * 128;
         const uint32_t o0 = (static_cast<uint32_t>(2 * cp) ^ sw) << 4, o1 = (static_cast<uint32_t>(2 * cp + 1) ^ sw) << 4;
-        if (!BWD) {
+        if (LIN) {
+          // the one Linear: acc + bias -> 16-bit -> this warp's staging slab -> TMA store (columns beyond n_out do not exist)
+          if (c * HC + cp * 16 < p.n_out) {
+            const float4* bs = reinterpret_cast<const float4*>(consts + c * HC + cp * 16);
+            uint32_t w[8];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bb = bs[i4];
+              const float2 a0 = add2(make_float2(__uint_as_float(r[4 * i4]), __uint_as_float(r[4 * i4 + 1])), make_float2(bb.x, bb.y));
+              const float2 a1 = add2(make_float2(__uint_as_float(r[4 * i4 + 2]), __uint_as_float(r[4 * i4 + 3])), make_float2(bb.z, bb.w));
+              w[2 * i4] = pack16<F16>(a0.x, a0.y); w[2 * i4 + 1] = pack16<F16>(a1.x, a1.y);
+            }
+            uint8_t* slab = gslab + (it & 1) * 1024;
+            if (elect_one()) tma_store_wait_read1();                 // the store issued two chunks ago has read this slab
+            __syncwarp();
+            *reinterpret_cast<uint4*>(slab + lane * 32) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(slab + lane * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            fence_proxy_async();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_3d(&tmU, slab, c * HC + cp * 16, row0 + q * 32, g);
+              tma_store_commit();
+            }
+          } else {
+            --it;                                                    // no store issued: keep the slab parity in step with the store groups
+          }
+        } else if (!BWD) {
           const float4* bs = reinterpret_cast<const float4*>(consts + c * HC + cp * 16);
           float y[16], d[16];
 #pragma unroll
@@ -516,6 +553,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 
       // forward, PIPE: the next tile's LayerNorm prologue comes BEFORE this tile's final epilogue -- its GEMM 1s then run under it
       if (!BWD && PIPE && tile + (int)gridDim.x < total_tiles) prologue(tile + gridDim.x, ti + 1);
+      if (LIN) {                                                     // no second GEMM, no final epilogue
+        mlp_epi_sync();                                              // the next tile's biases are in place for every warp
+        continue;
+      }
 
       // ---- final epilogue: acc2 (thread = row) -> transposition buffer -> row-wise phase with coalesced global traffic ----
       // what the row-wise phase needs from global memory is requested first: PG passes per group (register budget)

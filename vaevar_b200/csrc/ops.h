@@ -55,13 +55,14 @@ void set_gemm_trace(unsigned long long* dev_ptr);   // debug: GEMM descriptors b
 struct MlpDesc {
   CUtensorMap tmW1, tmW2, tmA, tmU;
   MlpArgs a;
-  int D, bwd;
+  int D, bwd, mode;             // mode: MlpMode
   const void* w_ptr;            // W1 | W2 as one contiguous block (null if they are not adjacent): what the GEMM before it prefetches
   unsigned long long w_bytes;
 };
 bool mlp_fused_supported(int D, int rows);
 const char* make_mlp_desc(MlpDesc* d, int D, bool bwd, const __nv_bfloat16* W1, const __nv_bfloat16* W2, const __nv_bfloat16* u,
                           const __nv_bfloat16* dy16, const MlpArgs& args);
+const char* make_lin_desc(MlpDesc* d, int D, const __nv_bfloat16* W, __nv_bfloat16* out16, long long ld_out, long long out_bs, const MlpArgs& args);
 void launch_mlp(const MlpDesc& d, cudaStream_t s);
 
 // ---- LayerNorm (one warp per row, fp32 statistics) -------------------------------------------

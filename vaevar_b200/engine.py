@@ -203,7 +203,7 @@ class Engine:
         n = self.lib.vv_profile_ops(self._h, app, int(bwd), reps, ms, kind, fl, mnk, cap, int(flush_l2))
         if n < 0:
             _lib.check(n)
-        names = ["gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "p2t", "t2p", "rope", "sd_attn", "patch32", "convt32", "mlp_fwd", "mlp_bwd"]
+        names = ["gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "p2t", "t2p", "rope", "sd_attn", "patch32", "convt32", "mlp_fwd", "mlp_bwd", "lin_fwd"]
         return [dict(kind=names[kind[i]], ms=ms[i], flop=fl[i], shape=tuple(mnk[4 * i:4 * i + 4])) for i in range(min(n, cap))]
 
     @property
