@@ -1,10 +1,12 @@
-// The MLP half of a tower Swin block in ONE kernel per direction (swinblock.py:13-29 Mlp, :304-307 x + mlp(norm2(x))):
+// The MLP half of a tower Swin block in ONE kernel per direction (swinblock.py:13-29 Mlp, :304-307 x + mlp(norm2(x))), and norm1 + qkv
+// of the same blocks (swinblock.py:268-269, 139) as a third mode of the same template:
 //
-//   forward    out = x1 + fc2( gelu( fc1( LN2(x1) ) ) )            saves gelu'(u) for the backward pass
-//   backward   dx1 = LN2^T( (dy W2 . gelu'(u)) W1 ) + dy            (input-VJP; weights are frozen, da_4dvar.py:590-603)
+//   MLP_FWD    out = x1 + fc2( gelu( fc1( LN2(x1) ) ) )            saves gelu'(u) for the backward pass
+//   MLP_BWD    dx1 = LN2^T( (dy W2 . gelu'(u)) W1 ) + dy            (input-VJP; weights are frozen, da_4dvar.py:590-603)
+//   MLP_LIN    qkv = LN1(x) Wqkv^T + b                              (LayerNorm prologue + one Linear, 16-bit output)
 //
-// The towers (d = 96 / 192, six variable groups batched) are K = 96 / 192 GEMMs: as four separate launches their cost was the
-// epilogue and the HBM round trips of the 4d-wide hidden activation (27 % of the step for 12 % of the flops).
+// The towers (d = 96 / 192, six variable groups batched) are K = 96 / 192 GEMMs: as separate launches their cost was the epilogue
+// and the HBM round trips of the 4d-wide hidden activation (27 % of the step for 12 % of the flops).
 // Here the hidden activation never leaves the SM: a CTA owns a 128-token tile and walks over the 4d hidden columns in chunks of 64,
 //
 //   GEMM 1 (chunk c)   acc1[c & 1] = A (128 x d)  *  W1[c]^T (64 x d)          tcgen05.mma.cta_group::1, M 128, N 64
@@ -12,17 +14,24 @@
 //   GEMM 2 (chunk c)   acc2 += h (128 x 64) * W2[:, c]^T (d x 64)               M 128, N d
 //
 // with acc1 double-buffered in TMEM so that GEMM 1 of chunk c + 1 runs under epilogue 1 of chunk c.  Both directions have this
-// shape (backward: A = dy, "W1" = W2^T, "W2" = W1^T), so one kernel template serves both.
-//   warp 0        TMA producer: a ring of weight chunks (W1[c] | W2[:, c]); backward also the dy tile and the saved gelu'(u) chunks,
-//                 which land in the very buffer epilogue 1 then overwrites with du
+// shape (backward: A = dy, "W1" = W2^T, "W2" = W1^T), so one kernel template serves both; MLP_LIN stops after epilogue 1 (acc1 + bias
+// -> 16 bit -> global).
+//   warp 0        TMA producer: a ring of weight chunks (W1[c] | W2[:, c]); backward also the dy tile and the saved gelu'(u) chunks --
+//                 up to a whole tile of them in flight (they stream from HBM) -- which land in the very buffers epilogue 1 then
+//                 overwrites in place with du
 //   warp 1        tcgen05.mma issuer, TMEM owner
 //   warps 2..17   sixteen epilogue warps (four per TMEM lane quarter, 16 hidden columns each per chunk; thread = token row).
-//                 Forward prologue: LayerNorm of the x1 tile (two-pass fp32, lanes across channels) straight into the swizzled
-//                 A operand -- norm2 is neither a launch nor a folded epilogue here, and the operand is the normalised value.
+//                 Forward prologue: LayerNorm of the x1 tile (two-pass fp32; 8 or 16 lanes per row, so every lane is busy and a row
+//                 reduction is 3 or 4 shuffles shared by the 4 or 2 rows of a warp pass) straight into the swizzled A operand -- the
+//                 LayerNorm is neither a launch nor a folded epilogue here, and the operand is the normalised value.  For d <= 96 the
+//                 NEXT tile's prologue runs before the current tile's final epilogue, whose first GEMMs then overlap it.
 //                 Final epilogue: acc2 is transposed through shared memory (thread = row -> lanes across channels) so that every
-//                 global access of the residual add / LayerNorm statistics / LayerNorm backward is coalesced.
-// Shared memory: weight ring | A tile | two hidden chunks | (forward) per-warp staging of the gelu' chunks for their TMA stores;
-// the transposition buffer of the final epilogue aliases A | hidden | staging, which are idle by then.
+//                 global access of the residual add / LayerNorm statistics / LayerNorm backward is coalesced; the backward's
+//                 row-wise phase is deferred into the next tile's chunk loop (the epilogue warps idle there: that loop runs at the
+//                 pace of the MMA-issue thread).  gelu'(u) and the MLP_LIN output leave through per-warp 32 x 16 slabs and TMA stores.
+// Shared memory: weight ring | A tile | hidden chunks | (forward) per-warp store slabs | (backward, d <= 96) transposition buffer;
+// otherwise the transposition buffer aliases hidden | slabs (and A for d >= 128), which are idle by then.
+// Measurements behind these choices: DESIGN.md section 6 ("Round 2, second half"); tools/mlp_probe.py, tools/mlp_trace.py, tools/ncu_mlp.sh.
 #pragma once
 #include "gemm_tcgen05.cuh"
 
