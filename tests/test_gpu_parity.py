@@ -703,3 +703,31 @@ def test_case_results_do_not_depend_on_the_rank_that_runs_them(chk):
     r0, r1 = records(3, 0, 2), records(3, 1, 2)   # the same cases dealt to two "ranks": 0 -> {0, 2}, 1 -> {1}
     assert r0[0] == serial[0] and r0[2] == serial[2] and r1[1] == serial[1]
     assert all(v[0] > 0 and v[2] != 0 for v in serial)
+
+
+def test_fused_tower_kernels_agree_with_the_separate_gemm_path(chk, monkeypatch):
+    """The tower blocks' fused kernels (mlp_fused.cuh: norm1 + qkv, the MLP half forward and its input-VJP) against the path they
+    replace (separate tcgen05 GEMMs with the folded LayerNorm, VV_NO_FUSED_MLP=1 -- still a supported switch): same J and gradient on a
+    T=3 window of the shrunken networks, and both within the usual gates of the CPU oracle."""
+    T = 3
+    res = {}
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("VV_NO_FUSED_MLP", raising=False)
+        else:
+            monkeypatch.setenv("VV_NO_FUSED_MLP", "1")
+        e, case, nets, oc = _small_engine_and_nets(T)
+        e.set_case(case["xb"], case["yo"], case["H"], case["R"], 1.0)
+        J, grad = e.cost_grad(torch.from_numpy(case["z"]).cuda())
+        res[fused] = (float(J[0]), grad.double().cpu().flatten(), e.last_launch_count)
+        e.close()
+    Jr, _, _, gr = oc.cost_and_grad(case["z"], oc.Case(case), nets)
+    gr = torch.from_numpy(gr).double().flatten()
+    (Jf, gf, nf), (Ju, gu, nu) = res[True], res[False]
+    cos = lambda a, b: float(a @ b / (a.norm() * b.norm()))
+    print(f"[parity fused vs separate] J rel {abs(Jf / Ju - 1):.2e}; grad cos {cos(gf, gu):.6f}; launches {nf} vs {nu}; "
+          f"vs oracle: J {abs(Jf / Jr - 1):.2e} / {abs(Ju / Jr - 1):.2e}, cos {cos(gf, gr):.6f} / {cos(gu, gr):.6f}")
+    assert nf < nu, "the fused path must be the one with fewer launches (is the switch read?)"
+    assert abs(Jf / Ju - 1) < 2e-4 and cos(gf, gu) > 0.9995
+    for J_, g_ in ((Jf, gf), (Ju, gu)):
+        assert abs(J_ / Jr - 1) < 1e-3 and abs(float(g_.norm() / gr.norm()) - 1) < 1e-2 and cos(g_, gr) > 0.999
