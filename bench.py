@@ -371,6 +371,9 @@ def main():
     roof_rows = [{"family": k, "launches_per_step": v[2], "ms_per_step": round(v[0], 3), "share_of_gemm_time": round(v[0] / max(gemm_ms, 1e-9), 3),
                   "TFLOP/s": round(v[1] / max(v[0], 1e-9) / 1e9, 1), "frac_of_sustained": round(v[1] / max(v[0], 1e-9) / 1e9 / sustained, 3)}
                  for k, v in fam.items()]
+    for r_ in roof_rows:                                      # dram__bytes_read + write of one d = 96 launch, `ncu --set full` (profiles/r2_ncu_mlp_*_summary.txt)
+        if "mlp_fused_kernel" in r_["family"]:
+            r_["dram_bytes_ncu"] = {"mlp forward 6x8192x96": 34.4e6, "mlp backward 6x8192x96": 99.6e6}
     # the trunk's fc1 shape alone, L2 flushed between launches (round 1's `roofline` row, kept as a second row)
     M, N, K = 2048, 4608, 1152
     A = torch.randn(1, M, K, device=dev).half(); W = (torch.randn(1, N, K, device=dev) * 0.05).half()
